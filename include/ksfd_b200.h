@@ -1,0 +1,179 @@
+/*
+ * ksfd_b200 — C ABI of the B200-native implicit time-stepping hot path of KSFD.
+ *
+ * This is the drop-in boundary: a plain C interface (pointers + sizes, no torch
+ * or C++ types) that a maintainer of leonavery/KSFD would bind from Python with
+ * ctypes.  Each entry point names the reference interface
+ * it replaces (file:line under the reference tree).
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error; the message of the
+ *    last error on the calling thread is returned by ksfd_last_error().
+ *  - all `double *` vector arguments are DEVICE pointers owned by the caller
+ *    (torch tensors on the Python side); no ownership is transferred.
+ *  - vectors hold the rank-local part of a field vector in the reference's
+ *    layout: fp64, Fortran order, dof fastest, then x, y, z
+ *    (KSFD/ksfdgrid.py:10-28); length dof * n_local_points.
+ *  - decomposition: 1-D slabs along the LAST spatial axis (y in 2-D, z in 3-D,
+ *    x in 1-D); ownership ranges equal PETSc DMDA's lx[i] = M/P + (M%P > i).
+ *  - `stream` is a cudaStream_t passed as void* (0 = default stream).
+ *  - a context is thread-compatible: use it from one host thread at a time.
+ */
+#ifndef KSFD_B200_H
+#define KSFD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KSFD_MAX_LIGANDS 7      /* dof <= 8 */
+#define KSFD_MAX_GROUPS 7
+#define KSFD_ABI_VERSION 1
+
+typedef struct ksfd_ctx ksfd_ctx;
+
+/*
+ * Plain-number problem description at one time t.  Replaces the constants the
+ * reference folds into its generated C ufuncs (KSFD/ksfdufunc.py:126-225) and
+ * the time-dependent scalar ufunc arguments (KSFD/ksfdsym.py:1432-1438).
+ * Potential: KSFD/ksfdligand.py:527-547,720-746; KSFD/ksfdsoln.py:147-161.
+ */
+typedef struct ksfd_physics {
+    int32_t ngroups;                       /* ligand groups with >= 1 ligand   */
+    int32_t nlig;                          /* total ligands (dof = nlig + 1)   */
+    int32_t cap_type;                      /* 0 = tophat, 1 = witch            */
+    int32_t reserved;
+    double s2, rhomax, cushion, maxscale;  /* G = V + s2*log(rho)              */
+    double rhomin, Umin;                   /* clamp (KSFD/ksfdsym.py:888-900)  */
+    double alpha[KSFD_MAX_GROUPS];
+    double beta[KSFD_MAX_GROUPS];
+    int32_t lig_group[KSFD_MAX_LIGANDS + 1]; /* group index of each ligand     */
+    double weight[KSFD_MAX_LIGANDS];
+    double s[KSFD_MAX_LIGANDS];
+    double gamma[KSFD_MAX_LIGANDS];
+    double D[KSFD_MAX_LIGANDS];
+    /* finite-difference weights per axis for offsets -2,-1,0,+1,+2
+       (KSFD/ksfdsym.py:391-436), computed on the host the way the reference
+       does so last-bit asymmetries are kept */
+    double w1[3][5];
+    double w2[3][5];
+} ksfd_physics;
+
+/* ---- library ---------------------------------------------------------- */
+int ksfd_abi_version(void);
+const char *ksfd_last_error(void);
+/* number of CUDA kernels launched by this library in this process so far */
+int64_t ksfd_launch_count(void);
+
+/* ---- context: grid + distribution (replaces KSFD.Grid's three PETSc DMDAs,
+ *      KSFD/ksfdgrid.py:61-177,388-411) -------------------------------- */
+int ksfd_ctx_create(ksfd_ctx **out, int dim, const int64_t n_global[3],
+                    int64_t last_start, int64_t last_count, int dof,
+                    int device);
+int ksfd_ctx_destroy(ksfd_ctx *ctx);
+int ksfd_set_physics(ksfd_ctx *ctx, const ksfd_physics *phys);
+/* kernel selection / tile tuning: key in {"variant","tx","ty","rz","threads"};
+   variant 0 = auto, 1 = naive direct kernels, 2 = marching kernels */
+int ksfd_set_option(ksfd_ctx *ctx, const char *key, int64_t value);
+int64_t ksfd_local_size(const ksfd_ctx *ctx);   /* dof * owned points */
+
+/* ---- multi-GPU: NCCL ring of slabs (replaces DMDA globalToLocal,
+ *      KSFD/ksfdsym.py:704,787,920,1203, and mpi allreduce,
+ *      KSFD/ksfdts.py:244,252,310-313) --------------------------------- */
+int ksfd_nccl_unique_id(const char *libnccl_path, char id_out[128]);
+int ksfd_comm_init(ksfd_ctx *ctx, const char *libnccl_path, int nranks,
+                   int rank, const char id[128]);
+/* fill this rank's ghost planes of `vec` (kept inside the context, slot 0..3) */
+int ksfd_halo_exchange(ksfd_ctx *ctx, const double *vec, int slot,
+                       void *stream);
+
+/* ---- operator: replaces Derivatives.groom/dfdt/velocity and implicitIF
+ *      (KSFD/ksfdsym.py:888-940,1188-1209; KSFD/ksfdts.py:563-596) ------- */
+int ksfd_groom(ksfd_ctx *ctx, double *u, void *stream);
+/* f_out = udot - (f(u) + src)  when udot != NULL   (implicitIF)
+   f_out =        f(u) + src    when udot == NULL   (Derivatives.dfdt)
+   src may be NULL (no source terms); u is clamped on the fly, not modified */
+int ksfd_residual(ksfd_ctx *ctx, const double *u, const double *udot,
+                  const double *src, double *f_out, void *stream);
+/* vmax_out[d] = max |grad_d G| over owned points, d < dim (device pointer);
+   caller reduces over ranks (ksfd_allreduce_max)  (KSFD/ksfdts.py:302-319) */
+int ksfd_velocity_max(ksfd_ctx *ctx, const double *u, double *vmax_out,
+                      void *stream);
+int ksfd_velocity(ksfd_ctx *ctx, const double *u, double *vel_out,
+                  void *stream);      /* (dim, owned points) F-order */
+
+/* ---- Jacobian action: replaces implicitIJ / Derivatives.Jacobian /
+ *      ksfdMat.setValuesJacobian (KSFD/ksfdts.py:598-640,
+ *      KSFD/ksfdsym.py:630-886, cython/ksfdMat/ksfdMat.pyx:55-180) ------- */
+/* linearise at u_lin: builds the per-point coefficient field and the
+   block-Jacobi preconditioner of A = shift*I - df/du on the device */
+int ksfd_jvp_setup(ksfd_ctx *ctx, const double *u_lin, double shift,
+                   void *stream);
+int ksfd_jvp(ksfd_ctx *ctx, const double *v, double *out, void *stream);
+/* out = A * M^{-1} v  (fused right-preconditioned operator) */
+int ksfd_jvp_precond(ksfd_ctx *ctx, const double *v, double *out,
+                     void *stream);
+int ksfd_pc_apply(ksfd_ctx *ctx, const double *r, double *z, void *stream);
+/* dense copy of the per-point diagonal blocks of A (dof*dof per point, row
+   major), for tests */
+int ksfd_block_diagonal(ksfd_ctx *ctx, double *blocks_out, void *stream);
+
+/* ---- fused BLAS-1 (replaces PETSc VecMAXPY/VecMDot/VecNorm) ------------ */
+int ksfd_mdot(ksfd_ctx *ctx, int nv, const double *const *vs, const double *w,
+              double *out_dev, void *stream);   /* out[i] = <vs[i], w> global */
+int ksfd_maxpy(ksfd_ctx *ctx, int nv, const double *coef_host,
+               const double *const *vs, double *y, void *stream);
+int ksfd_norm2(ksfd_ctx *ctx, const double *x, double *out_host);
+int ksfd_sum_dof0(ksfd_ctx *ctx, const double *u, double *out_host);
+int ksfd_scale_dof0(ksfd_ctx *ctx, double *u, double factor, void *stream);
+
+/* ---- linear solve: replaces KSP preonly + PC LU (MUMPS) with a
+ *      device-resident restarted GMRES, right-preconditioned by block
+ *      Jacobi.  Solves A x = rhs with A from the last ksfd_jvp_setup ------ */
+typedef struct ksfd_ksp_opts {
+    double rtol, atol, dtol;
+    int32_t max_it, restart;
+    int32_t reorth;            /* 0 = classical GS once, 1 = twice (CGS2) */
+    int32_t precond;           /* 0 = none, 1 = point-block Jacobi        */
+} ksfd_ksp_opts;
+typedef struct ksfd_ksp_result {
+    int32_t its, reason;       /* reason > 0 converged, < 0 diverged      */
+    double rnorm0, rnorm;
+} ksfd_ksp_result;
+int ksfd_gmres(ksfd_ctx *ctx, const double *rhs, double *x,
+               const ksfd_ksp_opts *opts, ksfd_ksp_result *res, void *stream);
+
+/* ---- time step: replaces PETSc TS.step() for -ts_type rosw (ra34pw2) and
+ *      beuler with -snes_type ksponly (call site KSFD/ksfdts.py:211) ------ */
+typedef void (*ksfd_time_cb)(double t, void *user);  /* set physics/sources */
+typedef struct ksfd_ts_opts {
+    int32_t ts_type;           /* 0 = rosw ra34pw2, 1 = beuler */
+    int32_t adapt;             /* 0 = none, 1 = basic          */
+    double atol, rtol;         /* TSSetTolerances               */
+    double clip_lo, clip_hi, dt_min, dt_max, safety, reject_safety;
+    int32_t max_reject;
+    int32_t reserved;
+    ksfd_ksp_opts ksp;
+} ksfd_ts_opts;
+typedef struct ksfd_ts_result {
+    double t_new, h_used, h_next, enorm;
+    int32_t accepted, rejections, ksp_its, ksp_fail;
+} ksfd_ts_result;
+/* advance u (in place) from t by one accepted step of size <= h.
+   src: device array of source terms or NULL; if cb != NULL it is called with
+   each stage time before the stage residual so the host can update physics /
+   refill src. */
+int ksfd_ts_step(ksfd_ctx *ctx, double *u, double t, double h,
+                 const ksfd_ts_opts *opts, const double *src, ksfd_time_cb cb,
+                 void *user, ksfd_ts_result *res, void *stream);
+
+/* scalar all-reduce helpers over the context communicator (host values) */
+int ksfd_allreduce_max(ksfd_ctx *ctx, double *vals_host, int n);
+int ksfd_allreduce_sum(ksfd_ctx *ctx, double *vals_host, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KSFD_B200_H */

@@ -1,0 +1,1311 @@
+// ksfd_b200: host side of the C ABI (include/ksfd_b200.h): context, kernel
+// launch heuristics, NCCL halo ring, device-resident GMRES, ROSW/BEuler step.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "blas1_kernels.cuh"
+#include "device_common.cuh"
+#include "march_kernels.cuh"
+#include "naive_kernels.cuh"
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int64_t g_launches = 0;
+
+static int fail(const std::string &m)
+{
+    g_err = m;
+    return 1;
+}
+#define CK(call)                                                              \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess)                                                \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define CKL()                                                                 \
+    do {                                                                      \
+        ++g_launches;                                                         \
+        cudaError_t e_ = cudaGetLastError();                                  \
+        if (e_ != cudaSuccess)                                                \
+            return fail(std::string("kernel launch: ") +                      \
+                        cudaGetErrorString(e_) + " at " + __FILE__ + ":" +    \
+                        std::to_string(__LINE__));                            \
+    } while (0)
+#define TRY(x)                 \
+    do {                       \
+        int r_ = (x);          \
+        if (r_) return r_;     \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// NCCL through dlopen (torch ships libnccl.so.2; no header needed)
+// ---------------------------------------------------------------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSum_ = 0, ncclMax_ = 2 };
+enum { ncclFloat64_ = 8 };
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t,
+                     cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load(const char *path)
+{
+    if (g_nccl.h) return 0;
+    void *h = nullptr;
+    if (path && path[0]) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(std::string("cannot dlopen libnccl: ") + dlerror());
+    g_nccl.h = h;
+#define SYM(n)                                                     \
+    *(void **)(&g_nccl.n) = dlsym(h, "nccl" #n);                   \
+    if (!g_nccl.n) return fail("libnccl lacks symbol nccl" #n);
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(Send) SYM(Recv)
+    SYM(AllReduce) SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
+#undef SYM
+    return 0;
+}
+#define NK(call)                                                          \
+    do {                                                                  \
+        int r_ = (call);                                                  \
+        if (r_ != 0)                                                      \
+            return fail(std::string(#call) + ": " + g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+#define KSFD_HALO_SLOTS 4
+#define KSFD_NSCAL 512          // device/host scalar scratch
+#define SC_H 0                  // Hessenberg column (<= 128)
+#define SC_H2 128               // second Gram-Schmidt pass
+#define SC_NORM 300
+#define SC_ENORM 301
+struct ksfd_ctx {
+    int dim = 0, dof = 0, device = 0;
+    long long n[3] = {1, 1, 1};
+    long long last_start = 0, last_count = 0, last_global = 0;
+    Geom g{};
+    DevPhys P{};
+    bool have_phys = false;
+    // options
+    int variant = 0, opt_tx = 0, opt_ty = 0, opt_rz = 0, opt_threads = 0;
+    // comm
+    int nranks = 1, rank = 0;
+    ncclComm_t comm = nullptr;
+    // halo slots: [lo(2 planes) | hi(2 planes)] per slot, sized for dof+2 stride
+    double *halo[KSFD_HALO_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    size_t halo_plane_doubles = 0;
+    // Jacobian state
+    double *coef = nullptr;      // ghosted (nloc+4 planes) x (dof+2)
+    double *pc = nullptr;        // nloc planes x dof
+    double shift = 0.0;
+    bool have_jac = false;
+    // reductions
+    double *partial = nullptr;   // [KSFD_MAXV+1][KSFD_RED_BLOCKS]
+    double *dscal = nullptr;     // device scalars (KSFD_NSCAL)
+    double *hscal = nullptr;     // pinned host scalars (KSFD_NSCAL)
+    void *plan_cache = nullptr;  // std::map<long long, MarchPlan>*
+    // solver workspace
+    double *krylov = nullptr;    // (restart+1) vectors
+    int krylov_cap = 0;
+    double *work[12] = {nullptr};
+    int sm_count = 148;
+    int max_smem = 232448;
+};
+
+static void free_plans(ksfd_ctx *c);
+static long long nlocal(const ksfd_ctx *c) { return c->g.npts * c->dof; }
+
+static int ensure_work(ksfd_ctx *c, int i)
+{
+    if (!c->work[i]) CK(cudaMalloc(&c->work[i], sizeof(double) * nlocal(c)));
+    return 0;
+}
+
+extern "C" int ksfd_abi_version(void) { return KSFD_ABI_VERSION; }
+extern "C" const char *ksfd_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t ksfd_launch_count(void) { return g_launches; }
+
+extern "C" int ksfd_ctx_create(ksfd_ctx **out, int dim, const int64_t n_global[3],
+                               int64_t last_start, int64_t last_count, int dof,
+                               int device)
+{
+    if (!out) return fail("ksfd_ctx_create: out is NULL");
+    if (dim < 1 || dim > 3) return fail("KSFD.Grid dimension must be 1, 2, or 3");
+    if (dof < 2 || dof > KSFD_MAX_LIGANDS + 1)
+        return fail("dof must be in [2, " + std::to_string(KSFD_MAX_LIGANDS + 1) + "]");
+    for (int d = 0; d < dim; ++d)
+        if (n_global[d] < 1) return fail("grid extents must be >= 1");
+    if (last_count < KSFD_SW)
+        return fail("each rank must own at least stencil_width planes");
+    if (last_start < 0 || last_start + last_count > n_global[dim - 1])
+        return fail("ownership range outside the grid");
+    CK(cudaSetDevice(device));
+    ksfd_ctx *c = new ksfd_ctx();
+    c->dim = dim;
+    c->dof = dof;
+    c->device = device;
+    for (int d = 0; d < dim; ++d) c->n[d] = n_global[d];
+    c->last_start = last_start;
+    c->last_count = last_count;
+    c->last_global = n_global[dim - 1];
+    Geom &g = c->g;
+    g.dim = dim;
+    g.dof = dof;
+    g.n0 = dim >= 2 ? (int)c->n[0] : 1;
+    g.n1 = dim >= 3 ? (int)c->n[1] : 1;
+    g.nloc = (int)last_count;
+    g.plane_pts = (long long)g.n0 * g.n1;
+    g.npts = g.plane_pts * g.nloc;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->max_smem = (int)prop.sharedMemPerBlockOptin;
+    CK(cudaMalloc(&c->partial, sizeof(double) * (KSFD_MAXV + 1) * KSFD_RED_BLOCKS));
+    CK(cudaMalloc(&c->dscal, sizeof(double) * KSFD_NSCAL));
+    CK(cudaMallocHost(&c->hscal, sizeof(double) * KSFD_NSCAL));
+    c->halo_plane_doubles = (size_t)g.plane_pts * (dof + 2);
+    *out = c;
+    return 0;
+}
+
+extern "C" int ksfd_ctx_destroy(ksfd_ctx *c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (auto &h : c->halo) cudaFree(h);
+    cudaFree(c->coef);
+    cudaFree(c->pc);
+    cudaFree(c->partial);
+    cudaFree(c->dscal);
+    cudaFreeHost(c->hscal);
+    cudaFree(c->krylov);
+    for (auto &w : c->work) cudaFree(w);
+    free_plans(c);
+    delete c;
+    return 0;
+}
+
+extern "C" int64_t ksfd_local_size(const ksfd_ctx *c) { return c ? nlocal(c) : 0; }
+
+extern "C" int ksfd_set_physics(ksfd_ctx *c, const ksfd_physics *p)
+{
+    if (!c || !p) return fail("ksfd_set_physics: NULL argument");
+    if (p->nlig != c->dof - 1)
+        return fail("physics.nlig must equal dof-1");
+    if (p->ngroups < 0 || p->ngroups > KSFD_MAX_GROUPS)
+        return fail("too many ligand groups");
+    if (!(p->cushion != 0.0) || !(p->rhomax != 0.0))
+        return fail("cushion and rhomax must be non-zero");
+    DevPhys &P = c->P;
+    P.ngroups = p->ngroups;
+    P.nlig = p->nlig;
+    P.cap_type = p->cap_type;
+    P.dim = c->dim;
+    P.s2 = p->s2;
+    P.rhomax = p->rhomax;
+    P.inv_cushion = 1.0 / p->cushion;
+    P.capscale = p->maxscale * p->s2;
+    P.rhomin = p->rhomin;
+    P.Umin = p->Umin;
+    P.inv_rhomax = 1.0 / p->rhomax;
+    for (int g = 0; g < KSFD_MAX_GROUPS; ++g) {
+        P.alpha[g] = p->alpha[g];
+        P.beta[g] = p->beta[g];
+    }
+    for (int l = 0; l < KSFD_MAX_LIGANDS; ++l) {
+        P.lig_group[l] = l < p->nlig ? p->lig_group[l] : -1;
+        P.weight[l] = p->weight[l];
+        P.s[l] = p->s[l];
+        P.gamma[l] = p->gamma[l];
+        P.D[l] = p->D[l];
+        if (l < p->nlig && (p->lig_group[l] < 0 || p->lig_group[l] >= p->ngroups))
+            return fail("lig_group out of range");
+    }
+    P.lig_group[KSFD_MAX_LIGANDS] = -1;
+    // the reference lays stencil axes out as x, y, z = axis 0,1,2; the last
+    // axis is the marching / decomposed one in every dimension.
+    for (int a = 0; a < 3; ++a)
+        for (int s = 0; s < 5; ++s) {
+            P.w1[a][s] = a < c->dim ? p->w1[a][s] : 0.0;
+            P.w2[a][s] = a < c->dim ? p->w2[a][s] : 0.0;
+        }
+    c->have_phys = true;
+    return 0;
+}
+
+static void invalidate_plans(ksfd_ctx *c);
+extern "C" int ksfd_set_option(ksfd_ctx *c, const char *key, int64_t v)
+{
+    if (!c || !key) return fail("ksfd_set_option: NULL argument");
+    std::string k(key);
+    if (k == "variant") c->variant = (int)v;
+    else if (k == "tx") c->opt_tx = (int)v;
+    else if (k == "ty") c->opt_ty = (int)v;
+    else if (k == "rz") c->opt_rz = (int)v;
+    else if (k == "threads") c->opt_threads = (int)v;
+    else return fail("unknown option " + k);
+    invalidate_plans(c);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// halos
+// ---------------------------------------------------------------------------
+extern "C" int ksfd_nccl_unique_id(const char *path, char id_out[128])
+{
+    TRY(nccl_load(path));
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, id.internal, 128);
+    return 0;
+}
+
+extern "C" int ksfd_comm_init(ksfd_ctx *c, const char *path, int nranks, int rank,
+                              const char id[128])
+{
+    if (!c) return fail("ksfd_comm_init: NULL ctx");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail("bad rank/nranks");
+    c->nranks = nranks;
+    c->rank = rank;
+    if (nranks == 1) return 0;
+    TRY(nccl_load(path));
+    CK(cudaSetDevice(c->device));
+    ncclUniqueId uid;
+    memcpy(uid.internal, id, 128);
+    NK(g_nccl.CommInitRank(&c->comm, nranks, uid, rank));
+    return 0;
+}
+
+// VecRef for a vector with `stride` doubles per point.  One rank: the ghost
+// planes alias the vector (periodic wrap).  Several ranks: ghost planes live in
+// halo slot `slot`, filled by exchange().
+static VecRef make_ref(const ksfd_ctx *c, const double *base, int stride, int slot)
+{
+    VecRef r;
+    r.base = base;
+    const long long ps = c->g.plane_pts * stride;
+    if (c->nranks == 1) {
+        r.lo = base + (long long)(c->g.nloc - KSFD_SW) * ps;
+        r.hi = base;
+    } else {
+        r.lo = c->halo[slot];
+        r.hi = c->halo[slot] + KSFD_SW * c->halo_plane_doubles;
+    }
+    return r;
+}
+
+static int exchange(ksfd_ctx *c, const double *vec, int stride, int slot,
+                    cudaStream_t st)
+{
+    if (c->nranks == 1) return 0;
+    if (slot < 0 || slot >= KSFD_HALO_SLOTS) return fail("bad halo slot");
+    if (!c->halo[slot])
+        CK(cudaMalloc(&c->halo[slot],
+                      sizeof(double) * 2 * KSFD_SW * c->halo_plane_doubles));
+    const size_t cnt = (size_t)KSFD_SW * c->g.plane_pts * stride;
+    const int up = (c->rank + 1) % c->nranks, dn = (c->rank + c->nranks - 1) % c->nranks;
+    double *lo = c->halo[slot];
+    double *hi = c->halo[slot] + KSFD_SW * c->halo_plane_doubles;
+    const double *top = vec + (size_t)(c->g.nloc - KSFD_SW) * c->g.plane_pts * stride;
+    // last-axis planes are contiguous (dof fastest, last axis slowest), so a
+    // ghost face is one contiguous block: no pack kernel is needed.
+    NK(g_nccl.GroupStart());
+    NK(g_nccl.Send(top, cnt, ncclFloat64_, up, c->comm, st));     // my top -> up's lo
+    NK(g_nccl.Recv(lo, cnt, ncclFloat64_, dn, c->comm, st));
+    NK(g_nccl.Send(vec, cnt, ncclFloat64_, dn, c->comm, st));     // my bottom -> dn's hi
+    NK(g_nccl.Recv(hi, cnt, ncclFloat64_, up, c->comm, st));
+    NK(g_nccl.GroupEnd());
+    return 0;
+}
+
+extern "C" int ksfd_halo_exchange(ksfd_ctx *c, const double *vec, int slot,
+                                  void *stream)
+{
+    if (!c || !vec) return fail("ksfd_halo_exchange: NULL argument");
+    return exchange(c, vec, c->dof, slot, (cudaStream_t)stream);
+}
+
+static int allreduce_dev(ksfd_ctx *c, double *buf, int n, int op, cudaStream_t st)
+{
+    if (c->nranks == 1) return 0;
+    NK(g_nccl.AllReduce(buf, buf, n, ncclFloat64_, op, c->comm, st));
+    return 0;
+}
+
+extern "C" int ksfd_allreduce_max(ksfd_ctx *c, double *vals, int n)
+{
+    if (!c || n > 64 || n < 0) return fail("ksfd_allreduce_max: bad argument");
+    if (c->nranks == 1) return 0;
+    CK(cudaMemcpy(c->dscal, vals, sizeof(double) * n, cudaMemcpyHostToDevice));
+    TRY(allreduce_dev(c, c->dscal, n, ncclMax_, 0));
+    CK(cudaMemcpy(vals, c->dscal, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int ksfd_allreduce_sum(ksfd_ctx *c, double *vals, int n)
+{
+    if (!c || n > 64) return fail("ksfd_allreduce_sum: bad argument");
+    if (c->nranks == 1) return 0;
+    CK(cudaMemcpy(c->dscal, vals, sizeof(double) * n, cudaMemcpyHostToDevice));
+    TRY(allreduce_dev(c, c->dscal, n, ncclSum_, 0));
+    CK(cudaMemcpy(vals, c->dscal, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// marching launch heuristics
+// ---------------------------------------------------------------------------
+struct MarchPlan {
+    MarchCfg cfg;
+    dim3 grid;
+    int threads;
+    size_t smem;
+};
+
+static bool use_march(const ksfd_ctx *c)
+{
+    if (c->variant == 1) return false;
+    if (c->dim < 2) return false;
+    if (c->dof - 1 > 4) return false;           // instantiated for nlig <= 4
+    if (c->variant == 2) return true;
+    return c->g.n0 >= 8 && c->g.nloc >= 4 && (c->dim == 2 || c->g.n1 >= 8);
+}
+
+static MarchPlan plan_march_search(const ksfd_ctx *c, int NF, double cstage, double cemit);
+typedef std::map<long long, MarchPlan> PlanMap;
+static void free_plans(ksfd_ctx *c)
+{
+    delete static_cast<PlanMap *>(c->plan_cache);
+    c->plan_cache = nullptr;
+}
+static void invalidate_plans(ksfd_ctx *c)
+{
+    if (c->plan_cache) static_cast<PlanMap *>(c->plan_cache)->clear();
+}
+static MarchPlan plan_march(ksfd_ctx *c, int NF, double cstage, double cemit)
+{
+    if (!c->plan_cache) c->plan_cache = new PlanMap();
+    PlanMap &pm = *static_cast<PlanMap *>(c->plan_cache);
+    const long long key = NF * 100000LL + (long long)(cstage * 10);
+    auto it = pm.find(key);
+    if (it != pm.end()) return it->second;
+    MarchPlan p = plan_march_search(c, NF, cstage, cemit);
+    pm[key] = p;
+    return p;
+}
+
+// cost weights (fp64 ops) of staging one lane / emitting one output
+static MarchPlan plan_march_search(const ksfd_ctx *c, int NF, double cstage, double cemit)
+{
+    const Geom &g = c->g;
+    const size_t per_lane = (size_t)KSFD_RING * NF * sizeof(double);
+    const int Lcap = (int)std::min<size_t>(c->max_smem / per_lane, 2048);
+    MarchPlan best{};
+    double best_cost = 1e300;
+    const int dim = c->dim;
+    for (int kx = 1; kx <= g.n0; ++kx) {
+        int OX = (g.n0 + kx - 1) / kx;
+        if (c->opt_tx > 0) OX = std::min(c->opt_tx, g.n0);
+        int LX = OX + 2 * KSFD_SW;
+        if (LX > Lcap) continue;
+        if (OX < 28 && kx > 1 && c->opt_tx <= 0) break;   // tiles this thin never win
+        int ntx = (g.n0 + OX - 1) / OX;
+        int oy_max = (dim == 3) ? std::min(g.n1, Lcap / LX - 2 * KSFD_SW) : 1;
+        if (oy_max < 1) continue;
+        for (int ky = 1; ky <= (dim == 3 ? g.n1 : 1); ++ky) {
+            int OY = 1, LY = 1, nty = 1;
+            if (dim == 3) {
+                OY = (g.n1 + ky - 1) / ky;
+                if (c->opt_ty > 0) OY = std::min(c->opt_ty, g.n1);
+                if (OY > oy_max) continue;
+                if (OY < 6 && ky > 1 && c->opt_ty <= 0) break;
+                LY = OY + 2 * KSFD_SW;
+                nty = (g.n1 + OY - 1) / OY;
+            }
+            const int L = LX * LY;
+            int threads = ((L + 1) / 2 + 31) / 32 * 32;
+            if (c->opt_threads > 0) threads = c->opt_threads;
+            if (threads > 1024 || 2 * threads < L) continue;
+            const size_t smem = per_lane * L;
+            int cta_per_sm = (int)std::min<size_t>(c->max_smem / smem, 2048 / threads);
+            if (cta_per_sm < 1) continue;
+            cta_per_sm = std::min(cta_per_sm, 8);
+            const long long cols = (long long)ntx * nty;
+            // candidate chunk counts
+            for (int chunks = 1; chunks <= g.nloc; chunks = chunks < 16 ? chunks + 1 : chunks + chunks / 8) {
+                int RZ = (g.nloc + chunks - 1) / chunks;
+                if (c->opt_rz > 0) RZ = std::min(c->opt_rz, g.nloc);
+                int nch = (g.nloc + RZ - 1) / RZ;
+                if (RZ < 2 && g.nloc > 2) break;
+                const long long ctas = cols * nch;
+                const double per_cta = (double)L * (RZ + 2 * KSFD_SW) * cstage +
+                                       (double)OX * OY * RZ * cemit +
+                                       2000.0;   // fixed CTA overhead
+                // SM-level time: CTAs are spread over the SMs; an SM with few
+                // resident warps cannot keep the fp64 pipe busy.
+                const double ctas_per_sm = std::ceil((double)ctas / c->sm_count);
+                const double warps = std::min<double>(ctas_per_sm, cta_per_sm) * threads / 32.0;
+                const double eff = std::min(1.0, 0.35 + 0.65 * warps / 16.0);
+                const double cost = ctas_per_sm * per_cta / eff;
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    best.cfg.LX = LX;
+                    best.cfg.LY = LY;
+                    best.cfg.RZ = RZ;
+                    best.grid = dim3(ntx, nty, nch);
+                    best.threads = threads;
+                    best.smem = smem;
+                }
+                if (c->opt_rz > 0) break;
+            }
+            if (dim != 3 || c->opt_ty > 0) break;
+        }
+        if (c->opt_tx > 0) break;
+    }
+    return best;
+}
+
+template <class K>
+static int set_smem(K kern, size_t smem)
+{
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)smem));
+    return 0;
+}
+
+template <int DIM, int NLIG>
+static int launch_residual_march(ksfd_ctx *c, VecRef u, const double *udot,
+                                 const double *src, double *out, cudaStream_t st)
+{
+    using Op = ResidualOp<DIM, NLIG>;
+    MarchPlan p = plan_march(c, Op::NF, 110.0, 25.0 * DIM + 15.0);
+    if (p.threads == 0) return fail("no marching tile fits");
+    Op op{u, udot, src, out};
+    auto kern = k_march<DIM, 2, Op>;
+    TRY(set_smem(kern, p.smem));
+    kern<<<p.grid, p.threads, p.smem, st>>>(c->g, c->P, p.cfg, op);
+    CKL();
+    return 0;
+}
+
+template <int DIM, int NLIG>
+static int launch_jvp_march(ksfd_ctx *c, VecRef coef, VecRef v, VecRef pc,
+                            bool precond, double *out, cudaStream_t st)
+{
+    double w2c = 0.0;
+    for (int a = 0; a < c->dim; ++a) w2c += c->P.w2[a][2];
+    if (precond) {
+        using Op = JvpOp<DIM, NLIG, true>;
+        MarchPlan p = plan_march(c, Op::NF, 25.0, 40.0 * DIM + 15.0);
+        if (p.threads == 0) return fail("no marching tile fits");
+        Op op{coef, v, pc, c->shift, w2c, out};
+        auto kern = k_march<DIM, 2, Op>;
+        TRY(set_smem(kern, p.smem));
+        kern<<<p.grid, p.threads, p.smem, st>>>(c->g, c->P, p.cfg, op);
+    } else {
+        using Op = JvpOp<DIM, NLIG, false>;
+        MarchPlan p = plan_march(c, Op::NF, 10.0, 40.0 * DIM + 15.0);
+        if (p.threads == 0) return fail("no marching tile fits");
+        Op op{coef, v, pc, c->shift, w2c, out};
+        auto kern = k_march<DIM, 2, Op>;
+        TRY(set_smem(kern, p.smem));
+        kern<<<p.grid, p.threads, p.smem, st>>>(c->g, c->P, p.cfg, op);
+    }
+    CKL();
+    return 0;
+}
+
+template <int DIM, int NLIG>
+static int launch_velocity_march(ksfd_ctx *c, VecRef u, double *vel, double *vmax,
+                                 cudaStream_t st)
+{
+    using Op = VelocityOp<DIM, NLIG>;
+    MarchPlan p = plan_march(c, Op::NF, 110.0, 6.0 * DIM);
+    if (p.threads == 0) return fail("no marching tile fits");
+    Op op{u, vel, vmax};
+    auto kern = k_march<DIM, 2, Op>;
+    TRY(set_smem(kern, p.smem));
+    kern<<<p.grid, p.threads, p.smem, st>>>(c->g, c->P, p.cfg, op);
+    CKL();
+    return 0;
+}
+
+#define DISPATCH_DIM_NLIG(FN, ...)                                         \
+    do {                                                                   \
+        const int nl_ = c->dof - 1;                                        \
+        if (c->dim == 2) {                                                 \
+            switch (nl_) {                                                 \
+            case 1: return FN<2, 1>(__VA_ARGS__);                          \
+            case 2: return FN<2, 2>(__VA_ARGS__);                          \
+            case 3: return FN<2, 3>(__VA_ARGS__);                          \
+            case 4: return FN<2, 4>(__VA_ARGS__);                          \
+            }                                                              \
+        } else if (c->dim == 3) {                                          \
+            switch (nl_) {                                                 \
+            case 1: return FN<3, 1>(__VA_ARGS__);                          \
+            case 2: return FN<3, 2>(__VA_ARGS__);                          \
+            case 3: return FN<3, 3>(__VA_ARGS__);                          \
+            case 4: return FN<3, 4>(__VA_ARGS__);                          \
+            }                                                              \
+        }                                                                  \
+        return fail("no marching kernel for this dim/dof");                \
+    } while (0)
+
+static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// ---------------------------------------------------------------------------
+// operator entry points
+// ---------------------------------------------------------------------------
+static int check_ready(const ksfd_ctx *c)
+{
+    if (!c) return fail("NULL context");
+    if (!c->have_phys) return fail("ksfd_set_physics has not been called");
+    return 0;
+}
+
+extern "C" int ksfd_groom(ksfd_ctx *c, double *u, void *stream)
+{
+    TRY(check_ready(c));
+    if (!u) return fail("ksfd_groom: NULL vector");
+    k_groom<<<nblk(nlocal(c), 256), 256, 0, (cudaStream_t)stream>>>(
+        c->g.npts, c->dof, c->P.rhomin, c->P.Umin, u);
+    CKL();
+    return 0;
+}
+
+static int residual_impl(ksfd_ctx *c, const double *u, const double *udot,
+                         const double *src, double *f, cudaStream_t st)
+{
+    TRY(exchange(c, u, c->dof, 0, st));
+    VecRef ur = make_ref(c, u, c->dof, 0);
+    if (use_march(c)) {
+        DISPATCH_DIM_NLIG(launch_residual_march, c, ur, udot, src, f, st);
+    }
+    k_residual_naive<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, ur, udot,
+                                                           src, f);
+    CKL();
+    return 0;
+}
+
+extern "C" int ksfd_residual(ksfd_ctx *c, const double *u, const double *udot,
+                             const double *src, double *f, void *stream)
+{
+    TRY(check_ready(c));
+    if (!u || !f) return fail("ksfd_residual: NULL vector");
+    return residual_impl(c, u, udot, src, f, (cudaStream_t)stream);
+}
+
+static int velocity_impl(ksfd_ctx *c, const double *u, double *vel, double *vmax,
+                         cudaStream_t st)
+{
+    TRY(exchange(c, u, c->dof, 0, st));
+    VecRef ur = make_ref(c, u, c->dof, 0);
+    if (vmax) CK(cudaMemsetAsync(vmax, 0, sizeof(double) * c->dim, st));
+    if (use_march(c)) {
+        DISPATCH_DIM_NLIG(launch_velocity_march, c, ur, vel, vmax, st);
+    }
+    k_velocity_naive<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, ur, vel, vmax);
+    CKL();
+    return 0;
+}
+
+extern "C" int ksfd_velocity_max(ksfd_ctx *c, const double *u, double *vmax,
+                                 void *stream)
+{
+    TRY(check_ready(c));
+    if (!u || !vmax) return fail("ksfd_velocity_max: NULL argument");
+    return velocity_impl(c, u, nullptr, vmax, (cudaStream_t)stream);
+}
+
+extern "C" int ksfd_velocity(ksfd_ctx *c, const double *u, double *vel, void *stream)
+{
+    TRY(check_ready(c));
+    if (!u || !vel) return fail("ksfd_velocity: NULL argument");
+    return velocity_impl(c, u, vel, nullptr, (cudaStream_t)stream);
+}
+
+// coef is stored ghosted along the last axis: base = coef + 2 planes
+static VecRef coef_ref(const ksfd_ctx *c)
+{
+    const long long ps = c->g.plane_pts * (c->dof + 2);
+    VecRef r;
+    r.lo = c->coef;
+    r.base = c->coef + KSFD_SW * ps;
+    r.hi = c->coef + (long long)(KSFD_SW + c->g.nloc) * ps;
+    return r;
+}
+
+static int jvp_setup_impl(ksfd_ctx *c, const double *u, double shift,
+                          double *blocks, cudaStream_t st)
+{
+    const Geom &g = c->g;
+    const long long gpts = (long long)(g.nloc + 2 * KSFD_SW) * g.plane_pts;
+    if (!c->coef) CK(cudaMalloc(&c->coef, sizeof(double) * gpts * (c->dof + 2)));
+    if (!c->pc) CK(cudaMalloc(&c->pc, sizeof(double) * g.npts * c->dof));
+    c->shift = shift;
+    if (u) {
+        TRY(exchange(c, u, c->dof, 0, st));
+        VecRef ur = make_ref(c, u, c->dof, 0);
+        k_coef_setup<<<nblk(gpts, 128), 128, 0, st>>>(g, c->P, ur, c->coef);
+        CKL();
+    }
+    k_pc_setup<<<nblk(g.npts, 128), 128, 0, st>>>(g, c->P, coef_ref(c), shift, c->pc,
+                                                  blocks);
+    CKL();
+    // ghost planes of the preconditioner field for the fused A*M^{-1} kernel
+    TRY(exchange(c, c->pc, c->dof, 2, st));
+    c->have_jac = true;
+    return 0;
+}
+
+extern "C" int ksfd_jvp_setup(ksfd_ctx *c, const double *u, double shift, void *stream)
+{
+    TRY(check_ready(c));
+    if (!u) return fail("ksfd_jvp_setup: NULL vector");
+    return jvp_setup_impl(c, u, shift, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int ksfd_block_diagonal(ksfd_ctx *c, double *blocks, void *stream)
+{
+    TRY(check_ready(c));
+    if (!c->have_jac) return fail("ksfd_jvp_setup has not been called");
+    CK(cudaMemsetAsync(blocks, 0, sizeof(double) * c->g.npts * c->dof * c->dof,
+                       (cudaStream_t)stream));
+    return jvp_setup_impl(c, nullptr, c->shift, blocks, (cudaStream_t)stream);
+}
+
+static int jvp_impl(ksfd_ctx *c, const double *v, double *out, bool precond,
+                    cudaStream_t st)
+{
+    if (!c->have_jac) return fail("ksfd_jvp_setup has not been called");
+    if (v == out) return fail("ksfd_jvp: in-place application is not supported");
+    TRY(exchange(c, v, c->dof, 1, st));
+    VecRef vr = make_ref(c, v, c->dof, 1);
+    VecRef pr = make_ref(c, c->pc, c->dof, 2);
+    VecRef cr = coef_ref(c);
+    if (use_march(c)) {
+        DISPATCH_DIM_NLIG(launch_jvp_march, c, cr, vr, pr, precond, out, st);
+    }
+    k_jvp_naive<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, cr, vr, pr,
+                                                      precond ? 1 : 0, c->shift, out);
+    CKL();
+    return 0;
+}
+
+extern "C" int ksfd_jvp(ksfd_ctx *c, const double *v, double *out, void *stream)
+{
+    TRY(check_ready(c));
+    if (!v || !out) return fail("ksfd_jvp: NULL vector");
+    return jvp_impl(c, v, out, false, (cudaStream_t)stream);
+}
+extern "C" int ksfd_jvp_precond(ksfd_ctx *c, const double *v, double *out, void *stream)
+{
+    TRY(check_ready(c));
+    if (!v || !out) return fail("ksfd_jvp_precond: NULL vector");
+    return jvp_impl(c, v, out, true, (cudaStream_t)stream);
+}
+
+extern "C" int ksfd_pc_apply(ksfd_ctx *c, const double *r, double *z, void *stream)
+{
+    TRY(check_ready(c));
+    if (!c->have_jac) return fail("ksfd_jvp_setup has not been called");
+    if (!r || !z) return fail("ksfd_pc_apply: NULL vector");
+    k_pc_apply<<<nblk(c->g.npts, 128), 128, 0, (cudaStream_t)stream>>>(
+        c->g, c->P, c->shift, c->pc, r, z);
+    CKL();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// BLAS-1
+// ---------------------------------------------------------------------------
+template <int NV>
+static int mdot_launch(ksfd_ctx *c, const VecList &vl, const double *w, cudaStream_t st)
+{
+    k_mdot<NV><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(nlocal(c), vl, w, c->partial);
+    CKL();
+    return 0;
+}
+
+// out_dev[i] = <vs[i], w>, i < nv (any nv); global over ranks
+static int mdot_impl(ksfd_ctx *c, int nv, const double *const *vs, const double *w,
+                     double *out_dev, cudaStream_t st)
+{
+    for (int b = 0; b < nv; b += KSFD_MAXV) {
+        const int m = std::min(KSFD_MAXV, nv - b);
+        VecList vl;
+        for (int i = 0; i < KSFD_MAXV; ++i) vl.v[i] = vs[b + std::min(i, m - 1)];
+        switch (m) {
+        case 1: TRY(mdot_launch<1>(c, vl, w, st)); break;
+        case 2: TRY(mdot_launch<2>(c, vl, w, st)); break;
+        case 3: TRY(mdot_launch<3>(c, vl, w, st)); break;
+        case 4: TRY(mdot_launch<4>(c, vl, w, st)); break;
+        case 5: TRY(mdot_launch<5>(c, vl, w, st)); break;
+        case 6: TRY(mdot_launch<6>(c, vl, w, st)); break;
+        case 7: TRY(mdot_launch<7>(c, vl, w, st)); break;
+        default: TRY(mdot_launch<8>(c, vl, w, st)); break;
+        }
+        k_reduce_partials<<<m, 128, 0, st>>>(m, KSFD_RED_BLOCKS, c->partial, out_dev + b, 0);
+        CKL();
+    }
+    TRY(allreduce_dev(c, out_dev, nv, ncclSum_, st));
+    return 0;
+}
+
+extern "C" int ksfd_mdot(ksfd_ctx *c, int nv, const double *const *vs,
+                         const double *w, double *out_dev, void *stream)
+{
+    if (!c || nv < 1 || !vs || !w || !out_dev) return fail("ksfd_mdot: bad argument");
+    return mdot_impl(c, nv, vs, w, out_dev, (cudaStream_t)stream);
+}
+
+template <int NV>
+static int maxpy_launch(ksfd_ctx *c, const CoefList &cl, const VecList &vl, double ys,
+                        double *y, cudaStream_t st)
+{
+    k_maxpy_host<NV><<<KSFD_RED_BLOCKS, 256, 0, st>>>(nlocal(c), cl, vl, ys, y);
+    CKL();
+    return 0;
+}
+
+// y = yscale*y + sum coef[i]*vs[i]
+static int maxpy_impl(ksfd_ctx *c, int nv, const double *coef, const double *const *vs,
+                      double yscale, double *y, cudaStream_t st)
+{
+    if (nv == 0) {
+        if (yscale == 1.0) return 0;
+        CoefList cl{};
+        VecList vl{};
+        vl.v[0] = y;
+        cl.c[0] = 0.0;
+        return maxpy_launch<1>(c, cl, vl, yscale, y, st);
+    }
+    for (int b = 0; b < nv; b += KSFD_MAXV) {
+        const int m = std::min(KSFD_MAXV, nv - b);
+        CoefList cl{};
+        VecList vl{};
+        for (int i = 0; i < m; ++i) {
+            cl.c[i] = coef[b + i];
+            vl.v[i] = vs[b + i];
+        }
+        const double ys = (b == 0) ? yscale : 1.0;
+        switch (m) {
+        case 1: TRY(maxpy_launch<1>(c, cl, vl, ys, y, st)); break;
+        case 2: TRY(maxpy_launch<2>(c, cl, vl, ys, y, st)); break;
+        case 3: TRY(maxpy_launch<3>(c, cl, vl, ys, y, st)); break;
+        case 4: TRY(maxpy_launch<4>(c, cl, vl, ys, y, st)); break;
+        case 5: TRY(maxpy_launch<5>(c, cl, vl, ys, y, st)); break;
+        case 6: TRY(maxpy_launch<6>(c, cl, vl, ys, y, st)); break;
+        case 7: TRY(maxpy_launch<7>(c, cl, vl, ys, y, st)); break;
+        default: TRY(maxpy_launch<8>(c, cl, vl, ys, y, st)); break;
+        }
+    }
+    return 0;
+}
+
+extern "C" int ksfd_maxpy(ksfd_ctx *c, int nv, const double *coef,
+                          const double *const *vs, double *y, void *stream)
+{
+    if (!c || nv < 0 || !y) return fail("ksfd_maxpy: bad argument");
+    return maxpy_impl(c, nv, coef, vs, 1.0, y, (cudaStream_t)stream);
+}
+
+// global 2-norm -> dscal[slot] on the device
+static int norm2_dev(ksfd_ctx *c, const double *x, int slot, cudaStream_t st)
+{
+    VecList vl;
+    for (int i = 0; i < KSFD_MAXV; ++i) vl.v[i] = x;
+    k_mdot<1><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(nlocal(c), vl, x, c->partial);
+    CKL();
+    if (c->nranks == 1) {
+        k_reduce_partials<<<1, 128, 0, st>>>(1, KSFD_RED_BLOCKS, c->partial, c->dscal + slot, 2);
+        CKL();
+    } else {
+        k_reduce_partials<<<1, 128, 0, st>>>(1, KSFD_RED_BLOCKS, c->partial, c->dscal + slot, 0);
+        CKL();
+        TRY(allreduce_dev(c, c->dscal + slot, 1, ncclSum_, st));
+        k_reduce_partials<<<1, 32, 0, st>>>(1, 1, c->dscal + slot, c->dscal + slot, 2);
+        CKL();
+    }
+    return 0;
+}
+
+static int fetch(ksfd_ctx *c, int slot, int n, cudaStream_t st)
+{
+    CK(cudaMemcpyAsync(c->hscal + slot, c->dscal + slot, sizeof(double) * n,
+                       cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int ksfd_norm2(ksfd_ctx *c, const double *x, double *out)
+{
+    if (!c || !x || !out) return fail("ksfd_norm2: bad argument");
+    TRY(norm2_dev(c, x, 0, 0));
+    TRY(fetch(c, 0, 1, 0));
+    *out = c->hscal[0];
+    return 0;
+}
+
+extern "C" int ksfd_sum_dof0(ksfd_ctx *c, const double *u, double *out)
+{
+    if (!c || !u || !out) return fail("ksfd_sum_dof0: bad argument");
+    k_sum_dof0<<<KSFD_RED_BLOCKS, KSFD_RED_THREADS>>>(c->g.npts, c->dof, u, c->partial);
+    CKL();
+    k_reduce_partials<<<1, 128>>>(1, KSFD_RED_BLOCKS, c->partial, c->dscal, 0);
+    CKL();
+    TRY(allreduce_dev(c, c->dscal, 1, ncclSum_, 0));
+    TRY(fetch(c, 0, 1, 0));
+    *out = c->hscal[0];
+    return 0;
+}
+
+extern "C" int ksfd_scale_dof0(ksfd_ctx *c, double *u, double f, void *stream)
+{
+    if (!c || !u) return fail("ksfd_scale_dof0: bad argument");
+    k_scale_dof0<<<KSFD_RED_BLOCKS, 256, 0, (cudaStream_t)stream>>>(c->g.npts, c->dof, f, u);
+    CKL();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// GMRES(m), right preconditioned by point-block Jacobi, device resident:
+// one fused A*M^{-1} stencil kernel, one fused multi-dot, one fused
+// orthogonalise+norm kernel per iteration; the host only sees the (j+2)
+// Hessenberg entries of the new column (one small D2H copy per iteration).
+// ---------------------------------------------------------------------------
+template <int NV>
+static int orth_launch(ksfd_ctx *c, const VecList &vl, const double *h, double *w,
+                       int want_norm, cudaStream_t st)
+{
+    k_orth_update<NV><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(nlocal(c), vl, h, w,
+                                                                   c->partial, want_norm);
+    CKL();
+    return 0;
+}
+
+static int orth_impl(ksfd_ctx *c, int nv, double *V, const double *h_dev, double *w,
+                     double *norm_dev, cudaStream_t st)
+{
+    const long long n = nlocal(c);
+    for (int b = 0; b < nv; b += KSFD_MAXV) {
+        const int m = std::min(KSFD_MAXV, nv - b);
+        const int last = (b + m >= nv);
+        VecList vl;
+        for (int i = 0; i < KSFD_MAXV; ++i) vl.v[i] = V + (long long)(b + std::min(i, m - 1)) * n;
+        switch (m) {
+        case 1: TRY(orth_launch<1>(c, vl, h_dev + b, w, last, st)); break;
+        case 2: TRY(orth_launch<2>(c, vl, h_dev + b, w, last, st)); break;
+        case 3: TRY(orth_launch<3>(c, vl, h_dev + b, w, last, st)); break;
+        case 4: TRY(orth_launch<4>(c, vl, h_dev + b, w, last, st)); break;
+        case 5: TRY(orth_launch<5>(c, vl, h_dev + b, w, last, st)); break;
+        case 6: TRY(orth_launch<6>(c, vl, h_dev + b, w, last, st)); break;
+        case 7: TRY(orth_launch<7>(c, vl, h_dev + b, w, last, st)); break;
+        default: TRY(orth_launch<8>(c, vl, h_dev + b, w, last, st)); break;
+        }
+    }
+    if (c->nranks == 1) {
+        k_reduce_partials<<<1, 128, 0, st>>>(1, KSFD_RED_BLOCKS, c->partial, norm_dev, 2);
+        CKL();
+    } else {
+        k_reduce_partials<<<1, 128, 0, st>>>(1, KSFD_RED_BLOCKS, c->partial, norm_dev, 0);
+        CKL();
+        TRY(allreduce_dev(c, norm_dev, 1, ncclSum_, st));
+        k_reduce_partials<<<1, 32, 0, st>>>(1, 1, norm_dev, norm_dev, 2);
+        CKL();
+    }
+    return 0;
+}
+
+static int gmres_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x,
+                      const ksfd_ksp_opts &o, ksfd_ksp_result *res, cudaStream_t st)
+{
+    const long long n = nlocal(c);
+    const int m = std::max(1, std::min(o.restart > 0 ? o.restart : 30, 60));
+    const int max_it = o.max_it > 0 ? o.max_it : 10000;
+    const bool pre = o.precond != 0;
+    if (c->krylov_cap < m + 1) {
+        cudaFree(c->krylov);
+        c->krylov = nullptr;
+        CK(cudaMalloc(&c->krylov, sizeof(double) * n * (m + 1)));
+        c->krylov_cap = m + 1;
+    }
+    TRY(ensure_work(c, 0));
+    double *V = c->krylov;
+    double *tmp = c->work[0];
+    double *hdev = c->dscal + SC_H;   // Hessenberg column j: hdev[0..j+1]
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), gg(m + 1), y(m);
+    CK(cudaMemsetAsync(x, 0, sizeof(double) * n, st));
+    int its = 0, reason = 0;
+    double rnorm0 = 0.0, rnorm = 0.0, tol = 0.0;
+    bool first = true;
+    while (true) {
+        const double *r;
+        double sign;
+        if (first) {
+            r = rhs;
+            sign = rhs_sign;
+        } else {
+            // r = sign*rhs - A x   (true residual at restart)
+            TRY(jvp_impl(c, x, tmp, false, st));
+            CoefList cl{};
+            VecList vl{};
+            cl.c[0] = rhs_sign;
+            vl.v[0] = rhs;
+            k_maxpy_host<1><<<KSFD_RED_BLOCKS, 256, 0, st>>>(n, cl, vl, -1.0, tmp);
+            CKL();
+            r = tmp;
+            sign = 1.0;
+        }
+        TRY(norm2_dev(c, r, SC_NORM, st));
+        TRY(fetch(c, SC_NORM, 1, st));
+        const double beta = c->hscal[SC_NORM];
+        if (first) {
+            rnorm0 = beta;
+            tol = std::max(o.rtol * beta, o.atol);
+            first = false;
+        }
+        rnorm = beta;
+        if (!(beta == beta)) { reason = -9; break; }          // NaN
+        if (beta <= tol || beta == 0.0) { reason = beta == 0.0 ? 3 : 2; break; }
+        if (its >= max_it) { reason = -3; break; }
+        k_scale_by_inv<<<KSFD_RED_BLOCKS, 256, 0, st>>>(n, r, c->dscal + SC_NORM, sign, V);
+        CKL();
+        gg.assign(m + 1, 0.0);
+        gg[0] = beta;
+        int j = 0;
+        bool done = false;
+        for (; j < m; ++j) {
+            double *w = V + (long long)(j + 1) * n;
+            TRY(jvp_impl(c, V + (long long)j * n, w, pre, st));
+            std::vector<const double *> vp(j + 1);
+            for (int i = 0; i <= j; ++i) vp[i] = V + (long long)i * n;
+            TRY(mdot_impl(c, j + 1, vp.data(), w, hdev, st));
+            TRY(orth_impl(c, j + 1, V, hdev, w, hdev + j + 1, st));
+            if (o.reorth) {
+                // second classical Gram-Schmidt pass (CGS2)
+                TRY(mdot_impl(c, j + 1, vp.data(), w, c->dscal + SC_H2, st));
+                TRY(orth_impl(c, j + 1, V, c->dscal + SC_H2, w, hdev + j + 1, st));
+                CK(cudaMemcpyAsync(c->hscal + SC_H2, c->dscal + SC_H2,
+                                   sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, st));
+            }
+            TRY(fetch(c, SC_H, j + 2, st));
+            double *Hc = &H[(size_t)j * (m + 1)];
+            for (int i = 0; i <= j + 1; ++i) Hc[i] = c->hscal[SC_H + i];
+            if (o.reorth)
+                for (int i = 0; i <= j; ++i) Hc[i] += c->hscal[SC_H2 + i];
+            const double hnext = Hc[j + 1];
+            if (hnext > 0.0) {
+                k_scale_by_inv<<<KSFD_RED_BLOCKS, 256, 0, st>>>(n, w, hdev + j + 1, 1.0, w);
+                CKL();
+            }
+            for (int i = 0; i < j; ++i) {
+                const double t = cs[i] * Hc[i] + sn[i] * Hc[i + 1];
+                Hc[i + 1] = -sn[i] * Hc[i] + cs[i] * Hc[i + 1];
+                Hc[i] = t;
+            }
+            const double den = std::hypot(Hc[j], Hc[j + 1]);
+            cs[j] = den > 0 ? Hc[j] / den : 1.0;
+            sn[j] = den > 0 ? Hc[j + 1] / den : 0.0;
+            Hc[j] = den;
+            Hc[j + 1] = 0.0;
+            gg[j + 1] = -sn[j] * gg[j];
+            gg[j] = cs[j] * gg[j];
+            rnorm = std::fabs(gg[j + 1]);
+            ++its;
+            if (!(rnorm == rnorm)) { reason = -9; done = true; ++j; break; }
+            if (rnorm <= tol) { reason = 2; done = true; ++j; break; }
+            if (o.dtol > 0 && rnorm > o.dtol * rnorm0) { reason = -4; done = true; ++j; break; }
+            if (its >= max_it) { reason = -3; done = true; ++j; break; }
+            if (hnext == 0.0) { reason = 2; done = true; ++j; break; }
+        }
+        // back substitution on the j x j triangle
+        const int k = j;
+        for (int i = k - 1; i >= 0; --i) {
+            double s = gg[i];
+            for (int q = i + 1; q < k; ++q) s -= H[(size_t)q * (m + 1) + i] * y[q];
+            y[i] = s / H[(size_t)i * (m + 1) + i];
+        }
+        if (reason != -9 && k > 0) {
+            std::vector<const double *> vp(k);
+            for (int i = 0; i < k; ++i) vp[i] = V + (long long)i * n;
+            if (pre) {
+                // x += M^{-1} (V y)
+                TRY(ensure_work(c, 1));
+                TRY(maxpy_impl(c, k, y.data(), vp.data(), 0.0, tmp, st));
+                k_pc_apply<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, c->shift,
+                                                                c->pc, tmp, c->work[1]);
+                CKL();
+                const double one = 1.0;
+                const double *wp = c->work[1];
+                TRY(maxpy_impl(c, 1, &one, &wp, 1.0, x, st));
+            } else {
+                TRY(maxpy_impl(c, k, y.data(), vp.data(), 1.0, x, st));
+            }
+        }
+        if (done) break;
+    }
+    if (res) {
+        res->its = its;
+        res->reason = reason;
+        res->rnorm0 = rnorm0;
+        res->rnorm = rnorm;
+    }
+    return 0;
+}
+
+extern "C" int ksfd_gmres(ksfd_ctx *c, const double *rhs, double *x,
+                          const ksfd_ksp_opts *o, ksfd_ksp_result *res, void *stream)
+{
+    TRY(check_ready(c));
+    if (!c->have_jac) return fail("ksfd_jvp_setup has not been called");
+    if (!rhs || !x || !o) return fail("ksfd_gmres: NULL argument");
+    return gmres_impl(c, rhs, 1.0, x, *o, res, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+// TS step.  ROSW 'ra34pw2' (Rang & Angermann 2005), transformed the way PETSc
+// TSRosWRegister does: At = A*inv(Gamma), bt = b*inv(Gamma), stage solves
+// with shift = 1/(h*gamma), Jacobian evaluated once at stage 0, -snes_type
+// ksponly (one linear solve per stage, zero initial guess).
+// ---------------------------------------------------------------------------
+struct RoswTab {
+    int s;
+    double At[4][4], Gi[4][4], bt[4], bet[4], asum[4], gamma;
+};
+
+static const RoswTab &ra34pw2()
+{
+    static RoswTab T;
+    static bool init = false;
+    if (init) return T;
+    const double g = 4.3586652150845900e-01;
+    const double A[4][4] = {{0, 0, 0, 0},
+                            {8.7173304301691801e-01, 0, 0, 0},
+                            {8.4457060015369423e-01, -1.1299064236484185e-01, 0, 0},
+                            {0, 0, 1.0, 0}};
+    const double Gm[4][4] = {{g, 0, 0, 0},
+                             {-8.7173304301691801e-01, g, 0, 0},
+                             {-9.0338057013044082e-01, 5.4180672388095326e-02, g, 0},
+                             {2.4212380706095346e-01, -1.2232505839045147e+00,
+                              5.4526025533510214e-01, g}};
+    const double b[4] = {2.4212380706095346e-01, -1.2232505839045147e+00,
+                         1.5452602553351020e+00, g};
+    const double be[4] = {3.7810903145819369e-01, -9.6042292212423178e-02,
+                          5.0000000000000000e-01, 2.1793326075422950e-01};
+    T.s = 4;
+    T.gamma = g;
+    // inverse of lower-triangular Gamma by forward substitution
+    for (int col = 0; col < 4; ++col)
+        for (int i = 0; i < 4; ++i) {
+            double s = (i == col) ? 1.0 : 0.0;
+            for (int k = 0; k < i; ++k) s -= Gm[i][k] * T.Gi[k][col];
+            T.Gi[i][col] = s / Gm[i][i];
+        }
+    for (int i = 0; i < 4; ++i) {
+        T.asum[i] = 0;
+        for (int j = 0; j < 4; ++j) {
+            T.asum[i] += A[i][j];
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s += A[i][k] * T.Gi[k][j];
+            T.At[i][j] = s;
+        }
+    }
+    for (int j = 0; j < 4; ++j) {
+        double s = 0, se = 0;
+        for (int k = 0; k < 4; ++k) {
+            s += b[k] * T.Gi[k][j];
+            se += be[k] * T.Gi[k][j];
+        }
+        T.bt[j] = s;
+        T.bet[j] = se;
+    }
+    init = true;
+    return T;
+}
+
+template <int NV>
+static int combine_launch(ksfd_ctx *c, const double *u, const VecList &Y, const CoefList &a,
+                          const CoefList &gm, double *Z, double *Zd, cudaStream_t st)
+{
+    k_stage_combine<NV><<<KSFD_RED_BLOCKS, 256, 0, st>>>(nlocal(c), u, Y, a, gm, Z, Zd);
+    CKL();
+    return 0;
+}
+
+static int rosw_attempt(ksfd_ctx *c, const double *u, double t, double h,
+                        const ksfd_ts_opts &o, const double *src, ksfd_time_cb cb,
+                        void *user, double *unew, double *enorm, int *ksp_its,
+                        int *ksp_fail, cudaStream_t st)
+{
+    const RoswTab &T = ra34pw2();
+    const long long n = nlocal(c);
+    for (int i = 2; i <= 9; ++i) TRY(ensure_work(c, i));
+    double *Y[4] = {c->work[2], c->work[3], c->work[4], c->work[5]};
+    double *Z = c->work[6], *Zd = c->work[7], *F = c->work[8];
+    *ksp_fail = 0;
+    for (int i = 0; i < T.s; ++i) {
+        const double ti = t + h * T.asum[i];
+        VecList yl{};
+        CoefList a{}, gm{};
+        for (int j = 0; j < 4; ++j) yl.v[j] = Y[std::min(j, std::max(i - 1, 0))];
+        for (int j = 0; j < i; ++j) {
+            a.c[j] = T.At[i][j];
+            gm.c[j] = T.Gi[i][j] / h;
+        }
+        const double *Zp = Z;
+        switch (i) {
+        case 0: Zp = u; CK(cudaMemsetAsync(Zd, 0, sizeof(double) * n, st)); break;
+        case 1: TRY(combine_launch<1>(c, u, yl, a, gm, Z, Zd, st)); break;
+        case 2: TRY(combine_launch<2>(c, u, yl, a, gm, Z, Zd, st)); break;
+        default: TRY(combine_launch<3>(c, u, yl, a, gm, Z, Zd, st)); break;
+        }
+        if (cb) {
+            CK(cudaStreamSynchronize(st));
+            cb(ti, user);
+        }
+        TRY(residual_impl(c, Zp, Zd, src, F, st));          // F = Zdot - f(Z)
+        if (i == 0) TRY(jvp_setup_impl(c, Zp, 1.0 / (h * T.gamma), nullptr, st));
+        ksfd_ksp_result kr{};
+        TRY(gmres_impl(c, F, -1.0, Y[i], o.ksp, &kr, st));  // A Y_i = -F
+        *ksp_its += kr.its;
+        if (kr.reason < 0) {
+            *ksp_fail = 1;
+            return 0;
+        }
+    }
+    VecList yl{};
+    CoefList b{}, be{};
+    for (int j = 0; j < 4; ++j) {
+        yl.v[j] = Y[j];
+        b.c[j] = T.bt[j];
+        be.c[j] = T.bet[j];
+    }
+    k_complete_step<4><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(
+        n, u, yl, b, be, o.atol, o.rtol, unew, c->partial);
+    CKL();
+    k_reduce_partials<<<1, 128, 0, st>>>(1, KSFD_RED_BLOCKS, c->partial, c->dscal + SC_ENORM, 0);
+    CKL();
+    TRY(allreduce_dev(c, c->dscal + SC_ENORM, 1, ncclSum_, st));
+    TRY(fetch(c, SC_ENORM, 1, st));
+    const double ntot = (double)c->g.plane_pts * (double)c->last_global * c->dof;
+    *enorm = std::sqrt(c->hscal[SC_ENORM] / ntot);
+    return 0;
+}
+
+static int beuler_attempt(ksfd_ctx *c, const double *u, double t, double h,
+                          const ksfd_ts_opts &o, const double *src, ksfd_time_cb cb,
+                          void *user, double *unew, int *ksp_its, int *ksp_fail,
+                          cudaStream_t st)
+{
+    const long long n = nlocal(c);
+    TRY(ensure_work(c, 2));
+    TRY(ensure_work(c, 8));
+    double *Y = c->work[2], *F = c->work[8];
+    if (cb) {
+        CK(cudaStreamSynchronize(st));
+        cb(t + h, user);
+    }
+    TRY(residual_impl(c, u, nullptr, src, F, st));          // F = f(u)
+    TRY(jvp_setup_impl(c, u, 1.0 / h, nullptr, st));
+    ksfd_ksp_result kr{};
+    TRY(gmres_impl(c, F, 1.0, Y, o.ksp, &kr, st));          // (I/h - J) Y = f(u)
+    *ksp_its += kr.its;
+    *ksp_fail = kr.reason < 0;
+    CK(cudaMemcpyAsync(unew, u, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    const double one = 1.0;
+    const double *yp = Y;
+    TRY(maxpy_impl(c, 1, &one, &yp, 1.0, unew, st));
+    return 0;
+}
+
+extern "C" int ksfd_ts_step(ksfd_ctx *c, double *u, double t, double h,
+                            const ksfd_ts_opts *o, const double *src, ksfd_time_cb cb,
+                            void *user, ksfd_ts_result *res, void *stream)
+{
+    TRY(check_ready(c));
+    if (!u || !o || !res) return fail("ksfd_ts_step: NULL argument");
+    if (!(h > 0.0)) return fail("ksfd_ts_step: step size must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = nlocal(c);
+    TRY(ensure_work(c, 9));
+    double *unew = c->work[9];
+    memset(res, 0, sizeof(*res));
+    const double safety0 = o->safety > 0 ? o->safety : 0.9;
+    const double rsafety = o->reject_safety > 0 ? o->reject_safety : 0.5;
+    const double clip_lo = o->clip_lo > 0 ? o->clip_lo : 0.1;
+    const double clip_hi = o->clip_hi > 0 ? o->clip_hi : 10.0;
+    const double dt_min = o->dt_min > 0 ? o->dt_min : 1e-20;
+    const double dt_max = o->dt_max > 0 ? o->dt_max : 1e50;
+    const int max_rej = o->max_reject > 0 ? o->max_reject : 10;
+    const int order = 3;
+    while (true) {
+        double enorm = 0.0;
+        int fail_ = 0;
+        if (o->ts_type == 1)
+            TRY(beuler_attempt(c, u, t, h, *o, src, cb, user, unew, &res->ksp_its, &fail_, st));
+        else
+            TRY(rosw_attempt(c, u, t, h, *o, src, cb, user, unew, &enorm,
+                             &res->ksp_its, &fail_, st));
+        if (fail_) {
+            res->ksp_fail = 1;
+            res->accepted = 0;
+            res->h_used = h;
+            res->h_next = h;
+            res->t_new = t;
+            return 0;
+        }
+        res->enorm = enorm;
+        bool accept = true;
+        double hnext = h;
+        if (o->adapt == 1 && o->ts_type != 1) {
+            // TSAdaptChoose_Basic
+            double safety = safety0;
+            if (enorm > 1.0) {
+                accept = false;
+                safety *= rsafety;
+            }
+            double hfac = enorm > 0.0 ? safety * std::pow(enorm, -1.0 / order) : clip_hi;
+            hfac = std::min(std::max(hfac, clip_lo), clip_hi);
+            hnext = std::min(std::max(h * hfac, dt_min), dt_max);
+        }
+        if (accept) {
+            CK(cudaMemcpyAsync(u, unew, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+            res->accepted = 1;
+            res->t_new = t + h;
+            res->h_used = h;
+            res->h_next = hnext;
+            return 0;
+        }
+        ++res->rejections;
+        if (res->rejections > max_rej || hnext < dt_min) {
+            res->accepted = 0;
+            res->t_new = t;
+            res->h_used = h;
+            res->h_next = hnext;
+            return 0;
+        }
+        h = hnext;
+    }
+}

@@ -1,0 +1,313 @@
+// Generic "direct" kernels: one thread per owned point, every stencil point
+// re-read from global memory and G recomputed per stencil point.  Runtime dim
+// (1,2,3) and nlig.  They are the 1-D path, the fallback for grids too small
+// to tile, and an independent on-device cross-check of the marching kernels
+// (tests/test_gpu_parity.py).  Not the performance path.
+#pragma once
+#include "device_common.cuh"
+
+struct PointIdx {
+    int i, j, k;            // x, y index in plane (0 when unused), plane k
+    long long pp;           // point offset inside the plane
+};
+
+__device__ __forceinline__ PointIdx decode_point(const Geom &g, long long p)
+{
+    PointIdx q;
+    q.k = (int)(p / g.plane_pts);
+    q.pp = p - (long long)q.k * g.plane_pts;
+    if (g.dim == 3) {
+        q.j = (int)(q.pp / g.n0);
+        q.i = (int)(q.pp - (long long)q.j * g.n0);
+    } else if (g.dim == 2) {
+        q.j = 0;
+        q.i = (int)q.pp;
+    } else {
+        q.i = q.j = 0;
+    }
+    return q;
+}
+
+// pointer to the `stride` doubles of the neighbour of q shifted by off along ax
+__device__ __forceinline__ const double *nbr_ptr(const Geom &g, const VecRef &v,
+                                                 const PointIdx &q, int ax,
+                                                 int off, int stride)
+{
+    int k = q.k;
+    long long pp = q.pp;
+    if (ax == g.dim - 1) {
+        k += off;
+    } else if (ax == 0) {
+        pp += wrapi(q.i + off, g.n0) - q.i;
+    } else {
+        pp += (long long)(wrapi(q.j + off, g.n1) - q.j) * g.n0;
+    }
+    return plane_ptr(v, k, g.nloc, g.plane_pts * stride) + pp * stride;
+}
+
+__device__ __forceinline__ void load_clamped(const DevPhys &P, const double *p,
+                                             double &rho, double *U)
+{
+    rho = clampv(p[0], P.rhomin);
+    for (int l = 0; l < P.nlig; ++l) U[l] = clampv(p[1 + l], P.Umin);
+}
+
+// f_out = udot - (f(u)+src)  or  f(u)+src
+__global__ void k_residual_naive(Geom g, DevPhys P, VecRef u,
+                                 const double *__restrict__ udot,
+                                 const double *__restrict__ src,
+                                 double *__restrict__ out)
+{
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= g.npts) return;
+    PointIdx q = decode_point(g, p);
+    const int dof = g.dof;
+    double rho0, U0[KSFD_MAX_LIGANDS];
+    load_clamped(P, nbr_ptr(g, u, q, 0, 0, dof), rho0, U0);
+    double G0 = G_point_rt(P, rho0, U0);
+    double acc = 0.0, lap = 0.0, lapU[KSFD_MAX_LIGANDS];
+    for (int l = 0; l < P.nlig; ++l) lapU[l] = 0.0;
+    for (int ax = 0; ax < g.dim; ++ax) {
+        double d1r = 0.0, d1G = 0.0, d2G = 0.0, d2U[KSFD_MAX_LIGANDS];
+        for (int l = 0; l < P.nlig; ++l) d2U[l] = 0.0;
+        for (int s = 0; s < 5; ++s) {
+            double rn, Un[KSFD_MAX_LIGANDS], Gn;
+            if (s == 2) {
+                rn = rho0; Gn = G0;
+                for (int l = 0; l < P.nlig; ++l) Un[l] = U0[l];
+            } else {
+                load_clamped(P, nbr_ptr(g, u, q, ax, s - 2, dof), rn, Un);
+                Gn = G_point_rt(P, rn, Un);
+            }
+            d1r = fma(P.w1[ax][s], rn, d1r);
+            d1G = fma(P.w1[ax][s], Gn, d1G);
+            d2G = fma(P.w2[ax][s], Gn, d2G);
+            for (int l = 0; l < P.nlig; ++l)
+                d2U[l] = fma(P.w2[ax][s], Un[l], d2U[l]);
+        }
+        acc = fma(d1r, d1G, acc);
+        lap += d2G;
+        for (int l = 0; l < P.nlig; ++l) lapU[l] += d2U[l];
+    }
+    double f[KSFD_MAX_LIGANDS + 1];
+    f[0] = fma(rho0, lap, acc);
+    for (int l = 0; l < P.nlig; ++l)
+        f[l + 1] = fma(P.D[l], lapU[l], fma(P.s[l], rho0, -P.gamma[l] * U0[l]));
+    for (int c = 0; c < dof; ++c) {
+        double v = f[c];
+        if (src) v += src[p * dof + c];
+        out[p * dof + c] = udot ? udot[p * dof + c] - v : v;
+    }
+}
+
+// vel[d + dim*p] = d/dx_d G ; optional per-axis max|.| via atomics
+__global__ void k_velocity_naive(Geom g, DevPhys P, VecRef u,
+                                 double *__restrict__ vel,
+                                 double *__restrict__ vmax)
+{
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    double vm[3] = {0.0, 0.0, 0.0};
+    if (p < g.npts) {
+        PointIdx q = decode_point(g, p);
+        double rho0, U0[KSFD_MAX_LIGANDS];
+        load_clamped(P, nbr_ptr(g, u, q, 0, 0, g.dof), rho0, U0);
+        double G0 = G_point_rt(P, rho0, U0);
+        for (int ax = 0; ax < g.dim; ++ax) {
+            double d1G = 0.0;
+            for (int s = 0; s < 5; ++s) {
+                double Gn = G0;
+                if (s != 2) {
+                    double rn, Un[KSFD_MAX_LIGANDS];
+                    load_clamped(P, nbr_ptr(g, u, q, ax, s - 2, g.dof), rn, Un);
+                    Gn = G_point_rt(P, rn, Un);
+                }
+                d1G = fma(P.w1[ax][s], Gn, d1G);
+            }
+            if (vel) vel[p * g.dim + ax] = d1G;
+            vm[ax] = fabs(d1G);
+        }
+    }
+    if (vmax) {
+        for (int ax = 0; ax < g.dim; ++ax) {
+            double m = warp_max(vm[ax]);
+            if ((threadIdx.x & 31) == 0) atomic_max_nonneg(vmax + ax, m);
+        }
+    }
+}
+
+// clamp in place (KSFD/ksfdts.py:231-237)
+__global__ void k_groom(long long npts, int dof, double rhomin, double Umin,
+                        double *__restrict__ u)
+{
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= npts * dof) return;
+    int c = (int)(e % dof);
+    u[e] = clampv(u[e], c == 0 ? rhomin : Umin);
+}
+
+// coefficient field over planes -2 .. nloc+1 (ghosted along the last axis):
+// coef[(plane+2)*plane_pts + pp][0..dof+1] = rho, G, dG/drho, dG/dU_l
+__global__ void k_coef_setup(Geom g, DevPhys P, VecRef u,
+                             double *__restrict__ coef)
+{
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long tot = (long long)(g.nloc + 2 * KSFD_SW) * g.plane_pts;
+    if (e >= tot) return;
+    int k = (int)(e / g.plane_pts) - KSFD_SW;
+    long long pp = e % g.plane_pts;
+    const double *p =
+        plane_ptr(u, k, g.nloc, g.plane_pts * g.dof) + pp * g.dof;
+    double rho, U[KSFD_MAX_LIGANDS], G, g_rho, g_U[KSFD_MAX_LIGANDS];
+    load_clamped(P, p, rho, U);
+    G_and_partials_rt(P, rho, U, G, g_rho, g_U);
+    double *c = coef + e * (g.dof + 2);
+    c[0] = rho;
+    c[1] = G;
+    c[2] = g_rho;
+    for (int l = 0; l < P.nlig; ++l) c[3 + l] = g_U[l];
+}
+
+// Point-block Jacobi of A = shift*I - J.  The diagonal block is
+//   [ a   b_1 .. b_n ]      a   = shift - dJ_rho/drho0
+//   [ c_1 d_1        ]      b_l = -dJ_rho/dU_l0      c_l = -s_l
+//   [ c_n        d_n ]      d_l = shift + gamma_l - D_l*sum_ax w2c
+// stored as pc[p] = ( 1/(a - sum b_l c_l/d_l),  b_1/d_1, .., b_n/d_n ).
+// If blocks != NULL the dense dof x dof blocks are written too (tests).
+__global__ void k_pc_setup(Geom g, DevPhys P, VecRef coef, double shift,
+                           double *__restrict__ pc, double *__restrict__ blocks)
+{
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= g.npts) return;
+    PointIdx q = decode_point(g, p);
+    const int cs = g.dof + 2;
+    const double *c0 = nbr_ptr(g, coef, q, 0, 0, cs);
+    double rho0 = c0[0];
+    double fac = 0.0, lap = 0.0, dir = 0.0, w2c = 0.0;
+    for (int ax = 0; ax < g.dim; ++ax) {
+        double d1r = 0.0, d1G = 0.0, d2G = 0.0;
+        for (int s = 0; s < 5; ++s) {
+            const double *cn = (s == 2) ? c0 : nbr_ptr(g, coef, q, ax, s - 2, cs);
+            d1r = fma(P.w1[ax][s], cn[0], d1r);
+            d1G = fma(P.w1[ax][s], cn[1], d1G);
+            d2G = fma(P.w2[ax][s], cn[1], d2G);
+        }
+        fac += d1r * P.w1[ax][2] + rho0 * P.w2[ax][2];
+        dir += P.w1[ax][2] * d1G;
+        lap += d2G;
+        w2c += P.w2[ax][2];
+    }
+    double Jrr = dir + fac * c0[2] + lap;
+    double a = shift - Jrr;
+    double schur = a;
+    double *o = pc + p * g.dof;
+    for (int l = 0; l < P.nlig; ++l) {
+        double b = -fac * c0[3 + l];
+        double d = shift + P.gamma[l] - P.D[l] * w2c;
+        double bd = b / d;
+        o[1 + l] = bd;
+        schur -= bd * (-P.s[l]);
+        if (blocks) {
+            double *B = blocks + p * g.dof * g.dof;
+            B[0 * g.dof + (1 + l)] = b;
+            B[(1 + l) * g.dof + 0] = -P.s[l];
+            for (int m = 0; m < P.nlig; ++m)
+                B[(1 + l) * g.dof + (1 + m)] = (m == l) ? d : 0.0;
+        }
+    }
+    o[0] = 1.0 / schur;
+    if (blocks) blocks[p * g.dof * g.dof] = a;
+}
+
+// z = M^{-1} r for one point (pcp = pc entry of that point)
+__device__ __forceinline__ void pc_point(const DevPhys &P, double shift,
+                                         double w2c_sum, const double *pcp,
+                                         const double *r, double *z, int nlig)
+{
+    double t = r[0];
+#pragma unroll
+    for (int l = 0; l < nlig; ++l) t = fma(-pcp[1 + l], r[1 + l], t);
+    double zr = pcp[0] * t;
+    z[0] = zr;
+#pragma unroll
+    for (int l = 0; l < nlig; ++l) {
+        double d = shift + P.gamma[l] - P.D[l] * w2c_sum;
+        z[1 + l] = (r[1 + l] + P.s[l] * zr) / d;
+    }
+}
+
+__device__ __forceinline__ double w2c_total(const DevPhys &P, int dim)
+{
+    double w = 0.0;
+    for (int ax = 0; ax < dim; ++ax) w += P.w2[ax][2];
+    return w;
+}
+
+__global__ void k_pc_apply(Geom g, DevPhys P, double shift,
+                           const double *__restrict__ pc,
+                           const double *__restrict__ r, double *__restrict__ z)
+{
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= g.npts) return;
+    double rr[KSFD_MAX_LIGANDS + 1], zz[KSFD_MAX_LIGANDS + 1];
+    for (int c = 0; c < g.dof; ++c) rr[c] = r[p * g.dof + c];
+    pc_point(P, shift, w2c_total(P, g.dim), pc + p * g.dof, rr, zz, P.nlig);
+    for (int c = 0; c < g.dof; ++c) z[p * g.dof + c] = zz[c];
+}
+
+// out = (shift*I - J(u_lin)) * v   (optionally v := M^{-1} v first)
+__global__ void k_jvp_naive(Geom g, DevPhys P, VecRef coef, VecRef v, VecRef pc,
+                            int precond, double shift, double *__restrict__ out)
+{
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= g.npts) return;
+    PointIdx q = decode_point(g, p);
+    const int dof = g.dof, cs = g.dof + 2;
+    const double w2c = w2c_total(P, g.dim);
+    double acc = 0.0, lapG = 0.0, lapdG = 0.0, lapV[KSFD_MAX_LIGANDS];
+    for (int l = 0; l < P.nlig; ++l) lapV[l] = 0.0;
+    double v0[KSFD_MAX_LIGANDS + 1], rho0 = 0.0;
+    for (int ax = 0; ax < g.dim; ++ax) {
+        double d1r = 0, d1G = 0, d1v = 0, d1dG = 0, d2G = 0, d2dG = 0;
+        double d2V[KSFD_MAX_LIGANDS];
+        for (int l = 0; l < P.nlig; ++l) d2V[l] = 0.0;
+        for (int s = 0; s < 5; ++s) {
+            const double *cn = nbr_ptr(g, coef, q, ax, s - 2, cs);
+            const double *vn = nbr_ptr(g, v, q, ax, s - 2, dof);
+            double vv[KSFD_MAX_LIGANDS + 1];
+            if (precond) {
+                double rr[KSFD_MAX_LIGANDS + 1];
+                for (int c = 0; c < dof; ++c) rr[c] = vn[c];
+                pc_point(P, shift, w2c, nbr_ptr(g, pc, q, ax, s - 2, dof), rr,
+                         vv, P.nlig);
+            } else {
+                for (int c = 0; c < dof; ++c) vv[c] = vn[c];
+            }
+            double dG = cn[2] * vv[0];
+            for (int l = 0; l < P.nlig; ++l) dG = fma(cn[3 + l], vv[1 + l], dG);
+            if (s == 2) {
+                rho0 = cn[0];
+                for (int c = 0; c < dof; ++c) v0[c] = vv[c];
+            }
+            d1r = fma(P.w1[ax][s], cn[0], d1r);
+            d1G = fma(P.w1[ax][s], cn[1], d1G);
+            d2G = fma(P.w2[ax][s], cn[1], d2G);
+            d1v = fma(P.w1[ax][s], vv[0], d1v);
+            d1dG = fma(P.w1[ax][s], dG, d1dG);
+            d2dG = fma(P.w2[ax][s], dG, d2dG);
+            for (int l = 0; l < P.nlig; ++l)
+                d2V[l] = fma(P.w2[ax][s], vv[1 + l], d2V[l]);
+        }
+        acc = fma(d1v, d1G, acc);
+        acc = fma(d1r, d1dG, acc);
+        lapG += d2G;
+        lapdG += d2dG;
+        for (int l = 0; l < P.nlig; ++l) lapV[l] += d2V[l];
+    }
+    double Jv0 = fma(rho0, lapdG, fma(v0[0], lapG, acc));
+    out[p * dof] = fma(shift, v0[0], -Jv0);
+    for (int l = 0; l < P.nlig; ++l) {
+        double JvU =
+            fma(P.D[l], lapV[l], fma(P.s[l], v0[0], -P.gamma[l] * v0[1 + l]));
+        out[p * dof + 1 + l] = fma(shift, v0[1 + l], -JvU);
+    }
+}

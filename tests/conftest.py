@@ -1,0 +1,19 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (B200)')
+
+
+@pytest.fixture(scope='session')
+def built_lib():
+    """Compile the CUDA library if it is stale (nvcc cross-compiles on CPU)."""
+    from ksfd_b200 import build
+    return build.build()

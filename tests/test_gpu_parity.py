@@ -1,0 +1,337 @@
+"""
+Parity of the CUDA path (through the C ABI) against
+  (1) golden vectors from the reference's own code (tests/golden/*.npz),
+  (2) the numpy oracle on seeded inputs at sizes it finishes in seconds,
+  (3) size-independent properties at the BASELINE sizes (1024^2, 256^3).
+
+Tolerances (fp64, max-norm relative to the largest entry of each dof):
+  residual / velocity   1e-11   (CUDA libm log/tanh 1-2 ulp + FMA contraction,
+                                 amplified by the stencil's cancellation)
+  J.v vs assembled J@v  1e-11
+  block-Jacobi blocks   1e-11
+"""
+import numpy as np
+import pytest
+
+from helpers import (golden_names, load_golden, oracle_physics, phys84,
+                     product_physics, random_state, relerr)
+
+pytestmark = pytest.mark.gpu
+
+TOL_F = 1e-11
+TOL_J = 1e-11
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def make_ctx(p, variant=0):
+    from ksfd_b200 import core
+    dof = 1 + sum(len(g[2]) for g in p['groups'])
+    ctx = core.Context(p['dim'], p['n'], dof)
+    ctx.set_physics(product_physics(p))
+    ctx.set_option('variant', variant)
+    return ctx
+
+
+def dev(a):
+    torch = _torch()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+def variants_for(p):
+    dof = 1 + sum(len(g[2]) for g in p['groups'])
+    if p['dim'] == 1 or dof - 1 > 4:
+        return [1]
+    return [1, 2]
+
+
+def per_dof_err(a, b, dof):
+    a = np.asarray(a).ravel()
+    b = np.asarray(b).ravel()
+    scale = max(np.abs(b).max(), 1e-300)
+    worst = 0.0
+    for c in range(dof):
+        ref = max(np.abs(b[c::dof]).max(), 1e-9 * scale)
+        worst = max(worst, np.abs(a[c::dof] - b[c::dof]).max() / ref)
+    return worst
+
+
+# ---------------------------------------------------------------------------
+# (1) golden vectors from the reference
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('name', golden_names())
+def test_golden_residual_velocity_jvp(name):
+    g, physs, nrec = load_golden(name)
+    for r in range(nrec):
+        p = physs[r]
+        for variant in variants_for(p):
+            ctx = make_ctx(p, variant)
+            dof = ctx.dof
+            u = dev(g['u_%d' % r])
+            src = dev(g['src_%d' % r])
+            f = ctx.residual(u, None, src).cpu().numpy()
+            assert per_dof_err(f, g['f_%d' % r], dof) < TOL_F, (name, r, variant)
+            # the field vector itself is not modified (clamp is on the fly)
+            assert np.array_equal(u.cpu().numpy(), g['u_%d' % r], equal_nan=True)
+            vel = ctx.velocity(u).cpu().numpy()
+            vr = g['vel_%d' % r]
+            assert (relerr(vel, vr) < TOL_F or np.abs(vel - vr).max() < 1e-12), \
+                (name, r, variant)
+            vm = ctx.velocity_max(u)
+            vref = np.abs(vr.reshape(-1, p['dim'])).max(axis=0)
+            assert np.allclose(vm, vref, rtol=1e-10, atol=1e-13)
+            ctx.jvp_setup(u, 0.0)
+            for m in range(3):
+                v = dev(g['v_%d' % r][m])
+                jv = -ctx.jvp(v).cpu().numpy()
+                assert per_dof_err(jv, g['Jv_%d' % r][m], dof) < TOL_J, \
+                    (name, r, variant, m)
+            ctx.close()
+
+
+# ---------------------------------------------------------------------------
+# (2) oracle on seeded inputs
+# ---------------------------------------------------------------------------
+CASES = [
+    ('1d', phys84(1, (200,))),
+    ('2d', phys84(2, (96, 80))),
+    ('2d_thin', phys84(2, (8, 40))),
+    ('2d_odd', phys84(2, (131, 67))),
+    ('3d', phys84(3, (24, 20, 28))),
+    ('3d_odd', phys84(3, (37, 9, 11))),
+]
+
+
+@pytest.mark.parametrize('label,p', CASES)
+def test_oracle_ifunction_jvp_pc(label, p):
+    from oracle import ksfd_oracle as O
+    ph = oracle_physics(p)
+    u = random_state(p, 11)
+    rng = np.random.default_rng(12)
+    udot = rng.standard_normal(u.size)
+    v = rng.standard_normal(u.size)
+    shift = 1.0 / (O.ROSW_GAMMA * 1e-3)
+    F_ref = O.ifunction(u, udot, ph).reshape(-1, order='F')
+    Jv_ref = O.jvp(u, v, shift, ph).reshape(-1, order='F')
+    blocks_ref = O.block_diagonal(u, shift, ph)
+    for variant in variants_for(p):
+        ctx = make_ctx(p, variant)
+        F = ctx.residual(dev(u), dev(udot)).cpu().numpy()
+        assert per_dof_err(F, F_ref, ph.dof) < TOL_F, (label, variant)
+        ctx.jvp_setup(dev(u), shift)
+        Jv = ctx.jvp(dev(v)).cpu().numpy()
+        assert per_dof_err(Jv, Jv_ref, ph.dof) < TOL_J, (label, variant)
+        blocks = ctx.block_diagonal().cpu().numpy()
+        assert relerr(blocks, blocks_ref) < TOL_J
+        # M^{-1} really inverts the diagonal blocks
+        z = ctx.pc_apply(dev(v)).cpu().numpy().reshape(-1, ph.dof)
+        back = np.einsum('prc,pc->pr', blocks_ref, z).reshape(-1)
+        assert relerr(back, v) < 1e-10
+        # fused A*M^{-1} == A(M^{-1} v)
+        fused = ctx.jvp(dev(v), precond=True).cpu().numpy()
+        two = ctx.jvp(ctx.pc_apply(dev(v))).cpu().numpy()
+        assert per_dof_err(fused, two, ph.dof) < 1e-12
+        ctx.close()
+
+
+def test_clamp_and_nan_handling():
+    from oracle import ksfd_oracle as O
+    p = phys84(2, (40, 36))
+    ph = oracle_physics(p)
+    u = random_state(p, 5)
+    rng = np.random.default_rng(6)
+    idx = rng.integers(0, u.size, 60)
+    u[idx[:20]] = -3.0
+    u[idx[20:40]] = np.nan
+    u[idx[40:]] = 0.0
+    f_ref = O.dfdt(u.copy(), ph).reshape(-1, order='F')
+    for variant in (1, 2):
+        ctx = make_ctx(p, variant)
+        f = ctx.residual(dev(u)).cpu().numpy()
+        assert per_dof_err(f, f_ref, ph.dof) < TOL_F
+        ug = ctx.groom(dev(u)).cpu().numpy()
+        ref = O.groom(u.copy().reshape(ph.Vshape, order='F'), ph).reshape(-1, order='F')
+        assert np.array_equal(ug, ref)                       # bit exact
+        assert np.array_equal(ctx.groom(dev(ug)).cpu().numpy(), ug)   # idempotent
+        ctx.close()
+
+
+def test_blas1_against_numpy():
+    p = phys84(2, (64, 48))
+    ctx = make_ctx(p)
+    rng = np.random.default_rng(3)
+    n = ctx.npts * ctx.dof
+    vs = [rng.standard_normal(n) for _ in range(11)]
+    w = rng.standard_normal(n)
+    d = ctx.mdot([dev(v) for v in vs], dev(w)).cpu().numpy()
+    assert np.allclose(d, [v @ w for v in vs], rtol=1e-12, atol=1e-9)
+    y = dev(w)
+    coefs = rng.standard_normal(11)
+    ctx.maxpy(y, coefs, [dev(v) for v in vs])
+    assert np.allclose(y.cpu().numpy(), w + sum(c * v for c, v in zip(coefs, vs)),
+                       rtol=1e-13, atol=1e-12)
+    assert abs(ctx.norm2(dev(w)) - np.linalg.norm(w)) < 1e-10
+    assert abs(ctx.sum_dof0(dev(w)) - w[0::ctx.dof].sum()) < 1e-9
+    ctx.close()
+
+
+@pytest.mark.parametrize('label,p', [('1d', phys84(1, (128,), h=1.0 / 128)),
+                                     ('2d', phys84(2, (40, 32))),
+                                     ('3d', phys84(3, (12, 10, 14)))])
+def test_gmres_against_direct_solve(label, p):
+    import scipy.sparse.linalg as spla
+    from oracle import ksfd_oracle as O
+    ph = oracle_physics(p)
+    u = random_state(p, 21)
+    rng = np.random.default_rng(22)
+    b = rng.standard_normal(u.size)
+    for shift in (1.0 / (O.ROSW_GAMMA * 1e-3), 1.0 / (O.ROSW_GAMMA * 1.0)):
+        A = O.ijacobian(u, shift, ph).tocsc()
+        x_ref = spla.splu(A).solve(b)
+        ctx = make_ctx(p)
+        ctx.jvp_setup(dev(u), shift)
+        for reorth in (0, 1):
+            x, res = ctx.gmres(dev(b), rtol=1e-12, max_it=2000, restart=30,
+                               reorth=reorth)
+            assert res.reason > 0, (label, shift, res.reason, res.its)
+            assert relerr(x.cpu().numpy(), x_ref) < 1e-8, (label, shift, res.its)
+        ctx.close()
+
+
+@pytest.mark.parametrize('label,p,h', [('1d', phys84(1, (64,), h=1.0 / 64), 0.5),
+                                       ('2d', phys84(2, (32, 24)), 1e-3),
+                                       ('2d_big_dt', phys84(2, (32, 24)), 0.25),
+                                       ('3d', phys84(3, (10, 12, 8)), 1e-3)])
+def test_rosw_step_and_trajectory(label, p, h):
+    """N-step ROSW trajectory vs the oracle (splu linear solves): rel 1e-8."""
+    from ksfd_b200 import core
+    from oracle import ksfd_oracle as O
+    ph = oracle_physics(p)
+    u0 = random_state(p, 31)
+    nsteps = 5
+    traj = O.integrate(u0, 0.0, h, nsteps, ph)
+    ctx = make_ctx(p)
+    opts = core.ts_options(adapt='none', ksp_rtol=1e-13, ksp_max_it=2000)
+    u = dev(u0)
+    t = 0.0
+    for k in range(nsteps):
+        ctx.groom(u)
+        res = ctx.ts_step(u, t, h, opts)
+        assert res.accepted == 1 and res.ksp_fail == 0
+        t = res.t_new
+        ref = traj[k][1].reshape(-1, order='F')
+        assert per_dof_err(u.cpu().numpy(), ref, ph.dof) < 1e-8, (label, k)
+    assert abs(t - nsteps * h) < 1e-12
+    ctx.close()
+
+
+def test_rosw_adaptive_matches_oracle():
+    from ksfd_b200 import core
+    from oracle import ksfd_oracle as O
+    p = phys84(2, (24, 20))
+    ph = oracle_physics(p)
+    u0 = random_state(p, 41)
+    adapt = dict(atol=0.01, rtol=1e-6, clip=(0.1, 5.0), dt_min=1e-20, dt_max=1e4)
+    # oracle loop
+    u = u0.reshape(ph.Vshape, order='F').copy()
+    t, h = 0.0, 1e-8
+    ref = []
+    for k in range(12):
+        u = O.groom(u, ph)
+        while True:
+            un, ue, _ = O.rosw_step(u, t, h, ph)
+            en = O.wnorm2(un, ue, adapt['atol'], adapt['rtol'])
+            ok, hn = O.adapt_basic(h, en, clip=adapt['clip'], dt_min=adapt['dt_min'],
+                                   dt_max=adapt['dt_max'])
+            if ok:
+                u, t = un, t + h
+                h = hn
+                break
+            h = hn
+        ref.append((t, h, u.copy()))
+    ctx = make_ctx(p)
+    opts = core.ts_options(adapt='basic', atol=0.01, rtol=1e-6, clip=(0.1, 5.0),
+                           dt_max=1e4, ksp_rtol=1e-13, ksp_max_it=2000)
+    ud = dev(u0)
+    t, h = 0.0, 1e-8
+    for k in range(12):
+        ctx.groom(ud)
+        res = ctx.ts_step(ud, t, h, opts)
+        assert res.accepted == 1
+        t, h = res.t_new, res.h_next
+        assert abs(t - ref[k][0]) <= 1e-6 * abs(ref[k][0]), (k, t, ref[k][0])
+        assert abs(h - ref[k][1]) <= 1e-5 * abs(ref[k][1]), (k, h, ref[k][1])
+        assert per_dof_err(ud.cpu().numpy(), ref[k][2].reshape(-1, order='F'),
+                           ph.dof) < 1e-8
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------
+# (3) BASELINE sizes: size-independent properties
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('label,p', [('1024^2', phys84(2, (1024, 1024))),
+                                     ('256^3', phys84(3, (256, 256, 256)))])
+def test_full_size_properties(label, p):
+    torch = _torch()
+    ctx = make_ctx(p, 2)
+    n = ctx.npts * ctx.dof
+    gen = torch.Generator(device='cuda').manual_seed(793817931)
+    rho = 9000.0 + 90.0 * torch.randn(ctx.npts, generator=gen, device='cuda',
+                                      dtype=torch.float64)
+    u = rho.repeat_interleave(ctx.dof).contiguous()
+    udot = torch.randn(n, generator=gen, device='cuda', dtype=torch.float64)
+    v = torch.randn(n, generator=gen, device='cuda', dtype=torch.float64)
+    w = torch.randn(n, generator=gen, device='cuda', dtype=torch.float64)
+    # marching kernels agree with the independent direct kernels
+    F2 = ctx.residual(u, udot)
+    ctx.set_option('variant', 1)
+    F1 = ctx.residual(u, udot)
+    ctx.set_option('variant', 2)
+    for c in range(ctx.dof):
+        d = (F2[c::ctx.dof] - F1[c::ctx.dof]).abs().max().item()
+        assert d / F1[c::ctx.dof].abs().max().item() < 1e-11, (label, c)
+    # F(u, udot) - F(u, 0) == udot  and  dfdt == -F(u, 0) bit exactly
+    f = ctx.residual(u)
+    F0 = ctx.residual(u, torch.zeros_like(u))
+    assert torch.equal(f, -F0)
+    # uniform state with s = gamma is an equilibrium
+    ueq = torch.full((n,), 9000.0, device='cuda', dtype=torch.float64)
+    assert ctx.residual(ueq).abs().max().item() < 1e-8
+    # translation equivariance under the periodic wrap (exact index mapping):
+    # shifting the field by whole planes of the last axis shifts the residual
+    plane = ctx.dof * int(np.prod(ctx.local_shape[:-1]))
+    ur = torch.roll(u, 3 * plane)
+    assert torch.equal(ctx.residual(ur), torch.roll(f, 3 * plane))
+    ur = torch.roll(u, 5 * ctx.dof)          # shift along x inside every row
+    if p['dim'] == 2:
+        rows = u.view(ctx.local_shape[1], -1)
+        ur = torch.roll(rows, 5 * ctx.dof, dims=1).reshape(-1)
+        fr = torch.roll(f.view(ctx.local_shape[1], -1), 5 * ctx.dof, dims=1).reshape(-1)
+        assert torch.equal(ctx.residual(ur), fr)
+    # J.v: linearity and agreement with the direct kernel and a finite difference
+    shift = 1.0 / (0.435866521508459 * 1e-3)
+    ctx.jvp_setup(u, shift)
+    a, b = 0.37, -1.9
+    lhs = ctx.jvp(a * v + b * w)
+    rhs = a * ctx.jvp(v) + b * ctx.jvp(w)
+    assert (lhs - rhs).abs().max().item() / rhs.abs().max().item() < 1e-13
+    Jv2 = ctx.jvp(v)
+    ctx.set_option('variant', 1)
+    Jv1 = ctx.jvp(v)
+    ctx.set_option('variant', 2)
+    assert (Jv2 - Jv1).abs().max().item() / Jv1.abs().max().item() < 1e-12
+    eps = 1e-4
+    fd = (ctx.residual(u + eps * v) - ctx.residual(u - eps * v)) / (2 * eps)
+    Jv = shift * v - ctx.jvp(v)
+    for c in range(ctx.dof):
+        d = (Jv[c::ctx.dof] - fd[c::ctx.dof]).abs().max().item()
+        assert d / fd[c::ctx.dof].abs().max().item() < 1e-6, (label, c)
+    # GMRES solves the full-size system to the requested tolerance
+    x, res = ctx.gmres(udot, rtol=1e-8, max_it=200)
+    assert res.reason > 0
+    r = udot - ctx.jvp(x)
+    assert ctx.norm2(r) <= 1.5e-8 * ctx.norm2(udot)
+    ctx.close()
