@@ -67,3 +67,48 @@ def relerr(a, b, dof=None):
         return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
     return max(float(np.abs(a[c::dof] - b[c::dof]).max()
                      / max(np.abs(b[c::dof]).max(), 1e-300)) for c in range(dof))
+
+
+EPS = 2.220446049250313e-16
+
+
+def cond_scale(ph, u):
+    """
+    Per-dof conditioning scale of the discrete f(u): the stencil sums cancel
+    (f_rho = grad(rho).grad(G) + rho*lap(G) with G nearly constant), so the
+    attainable absolute accuracy of ANY fp64 evaluation order is
+    ~eps * sum|w_k a_k|, not eps*|f|.  Returns, per dof, sum over the stencil
+    of |weight|*|value| bounds:  rho*sum|w2|*|G| + (sum|w1| rho)(sum|w1| |G|)
+    for the rho row, gamma*U + s*rho + D*sum|w2|*U for the ligand rows.
+    """
+    from oracle import ksfd_oracle as O
+    ua = np.array(u, dtype=float).reshape(ph.Vshape, order='F')
+    farr = O.groom(O.ghost_fill(ua, ph.dim), ph)
+    G = np.abs(O.G_of(farr, ph)).max()
+    rho = np.abs(farr[0]).max()
+    w1 = sum(np.abs(w).sum() for w in ph.w1)
+    w2 = sum(np.abs(w).sum() for w in ph.w2)
+    out = [rho * w2 * G + sum(np.abs(a).sum() * rho * np.abs(a).sum() * G
+                              for a in ph.w1)]
+    for l, lig in enumerate(ph.ligands()):
+        U = np.abs(farr[l + 1]).max()
+        out.append(lig['gamma'] * U + lig['s'] * rho + lig['D'] * w2 * U)
+    return np.array(out)
+
+
+def check_field(a, b, dof, rtol, cond=None, ncond=64.0):
+    """
+    assert-able error measure: per dof, max|a-b| must be below
+    rtol*max|b_dof| + ncond*eps*cond_dof.  Returns the worst ratio
+    err/allowed (pass iff < 1).
+    """
+    a = np.asarray(a).ravel()
+    b = np.asarray(b).ravel()
+    worst = 0.0
+    for c in range(dof):
+        err = np.abs(a[c::dof] - b[c::dof]).max()
+        allowed = rtol * np.abs(b[c::dof]).max()
+        if cond is not None:
+            allowed += ncond * EPS * cond[c]
+        worst = max(worst, err / max(allowed, 1e-300))
+    return worst

@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
-from helpers import golden_names, load_golden, oracle_physics, relerr
+from helpers import (check_field, cond_scale, golden_names, load_golden,
+                     oracle_physics, relerr)
 from oracle import ksfd_oracle as O
 
 NAMES = golden_names()
@@ -32,12 +33,10 @@ def test_dfdt_velocity(name):
         src = g['src_%d' % r].reshape((ph.dof,) + ph.n, order='F')
         f = O.dfdt(g['u_%d' % r], ph, sources=list(src)).reshape(-1, order='F')
         fr = g['f_%d' % r]
-        scale = max(np.abs(fr).max(), 1e-300)
-        # per-dof relative error; rows whose reference is ~0 use the global scale
-        for c in range(ph.dof):
-            d = np.abs(f[c::ph.dof] - fr[c::ph.dof]).max()
-            ref = max(np.abs(fr[c::ph.dof]).max(), 1e-9 * scale)
-            assert d / ref < TOL_F, (name, r, c, d / ref)
+        # relative to max|f| per dof, plus the cancellation floor of the stencil
+        # (smooth states: |f| << sum|w_k a_k|, see helpers.cond_scale)
+        bad = check_field(f, fr, ph.dof, TOL_F, cond_scale(ph, g['u_%d' % r]))
+        assert bad < 1.0, (name, r, bad)
         v = O.velocity(g['u_%d' % r], ph).reshape(-1, order='F')
         vr = g['vel_%d' % r]
         assert relerr(v, vr) < TOL_F or np.abs(v - vr).max() < 1e-13, (name, r)
@@ -75,7 +74,7 @@ def test_uniform_equilibrium():
     ph = oracle_physics(phys84(2, (16, 12)))
     u = np.full(ph.dof * ph.npts, 9000.0)
     f = O.dfdt(u, ph)
-    assert np.abs(f).max() < 2e-9      # ~ rho*|G|/h^2 * eps
+    assert np.abs(f).max() < 1e-8      # ~ rho*|G|*sum|w2| * eps (weights do not cancel bitwise)
 
 
 def test_jacobian_is_derivative_3d():
