@@ -1,0 +1,386 @@
+#!/usr/bin/env python3
+"""
+bench.py — headline benchmark of the KSFD implicit time-stepping hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+Workload (BASELINE.json configs[2]): 2-D 1024x1024 per-GPU tile, dof 3,
+options84 physics (reference options84:20-46), h = 1/384, periodic, synthetic
+random IC (rho = 9000 + 90 N(0,1), U = rho), fixed dt = 1e-3, ROSW ra34pw2,
+one "step" = one implicit time step as the reference's loop does it
+(KSFD/ksfdts.py:202-228): groom, TS.step (4 residuals + 1 Jacobian set-up +
+4 linear solves), CFL velocity max.  For N > 1 the tile is fixed per GPU (weak
+scaling): global grid 1024 x (1024 N), slab-decomposed along y with an NCCL
+halo ring; value = grid-point-steps per second of the whole job.
+
+Prints ONE JSON line (rank 0).  Extra keys: roofline (dominant kernel = fused
+J.v), residual/jvp kernel numbers at 1024^2 and 256^3, cpu_baseline, e2e,
+clocks, gpu_launches.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+TILE = 1024
+H = 1.0 / 384
+DT = 1e-3
+KSP_RTOL = 1e-8
+SEED = 793817931
+ROSW_GAMMA = 0.435866521508459
+ALG_BYTES_PER_PT = 72.0          # read u/v + read udot/coef-equivalent + write
+
+
+def phys_dict(dim, n):
+    from helpers import phys84
+    return phys84(dim, n, H)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        return float(json.load(open(p))['hbm_gbs']), 'measured'
+    return 6650.0, 'fallback'
+
+
+# ---------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.stop = threading.Event()
+        self.th = None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                o = subprocess.run(
+                    ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                     '--format=csv,noheader,nounits'],
+                    capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.samples.append([x.strip() for x in o.split(',')])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+            except Exception:
+                continue
+            for nme, v in zip(names, s[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(nme)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline: the oracle port (numpy + SuperLU) on a bounded sample
+# ---------------------------------------------------------------------------
+def _cpu_worker(args):
+    n, nsteps, seed = args
+    from helpers import oracle_physics, random_state
+    from oracle import ksfd_oracle as O
+    p = phys_dict(2, (n, n))
+    ph = oracle_physics(p)
+    u = random_state(p, seed, rel=0.0).reshape(ph.Vshape, order='F')
+    t0 = time.perf_counter()
+    t = 0.0
+    for k in range(nsteps):
+        u = O.groom(u, ph)
+        u, _, _ = O.rosw_step(u, t, DT, ph)
+        O.cfl_maxh(u, ph)
+        t += DT
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(nsteps=1, n=96, procs=1):
+    """Oracle port timed on `procs` host cores (independent replicas, the way
+    mpiexec ranks would each own a tile; no halo cost charged)."""
+    import multiprocessing as mp
+    if procs > 1:
+        with mp.get_context('fork').Pool(procs) as pool:
+            times = pool.map(_cpu_worker, [(n, nsteps, 100 + i) for i in range(procs)])
+    else:
+        times = [_cpu_worker((n, nsteps, 100))]
+    wall = max(times)
+    return dict(value=procs * n * n * nsteps / wall / 1e6, unit='Mpts*steps/s',
+                cores=procs, kind='port',
+                sample='%d ROSW step(s) of a %dx%d tile per core (oracle numpy '
+                       '+ scipy SuperLU/MMD instead of MUMPS, same physics/h/dt), %d independent tiles'
+                       % (nsteps, n, n, procs),
+                seconds=wall)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    procs = min(os.cpu_count() or 1, 32)
+    n = 96
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_baseline(1, n, procs)
+    t0 = time.perf_counter()
+    cb = cpu_baseline(args.steps, n, procs)
+    wall = time.perf_counter() - t0
+    line = dict(impl='reference', metric='implicit TS throughput (ROSW steps x grid points)',
+                value=cb['value'], unit='Mpts*steps/s', n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * cb['seconds'] / max(args.steps, 1),
+                higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f64', data='synthetic',
+                config=dict(workload='2-D %dx%d tile per core, dof 3, options84 physics, '
+                                     'h=1/384, dt=1e-3, ROSW ra34pw2 + direct LU' % (n, n)),
+                cpu_baseline=dict(value=cb['value'], unit=cb['unit'], cores=procs,
+                                  kind='port', sample=cb['sample']),
+                e2e=dict(value=cb['value'], unit='Mpts*steps/s',
+                         h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                wall_s=wall)
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# native arm
+# ---------------------------------------------------------------------------
+def time_kernel(fn, nrot, reps, warm=3):
+    """Average CUDA-event time (us) of fn(i) over reps launches, rotating over
+    nrot buffer sets so that successive launches read cold (non-L2) data."""
+    import torch
+    for i in range(warm):
+        fn(i % nrot)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        fn(i % nrot)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / reps
+
+
+def kernel_rooflines(dim, n, reps=20):
+    """residual and J.v kernel throughput on one GPU for grid n."""
+    import torch
+    from helpers import product_physics
+    from ksfd_b200 import core
+    peak, src = measured_peak()
+    p = phys_dict(dim, n)
+    ctx = core.Context(dim, n, 3)
+    ctx.set_physics(product_physics(p))
+    npts, N = ctx.npts, ctx.npts * 3
+    nrot = max(2, int(2.5 * 126e6 // (N * 8 * 3)) + 1)
+    gen = torch.Generator(device='cuda').manual_seed(SEED)
+    us = [(9000 + 90 * torch.randn(npts, generator=gen, device='cuda',
+                                   dtype=torch.float64)).repeat_interleave(3).contiguous()
+          for _ in range(nrot)]
+    vs = [torch.randn(N, generator=gen, device='cuda', dtype=torch.float64)
+          for _ in range(nrot)]
+    outs = [torch.empty(N, device='cuda', dtype=torch.float64) for _ in range(nrot)]
+    ctx.jvp_setup(us[0], 1.0 / (ROSW_GAMMA * DT))
+    out = {}
+    for name, fn in (('residual', lambda i: ctx.residual(us[i], vs[i], None, outs[i])),
+                     ('jvp', lambda i: ctx.jvp(vs[i], outs[i])),
+                     ('jvp_precond', lambda i: ctx.jvp(vs[i], outs[i], precond=True))):
+        us_ = time_kernel(fn, nrot, reps)
+        ach = npts * ALG_BYTES_PER_PT / (us_ * 1e-6) / 1e9
+        out[name] = dict(us=us_, gpts_per_s=npts / us_ / 1e3, achieved_gbs=ach,
+                         frac=ach / peak)
+    ctx.close()
+    del us, vs, outs
+    torch.cuda.empty_cache()
+    return out, peak, src
+
+
+def native_arm(args):
+    import torch
+    import torch.distributed as dist
+    from helpers import product_physics
+    from ksfd_b200 import _lib, core
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the native arm has no CPU fallback')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    n = (TILE, TILE * world)
+    p = phys_dict(2, n)
+    ctx = core.Context(2, n, 3, device=local, rank=rank, nranks=world)
+    ctx.set_physics(product_physics(p))
+    if world > 1:
+        from ksfd_b200 import parallel
+        parallel.init_comm(ctx)
+    # synthetic IC, per-rank stream as the reference spawns it
+    # (KSFD/ksfdrandom.py:46-49)
+    rng = np.random.default_rng(np.random.SeedSequence(SEED).spawn(world)[rank])
+    rho = 9000.0 + 90.0 * rng.standard_normal(ctx.npts)
+    u_host = torch.from_numpy(np.repeat(rho, 3)).pin_memory()   # reference layout
+    u_ref = u_host.cuda()
+    u = ctx.to_internal(u_ref)                                  # internal layout
+    opts = core.ts_options(ts_type='rosw', adapt='none', atol=0.01, rtol=1e-6,
+                           ksp_rtol=KSP_RTOL, ksp_max_it=2000, restart=30)
+    state = dict(t=0.0, its=0)
+
+    def step():
+        ctx.groom(u)
+        r = ctx.ts_step(u, state['t'], DT, opts)
+        if not r.accepted:
+            raise RuntimeError('time step failed (ksp_fail=%d)' % r.ksp_fail)
+        state['t'] = r.t_new
+        state['its'] += r.ksp_its
+        return ctx.velocity_max(u)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    # ---- device-resident timing -----------------------------------------
+    barrier()
+    state['its'] = 0
+    l0 = _lib.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as cs:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = _lib.launch_count() - l0
+    its_per_step = state['its'] / max(args.steps, 1)
+    gpts = n[0] * n[1]
+    value = gpts * args.steps / (ms * 1e-3) / 1e6
+    # ---- end-to-end through host buffers --------------------------------
+    out_host = torch.empty_like(u_host)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    esteps = max(1, min(args.steps, 10))
+    for _ in range(esteps):
+        u_ref.copy_(u_host, non_blocking=True)      # H2D of the step's input
+        ctx.to_internal(u_ref, out=u)               # reference -> internal layout
+        step()
+        ctx.from_internal(u, out=u_ref)
+        out_host.copy_(u_ref, non_blocking=True)    # D2H of the step's result
+        torch.cuda.synchronize()
+        u_host.copy_(out_host)
+    t1.record()
+    barrier()
+    ems = torch.tensor([t0.elapsed_time(t1)], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+    e2e_val = gpts * esteps / (float(ems.item()) * 1e-3) / 1e6
+    nbytes = ctx.npts * 3 * 8
+    ctx.close()
+
+    extra = {}
+    roof = None
+    cpu = None
+    if rank == 0:
+        torch.cuda.empty_cache()
+        k2, peak, psrc = kernel_rooflines(2, (TILE, TILE))
+        extra['kernels_1024x1024'] = k2
+        if not args.quick:
+            k3, _, _ = kernel_rooflines(3, (256, 256, 256), reps=10)
+            extra['kernels_256x256x256'] = k3
+        dom = k2['jvp_precond']
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get('jvp_precond_1024x1024_bytes_per_launch')
+        roof = dict(bound='hbm', kernel='k_march<2,JvpOp<2,2,precond>> (fused A*M^-1 v)',
+                    achieved=dom['achieved_gbs'], peak=peak, unit='GB/s',
+                    frac=dom['frac'], traffic=traffic, peak_source=psrc,
+                    algorithmic_bytes_per_point=ALG_BYTES_PER_PT,
+                    points_per_launch=TILE * TILE, us_per_launch=dom['us'])
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_baseline(2, 96, 1)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = dict(metric='implicit TS throughput (ROSW steps x grid points)',
+                value=value, unit='Mpts*steps/s', n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms / args.steps,
+                higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='f64', data='synthetic',
+                steps_per_sec=args.steps / (ms * 1e-3),
+                config=dict(workload='2-D 1024x1024 tile per GPU (global 1024x%d), dof 3, '
+                                     'options84 physics, h=1/384, dt=1e-3, ROSW ra34pw2, '
+                                     'GMRES(30)+point-block-Jacobi rtol %.0e' % (n[1], KSP_RTOL),
+                            parallelism='slab%d' % world,
+                            l2='step working set ~1 GB (31 Krylov + 10 stage vectors of '
+                               '25 MB) exceeds the 126 MB L2; kernel-only timings rotate '
+                               'over >2.5x L2 of distinct buffers'),
+                gmres_its_per_step=its_per_step,
+                gpu_launches=int(launches),
+                clocks=cs.summary(),
+                e2e=dict(value=e2e_val, unit='Mpts*steps/s',
+                         h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes,
+                         steps=esteps),
+                roofline=roof, cpu_baseline=cpu, **extra)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--quick', action='store_true', help='skip the 256^3 kernel timings')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        reference_arm(args)
+    else:
+        native_arm(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -11,9 +11,15 @@
  *    last error on the calling thread is returned by ksfd_last_error().
  *  - all `double *` vector arguments are DEVICE pointers owned by the caller
  *    (torch tensors on the Python side); no ownership is transferred.
- *  - vectors hold the rank-local part of a field vector in the reference's
- *    layout: fp64, Fortran order, dof fastest, then x, y, z
- *    (KSFD/ksfdgrid.py:10-28); length dof * n_local_points.
+ *  - device vectors hold the rank-local part of a field vector (length
+ *    dof * n_local_points) in the library's INTERNAL "plane-SoA" layout:
+ *        element(k, c, pp) = (k * dof + c) * plane_pts + pp
+ *    (k = plane of the last axis, c = dof, pp = x + nx*y inside the plane) so
+ *    that kernels read every field fully coalesced.  The reference's layout
+ *    (fp64, Fortran order, dof fastest, then x, y, z; KSFD/ksfdgrid.py:10-28)
+ *    exists at the boundary only: ksfd_to_internal / ksfd_from_internal
+ *    convert between the two on the device (bit-exact permutations; in 1-D
+ *    the layouts coincide).
  *  - decomposition: 1-D slabs along the LAST spatial axis (y in 2-D, z in 3-D,
  *    x in 1-D); ownership ranges equal PETSc DMDA's lx[i] = M/P + (M%P > i).
  *  - `stream` is a cudaStream_t passed as void* (0 = default stream).
@@ -74,10 +80,18 @@ int ksfd_ctx_create(ksfd_ctx **out, int dim, const int64_t n_global[3],
                     int device);
 int ksfd_ctx_destroy(ksfd_ctx *ctx);
 int ksfd_set_physics(ksfd_ctx *ctx, const ksfd_physics *phys);
-/* kernel selection / tile tuning: key in {"variant","tx","ty","rz","threads"};
-   variant 0 = auto, 1 = naive direct kernels, 2 = marching kernels */
+/* kernel selection / tile tuning: key in {"variant","tile","rz"};
+   variant 0 = auto, 1 = naive direct kernels, 2 = marching kernels;
+   tile = index of the marching tile shape (-1 = auto), rz = planes per CTA */
 int ksfd_set_option(ksfd_ctx *ctx, const char *key, int64_t value);
 int64_t ksfd_local_size(const ksfd_ctx *ctx);   /* dof * owned points */
+
+/* ---- layout boundary: reference layout (what PETSc Vec.array / the HDF5
+ *      TimeSeries hold, KSFD/ksfdtimeseries.py:485-488) <-> internal ------ */
+int ksfd_to_internal(ksfd_ctx *ctx, const double *ref_dev, double *out_dev,
+                     int nfields, void *stream);
+int ksfd_from_internal(ksfd_ctx *ctx, const double *in_dev, double *ref_dev,
+                       int nfields, void *stream);
 
 /* ---- multi-GPU: NCCL ring of slabs (replaces DMDA globalToLocal,
  *      KSFD/ksfdsym.py:704,787,920,1203, and mpi allreduce,
@@ -102,7 +116,7 @@ int ksfd_residual(ksfd_ctx *ctx, const double *u, const double *udot,
 int ksfd_velocity_max(ksfd_ctx *ctx, const double *u, double *vmax_out,
                       void *stream);
 int ksfd_velocity(ksfd_ctx *ctx, const double *u, double *vel_out,
-                  void *stream);      /* (dim, owned points) F-order */
+                  void *stream);      /* internal layout with dim fields */
 
 /* ---- Jacobian action: replaces implicitIJ / Derivatives.Jacobian /
  *      ksfdMat.setValuesJacobian (KSFD/ksfdts.py:598-640,

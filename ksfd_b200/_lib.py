@@ -17,6 +17,7 @@ EXPORTS = [
     'ksfd_abi_version', 'ksfd_last_error', 'ksfd_launch_count',
     'ksfd_ctx_create', 'ksfd_ctx_destroy', 'ksfd_set_physics',
     'ksfd_set_option', 'ksfd_local_size',
+    'ksfd_to_internal', 'ksfd_from_internal',
     'ksfd_nccl_unique_id', 'ksfd_comm_init', 'ksfd_halo_exchange',
     'ksfd_groom', 'ksfd_residual', 'ksfd_velocity_max', 'ksfd_velocity',
     'ksfd_jvp_setup', 'ksfd_jvp', 'ksfd_jvp_precond', 'ksfd_pc_apply',
@@ -100,6 +101,8 @@ def load():
     lib.ksfd_ctx_destroy.argtypes = [vp]
     lib.ksfd_set_physics.argtypes = [vp, C.POINTER(Physics)]
     lib.ksfd_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.ksfd_to_internal.argtypes = [vp, dp, dp, i32, vp]
+    lib.ksfd_from_internal.argtypes = [vp, dp, dp, i32, vp]
     lib.ksfd_nccl_unique_id.argtypes = [C.c_char_p, C.c_char_p]
     lib.ksfd_comm_init.argtypes = [vp, C.c_char_p, i32, i32, C.c_char_p]
     lib.ksfd_halo_exchange.argtypes = [vp, dp, i32, vp]

@@ -146,6 +146,38 @@ class Context:
                             'elements' % n)
         return t
 
+    # -- layout boundary ---------------------------------------------------
+    def to_internal(self, ref, nfields=None, out=None):
+        """device tensor in the reference layout (dof fastest) -> internal."""
+        import torch
+        nf = self.dof if nfields is None else int(nfields)
+        self._chk(ref, self.npts * nf)
+        out = torch.empty_like(ref) if out is None else self._chk(out, self.npts * nf)
+        _lib.check(self.lib.ksfd_to_internal(self.h, _ptr(ref), _ptr(out), nf,
+                                             _stream()))
+        return out
+
+    def from_internal(self, t, nfields=None, out=None):
+        """internal layout -> device tensor in the reference layout."""
+        import torch
+        nf = self.dof if nfields is None else int(nfields)
+        self._chk(t, self.npts * nf)
+        out = torch.empty_like(t) if out is None else self._chk(out, self.npts * nf)
+        _lib.check(self.lib.ksfd_from_internal(self.h, _ptr(t), _ptr(out), nf,
+                                               _stream()))
+        return out
+
+    def upload(self, host_array, nfields=None):
+        """numpy array in the reference layout (flat, dof fastest) -> device
+        vector in the internal layout."""
+        import torch
+        a = np.ascontiguousarray(np.asarray(host_array, dtype=np.float64).ravel())
+        return self.to_internal(torch.from_numpy(a).to(self.tdev), nfields)
+
+    def download(self, t, nfields=None):
+        """device vector (internal layout) -> numpy array, reference layout."""
+        return self.from_internal(t, nfields).cpu().numpy()
+
     def set_physics(self, phys):
         self.phys = phys
         _lib.check(self.lib.ksfd_set_physics(self.h, C.byref(phys)))

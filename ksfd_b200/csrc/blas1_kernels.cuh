@@ -173,22 +173,26 @@ k_complete_step(long long n, const double *__restrict__ u, VecList Y, CoefList b
     block_reduce_store<1>(acc, partial, KSFD_RED_BLOCKS);
 }
 
-// partial sums of u[dof*p] (worm count, KSFD/ksfdts.py:239-246)
+// partial sums of field 0 (worm count, KSFD/ksfdts.py:239-246); plane-SoA
 __global__ void __launch_bounds__(KSFD_RED_THREADS)
-k_sum_dof0(long long npts, int dof, const double *__restrict__ u,
+k_sum_dof0(long long npts, long long plane_pts, int dof, const double *__restrict__ u,
            double *__restrict__ partial)
 {
     double acc[1] = {0.0};
     for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npts;
-         p += (long long)gridDim.x * blockDim.x)
-        acc[0] += u[p * dof];
+         p += (long long)gridDim.x * blockDim.x) {
+        const long long k = p / plane_pts;
+        acc[0] += u[k * dof * plane_pts + (p - k * plane_pts)];
+    }
     block_reduce_store<1>(acc, partial, KSFD_RED_BLOCKS);
 }
 
-__global__ void k_scale_dof0(long long npts, int dof, double f,
+__global__ void k_scale_dof0(long long npts, long long plane_pts, int dof, double f,
                              double *__restrict__ u)
 {
     for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npts;
-         p += (long long)gridDim.x * blockDim.x)
-        u[p * dof] *= f;
+         p += (long long)gridDim.x * blockDim.x) {
+        const long long k = p / plane_pts;
+        u[k * dof * plane_pts + (p - k * plane_pts)] *= f;
+    }
 }

@@ -1,16 +1,24 @@
 // Device-side data structures and pointwise physics shared by all kernels.
 //
-// Layout of every field vector: fp64, dof fastest, then x, y, z (reference
-// KSFD/ksfdgrid.py:10-28).  A rank owns `nloc` planes of the LAST spatial
-// axis; the two ghost planes on either side are reached through VecRef.lo /
-// VecRef.hi (on one rank they alias the vector itself: periodic wrap).
+// INTERNAL device layout of every field vector ("plane-SoA"): for each plane
+// k of the LAST spatial axis, the nf fields of that plane are stored one after
+// the other, each as plane_pts contiguous fp64 values (x fastest, then y):
+//     element(k, c, pp) = ((k * nf + c) * plane_pts + pp)
+// so that a warp reading one field of consecutive x points issues one fully
+// coalesced 256-byte request, and the two ghost planes of a slab are still
+// one contiguous block.  The reference layout (dof fastest, then x, y, z;
+// KSFD/ksfdgrid.py:10-28) exists only at the boundary: ksfd_to_internal /
+// ksfd_from_internal convert (in 1-D the two layouts coincide).
+// A rank owns `nloc` planes; the two ghost planes on either side are reached
+// through VecRef.lo / VecRef.hi (on one rank they alias the vector itself:
+// periodic wrap).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../include/ksfd_b200.h"
 
 #define KSFD_SW 2                       // stencil width (order 3)
-#define KSFD_RING 6                     // ring slots of the marching kernels
+#define KSFD_RING 4                     // smem ring slots of the marching kernels
 
 struct DevPhys {
     int ngroups, nlig, cap_type, dim;
@@ -59,6 +67,88 @@ __device__ __forceinline__ double clampv(double x, double lo)
 }
 
 // ---------------------------------------------------------------------------
+// fp64 log / tanh with their polynomial coefficients in the constant bank
+// (DFMA takes c[bank][off] operands directly; CUDA's libm materialises every
+// coefficient with two UMOVs, ~110 extra issue slots per G evaluation).
+// Accuracy: < 1 ulp (log, fdlibm __ieee754_log scheme) and < 2 ulp (tanh via
+// expm1-free exp), same class as the libm routines they replace; arguments
+// outside the fast range fall back to libm.
+// ---------------------------------------------------------------------------
+__constant__ double c_log[10] = {
+    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+    2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+    1.479819860511658591e-01,
+    6.93147180369123816490e-01,      // ln2_hi
+    1.90821492927058770002e-10,      // ln2_lo
+    0.0};
+
+// n/d for finite normal operands of moderate magnitude (no overflow/underflow
+// handling): MUFU.RCP64H seed + two Newton steps + one residual correction.
+__device__ __forceinline__ double fast_div(double n, double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    const double q = n * r;
+    return fma(fma(-d, q, n), r, q);
+}
+
+__device__ __forceinline__ double fast_log(double x)
+{
+    int hx = __double2hiint(x);
+    const int lx = __double2loint(x);
+    // fast path: positive, normal, finite; everything else goes to libm
+    if (hx < 0x00100000 || hx >= 0x7ff00000) return log(x);
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int i = (hx + 0x95f64) & 0x100000;
+    const double m = __hiloint2double(hx | (i ^ 0x3ff00000), lx);   // [sqrt2/2, sqrt2)
+    k += (i >> 20);
+    const double f = m - 1.0;
+    const double s = fast_div(f, 2.0 + f);
+    const double dk = (double)k;
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * fma(w, fma(w, c_log[5], c_log[3]), c_log[1]);
+    const double t2 = z * fma(w, fma(w, fma(w, c_log[6], c_log[4]), c_log[2]), c_log[0]);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    return fma(dk, c_log[7], -((hfsq - fma(s, hfsq + R, dk * c_log[8])) - f));
+}
+
+__constant__ double c_exp[14] = {
+    1.4426950408889634e+00,          // 1/ln2
+    6.93147180369123816490e-01,      // ln2_hi
+    1.90821492927058770002e-10,      // ln2_lo
+    // exp(r) - 1 - r = r^2 * (1/2! + r/3! + ...), |r| <= ln2/2
+    5.0000000000000000e-01, 1.6666666666666666e-01, 4.1666666666666664e-02,
+    8.3333333333333332e-03, 1.3888888888888889e-03, 1.9841269841269841e-04,
+    2.4801587301587302e-05, 2.7557319223985893e-06, 2.7557319223985888e-07,
+    2.5052108385441720e-08, 2.0876756987868100e-09};
+
+// tanh(x) = expm1(2|x|) / (expm1(2|x|) + 2), sign restored; expm1 is formed
+// without cancellation as 2^k*p + (2^k - 1) with p = exp(r) - 1.
+__device__ __forceinline__ double fast_tanh(double x)
+{
+    const double a = fabs(x);
+    if (!(a < 20.0)) return (a != a) ? x : copysign(1.0, x);
+    const double y = a + a;
+    const double kd = rint(y * c_exp[0]);
+    const int k = (int)kd;
+    const double r = fma(-kd, c_exp[2], fma(-kd, c_exp[1], y));
+    double p = c_exp[13];
+#pragma unroll
+    for (int i = 12; i >= 3; --i) p = fma(p, r, c_exp[i]);
+    p = fma(p * r, r, r);                                 // exp(r) - 1
+    const double s2k = __hiloint2double((1023 + k) << 20, 0);   // 2^k, k in [0, 58]
+    const double em1 = fma(s2k, p, s2k - 1.0);
+    return copysign(fast_div(em1, em1 + 2.0), x);
+}
+
+// ---------------------------------------------------------------------------
 // Pointwise free energy G(rho, U) = V + s2*log(rho)
 // (KSFD/ksfdsym.py:983-990; KSFD/ksfdligand.py:527-547; ksfdsoln.py:147-161)
 // ---------------------------------------------------------------------------
@@ -66,15 +156,15 @@ template <int NLIG>
 __device__ __forceinline__ double G_point(const DevPhys &P, double rho,
                                           const double *U)
 {
-    double G = P.s2 * log(rho);
+    double G = P.s2 * fast_log(rho);
     for (int g = 0; g < P.ngroups; ++g) {
         double sU = 0.0;
 #pragma unroll
         for (int l = 0; l < NLIG; ++l)
             if (P.lig_group[l] == g) sU = fma(P.weight[l], U[l], sU);
-        G = fma(-P.beta[g], log(P.alpha[g] + sU), G);
+        G = fma(-P.beta[g], fast_log(P.alpha[g] + sU), G);
     }
-    double th = tanh((rho - P.rhomax) * P.inv_cushion);
+    double th = fast_tanh((rho - P.rhomax) * P.inv_cushion);
     double cap = P.capscale * (th + 1.0);
     if (P.cap_type == 1) cap *= rho * P.inv_rhomax;
     return G + cap;

@@ -108,7 +108,8 @@ struct ksfd_ctx {
     DevPhys P{};
     bool have_phys = false;
     // options
-    int variant = 0, opt_tx = 0, opt_ty = 0, opt_rz = 0, opt_threads = 0;
+    int variant = 0, opt_tx = -1, opt_rz = 0;
+    bool opt_tile_set = false;
     // comm
     int nranks = 1, rank = 0;
     ncclComm_t comm = nullptr;
@@ -134,6 +135,7 @@ struct ksfd_ctx {
 };
 
 static void free_plans(ksfd_ctx *c);
+static void invalidate_plans(ksfd_ctx *c);
 static long long nlocal(const ksfd_ctx *c) { return c->g.npts * c->dof; }
 
 static int ensure_work(ksfd_ctx *c, int i)
@@ -255,16 +257,13 @@ extern "C" int ksfd_set_physics(ksfd_ctx *c, const ksfd_physics *p)
     return 0;
 }
 
-static void invalidate_plans(ksfd_ctx *c);
 extern "C" int ksfd_set_option(ksfd_ctx *c, const char *key, int64_t v)
 {
     if (!c || !key) return fail("ksfd_set_option: NULL argument");
     std::string k(key);
     if (k == "variant") c->variant = (int)v;
-    else if (k == "tx") c->opt_tx = (int)v;
-    else if (k == "ty") c->opt_ty = (int)v;
+    else if (k == "tile") { c->opt_tx = (int)v; c->opt_tile_set = v >= 0; }
     else if (k == "rz") c->opt_rz = (int)v;
-    else if (k == "threads") c->opt_threads = (int)v;
     else return fail("unknown option " + k);
     invalidate_plans(c);
     return 0;
@@ -377,10 +376,12 @@ extern "C" int ksfd_allreduce_sum(ksfd_ctx *c, double *vals, int n)
 // marching launch heuristics
 // ---------------------------------------------------------------------------
 struct MarchPlan {
-    MarchCfg cfg;
+    int tile = -1;              // index into the candidate list
+    int RZ = 0;
     dim3 grid;
-    int threads;
-    size_t smem;
+};
+struct TileCand {
+    int TXL, TYL, occ;          // lanes (= threads) and resident CTAs per SM
 };
 
 static bool use_march(const ksfd_ctx *c)
@@ -392,7 +393,6 @@ static bool use_march(const ksfd_ctx *c)
     return c->g.n0 >= 8 && c->g.nloc >= 4 && (c->dim == 2 || c->g.n1 >= 8);
 }
 
-static MarchPlan plan_march_search(const ksfd_ctx *c, int NF, double cstage, double cemit);
 typedef std::map<long long, MarchPlan> PlanMap;
 static void free_plans(ksfd_ctx *c)
 {
@@ -403,110 +403,119 @@ static void invalidate_plans(ksfd_ctx *c)
 {
     if (c->plan_cache) static_cast<PlanMap *>(c->plan_cache)->clear();
 }
-static MarchPlan plan_march(ksfd_ctx *c, int NF, double cstage, double cemit)
-{
-    if (!c->plan_cache) c->plan_cache = new PlanMap();
-    PlanMap &pm = *static_cast<PlanMap *>(c->plan_cache);
-    const long long key = NF * 100000LL + (long long)(cstage * 10);
-    auto it = pm.find(key);
-    if (it != pm.end()) return it->second;
-    MarchPlan p = plan_march_search(c, NF, cstage, cemit);
-    pm[key] = p;
-    return p;
-}
 
-// cost weights (fp64 ops) of staging one lane / emitting one output
-static MarchPlan plan_march_search(const ksfd_ctx *c, int NF, double cstage, double cemit)
+// Pick tile + planes-per-CTA.  Cost model: waves of CTAs over the SMs times the
+// work of one CTA (stage cost on every lane of RZ+4 planes + emit cost on the
+// interior lanes of RZ planes + a fixed start-up cost).
+static MarchPlan plan_search(const ksfd_ctx *c, const TileCand *cand, int ncand,
+                             double cstage, double cemit)
 {
     const Geom &g = c->g;
-    const size_t per_lane = (size_t)KSFD_RING * NF * sizeof(double);
-    const int Lcap = (int)std::min<size_t>(c->max_smem / per_lane, 2048);
-    MarchPlan best{};
+    MarchPlan best;
     double best_cost = 1e300;
-    const int dim = c->dim;
-    for (int kx = 1; kx <= g.n0; ++kx) {
-        int OX = (g.n0 + kx - 1) / kx;
-        if (c->opt_tx > 0) OX = std::min(c->opt_tx, g.n0);
-        int LX = OX + 2 * KSFD_SW;
-        if (LX > Lcap) continue;
-        if (OX < 28 && kx > 1 && c->opt_tx <= 0) break;   // tiles this thin never win
-        int ntx = (g.n0 + OX - 1) / OX;
-        int oy_max = (dim == 3) ? std::min(g.n1, Lcap / LX - 2 * KSFD_SW) : 1;
-        if (oy_max < 1) continue;
-        for (int ky = 1; ky <= (dim == 3 ? g.n1 : 1); ++ky) {
-            int OY = 1, LY = 1, nty = 1;
-            if (dim == 3) {
-                OY = (g.n1 + ky - 1) / ky;
-                if (c->opt_ty > 0) OY = std::min(c->opt_ty, g.n1);
-                if (OY > oy_max) continue;
-                if (OY < 6 && ky > 1 && c->opt_ty <= 0) break;
-                LY = OY + 2 * KSFD_SW;
-                nty = (g.n1 + OY - 1) / OY;
+    for (int t = 0; t < ncand; ++t) {
+        if (c->opt_tx >= 0 && c->opt_tx < ncand && c->opt_tile_set && t != c->opt_tx) continue;
+        const int OX = cand[t].TXL - 2 * KSFD_SW;
+        const int OY = c->dim == 3 ? cand[t].TYL - 2 * KSFD_SW : 1;
+        const int ntx = (g.n0 + OX - 1) / OX;
+        const int nty = c->dim == 3 ? (g.n1 + OY - 1) / OY : 1;
+        const long long cols = (long long)ntx * nty;
+        const int L = cand[t].TXL * cand[t].TYL;
+        const int occ = std::max(1, cand[t].occ);
+        const double slots = (double)c->sm_count * occ;
+        for (int chunks = 1; chunks <= g.nloc; chunks = chunks < 32 ? chunks + 1 : chunks + chunks / 16) {
+            int RZ = (g.nloc + chunks - 1) / chunks;
+            if (c->opt_rz > 0) RZ = std::min(c->opt_rz, g.nloc);
+            const int nch = (g.nloc + RZ - 1) / RZ;
+            if (RZ < 2 && g.nloc > 2) break;
+            const double ctas = (double)cols * nch;
+            const double per_cta = (double)L * (RZ + 2 * KSFD_SW) * cstage +
+                                   (double)OX * OY * RZ * cemit + 3000.0 * L / 32.0;
+            // CTAs run `occ` at a time per SM and share its pipes: time ~ work
+            // per SM, rounded up to whole waves of resident CTAs
+            const double waves = std::ceil(ctas / slots);
+            const double cost = waves * occ * per_cta;
+            if (cost < best_cost) {
+                best_cost = cost;
+                best.tile = t;
+                best.RZ = RZ;
+                best.grid = dim3(ntx, nty, nch);
             }
-            const int L = LX * LY;
-            int threads = ((L + 1) / 2 + 31) / 32 * 32;
-            if (c->opt_threads > 0) threads = c->opt_threads;
-            if (threads > 1024 || 2 * threads < L) continue;
-            const size_t smem = per_lane * L;
-            int cta_per_sm = (int)std::min<size_t>(c->max_smem / smem, 2048 / threads);
-            if (cta_per_sm < 1) continue;
-            cta_per_sm = std::min(cta_per_sm, 8);
-            const long long cols = (long long)ntx * nty;
-            // candidate chunk counts
-            for (int chunks = 1; chunks <= g.nloc; chunks = chunks < 16 ? chunks + 1 : chunks + chunks / 8) {
-                int RZ = (g.nloc + chunks - 1) / chunks;
-                if (c->opt_rz > 0) RZ = std::min(c->opt_rz, g.nloc);
-                int nch = (g.nloc + RZ - 1) / RZ;
-                if (RZ < 2 && g.nloc > 2) break;
-                const long long ctas = cols * nch;
-                const double per_cta = (double)L * (RZ + 2 * KSFD_SW) * cstage +
-                                       (double)OX * OY * RZ * cemit +
-                                       2000.0;   // fixed CTA overhead
-                // SM-level time: CTAs are spread over the SMs; an SM with few
-                // resident warps cannot keep the fp64 pipe busy.
-                const double ctas_per_sm = std::ceil((double)ctas / c->sm_count);
-                const double warps = std::min<double>(ctas_per_sm, cta_per_sm) * threads / 32.0;
-                const double eff = std::min(1.0, 0.35 + 0.65 * warps / 16.0);
-                const double cost = ctas_per_sm * per_cta / eff;
-                if (cost < best_cost) {
-                    best_cost = cost;
-                    best.cfg.LX = LX;
-                    best.cfg.LY = LY;
-                    best.cfg.RZ = RZ;
-                    best.grid = dim3(ntx, nty, nch);
-                    best.threads = threads;
-                    best.smem = smem;
-                }
-                if (c->opt_rz > 0) break;
-            }
-            if (dim != 3 || c->opt_ty > 0) break;
+            if (c->opt_rz > 0) break;
         }
-        if (c->opt_tx > 0) break;
     }
     return best;
 }
 
-template <class K>
-static int set_smem(K kern, size_t smem)
+static MarchPlan plan_march(ksfd_ctx *c, long long key, const TileCand *cand, int ncand,
+                            double cstage, double cemit)
 {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)smem));
+    if (!c->plan_cache) c->plan_cache = new PlanMap();
+    PlanMap &pm = *static_cast<PlanMap *>(c->plan_cache);
+    auto it = pm.find(key);
+    if (it != pm.end()) return it->second;
+    MarchPlan p = plan_search(c, cand, ncand, cstage, cemit);
+    pm[key] = p;
+    return p;
+}
+
+template <int DIM, int TXL, int TYL, class Op>
+static int tile_occupancy()
+{
+    static int occ = -1;
+    if (occ >= 0) return occ;
+    auto kern = k_march<DIM, TXL, TYL, Op>;
+    const size_t smem = sizeof(double) * KSFD_RING * Op::NF * TXL * TYL;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        occ = 0;
+        return occ;
+    }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, TXL * TYL, smem) !=
+        cudaSuccess) {
+        cudaGetLastError();
+        nb = 0;
+    }
+    occ = nb;
+    return occ;
+}
+
+template <int DIM, int TXL, int TYL, class Op>
+static int launch_tile(ksfd_ctx *c, const Op &op, const MarchPlan &p, cudaStream_t st)
+{
+    auto kern = k_march<DIM, TXL, TYL, Op>;
+    const size_t smem = sizeof(double) * KSFD_RING * Op::NF * TXL * TYL;
+    kern<<<p.grid, TXL * TYL, smem, st>>>(c->g, c->P, p.RZ, op);
+    CKL();
     return 0;
+}
+
+// tile candidates: 2-D {128, 256} lanes in x; 3-D {36x12, 36x16} lanes
+template <int DIM, class Op>
+static int launch_op(ksfd_ctx *c, const Op &op, int opkey, double cstage, double cemit,
+                     cudaStream_t st)
+{
+    constexpr int AX = (DIM == 2) ? 128 : 36, AY = (DIM == 2) ? 1 : 12;
+    constexpr int BX = (DIM == 2) ? 256 : 36, BY = (DIM == 2) ? 1 : 16;
+    TileCand cand[2] = {{AX, AY, tile_occupancy<DIM, AX, AY, Op>()},
+                        {BX, BY, tile_occupancy<DIM, BX, BY, Op>()}};
+    int ncand = 2;
+    if (cand[1].occ == 0) ncand = 1;
+    if (cand[0].occ == 0) return fail("marching kernel does not fit on this device");
+    MarchPlan p = plan_march(c, opkey * 100 + DIM * 10 + Op::NF, cand, ncand, cstage, cemit);
+    if (p.tile < 0) return fail("no marching tile fits");
+    if (p.tile == 0) return launch_tile<DIM, AX, AY, Op>(c, op, p, st);
+    return launch_tile<DIM, BX, BY, Op>(c, op, p, st);
 }
 
 template <int DIM, int NLIG>
 static int launch_residual_march(ksfd_ctx *c, VecRef u, const double *udot,
                                  const double *src, double *out, cudaStream_t st)
 {
-    using Op = ResidualOp<DIM, NLIG>;
-    MarchPlan p = plan_march(c, Op::NF, 110.0, 25.0 * DIM + 15.0);
-    if (p.threads == 0) return fail("no marching tile fits");
-    Op op{u, udot, src, out};
-    auto kern = k_march<DIM, 2, Op>;
-    TRY(set_smem(kern, p.smem));
-    kern<<<p.grid, p.threads, p.smem, st>>>(c->g, c->P, p.cfg, op);
-    CKL();
-    return 0;
+    ResidualOp<DIM, NLIG> op{u, udot, src, out};
+    return launch_op<DIM>(c, op, 1, 130.0, 25.0 * DIM + 15.0, st);
 }
 
 template <int DIM, int NLIG>
@@ -516,39 +525,19 @@ static int launch_jvp_march(ksfd_ctx *c, VecRef coef, VecRef v, VecRef pc,
     double w2c = 0.0;
     for (int a = 0; a < c->dim; ++a) w2c += c->P.w2[a][2];
     if (precond) {
-        using Op = JvpOp<DIM, NLIG, true>;
-        MarchPlan p = plan_march(c, Op::NF, 25.0, 40.0 * DIM + 15.0);
-        if (p.threads == 0) return fail("no marching tile fits");
-        Op op{coef, v, pc, c->shift, w2c, out};
-        auto kern = k_march<DIM, 2, Op>;
-        TRY(set_smem(kern, p.smem));
-        kern<<<p.grid, p.threads, p.smem, st>>>(c->g, c->P, p.cfg, op);
-    } else {
-        using Op = JvpOp<DIM, NLIG, false>;
-        MarchPlan p = plan_march(c, Op::NF, 10.0, 40.0 * DIM + 15.0);
-        if (p.threads == 0) return fail("no marching tile fits");
-        Op op{coef, v, pc, c->shift, w2c, out};
-        auto kern = k_march<DIM, 2, Op>;
-        TRY(set_smem(kern, p.smem));
-        kern<<<p.grid, p.threads, p.smem, st>>>(c->g, c->P, p.cfg, op);
+        JvpOp<DIM, NLIG, true> op{coef, v, pc, c->shift, w2c, out};
+        return launch_op<DIM>(c, op, 2, 40.0, 40.0 * DIM + 15.0, st);
     }
-    CKL();
-    return 0;
+    JvpOp<DIM, NLIG, false> op{coef, v, pc, c->shift, w2c, out};
+    return launch_op<DIM>(c, op, 3, 25.0, 40.0 * DIM + 15.0, st);
 }
 
 template <int DIM, int NLIG>
 static int launch_velocity_march(ksfd_ctx *c, VecRef u, double *vel, double *vmax,
                                  cudaStream_t st)
 {
-    using Op = VelocityOp<DIM, NLIG>;
-    MarchPlan p = plan_march(c, Op::NF, 110.0, 6.0 * DIM);
-    if (p.threads == 0) return fail("no marching tile fits");
-    Op op{u, vel, vmax};
-    auto kern = k_march<DIM, 2, Op>;
-    TRY(set_smem(kern, p.smem));
-    kern<<<p.grid, p.threads, p.smem, st>>>(c->g, c->P, p.cfg, op);
-    CKL();
-    return 0;
+    VelocityOp<DIM, NLIG> op{u, vel, vmax};
+    return launch_op<DIM>(c, op, 4, 130.0, 6.0 * DIM, st);
 }
 
 #define DISPATCH_DIM_NLIG(FN, ...)                                         \
@@ -589,7 +578,29 @@ extern "C" int ksfd_groom(ksfd_ctx *c, double *u, void *stream)
     TRY(check_ready(c));
     if (!u) return fail("ksfd_groom: NULL vector");
     k_groom<<<nblk(nlocal(c), 256), 256, 0, (cudaStream_t)stream>>>(
-        c->g.npts, c->dof, c->P.rhomin, c->P.Umin, u);
+        c->g, c->P.rhomin, c->P.Umin, u);
+    CKL();
+    return 0;
+}
+
+extern "C" int ksfd_to_internal(ksfd_ctx *c, const double *ref, double *out, int nfields,
+                                void *stream)
+{
+    if (!c || !ref || !out || nfields < 1 || ref == out)
+        return fail("ksfd_to_internal: bad argument");
+    k_to_internal<<<nblk(c->g.npts * nfields, 256), 256, 0, (cudaStream_t)stream>>>(
+        c->g, nfields, ref, out);
+    CKL();
+    return 0;
+}
+
+extern "C" int ksfd_from_internal(ksfd_ctx *c, const double *in, double *ref, int nfields,
+                                  void *stream)
+{
+    if (!c || !ref || !in || nfields < 1 || ref == in)
+        return fail("ksfd_from_internal: bad argument");
+    k_from_internal<<<nblk(c->g.npts * nfields, 256), 256, 0, (cudaStream_t)stream>>>(
+        c->g, nfields, in, ref);
     CKL();
     return 0;
 }
@@ -871,7 +882,7 @@ extern "C" int ksfd_norm2(ksfd_ctx *c, const double *x, double *out)
 extern "C" int ksfd_sum_dof0(ksfd_ctx *c, const double *u, double *out)
 {
     if (!c || !u || !out) return fail("ksfd_sum_dof0: bad argument");
-    k_sum_dof0<<<KSFD_RED_BLOCKS, KSFD_RED_THREADS>>>(c->g.npts, c->dof, u, c->partial);
+    k_sum_dof0<<<KSFD_RED_BLOCKS, KSFD_RED_THREADS>>>(c->g.npts, c->g.plane_pts, c->dof, u, c->partial);
     CKL();
     k_reduce_partials<<<1, 128>>>(1, KSFD_RED_BLOCKS, c->partial, c->dscal, 0);
     CKL();
@@ -884,7 +895,7 @@ extern "C" int ksfd_sum_dof0(ksfd_ctx *c, const double *u, double *out)
 extern "C" int ksfd_scale_dof0(ksfd_ctx *c, double *u, double f, void *stream)
 {
     if (!c || !u) return fail("ksfd_scale_dof0: bad argument");
-    k_scale_dof0<<<KSFD_RED_BLOCKS, 256, 0, (cudaStream_t)stream>>>(c->g.npts, c->dof, f, u);
+    k_scale_dof0<<<KSFD_RED_BLOCKS, 256, 0, (cudaStream_t)stream>>>(c->g.npts, c->g.plane_pts, c->dof, f, u);
     CKL();
     return 0;
 }

@@ -1,8 +1,10 @@
 // Generic "direct" kernels: one thread per owned point, every stencil point
-// re-read from global memory and G recomputed per stencil point.  Runtime dim
-// (1,2,3) and nlig.  They are the 1-D path, the fallback for grids too small
-// to tile, and an independent on-device cross-check of the marching kernels
-// (tests/test_gpu_parity.py).  Not the performance path.
+// re-read from global memory and G recomputed per stencil point (libm
+// log/tanh).  Runtime dim (1,2,3) and nlig.  They are the 1-D path, the
+// fallback for grids too small to tile, and an independent on-device
+// cross-check of the marching kernels (tests/test_gpu_parity.py).  Not the
+// performance path.  Also: layout converters, clamp, coefficient / block-Jacobi
+// set-up (pointwise, run once per Jacobian).
 #pragma once
 #include "device_common.cuh"
 
@@ -28,10 +30,16 @@ __device__ __forceinline__ PointIdx decode_point(const Geom &g, long long p)
     return q;
 }
 
-// pointer to the `stride` doubles of the neighbour of q shifted by off along ax
-__device__ __forceinline__ const double *nbr_ptr(const Geom &g, const VecRef &v,
-                                                 const PointIdx &q, int ax,
-                                                 int off, int stride)
+// A point of a plane-SoA vector: field c is at p[c * fs]
+struct PtRef {
+    const double *p;
+    long long fs;           // field stride = plane_pts
+    __device__ __forceinline__ double operator[](int c) const { return p[c * fs]; }
+};
+
+// neighbour of q shifted by off along ax, in a vector with nf fields
+__device__ __forceinline__ PtRef nbr(const Geom &g, const VecRef &v,
+                                     const PointIdx &q, int ax, int off, int nf)
 {
     int k = q.k;
     long long pp = q.pp;
@@ -42,14 +50,50 @@ __device__ __forceinline__ const double *nbr_ptr(const Geom &g, const VecRef &v,
     } else {
         pp += (long long)(wrapi(q.j + off, g.n1) - q.j) * g.n0;
     }
-    return plane_ptr(v, k, g.nloc, g.plane_pts * stride) + pp * stride;
+    PtRef r;
+    r.p = plane_ptr(v, k, g.nloc, g.plane_pts * nf) + pp;
+    r.fs = g.plane_pts;
+    return r;
 }
 
-__device__ __forceinline__ void load_clamped(const DevPhys &P, const double *p,
+// flat element index of (point p, field c) in an nf-field plane-SoA vector
+__device__ __forceinline__ long long el(const Geom &g, const PointIdx &q, int c, int nf)
+{
+    return ((long long)q.k * nf + c) * g.plane_pts + q.pp;
+}
+
+__device__ __forceinline__ void load_clamped(const DevPhys &P, const PtRef &p,
                                              double &rho, double *U)
 {
     rho = clampv(p[0], P.rhomin);
     for (int l = 0; l < P.nlig; ++l) U[l] = clampv(p[1 + l], P.Umin);
+}
+
+// ---- layout converters (the boundary) ---------------------------------------
+// reference layout: ref[c + nf*p], p = pp + plane_pts*k  (dof fastest)
+__global__ void k_to_internal(Geom g, int nf, const double *__restrict__ ref,
+                              double *__restrict__ out)
+{
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= g.npts * nf) return;
+    // e enumerates the INTERNAL index so that stores are coalesced
+    long long k = e / (g.plane_pts * nf);
+    long long r = e - k * g.plane_pts * nf;
+    int c = (int)(r / g.plane_pts);
+    long long pp = r - (long long)c * g.plane_pts;
+    out[e] = ref[(k * g.plane_pts + pp) * nf + c];
+}
+
+__global__ void k_from_internal(Geom g, int nf, const double *__restrict__ in,
+                                double *__restrict__ ref)
+{
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= g.npts * nf) return;
+    long long k = e / (g.plane_pts * nf);
+    long long r = e - k * g.plane_pts * nf;
+    int c = (int)(r / g.plane_pts);
+    long long pp = r - (long long)c * g.plane_pts;
+    ref[(k * g.plane_pts + pp) * nf + c] = in[e];
 }
 
 // f_out = udot - (f(u)+src)  or  f(u)+src
@@ -63,7 +107,7 @@ __global__ void k_residual_naive(Geom g, DevPhys P, VecRef u,
     PointIdx q = decode_point(g, p);
     const int dof = g.dof;
     double rho0, U0[KSFD_MAX_LIGANDS];
-    load_clamped(P, nbr_ptr(g, u, q, 0, 0, dof), rho0, U0);
+    load_clamped(P, nbr(g, u, q, 0, 0, dof), rho0, U0);
     double G0 = G_point_rt(P, rho0, U0);
     double acc = 0.0, lap = 0.0, lapU[KSFD_MAX_LIGANDS];
     for (int l = 0; l < P.nlig; ++l) lapU[l] = 0.0;
@@ -76,7 +120,7 @@ __global__ void k_residual_naive(Geom g, DevPhys P, VecRef u,
                 rn = rho0; Gn = G0;
                 for (int l = 0; l < P.nlig; ++l) Un[l] = U0[l];
             } else {
-                load_clamped(P, nbr_ptr(g, u, q, ax, s - 2, dof), rn, Un);
+                load_clamped(P, nbr(g, u, q, ax, s - 2, dof), rn, Un);
                 Gn = G_point_rt(P, rn, Un);
             }
             d1r = fma(P.w1[ax][s], rn, d1r);
@@ -94,13 +138,14 @@ __global__ void k_residual_naive(Geom g, DevPhys P, VecRef u,
     for (int l = 0; l < P.nlig; ++l)
         f[l + 1] = fma(P.D[l], lapU[l], fma(P.s[l], rho0, -P.gamma[l] * U0[l]));
     for (int c = 0; c < dof; ++c) {
+        const long long e = el(g, q, c, dof);
         double v = f[c];
-        if (src) v += src[p * dof + c];
-        out[p * dof + c] = udot ? udot[p * dof + c] - v : v;
+        if (src) v += src[e];
+        out[e] = udot ? udot[e] - v : v;
     }
 }
 
-// vel[d + dim*p] = d/dx_d G ; optional per-axis max|.| via atomics
+// vel(field d) = d/dx_d G (plane-SoA with dim fields); optional per-axis max
 __global__ void k_velocity_naive(Geom g, DevPhys P, VecRef u,
                                  double *__restrict__ vel,
                                  double *__restrict__ vmax)
@@ -110,7 +155,7 @@ __global__ void k_velocity_naive(Geom g, DevPhys P, VecRef u,
     if (p < g.npts) {
         PointIdx q = decode_point(g, p);
         double rho0, U0[KSFD_MAX_LIGANDS];
-        load_clamped(P, nbr_ptr(g, u, q, 0, 0, g.dof), rho0, U0);
+        load_clamped(P, nbr(g, u, q, 0, 0, g.dof), rho0, U0);
         double G0 = G_point_rt(P, rho0, U0);
         for (int ax = 0; ax < g.dim; ++ax) {
             double d1G = 0.0;
@@ -118,12 +163,12 @@ __global__ void k_velocity_naive(Geom g, DevPhys P, VecRef u,
                 double Gn = G0;
                 if (s != 2) {
                     double rn, Un[KSFD_MAX_LIGANDS];
-                    load_clamped(P, nbr_ptr(g, u, q, ax, s - 2, g.dof), rn, Un);
+                    load_clamped(P, nbr(g, u, q, ax, s - 2, g.dof), rn, Un);
                     Gn = G_point_rt(P, rn, Un);
                 }
                 d1G = fma(P.w1[ax][s], Gn, d1G);
             }
-            if (vel) vel[p * g.dim + ax] = d1G;
+            if (vel) vel[el(g, q, ax, g.dim)] = d1G;
             vm[ax] = fabs(d1G);
         }
     }
@@ -136,43 +181,46 @@ __global__ void k_velocity_naive(Geom g, DevPhys P, VecRef u,
 }
 
 // clamp in place (KSFD/ksfdts.py:231-237)
-__global__ void k_groom(long long npts, int dof, double rhomin, double Umin,
-                        double *__restrict__ u)
+__global__ void k_groom(Geom g, double rhomin, double Umin, double *__restrict__ u)
 {
     long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (e >= npts * dof) return;
-    int c = (int)(e % dof);
+    if (e >= g.npts * g.dof) return;
+    int c = (int)((e / g.plane_pts) % g.dof);
     u[e] = clampv(u[e], c == 0 ? rhomin : Umin);
 }
 
-// coefficient field over planes -2 .. nloc+1 (ghosted along the last axis):
-// coef[(plane+2)*plane_pts + pp][0..dof+1] = rho, G, dG/drho, dG/dU_l
+// coefficient field over planes -2 .. nloc+1 (ghosted along the last axis),
+// plane-SoA with dof+2 fields: rho, G, dG/drho, dG/dU_l
 __global__ void k_coef_setup(Geom g, DevPhys P, VecRef u,
                              double *__restrict__ coef)
 {
     long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long tot = (long long)(g.nloc + 2 * KSFD_SW) * g.plane_pts;
     if (e >= tot) return;
-    int k = (int)(e / g.plane_pts) - KSFD_SW;
-    long long pp = e % g.plane_pts;
-    const double *p =
-        plane_ptr(u, k, g.nloc, g.plane_pts * g.dof) + pp * g.dof;
+    long long kg = e / g.plane_pts;             // ghosted plane index
+    int k = (int)kg - KSFD_SW;
+    long long pp = e - kg * g.plane_pts;
+    PtRef p;
+    p.p = plane_ptr(u, k, g.nloc, g.plane_pts * g.dof) + pp;
+    p.fs = g.plane_pts;
     double rho, U[KSFD_MAX_LIGANDS], G, g_rho, g_U[KSFD_MAX_LIGANDS];
     load_clamped(P, p, rho, U);
     G_and_partials_rt(P, rho, U, G, g_rho, g_U);
-    double *c = coef + e * (g.dof + 2);
+    const int cs = g.dof + 2;
+    double *c = coef + (kg * cs) * g.plane_pts + pp;
     c[0] = rho;
-    c[1] = G;
-    c[2] = g_rho;
-    for (int l = 0; l < P.nlig; ++l) c[3 + l] = g_U[l];
+    c[g.plane_pts] = G;
+    c[2 * g.plane_pts] = g_rho;
+    for (int l = 0; l < P.nlig; ++l) c[(3 + l) * g.plane_pts] = g_U[l];
 }
 
 // Point-block Jacobi of A = shift*I - J.  The diagonal block is
 //   [ a   b_1 .. b_n ]      a   = shift - dJ_rho/drho0
 //   [ c_1 d_1        ]      b_l = -dJ_rho/dU_l0      c_l = -s_l
 //   [ c_n        d_n ]      d_l = shift + gamma_l - D_l*sum_ax w2c
-// stored as pc[p] = ( 1/(a - sum b_l c_l/d_l),  b_1/d_1, .., b_n/d_n ).
-// If blocks != NULL the dense dof x dof blocks are written too (tests).
+// stored (plane-SoA, dof fields) as ( 1/(a - sum b_l c_l/d_l), b_1/d_1, .. ).
+// If blocks != NULL the dense dof x dof blocks are written too (tests;
+// row-major per point in natural point order).
 __global__ void k_pc_setup(Geom g, DevPhys P, VecRef coef, double shift,
                            double *__restrict__ pc, double *__restrict__ blocks)
 {
@@ -180,13 +228,13 @@ __global__ void k_pc_setup(Geom g, DevPhys P, VecRef coef, double shift,
     if (p >= g.npts) return;
     PointIdx q = decode_point(g, p);
     const int cs = g.dof + 2;
-    const double *c0 = nbr_ptr(g, coef, q, 0, 0, cs);
+    PtRef c0 = nbr(g, coef, q, 0, 0, cs);
     double rho0 = c0[0];
     double fac = 0.0, lap = 0.0, dir = 0.0, w2c = 0.0;
     for (int ax = 0; ax < g.dim; ++ax) {
         double d1r = 0.0, d1G = 0.0, d2G = 0.0;
         for (int s = 0; s < 5; ++s) {
-            const double *cn = (s == 2) ? c0 : nbr_ptr(g, coef, q, ax, s - 2, cs);
+            PtRef cn = (s == 2) ? c0 : nbr(g, coef, q, ax, s - 2, cs);
             d1r = fma(P.w1[ax][s], cn[0], d1r);
             d1G = fma(P.w1[ax][s], cn[1], d1G);
             d2G = fma(P.w2[ax][s], cn[1], d2G);
@@ -199,12 +247,11 @@ __global__ void k_pc_setup(Geom g, DevPhys P, VecRef coef, double shift,
     double Jrr = dir + fac * c0[2] + lap;
     double a = shift - Jrr;
     double schur = a;
-    double *o = pc + p * g.dof;
     for (int l = 0; l < P.nlig; ++l) {
         double b = -fac * c0[3 + l];
         double d = shift + P.gamma[l] - P.D[l] * w2c;
         double bd = b / d;
-        o[1 + l] = bd;
+        pc[el(g, q, 1 + l, g.dof)] = bd;
         schur -= bd * (-P.s[l]);
         if (blocks) {
             double *B = blocks + p * g.dof * g.dof;
@@ -214,11 +261,11 @@ __global__ void k_pc_setup(Geom g, DevPhys P, VecRef coef, double shift,
                 B[(1 + l) * g.dof + (1 + m)] = (m == l) ? d : 0.0;
         }
     }
-    o[0] = 1.0 / schur;
+    pc[el(g, q, 0, g.dof)] = 1.0 / schur;
     if (blocks) blocks[p * g.dof * g.dof] = a;
 }
 
-// z = M^{-1} r for one point (pcp = pc entry of that point)
+// z = M^{-1} r for one point; pcp[0] = 1/schur, pcp[1+l] = b_l/d_l
 __device__ __forceinline__ void pc_point(const DevPhys &P, double shift,
                                          double w2c_sum, const double *pcp,
                                          const double *r, double *z, int nlig)
@@ -248,10 +295,15 @@ __global__ void k_pc_apply(Geom g, DevPhys P, double shift,
 {
     long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (p >= g.npts) return;
-    double rr[KSFD_MAX_LIGANDS + 1], zz[KSFD_MAX_LIGANDS + 1];
-    for (int c = 0; c < g.dof; ++c) rr[c] = r[p * g.dof + c];
-    pc_point(P, shift, w2c_total(P, g.dim), pc + p * g.dof, rr, zz, P.nlig);
-    for (int c = 0; c < g.dof; ++c) z[p * g.dof + c] = zz[c];
+    PointIdx q = decode_point(g, p);
+    double rr[KSFD_MAX_LIGANDS + 1], zz[KSFD_MAX_LIGANDS + 1], pp[KSFD_MAX_LIGANDS + 1];
+    for (int c = 0; c < g.dof; ++c) {
+        const long long e = el(g, q, c, g.dof);
+        rr[c] = r[e];
+        pp[c] = pc[e];
+    }
+    pc_point(P, shift, w2c_total(P, g.dim), pp, rr, zz, P.nlig);
+    for (int c = 0; c < g.dof; ++c) z[el(g, q, c, g.dof)] = zz[c];
 }
 
 // out = (shift*I - J(u_lin)) * v   (optionally v := M^{-1} v first)
@@ -271,14 +323,17 @@ __global__ void k_jvp_naive(Geom g, DevPhys P, VecRef coef, VecRef v, VecRef pc,
         double d2V[KSFD_MAX_LIGANDS];
         for (int l = 0; l < P.nlig; ++l) d2V[l] = 0.0;
         for (int s = 0; s < 5; ++s) {
-            const double *cn = nbr_ptr(g, coef, q, ax, s - 2, cs);
-            const double *vn = nbr_ptr(g, v, q, ax, s - 2, dof);
+            PtRef cn = nbr(g, coef, q, ax, s - 2, cs);
+            PtRef vn = nbr(g, v, q, ax, s - 2, dof);
             double vv[KSFD_MAX_LIGANDS + 1];
             if (precond) {
-                double rr[KSFD_MAX_LIGANDS + 1];
-                for (int c = 0; c < dof; ++c) rr[c] = vn[c];
-                pc_point(P, shift, w2c, nbr_ptr(g, pc, q, ax, s - 2, dof), rr,
-                         vv, P.nlig);
+                double rr[KSFD_MAX_LIGANDS + 1], pp[KSFD_MAX_LIGANDS + 1];
+                PtRef pn = nbr(g, pc, q, ax, s - 2, dof);
+                for (int c = 0; c < dof; ++c) {
+                    rr[c] = vn[c];
+                    pp[c] = pn[c];
+                }
+                pc_point(P, shift, w2c, pp, rr, vv, P.nlig);
             } else {
                 for (int c = 0; c < dof; ++c) vv[c] = vn[c];
             }
@@ -304,10 +359,10 @@ __global__ void k_jvp_naive(Geom g, DevPhys P, VecRef coef, VecRef v, VecRef pc,
         for (int l = 0; l < P.nlig; ++l) lapV[l] += d2V[l];
     }
     double Jv0 = fma(rho0, lapdG, fma(v0[0], lapG, acc));
-    out[p * dof] = fma(shift, v0[0], -Jv0);
+    out[el(g, q, 0, dof)] = fma(shift, v0[0], -Jv0);
     for (int l = 0; l < P.nlig; ++l) {
         double JvU =
             fma(P.D[l], lapV[l], fma(P.s[l], v0[0], -P.gamma[l] * v0[1 + l]));
-        out[p * dof + 1 + l] = fma(shift, v0[1 + l], -JvU);
+        out[el(g, q, 1 + l, dof)] = fma(shift, v0[1 + l], -JvU);
     }
 }

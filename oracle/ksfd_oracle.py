@@ -443,7 +443,8 @@ def rosw_step(u, t, h, ph, sources_fn=None, linear_solve=None, tab=None):
         if lu is None:
             shift = 1.0 / (h * ROSW_GAMMA)
             Jm = ijacobian(Z, shift, ph).tocsc()
-            lu = linear_solve(Jm) if linear_solve else spla.splu(Jm).solve
+            lu = (linear_solve(Jm) if linear_solve else
+                  spla.splu(Jm, permc_spec='MMD_AT_PLUS_A').solve)
         y = lu(-F.ravel(order='F')).reshape(shape, order='F')
         Y.append(y)
     unew = u.copy()
@@ -462,7 +463,8 @@ def beuler_step(u, t, h, ph, sources_fn=None):
     src = sources_fn(t + h) if sources_fn else None
     F = -dfdt(u, ph, src)
     Jm = ijacobian(u, 1.0 / h, ph).tocsc()
-    y = spla.splu(Jm).solve(-F.ravel(order='F')).reshape(shape, order='F')
+    y = spla.splu(Jm, permc_spec='MMD_AT_PLUS_A').solve(
+        -F.ravel(order='F')).reshape(shape, order='F')
     return u + y
 
 
@@ -512,3 +514,4 @@ def integrate(u0, t0, h, nsteps, ph, sources_fn=None, groom_each_step=True,
             out.append((t, u.copy()))
         h = hn
     return out
+

@@ -29,8 +29,7 @@ def run(dim, n, sweeps):
     ctx.jvp_setup(us[0], 1.0/(0.435866521508459*1e-3))
     out = []
     for opt in sweeps:
-        for k in ('variant','tx','ty','rz','threads'):
-            ctx.set_option(k, opt.get(k, 0))
+        ctx.set_option('variant', opt.get('variant', 0)); ctx.set_option('tile', opt.get('tile', -1)); ctx.set_option('rz', opt.get('rz', 0))
         try:
             r = timeit(lambda i: ctx.residual(us[i], uds[i], None, outs[i]), nrot)
             j = timeit(lambda i: ctx.jvp(uds[i], outs[i]), nrot)
@@ -50,12 +49,12 @@ if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
     if which in ('all','2d'):
         sw = [dict(variant=0), dict(variant=1)]
-        for tx, rz in itertools.product((128, 256, 512, 1024), (8, 16, 32, 64)):
-            sw.append(dict(variant=2, tx=tx, rz=rz))
+        for tile, rz in itertools.product((0, 1), (8, 12, 16, 24, 32, 64)):
+            sw.append(dict(variant=2, tile=tile, rz=rz))
         run(2, (1024,1024), sw)
-        run(2, (4096,4096), [dict(variant=0), dict(variant=2, tx=512, rz=64), dict(variant=2, tx=1024, rz=128), dict(variant=2, tx=256, rz=64)])
+        run(2, (4096,4096), [dict(variant=0)] + [dict(variant=2, tile=t, rz=rz) for t in (0,1) for rz in (32, 64, 128)])
     if which in ('all','3d'):
         sw = [dict(variant=0), dict(variant=1)]
-        for tx, ty, rz in itertools.product((32, 64, 128, 256), (8, 16, 28), (32, 64, 256)):
-            sw.append(dict(variant=2, tx=tx, ty=ty, rz=rz))
+        for tile, rz in itertools.product((0, 1), (16, 32, 64, 128, 256)):
+            sw.append(dict(variant=2, tile=tile, rz=rz))
         run(3, (256,256,256), sw)

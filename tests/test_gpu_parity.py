@@ -38,6 +38,7 @@ def make_ctx(p, variant=0):
 
 
 def dev(a):
+    """plain H2D copy (layout-agnostic data: BLAS-1 tests)"""
     torch = _torch()
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
 
@@ -71,15 +72,15 @@ def test_golden_residual_velocity_jvp(name):
         for variant in variants_for(p):
             ctx = make_ctx(p, variant)
             dof = ctx.dof
-            u = dev(g['u_%d' % r])
-            src = dev(g['src_%d' % r])
-            f = ctx.residual(u, None, src).cpu().numpy()
+            u = ctx.upload(g['u_%d' % r])
+            src = ctx.upload(g['src_%d' % r])
+            f = ctx.download(ctx.residual(u, None, src))
             cond = cond_scale(oracle_physics(p), g['u_%d' % r])
             assert check_field(f, g['f_%d' % r], dof, TOL_F, cond) < 1.0, \
                 (name, r, variant)
             # the field vector itself is not modified (clamp is on the fly)
-            assert np.array_equal(u.cpu().numpy(), g['u_%d' % r], equal_nan=True)
-            vel = ctx.velocity(u).cpu().numpy()
+            assert np.array_equal(ctx.download(u), g['u_%d' % r], equal_nan=True)
+            vel = ctx.download(ctx.velocity(u), ctx.dim)
             vr = g['vel_%d' % r]
             assert (relerr(vel, vr) < TOL_F or np.abs(vel - vr).max() < 1e-12), \
                 (name, r, variant)
@@ -88,8 +89,8 @@ def test_golden_residual_velocity_jvp(name):
             assert np.allclose(vm, vref, rtol=1e-10, atol=1e-13)
             ctx.jvp_setup(u, 0.0)
             for m in range(3):
-                v = dev(g['v_%d' % r][m])
-                jv = -ctx.jvp(v).cpu().numpy()
+                v = ctx.upload(g['v_%d' % r][m])
+                jv = -ctx.download(ctx.jvp(v))
                 assert per_dof_err(jv, g['Jv_%d' % r][m], dof) < TOL_J, \
                     (name, r, variant, m)
             ctx.close()
@@ -122,21 +123,21 @@ def test_oracle_ifunction_jvp_pc(label, p):
     blocks_ref = O.block_diagonal(u, shift, ph)
     for variant in variants_for(p):
         ctx = make_ctx(p, variant)
-        F = ctx.residual(dev(u), dev(udot)).cpu().numpy()
+        F = ctx.download(ctx.residual(ctx.upload(u), ctx.upload(udot)))
         assert check_field(F, F_ref, ph.dof, TOL_F, cond_scale(ph, u)) < 1.0, \
             (label, variant)
-        ctx.jvp_setup(dev(u), shift)
-        Jv = ctx.jvp(dev(v)).cpu().numpy()
+        ctx.jvp_setup(ctx.upload(u), shift)
+        Jv = ctx.download(ctx.jvp(ctx.upload(v)))
         assert per_dof_err(Jv, Jv_ref, ph.dof) < TOL_J, (label, variant)
         blocks = ctx.block_diagonal().cpu().numpy()
         assert relerr(blocks, blocks_ref) < TOL_J
         # M^{-1} really inverts the diagonal blocks
-        z = ctx.pc_apply(dev(v)).cpu().numpy().reshape(-1, ph.dof)
+        z = ctx.download(ctx.pc_apply(ctx.upload(v))).reshape(-1, ph.dof)
         back = np.einsum('prc,pc->pr', blocks_ref, z).reshape(-1)
         assert relerr(back, v) < 1e-10
         # fused A*M^{-1} == A(M^{-1} v)
-        fused = ctx.jvp(dev(v), precond=True).cpu().numpy()
-        two = ctx.jvp(ctx.pc_apply(dev(v))).cpu().numpy()
+        fused = ctx.download(ctx.jvp(ctx.upload(v), precond=True))
+        two = ctx.download(ctx.jvp(ctx.pc_apply(ctx.upload(v))))
         assert per_dof_err(fused, two, ph.dof) < 1e-12
         ctx.close()
 
@@ -154,12 +155,12 @@ def test_clamp_and_nan_handling():
     f_ref = O.dfdt(u.copy(), ph).reshape(-1, order='F')
     for variant in (1, 2):
         ctx = make_ctx(p, variant)
-        f = ctx.residual(dev(u)).cpu().numpy()
+        f = ctx.download(ctx.residual(ctx.upload(u)))
         assert check_field(f, f_ref, ph.dof, TOL_F, cond_scale(ph, u)) < 1.0
-        ug = ctx.groom(dev(u)).cpu().numpy()
+        ug = ctx.download(ctx.groom(ctx.upload(u)))
         ref = O.groom(u.copy().reshape(ph.Vshape, order='F'), ph).reshape(-1, order='F')
         assert np.array_equal(ug, ref)                       # bit exact
-        assert np.array_equal(ctx.groom(dev(ug)).cpu().numpy(), ug)   # idempotent
+        assert np.array_equal(ctx.download(ctx.groom(ctx.upload(ug))), ug)   # idempotent
         ctx.close()
 
 
@@ -178,7 +179,13 @@ def test_blas1_against_numpy():
     assert np.allclose(y.cpu().numpy(), w + sum(c * v for c, v in zip(coefs, vs)),
                        rtol=1e-13, atol=1e-12)
     assert abs(ctx.norm2(dev(w)) - np.linalg.norm(w)) < 1e-10
-    assert abs(ctx.sum_dof0(dev(w)) - w[0::ctx.dof].sum()) < 1e-9
+    assert abs(ctx.sum_dof0(ctx.upload(w)) - w[0::ctx.dof].sum()) < 1e-9
+    # layout converters are exact inverse permutations with the documented map
+    wi = ctx.upload(w)
+    assert np.array_equal(ctx.download(wi), w)
+    nx, ny = ctx.local_shape
+    ref = w.reshape(ny, nx, ctx.dof).transpose(0, 2, 1).reshape(-1)   # (k, c, x)
+    assert np.array_equal(wi.cpu().numpy(), ref)
     ctx.close()
 
 
@@ -196,12 +203,12 @@ def test_gmres_against_direct_solve(label, p):
         A = O.ijacobian(u, shift, ph).tocsc()
         x_ref = spla.splu(A).solve(b)
         ctx = make_ctx(p)
-        ctx.jvp_setup(dev(u), shift)
+        ctx.jvp_setup(ctx.upload(u), shift)
         for reorth in (0, 1):
-            x, res = ctx.gmres(dev(b), rtol=1e-12, max_it=2000, restart=30,
+            x, res = ctx.gmres(ctx.upload(b), rtol=1e-12, max_it=2000, restart=30,
                                reorth=reorth)
             assert res.reason > 0, (label, shift, res.reason, res.its)
-            assert relerr(x.cpu().numpy(), x_ref) < 1e-8, (label, shift, res.its)
+            assert relerr(ctx.download(x), x_ref) < 1e-8, (label, shift, res.its)
         ctx.close()
 
 
@@ -219,7 +226,7 @@ def test_rosw_step_and_trajectory(label, p, h):
     traj = O.integrate(u0, 0.0, h, nsteps, ph)
     ctx = make_ctx(p)
     opts = core.ts_options(adapt='none', ksp_rtol=1e-13, ksp_max_it=2000)
-    u = dev(u0)
+    u = ctx.upload(u0)
     t = 0.0
     for k in range(nsteps):
         ctx.groom(u)
@@ -227,7 +234,7 @@ def test_rosw_step_and_trajectory(label, p, h):
         assert res.accepted == 1 and res.ksp_fail == 0
         t = res.t_new
         ref = traj[k][1].reshape(-1, order='F')
-        assert per_dof_err(u.cpu().numpy(), ref, ph.dof) < 1e-8, (label, k)
+        assert per_dof_err(ctx.download(u), ref, ph.dof) < 1e-8, (label, k)
     assert abs(t - nsteps * h) < 1e-12
     ctx.close()
 
@@ -259,7 +266,7 @@ def test_rosw_adaptive_matches_oracle():
     ctx = make_ctx(p)
     opts = core.ts_options(adapt='basic', atol=0.01, rtol=1e-6, clip=(0.1, 5.0),
                            dt_max=1e4, ksp_rtol=1e-13, ksp_max_it=2000)
-    ud = dev(u0)
+    ud = ctx.upload(u0)
     t, h = 0.0, 1e-8
     for k in range(12):
         ctx.groom(ud)
@@ -268,7 +275,7 @@ def test_rosw_adaptive_matches_oracle():
         t, h = res.t_new, res.h_next
         assert abs(t - ref[k][0]) <= 1e-6 * abs(ref[k][0]), (k, t, ref[k][0])
         assert abs(h - ref[k][1]) <= 1e-5 * abs(ref[k][1]), (k, h, ref[k][1])
-        assert per_dof_err(ud.cpu().numpy(), ref[k][2].reshape(-1, order='F'),
+        assert per_dof_err(ctx.download(ud), ref[k][2].reshape(-1, order='F'),
                            ph.dof) < 1e-8
     ctx.close()
 
@@ -294,9 +301,10 @@ def test_full_size_properties(label, p):
     ctx.set_option('variant', 1)
     F1 = ctx.residual(u, udot)
     ctx.set_option('variant', 2)
+    F1r, F2r = ctx.from_internal(F1), ctx.from_internal(F2)
     for c in range(ctx.dof):
-        d = (F2[c::ctx.dof] - F1[c::ctx.dof]).abs().max().item()
-        assert d / F1[c::ctx.dof].abs().max().item() < 1e-11, (label, c)
+        d = (F2r[c::ctx.dof] - F1r[c::ctx.dof]).abs().max().item()
+        assert d / F1r[c::ctx.dof].abs().max().item() < 1e-11, (label, c)
     # F(u, udot) - F(u, 0) == udot  and  dfdt == -F(u, 0) bit exactly
     f = ctx.residual(u)
     F0 = ctx.residual(u, torch.zeros_like(u))
@@ -309,12 +317,10 @@ def test_full_size_properties(label, p):
     plane = ctx.dof * int(np.prod(ctx.local_shape[:-1]))
     ur = torch.roll(u, 3 * plane)
     assert torch.equal(ctx.residual(ur), torch.roll(f, 3 * plane))
-    ur = torch.roll(u, 5 * ctx.dof)          # shift along x inside every row
-    if p['dim'] == 2:
-        rows = u.view(ctx.local_shape[1], -1)
-        ur = torch.roll(rows, 5 * ctx.dof, dims=1).reshape(-1)
-        fr = torch.roll(f.view(ctx.local_shape[1], -1), 5 * ctx.dof, dims=1).reshape(-1)
-        assert torch.equal(ctx.residual(ur), fr)
+    nx = ctx.local_shape[0]
+    ur = torch.roll(u.view(-1, nx), 5, dims=1).reshape(-1)      # every x-line
+    fr = torch.roll(f.view(-1, nx), 5, dims=1).reshape(-1)
+    assert torch.equal(ctx.residual(ur), fr)
     # J.v: linearity and agreement with the direct kernel and a finite difference
     shift = 1.0 / (0.435866521508459 * 1e-3)
     ctx.jvp_setup(u, shift)
@@ -329,7 +335,8 @@ def test_full_size_properties(label, p):
     assert (Jv2 - Jv1).abs().max().item() / Jv1.abs().max().item() < 1e-12
     eps = 1e-4
     fd = (ctx.residual(u + eps * v) - ctx.residual(u - eps * v)) / (2 * eps)
-    Jv = shift * v - ctx.jvp(v)
+    Jv = ctx.from_internal(shift * v - ctx.jvp(v))
+    fd = ctx.from_internal(fd)
     for c in range(ctx.dof):
         d = (Jv[c::ctx.dof] - fd[c::ctx.dof]).abs().max().item()
         assert d / fd[c::ctx.dof].abs().max().item() < 1e-6, (label, c)
