@@ -112,6 +112,79 @@ k_orth_update(long long n, VecList vs, const double *__restrict__ h,
     if (want_norm) block_reduce_store<1>(acc, partial, KSFD_RED_BLOCKS);
 }
 
+// Gram-Schmidt bookkeeping of one Arnoldi step, one block:
+//   h[i] = sum_b partial[i][b]  for i < nv (the last one is <w,w>);
+//   then with ALL h[0..j] (earlier batches already reduced into h):
+//   hn2 = <w,w> - sum_i h[i]^2 ;  h[j+1] = sqrt(hn2) ;  aux[0] = 1/h[j+1]
+//   aux[1] = 1 if the subtraction cancelled too much (caller recomputes the
+//   norm explicitly), else 0.
+// nv_batch partial rows are reduced into h[off .. off+nv_batch); j+1 = index of
+// the <w,w> entry.
+__global__ void k_gs_finalize(int nv_batch, int off, int jp1, int nblocks,
+                              const double *__restrict__ partial,
+                              double *__restrict__ h, double *__restrict__ aux,
+                              double thresh)
+{
+    __shared__ double sums[KSFD_MAXV + 1];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    for (int i = w; i < nv_batch; i += blockDim.x >> 5) {
+        double s = 0.0;
+        for (int b = l; b < nblocks; b += 32) s += partial[(size_t)i * KSFD_RED_BLOCKS + b];
+        s = warp_sum(s);
+        if (l == 0) sums[i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nv_batch; ++i) h[off + i] = sums[i];
+        const double ww = h[jp1];
+        double ss = 0.0;
+        for (int i = 0; i < jp1; ++i) ss = fma(h[i], h[i], ss);
+        const double hn2 = ww - ss;
+        const bool bad = !(hn2 > thresh * ww);
+        const double hn = bad ? 1.0 : sqrt(hn2);
+        h[jp1] = bad ? 0.0 : hn;
+        aux[0] = 1.0 / hn;
+        aux[1] = bad ? 1.0 : 0.0;
+    }
+}
+
+// same finalisation when the sums are already in h (multi-rank: after the
+// all-reduce of the partial dot products)
+__global__ void k_gs_finalize_only(int jp1, double *__restrict__ h,
+                                   double *__restrict__ aux, double thresh)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const double ww = h[jp1];
+        double ss = 0.0;
+        for (int i = 0; i < jp1; ++i) ss = fma(h[i], h[i], ss);
+        const double hn2 = ww - ss;
+        const bool bad = !(hn2 > thresh * ww);
+        const double hn = bad ? 1.0 : sqrt(hn2);
+        h[jp1] = bad ? 0.0 : hn;
+        aux[0] = 1.0 / hn;
+        aux[1] = bad ? 1.0 : 0.0;
+    }
+}
+
+// w = (w - sum_i h[i]*V_i) * scale,  scale = *inv (device) or 1 if inv == NULL
+template <int NV>
+__global__ void __launch_bounds__(KSFD_RED_THREADS)
+k_orth_scale(long long n, VecList vs, const double *__restrict__ h,
+             const double *__restrict__ inv, double *__restrict__ w)
+{
+    double hh[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) hh[i] = h[i];
+    const double sc = inv ? inv[0] : 1.0;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+         e += (long long)gridDim.x * blockDim.x) {
+        double s = w[e];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) s = fma(-hh[i], __ldg(vs.v[i] + e), s);
+        w[e] = s * sc;
+    }
+}
+
 // y = x * (sign / *norm)     (Krylov vector normalisation; norm on device)
 __global__ void k_scale_by_inv(long long n, const double *x,
                                const double *__restrict__ norm, double sign,

@@ -83,14 +83,14 @@ __constant__ double c_log[10] = {
     0.0};
 
 // n/d for finite normal operands of moderate magnitude (no overflow/underflow
-// handling): MUFU.RCP64H seed + two Newton steps + one residual correction.
+// handling): MUFU.RCP64H seed + one Newton step + one residual correction.
 __device__ __forceinline__ double fast_div(double n, double d)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    double e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-d, r, 1.0);
+    // seed ~2^-20 -> one Newton step ~2^-40 -> quotient with residual
+    // correction: error ~2^-80 before the final rounding
+    const double e = fma(-d, r, 1.0);
     r = fma(r, e, r);
     const double q = n * r;
     return fma(fma(-d, q, n), r, q);
@@ -101,7 +101,7 @@ __device__ __forceinline__ double fast_log(double x)
     int hx = __double2hiint(x);
     const int lx = __double2loint(x);
     // fast path: positive, normal, finite; everything else goes to libm
-    if (hx < 0x00100000 || hx >= 0x7ff00000) return log(x);
+    if ((unsigned)(hx - 0x00100000) >= 0x7fe00000u) return log(x);
     int k = (hx >> 20) - 1023;
     hx &= 0x000fffff;
     const int i = (hx + 0x95f64) & 0x100000;
@@ -139,9 +139,17 @@ __device__ __forceinline__ double fast_tanh(double x)
     const double kd = rint(y * c_exp[0]);
     const int k = (int)kd;
     const double r = fma(-kd, c_exp[2], fma(-kd, c_exp[1], y));
-    double p = c_exp[13];
-#pragma unroll
-    for (int i = 12; i >= 3; --i) p = fma(p, r, c_exp[i]);
+    // P(r) = sum_{i=0}^{10} c[3+i] r^i by Estrin's scheme (short dependency chains)
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double p01 = fma(c_exp[4], r, c_exp[3]);
+    const double p23 = fma(c_exp[6], r, c_exp[5]);
+    const double p45 = fma(c_exp[8], r, c_exp[7]);
+    const double p67 = fma(c_exp[10], r, c_exp[9]);
+    const double p89 = fma(c_exp[12], r, c_exp[11]);
+    const double p03 = fma(p23, r2, p01);
+    const double p47 = fma(p67, r2, p45);
+    const double p8a = fma(c_exp[13], r2, p89);
+    double p = fma(p8a, r8, fma(p47, r4, p03));
     p = fma(p * r, r, r);                                 // exp(r) - 1
     const double s2k = __hiloint2double((1023 + k) << 20, 0);   // 2^k, k in [0, 58]
     const double em1 = fma(s2k, p, s2k - 1.0);
@@ -156,15 +164,20 @@ template <int NLIG>
 __device__ __forceinline__ double G_point(const DevPhys &P, double rho,
                                           const double *U)
 {
+    // straight-line code (groups unrolled: ngroups <= NLIG) so that the
+    // independent log/tanh evaluations interleave and hide fp64 latency
     double G = P.s2 * fast_log(rho);
-    for (int g = 0; g < P.ngroups; ++g) {
-        double sU = 0.0;
+    const double th = fast_tanh((rho - P.rhomax) * P.inv_cushion);
 #pragma unroll
-        for (int l = 0; l < NLIG; ++l)
-            if (P.lig_group[l] == g) sU = fma(P.weight[l], U[l], sU);
-        G = fma(-P.beta[g], fast_log(P.alpha[g] + sU), G);
+    for (int g = 0; g < NLIG; ++g) {
+        if (g < P.ngroups) {
+            double sU = 0.0;
+#pragma unroll
+            for (int l = 0; l < NLIG; ++l)
+                if (P.lig_group[l] == g) sU = fma(P.weight[l], U[l], sU);
+            G = fma(-P.beta[g], fast_log(P.alpha[g] + sU), G);
+        }
     }
-    double th = fast_tanh((rho - P.rhomax) * P.inv_cushion);
     double cap = P.capscale * (th + 1.0);
     if (P.cap_type == 1) cap *= rho * P.inv_rhomax;
     return G + cap;

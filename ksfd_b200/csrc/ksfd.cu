@@ -100,6 +100,7 @@ static int nccl_load(const char *path)
 #define SC_H2 128               // second Gram-Schmidt pass
 #define SC_NORM 300
 #define SC_ENORM 301
+#define SC_AUX 126               // [inv h_{j+1}, cancellation flag], right after the column
 struct ksfd_ctx {
     int dim = 0, dof = 0, device = 0;
     long long n[3] = {1, 1, 1};
@@ -492,13 +493,14 @@ static int launch_tile(ksfd_ctx *c, const Op &op, const MarchPlan &p, cudaStream
     return 0;
 }
 
-// tile candidates: 2-D {128, 256} lanes in x; 3-D {36x12, 36x16} lanes
+// tile candidates: 2-D {128, 256} lanes in x; 3-D {36x12, 36x14} lanes
+// (36x16 = 576 threads caps registers at 96 and spills)
 template <int DIM, class Op>
 static int launch_op(ksfd_ctx *c, const Op &op, int opkey, double cstage, double cemit,
                      cudaStream_t st)
 {
     constexpr int AX = (DIM == 2) ? 128 : 36, AY = (DIM == 2) ? 1 : 12;
-    constexpr int BX = (DIM == 2) ? 256 : 36, BY = (DIM == 2) ? 1 : 16;
+    constexpr int BX = (DIM == 2) ? 256 : 36, BY = (DIM == 2) ? 1 : 14;
     TileCand cand[2] = {{AX, AY, tile_occupancy<DIM, AX, AY, Op>()},
                         {BX, BY, tile_occupancy<DIM, BX, BY, Op>()}};
     int ncand = 2;
@@ -949,6 +951,81 @@ static int orth_impl(ksfd_ctx *c, int nv, double *V, const double *h_dev, double
     return 0;
 }
 
+template <int NV>
+static int orth_scale_launch(ksfd_ctx *c, const VecList &vl, const double *h,
+                             const double *inv, double *w, cudaStream_t st)
+{
+    k_orth_scale<NV><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(nlocal(c), vl, h, inv, w);
+    CKL();
+    return 0;
+}
+
+// One classical Gram-Schmidt Arnoldi step with the norm of the new vector
+// obtained from <w,w> - sum h_i^2 (no second pass over w):
+//   mdot over (V_0..V_j, w) -> h[0..j], <w,w> ; finalize -> h[j+1], 1/h[j+1] ;
+//   w <- (w - V h)/h[j+1]   in one pass.
+// Leaves h[0..j+1] in dscal[SC_H..] and [inv, flag] in dscal[SC_AUX..].
+static int cgs_fused_step(ksfd_ctx *c, int j, double *V, double *w, cudaStream_t st)
+{
+    const long long n = nlocal(c);
+    double *hdev = c->dscal + SC_H;
+    double *aux = c->dscal + SC_AUX;
+    const int nv = j + 2;                     // V_0..V_j and w itself
+    const double thresh = 1e-4;
+    for (int b = 0; b < nv; b += KSFD_MAXV) {
+        const int m = std::min(KSFD_MAXV, nv - b);
+        const bool last = b + m >= nv;
+        VecList vl;
+        for (int i = 0; i < KSFD_MAXV; ++i) {
+            const int idx = b + std::min(i, m - 1);
+            vl.v[i] = (idx == j + 1) ? w : V + (long long)idx * n;
+        }
+        switch (m) {
+        case 1: TRY(mdot_launch<1>(c, vl, w, st)); break;
+        case 2: TRY(mdot_launch<2>(c, vl, w, st)); break;
+        case 3: TRY(mdot_launch<3>(c, vl, w, st)); break;
+        case 4: TRY(mdot_launch<4>(c, vl, w, st)); break;
+        case 5: TRY(mdot_launch<5>(c, vl, w, st)); break;
+        case 6: TRY(mdot_launch<6>(c, vl, w, st)); break;
+        case 7: TRY(mdot_launch<7>(c, vl, w, st)); break;
+        default: TRY(mdot_launch<8>(c, vl, w, st)); break;
+        }
+        if (last && c->nranks == 1) {
+            k_gs_finalize<<<1, 256, 0, st>>>(m, b, j + 1, KSFD_RED_BLOCKS, c->partial, hdev,
+                                             aux, thresh);
+            CKL();
+        } else {
+            k_reduce_partials<<<m, 128, 0, st>>>(m, KSFD_RED_BLOCKS, c->partial, hdev + b, 0);
+            CKL();
+        }
+    }
+    if (c->nranks > 1) {
+        TRY(allreduce_dev(c, hdev, nv, ncclSum_, st));
+        k_gs_finalize_only<<<1, 32, 0, st>>>(j + 1, hdev, aux, thresh);
+        CKL();
+    }
+    const int no = j + 1;
+    for (int b = 0; b < no; b += KSFD_MAXV) {
+        const int m = std::min(KSFD_MAXV, no - b);
+        const bool last = b + m >= no;
+        VecList vl;
+        for (int i = 0; i < KSFD_MAXV; ++i)
+            vl.v[i] = V + (long long)(b + std::min(i, m - 1)) * n;
+        const double *inv = last ? aux : nullptr;
+        switch (m) {
+        case 1: TRY(orth_scale_launch<1>(c, vl, hdev + b, inv, w, st)); break;
+        case 2: TRY(orth_scale_launch<2>(c, vl, hdev + b, inv, w, st)); break;
+        case 3: TRY(orth_scale_launch<3>(c, vl, hdev + b, inv, w, st)); break;
+        case 4: TRY(orth_scale_launch<4>(c, vl, hdev + b, inv, w, st)); break;
+        case 5: TRY(orth_scale_launch<5>(c, vl, hdev + b, inv, w, st)); break;
+        case 6: TRY(orth_scale_launch<6>(c, vl, hdev + b, inv, w, st)); break;
+        case 7: TRY(orth_scale_launch<7>(c, vl, hdev + b, inv, w, st)); break;
+        default: TRY(orth_scale_launch<8>(c, vl, hdev + b, inv, w, st)); break;
+        }
+    }
+    return 0;
+}
+
 static int gmres_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x,
                       const ksfd_ksp_opts &o, ksfd_ksp_result *res, cudaStream_t st)
 {
@@ -1007,27 +1084,47 @@ static int gmres_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x
         gg[0] = beta;
         int j = 0;
         bool done = false;
+        // Single-pass classical Gram-Schmidt loses orthogonality like
+        // eps*kappa^2, kappa ~ (residual reduction inside the cycle), which
+        // makes the recurrence residual unreliable beyond ~1e-6.  Instead of
+        // paying for a second orthogonalisation pass every iteration, a cycle
+        // is closed (x updated, TRUE residual recomputed) once it has reduced
+        // the residual by 1e-5; the next cycle starts from exact data.
+        const double cycle_tol = o.reorth ? tol : std::max(tol, 1e-5 * beta);
         for (; j < m; ++j) {
             double *w = V + (long long)(j + 1) * n;
             TRY(jvp_impl(c, V + (long long)j * n, w, pre, st));
-            std::vector<const double *> vp(j + 1);
-            for (int i = 0; i <= j; ++i) vp[i] = V + (long long)i * n;
-            TRY(mdot_impl(c, j + 1, vp.data(), w, hdev, st));
-            TRY(orth_impl(c, j + 1, V, hdev, w, hdev + j + 1, st));
-            if (o.reorth) {
+            double *Hc = &H[(size_t)j * (m + 1)];
+            bool explicit_norm = o.reorth != 0;
+            if (!o.reorth) {
+                // fused single-pass CGS: 4 launches, norm from <w,w> - |h|^2
+                TRY(cgs_fused_step(c, j, V, w, st));
+                TRY(fetch(c, SC_H, 128, st));      // column + aux in one copy
+                for (int i = 0; i <= j + 1; ++i) Hc[i] = c->hscal[SC_H + i];
+                if (c->hscal[SC_AUX + 1] != 0.0) {
+                    // heavy cancellation: w was orthogonalised but left unscaled;
+                    // take its norm explicitly
+                    TRY(norm2_dev(c, w, SC_H + j + 1, st));
+                    TRY(fetch(c, SC_H + j + 1, 1, st));
+                    Hc[j + 1] = c->hscal[SC_H + j + 1];
+                    explicit_norm = true;
+                }
+            } else {
+                std::vector<const double *> vp(j + 1);
+                for (int i = 0; i <= j; ++i) vp[i] = V + (long long)i * n;
+                TRY(mdot_impl(c, j + 1, vp.data(), w, hdev, st));
+                TRY(orth_impl(c, j + 1, V, hdev, w, hdev + j + 1, st));
                 // second classical Gram-Schmidt pass (CGS2)
                 TRY(mdot_impl(c, j + 1, vp.data(), w, c->dscal + SC_H2, st));
                 TRY(orth_impl(c, j + 1, V, c->dscal + SC_H2, w, hdev + j + 1, st));
                 CK(cudaMemcpyAsync(c->hscal + SC_H2, c->dscal + SC_H2,
                                    sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, st));
-            }
-            TRY(fetch(c, SC_H, j + 2, st));
-            double *Hc = &H[(size_t)j * (m + 1)];
-            for (int i = 0; i <= j + 1; ++i) Hc[i] = c->hscal[SC_H + i];
-            if (o.reorth)
+                TRY(fetch(c, SC_H, j + 2, st));
+                for (int i = 0; i <= j + 1; ++i) Hc[i] = c->hscal[SC_H + i];
                 for (int i = 0; i <= j; ++i) Hc[i] += c->hscal[SC_H2 + i];
+            }
             const double hnext = Hc[j + 1];
-            if (hnext > 0.0) {
+            if (explicit_norm && hnext > 0.0) {
                 k_scale_by_inv<<<KSFD_RED_BLOCKS, 256, 0, st>>>(n, w, hdev + j + 1, 1.0, w);
                 CKL();
             }
@@ -1046,10 +1143,11 @@ static int gmres_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x
             rnorm = std::fabs(gg[j + 1]);
             ++its;
             if (!(rnorm == rnorm)) { reason = -9; done = true; ++j; break; }
-            if (rnorm <= tol) { reason = 2; done = true; ++j; break; }
+            if (rnorm <= tol && cycle_tol <= tol) { reason = 2; done = true; ++j; break; }
             if (o.dtol > 0 && rnorm > o.dtol * rnorm0) { reason = -4; done = true; ++j; break; }
             if (its >= max_it) { reason = -3; done = true; ++j; break; }
             if (hnext == 0.0) { reason = 2; done = true; ++j; break; }
+            if (rnorm <= cycle_tol) { ++j; break; }       // close the cycle, re-verify
         }
         // back substitution on the j x j triangle
         const int k = j;
