@@ -1,0 +1,87 @@
+"""
+Random initial conditions and per-rank RNG streams (reference
+KSFD/ksfdrandom.py).  Host-side, runs once per run.
+
+Generator: numpy Generator seeded with SeedSequence(seed).spawn(size)[rank]
+           (reference :13-60).
+random_function: random values on a coarse periodic grid blended onto the
+           fine grid with the cubic hat f(x) = 2x^3 - 3x^2 + 1 per axis
+           (reference :108-220).  The reference does this with a KD-tree
+           query per coarse vertex; the result is a separable (tensor
+           product) interpolation, computed here with one small matrix per
+           axis.  The reference flattens both grids in C order while its Vecs
+           are in Fortran order (:180-183,:214-217); that index scramble is
+           reproduced literally so that equal seeds give equal fields.
+"""
+import numpy as np
+from numpy.random import SeedSequence, default_rng
+
+
+class Generator:
+    _rng = None
+    _seeds = None
+
+    def __init__(self, seed=None, comm=None):
+        if seed is None and type(self)._rng is not None:
+            return
+        rank = comm.rank if comm is not None else 0
+        size = comm.size if comm is not None else 1
+        seeds = SeedSequence(seed).spawn(size)
+        type(self)._seeds = seeds
+        type(self)._rng = default_rng(seeds[rank])
+
+    def __call__(self):
+        return self.get_rng()
+
+    @classmethod
+    def get_rng(cls):
+        if cls._rng is None:
+            cls()
+        return cls._rng
+
+
+def _hat(x):
+    return 2 * x ** 3 - 3 * x ** 2 + 1
+
+
+def random_function(grid, randgrid=None, vals=None, mu=0.0, sigma=0.01, tol=1e-10,
+                    seed=None):
+    """Scalar random field on `grid` (single rank); returns a Vec (dof 1)."""
+    from .grid import DMDA
+    if randgrid is None:
+        randgrid = grid
+    if grid.dim != randgrid.dim:
+        raise ValueError('randgrid and grid must have the same dimension')
+    if grid.comm.size != 1:
+        raise NotImplementedError('random_function: generate on one rank and scatter')
+    if vals is None:
+        vals = randgrid.Sdmda.createGlobalVec()
+        vals.array = Generator(seed=seed, comm=grid.comm)().normal(
+            loc=mu, scale=sigma, size=vals.array.shape)
+    out = grid.Sdmda.createGlobalVec()
+    if np.all(randgrid.nps == grid.nps) and np.all(randgrid.spacing == grid.spacing):
+        out.array = vals.array
+        return out
+    dim = grid.dim
+    sw = randgrid.stencil_width
+    lvals = randgrid.Sdmda.createLocalVec()
+    randgrid.Sdmda.globalToLocal(vals, lvals)
+    # the reference indexes the (Fortran-ordered) local array with C-order
+    # point numbers
+    L = np.asarray(lvals.array).reshape(randgrid.Sashape, order='C')
+    W = []
+    for d in range(dim):
+        hs = randgrid.spacing[d]
+        # extended (non-wrapped) coarse coordinates, incl. ghost vertices
+        # NOTE: same C-order scramble applies to the coordinates: vertex number
+        # v = C-order index, coordinates taken from the C-order flattening too,
+        # so per-axis coordinate tables are consistent with L's axes
+        X = (np.arange(-sw, randgrid.nps[d] + sw)) * hs
+        x = np.arange(grid.nps[d]) * grid.spacing[d]
+        r = np.abs(x[:, None] - X[None, :]) / hs
+        W.append(np.where(r < 1 - tol, _hat(r), 0.0))
+    R = L
+    for d in range(dim):
+        R = np.moveaxis(np.tensordot(W[d], R, axes=([1], [d])), 0, d)
+    out.array = R.reshape(-1, order='C')
+    return out

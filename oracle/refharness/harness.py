@@ -91,6 +91,9 @@ def load_reference():
     stubs.install()
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
+    # numpy 2 removed np.product (used at KSFD/ksfdrandom.py:197)
+    if not hasattr(np, 'product'):
+        np.product = np.prod
     import sympy as sy
     # sympy >= 1.9 raises when '' reaches Basic.subs (ksfdsoln.py:321); older
     # sympy silently skipped such pairs.  Restore the old behaviour.

@@ -1,0 +1,90 @@
+"""
+Multi-rank host logic on CPU (gloo, world_size 2 and 3): slab ownership,
+neighbour ring, and the halo exchange plan, checked bit-exactly against
+np.pad(mode='wrap') — the semantics of the reference's DMDA globalToLocal
+(KSFD/ksfdsym.py:703-705, 919-920).  The data-path exchange on GPUs
+(ncclSend/Recv in libksfd_b200.so) posts exactly the messages of
+parallel.exchange_plan.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, dof, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from ksfd_b200.core import dmda_ownership
+        from ksfd_b200.grid import Comm, Grid
+        from ksfd_b200 import parallel
+        glob = np.arange(dof * int(np.prod(n)), dtype=float).reshape((dof,) + tuple(n), order='F')
+        start, count = dmda_ownership(n[-1], world)[rank]
+        local = glob[..., start:start + count]
+        lo, hi = parallel.host_halo_exchange(local, n[-1])
+        pad = np.pad(glob, [(0, 0)] * (glob.ndim - 1) + [(2, 2)], mode='wrap')
+        ok = (np.array_equal(lo, pad[..., start:start + 2]) and
+              np.array_equal(hi, pad[..., start + count + 2:start + count + 4]))
+        # the index description agrees with what was received
+        slo, shi = parallel.ghost_sources(n[-1], world, rank)
+        ok = ok and np.array_equal(lo, glob[..., slo]) and np.array_equal(hi, glob[..., shi])
+        # Grid + DMDA.globalToLocal over ranks == wrap pad of the global array
+        kw = dict(dim=len(n), dof=dof, nx=n[0])
+        if len(n) > 1:
+            kw['ny'] = n[1]
+        if len(n) > 2:
+            kw['nz'] = n[2]
+        g = Grid(comm=Comm(rank, world), **kw)
+        ok = ok and g.ranges[-1] == (start, start + count)
+        v = g.Vdmda.createGlobalVec()
+        v.array = local.reshape(-1, order='F')
+        l = g.Vdmda.createLocalVec()
+        g.Vdmda.globalToLocal(v, l)
+        full = np.pad(glob, [(0, 0)] + [(2, 2)] * len(n), mode='wrap')
+        want = full[..., start:start + count + 4]
+        ok = ok and np.array_equal(l.array.reshape(g.Vashape, order='F'), want)
+        c = Comm(rank, world)
+        ok = ok and c.allreduce(float(rank + 1), 'sum') == world * (world + 1) / 2
+        ok = ok and c.allreduce(float(rank), 'max') == world - 1
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,n,dof', [(2, (6, 10), 3), (3, (5, 4, 11), 2), (2, (9,), 3)])
+def test_slab_halo_exchange_gloo(world, n, dof):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, dof, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, True) for r in range(world)]
+
+
+def test_exchange_plan_and_ring():
+    from ksfd_b200 import parallel
+    assert parallel.neighbours(0, 4) == (3, 1) and parallel.neighbours(3, 4) == (2, 0)
+    plan = parallel.exchange_plan(1024, 8, 0)
+    assert plan == [('send', 1, (126, 128)), ('recv', 7, 'lo'),
+                    ('send', 7, (0, 2)), ('recv', 1, 'hi')]
+    lo, hi = parallel.ghost_sources(1024, 8, 0)
+    assert lo == [1022, 1023] and hi == [128, 129]
+    lo, hi = parallel.ghost_sources(10, 3, 2)       # 4,3,3 split
+    assert lo == [5, 6] and hi == [0, 1]
