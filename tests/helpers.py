@@ -10,8 +10,11 @@ GOLD = os.path.join(HERE, 'golden')
 
 
 def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0]
-                  for p in glob.glob(os.path.join(GOLD, '*.npz')))
+    """Operator fixtures (oracle/make_golden.py); host_*.npz hold host-mirror
+    fixtures (oracle/make_golden_host.py) and are read by test_host_mirror."""
+    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0]
+                              for p in glob.glob(os.path.join(GOLD, '*.npz')))
+                  if not n.startswith('host_'))
 
 
 def load_golden(name):
