@@ -13,13 +13,19 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libksfd_b200.so')
-SOURCES = ['ksfd.cu']
+# (source, extra defines, object name): the marching kernels are compiled once
+# per dimension so the objects build in parallel
+UNITS = [('ksfd.cu', [], 'ksfd.o')] + [
+    (src, ['-DKSFD_MARCH_DIM=%d' % d], '%s_d%d.o' % (src[:-3], d))
+    for src in ('march_res.cu', 'march_jvp.cu', 'march_vel.cu') for d in (2, 3)]
 HEADERS = ['device_common.cuh', 'naive_kernels.cuh', 'march_kernels.cuh',
-           'blas1_kernels.cuh', os.path.join('..', '..', 'include', 'ksfd_b200.h')]
+           'march_launch.cuh', 'ctx.h', 'blas1_kernels.cuh',
+           os.path.join('..', '..', 'include', 'ksfd_b200.h')]
+OBJDIR = os.path.join(HERE, 'build')
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
-    '-std=c++17', '-Xcompiler', '-fPIC', '-shared',
+    '-std=c++17', '-Xcompiler', '-fPIC',
 ]
 
 
@@ -34,27 +40,40 @@ def is_stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    for f in SOURCES + HEADERS + [os.path.join('..', 'build.py')]:
+    for f in [u[0] for u in UNITS] + HEADERS + [os.path.join('..', 'build.py')]:
         if os.path.getmtime(os.path.join(CSRC, f)) > t:
             return True
     return False
+
+
+def _compile(unit, verbose):
+    src, defs, obj = unit
+    cmd = [nvcc_path()] + NVCC_FLAGS + defs + ['-c', os.path.join(CSRC, src),
+                                               '-o', os.path.join(OBJDIR, obj)]
+    if verbose:
+        cmd[1:1] = ['-Xptxas', '-v']
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return unit, r
 
 
 def build(force=False, verbose=False):
     """Compile libksfd_b200.so if missing or older than its sources."""
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ['-o', LIB] + \
-        [os.path.join(CSRC, s) for s in SOURCES] + ['-ldl']
-    if verbose:
-        cmd.insert(1, '-Xptxas')
-        cmd.insert(2, '-v')
-        print(' '.join(cmd))
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJDIR, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 1)) as ex:
+        results = list(ex.map(lambda u: _compile(u, verbose), UNITS))
+    for unit, r in results:
+        if r.returncode != 0:
+            raise RuntimeError('nvcc failed on %s:\n%s%s' % (unit[0], r.stdout, r.stderr))
+        if verbose:
+            print(r.stderr)
+    cmd = [nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-shared',
+           '-o', LIB] + [os.path.join(OBJDIR, u[2]) for u in UNITS] + ['-ldl']
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+        raise RuntimeError('link failed:\n' + r.stdout + r.stderr)
     return LIB
 
 

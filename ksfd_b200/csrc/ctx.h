@@ -1,0 +1,88 @@
+// Host-side context shared by the translation units of libksfd_b200.so.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <cuda_runtime.h>
+
+#include "device_common.cuh"
+
+// ---------------------------------------------------------------------------
+// errors (thread-local last message; every entry point returns 0 / non-zero)
+// ---------------------------------------------------------------------------
+int ksfd_fail(const std::string &m);
+void ksfd_count_launch();
+#define fail ksfd_fail
+#define CK(call)                                                              \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess)                                                \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define CKL()                                                                 \
+    do {                                                                      \
+        ksfd_count_launch();                                                  \
+        cudaError_t e_ = cudaGetLastError();                                  \
+        if (e_ != cudaSuccess)                                                \
+            return fail(std::string("kernel launch: ") +                      \
+                        cudaGetErrorString(e_) + " at " + __FILE__ + ":" +    \
+                        std::to_string(__LINE__));                            \
+    } while (0)
+#define TRY(x)                 \
+    do {                       \
+        int r_ = (x);          \
+        if (r_) return r_;     \
+    } while (0)
+
+typedef struct ncclComm *ncclComm_t;
+
+#define KSFD_HALO_SLOTS 4
+#define KSFD_NSCAL 512          // device/host scalar scratch
+
+struct ksfd_ctx {
+    int dim = 0, dof = 0, device = 0;
+    long long n[3] = {1, 1, 1};
+    long long last_start = 0, last_count = 0, last_global = 0;
+    Geom g{};
+    DevPhys P{};
+    bool have_phys = false;
+    // options
+    int variant = 0, opt_tx = -1, opt_rz = 0;
+    bool opt_tile_set = false;
+    // comm
+    int nranks = 1, rank = 0;
+    ncclComm_t comm = nullptr;
+    // halo slots: [lo(2 planes) | hi(2 planes)] per slot, sized for dof+2 stride
+    double *halo[KSFD_HALO_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    size_t halo_plane_doubles = 0;
+    // Jacobian state
+    double *coef = nullptr;      // ghosted (nloc+4 planes) x (dof+2)
+    double *pc = nullptr;        // nloc planes x 1: inverse Schur pivot per point
+    double shift = 0.0;
+    double invd[KSFD_MAX_LIGANDS] = {0};   // 1/(shift + gamma_l - D_l*w2c)
+    bool have_jac = false;
+    // reductions
+    double *partial = nullptr;   // [KSFD_MAXV+1][KSFD_RED_BLOCKS]
+    double *dscal = nullptr;     // device scalars (KSFD_NSCAL)
+    double *hscal = nullptr;     // pinned host scalars (KSFD_NSCAL)
+    void *plan_cache = nullptr;  // std::map<long long, MarchPlan>*
+    // solver workspace
+    double *krylov = nullptr;    // (restart+1) vectors
+    int krylov_cap = 0;
+    double *work[12] = {nullptr};
+    int sm_count = 148;
+    int max_smem = 232448;
+};
+
+// marching-kernel launchers (march_res.cu, march_jvp.cu, march_vel.cu); each is
+// compiled once per dimension (-DKSFD_MARCH_DIM=2|3)
+#define KSFD_DECL_MARCH(D)                                                            \
+    int ksfd_march_residual_d##D(ksfd_ctx *c, VecRef u, const double *udot,           \
+                                 const double *src, double *out, cudaStream_t st);    \
+    int ksfd_march_jvp_d##D(ksfd_ctx *c, VecRef coef, VecRef v, VecRef pc,            \
+                            bool precond, double *out, cudaStream_t st);              \
+    int ksfd_march_velocity_d##D(ksfd_ctx *c, VecRef u, double *vel, double *vmax,    \
+                                 cudaStream_t st);
+KSFD_DECL_MARCH(2)
+KSFD_DECL_MARCH(3)
+void ksfd_free_plans(ksfd_ctx *c);
+void ksfd_invalidate_plans(ksfd_ctx *c);

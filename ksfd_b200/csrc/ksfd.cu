@@ -10,8 +10,8 @@
 #include <vector>
 
 #include "blas1_kernels.cuh"
-#include "device_common.cuh"
-#include "march_kernels.cuh"
+#include "ctx.h"
+#include "march_launch.cuh"
 #include "naive_kernels.cuh"
 
 // ---------------------------------------------------------------------------
@@ -20,36 +20,16 @@
 static thread_local std::string g_err;
 static int64_t g_launches = 0;
 
-static int fail(const std::string &m)
+int ksfd_fail(const std::string &m)
 {
     g_err = m;
     return 1;
 }
-#define CK(call)                                                              \
-    do {                                                                      \
-        cudaError_t e_ = (call);                                              \
-        if (e_ != cudaSuccess)                                                \
-            return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); \
-    } while (0)
-#define CKL()                                                                 \
-    do {                                                                      \
-        ++g_launches;                                                         \
-        cudaError_t e_ = cudaGetLastError();                                  \
-        if (e_ != cudaSuccess)                                                \
-            return fail(std::string("kernel launch: ") +                      \
-                        cudaGetErrorString(e_) + " at " + __FILE__ + ":" +    \
-                        std::to_string(__LINE__));                            \
-    } while (0)
-#define TRY(x)                 \
-    do {                       \
-        int r_ = (x);          \
-        if (r_) return r_;     \
-    } while (0)
+void ksfd_count_launch() { ++g_launches; }
 
 // ---------------------------------------------------------------------------
 // NCCL through dlopen (torch ships libnccl.so.2; no header needed)
 // ---------------------------------------------------------------------------
-typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSum_ = 0, ncclMax_ = 2 };
 enum { ncclFloat64_ = 8 };
@@ -94,49 +74,11 @@ static int nccl_load(const char *path)
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
-#define KSFD_HALO_SLOTS 4
-#define KSFD_NSCAL 512          // device/host scalar scratch
 #define SC_H 0                  // Hessenberg column (<= 128)
 #define SC_H2 128               // second Gram-Schmidt pass
 #define SC_NORM 300
 #define SC_ENORM 301
 #define SC_AUX 126               // [inv h_{j+1}, cancellation flag], right after the column
-struct ksfd_ctx {
-    int dim = 0, dof = 0, device = 0;
-    long long n[3] = {1, 1, 1};
-    long long last_start = 0, last_count = 0, last_global = 0;
-    Geom g{};
-    DevPhys P{};
-    bool have_phys = false;
-    // options
-    int variant = 0, opt_tx = -1, opt_rz = 0;
-    bool opt_tile_set = false;
-    // comm
-    int nranks = 1, rank = 0;
-    ncclComm_t comm = nullptr;
-    // halo slots: [lo(2 planes) | hi(2 planes)] per slot, sized for dof+2 stride
-    double *halo[KSFD_HALO_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
-    size_t halo_plane_doubles = 0;
-    // Jacobian state
-    double *coef = nullptr;      // ghosted (nloc+4 planes) x (dof+2)
-    double *pc = nullptr;        // nloc planes x dof
-    double shift = 0.0;
-    bool have_jac = false;
-    // reductions
-    double *partial = nullptr;   // [KSFD_MAXV+1][KSFD_RED_BLOCKS]
-    double *dscal = nullptr;     // device scalars (KSFD_NSCAL)
-    double *hscal = nullptr;     // pinned host scalars (KSFD_NSCAL)
-    void *plan_cache = nullptr;  // std::map<long long, MarchPlan>*
-    // solver workspace
-    double *krylov = nullptr;    // (restart+1) vectors
-    int krylov_cap = 0;
-    double *work[12] = {nullptr};
-    int sm_count = 148;
-    int max_smem = 232448;
-};
-
-static void free_plans(ksfd_ctx *c);
-static void invalidate_plans(ksfd_ctx *c);
 static long long nlocal(const ksfd_ctx *c) { return c->g.npts * c->dof; }
 
 static int ensure_work(ksfd_ctx *c, int i)
@@ -205,7 +147,7 @@ extern "C" int ksfd_ctx_destroy(ksfd_ctx *c)
     cudaFreeHost(c->hscal);
     cudaFree(c->krylov);
     for (auto &w : c->work) cudaFree(w);
-    free_plans(c);
+    ksfd_free_plans(c);
     delete c;
     return 0;
 }
@@ -233,9 +175,11 @@ extern "C" int ksfd_set_physics(ksfd_ctx *c, const ksfd_physics *p)
     P.rhomin = p->rhomin;
     P.Umin = p->Umin;
     P.inv_rhomax = 1.0 / p->rhomax;
+    // group slots beyond ngroups are neutral (alpha 1, beta 0): the marching
+    // kernels evaluate all slots without tests
     for (int g = 0; g < KSFD_MAX_GROUPS; ++g) {
-        P.alpha[g] = p->alpha[g];
-        P.beta[g] = p->beta[g];
+        P.alpha[g] = g < p->ngroups ? p->alpha[g] : 1.0;
+        P.beta[g] = g < p->ngroups ? p->beta[g] : 0.0;
     }
     for (int l = 0; l < KSFD_MAX_LIGANDS; ++l) {
         P.lig_group[l] = l < p->nlig ? p->lig_group[l] : -1;
@@ -254,6 +198,33 @@ extern "C" int ksfd_set_physics(ksfd_ctx *c, const ksfd_physics *p)
             P.w1[a][s] = a < c->dim ? p->w1[a][s] : 0.0;
             P.w2[a][s] = a < c->dim ? p->w2[a][s] : 0.0;
         }
+    for (int g = 0; g < KSFD_MAX_GROUPS; ++g)
+        for (int l = 0; l < KSFD_MAX_LIGANDS; ++l)
+            P.Wgl[g][l] = (l < p->nlig && p->lig_group[l] == g) ? p->weight[l] : 0.0;
+    P.w2c = 0.0;
+    for (int a = 0; a < c->dim; ++a) P.w2c += P.w2[a][2];
+    // symmetric-stencil constants and the check that the reference weights
+    // follow the (1,-8,0,8,-1)/(12h), (-1,16,-30,16,-1)/(12h^2) pattern to
+    // rounding (they do for every order-3 grid; KSFD/ksfdsym.py:391-436)
+    P.sym_ok = 1;
+    for (int a = 0; a < 3; ++a) {
+        P.c1[a] = P.c2[a] = P.c1sq[a] = 0.0;
+        if (a >= c->dim) continue;
+        const double c1 = P.w1[a][3] / 8.0, c2 = P.w2[a][1] / 16.0;
+        P.c1[a] = c1;
+        P.c2[a] = c2;
+        P.c1sq[a] = c1 * c1;
+        const double e1 = 8e-16 * std::fabs(8.0 * c1), e2 = 8e-16 * std::fabs(30.0 * c2);
+        const double r1[5] = {c1, -8.0 * c1, 0.0, 8.0 * c1, -c1};
+        const double r2[5] = {-c2, 16.0 * c2, -30.0 * c2, 16.0 * c2, -c2};
+        for (int s = 0; s < 5; ++s)
+            if (!(std::fabs(P.w1[a][s] - r1[s]) <= e1) || !(std::fabs(P.w2[a][s] - r2[s]) <= e2))
+                P.sym_ok = 0;
+    }
+    P.ycap1 = -2.0 * P.inv_cushion;
+    P.ycap0 = 2.0 * P.rhomax * P.inv_cushion;
+    P.capscale2 = 2.0 * P.capscale;
+    P.mk = fastk_default();
     c->have_phys = true;
     return 0;
 }
@@ -266,7 +237,7 @@ extern "C" int ksfd_set_option(ksfd_ctx *c, const char *key, int64_t v)
     else if (k == "tile") { c->opt_tx = (int)v; c->opt_tile_set = v >= 0; }
     else if (k == "rz") c->opt_rz = (int)v;
     else return fail("unknown option " + k);
-    invalidate_plans(c);
+    ksfd_invalidate_plans(c);
     return 0;
 }
 
@@ -374,194 +345,28 @@ extern "C" int ksfd_allreduce_sum(ksfd_ctx *c, double *vals, int n)
 }
 
 // ---------------------------------------------------------------------------
-// marching launch heuristics
+// marching kernels: plan cache + dispatch (kernels live in march_*.cu)
 // ---------------------------------------------------------------------------
-struct MarchPlan {
-    int tile = -1;              // index into the candidate list
-    int RZ = 0;
-    dim3 grid;
-};
-struct TileCand {
-    int TXL, TYL, occ;          // lanes (= threads) and resident CTAs per SM
-};
+
+void ksfd_free_plans(ksfd_ctx *c)
+{
+    delete static_cast<PlanMap *>(c->plan_cache);
+    c->plan_cache = nullptr;
+}
+void ksfd_invalidate_plans(ksfd_ctx *c)
+{
+    if (c->plan_cache) static_cast<PlanMap *>(c->plan_cache)->clear();
+}
 
 static bool use_march(const ksfd_ctx *c)
 {
     if (c->variant == 1) return false;
     if (c->dim < 2) return false;
     if (c->dof - 1 > 4) return false;           // instantiated for nlig <= 4
+    if (!c->P.sym_ok) return false;             // weights off the symmetric pattern
     if (c->variant == 2) return true;
     return c->g.n0 >= 8 && c->g.nloc >= 4 && (c->dim == 2 || c->g.n1 >= 8);
 }
-
-typedef std::map<long long, MarchPlan> PlanMap;
-static void free_plans(ksfd_ctx *c)
-{
-    delete static_cast<PlanMap *>(c->plan_cache);
-    c->plan_cache = nullptr;
-}
-static void invalidate_plans(ksfd_ctx *c)
-{
-    if (c->plan_cache) static_cast<PlanMap *>(c->plan_cache)->clear();
-}
-
-// Pick tile + planes-per-CTA.  Cost model: waves of CTAs over the SMs times the
-// work of one CTA (stage cost on every lane of RZ+4 planes + emit cost on the
-// interior lanes of RZ planes + a fixed start-up cost).
-static MarchPlan plan_search(const ksfd_ctx *c, const TileCand *cand, int ncand,
-                             double cstage, double cemit)
-{
-    const Geom &g = c->g;
-    MarchPlan best;
-    double best_cost = 1e300;
-    for (int t = 0; t < ncand; ++t) {
-        if (c->opt_tx >= 0 && c->opt_tx < ncand && c->opt_tile_set && t != c->opt_tx) continue;
-        const int OX = cand[t].TXL - 2 * KSFD_SW;
-        const int OY = c->dim == 3 ? cand[t].TYL - 2 * KSFD_SW : 1;
-        const int ntx = (g.n0 + OX - 1) / OX;
-        const int nty = c->dim == 3 ? (g.n1 + OY - 1) / OY : 1;
-        const long long cols = (long long)ntx * nty;
-        const int L = cand[t].TXL * cand[t].TYL;
-        const int occ = std::max(1, cand[t].occ);
-        const double slots = (double)c->sm_count * occ;
-        for (int chunks = 1; chunks <= g.nloc; chunks = chunks < 32 ? chunks + 1 : chunks + chunks / 16) {
-            int RZ = (g.nloc + chunks - 1) / chunks;
-            if (c->opt_rz > 0) RZ = std::min(c->opt_rz, g.nloc);
-            const int nch = (g.nloc + RZ - 1) / RZ;
-            if (RZ < 2 && g.nloc > 2) break;
-            const double ctas = (double)cols * nch;
-            const double per_cta = (double)L * (RZ + 2 * KSFD_SW) * cstage +
-                                   (double)OX * OY * RZ * cemit + 3000.0 * L / 32.0;
-            // CTAs run `occ` at a time per SM and share its pipes: time ~ work
-            // per SM, rounded up to whole waves of resident CTAs
-            const double waves = std::ceil(ctas / slots);
-            const double cost = waves * occ * per_cta;
-            if (cost < best_cost) {
-                best_cost = cost;
-                best.tile = t;
-                best.RZ = RZ;
-                best.grid = dim3(ntx, nty, nch);
-            }
-            if (c->opt_rz > 0) break;
-        }
-    }
-    return best;
-}
-
-static MarchPlan plan_march(ksfd_ctx *c, long long key, const TileCand *cand, int ncand,
-                            double cstage, double cemit)
-{
-    if (!c->plan_cache) c->plan_cache = new PlanMap();
-    PlanMap &pm = *static_cast<PlanMap *>(c->plan_cache);
-    auto it = pm.find(key);
-    if (it != pm.end()) return it->second;
-    MarchPlan p = plan_search(c, cand, ncand, cstage, cemit);
-    pm[key] = p;
-    return p;
-}
-
-template <int DIM, int TXL, int TYL, class Op>
-static int tile_occupancy()
-{
-    static int occ = -1;
-    if (occ >= 0) return occ;
-    auto kern = k_march<DIM, TXL, TYL, Op>;
-    const size_t smem = sizeof(double) * KSFD_RING * Op::NF * TXL * TYL;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem) != cudaSuccess) {
-        cudaGetLastError();
-        occ = 0;
-        return occ;
-    }
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, TXL * TYL, smem) !=
-        cudaSuccess) {
-        cudaGetLastError();
-        nb = 0;
-    }
-    occ = nb;
-    return occ;
-}
-
-template <int DIM, int TXL, int TYL, class Op>
-static int launch_tile(ksfd_ctx *c, const Op &op, const MarchPlan &p, cudaStream_t st)
-{
-    auto kern = k_march<DIM, TXL, TYL, Op>;
-    const size_t smem = sizeof(double) * KSFD_RING * Op::NF * TXL * TYL;
-    kern<<<p.grid, TXL * TYL, smem, st>>>(c->g, c->P, p.RZ, op);
-    CKL();
-    return 0;
-}
-
-// tile candidates: 2-D {128, 256} lanes in x; 3-D {36x12, 36x14} lanes
-// (36x16 = 576 threads caps registers at 96 and spills)
-template <int DIM, class Op>
-static int launch_op(ksfd_ctx *c, const Op &op, int opkey, double cstage, double cemit,
-                     cudaStream_t st)
-{
-    constexpr int AX = (DIM == 2) ? 128 : 36, AY = (DIM == 2) ? 1 : 12;
-    constexpr int BX = (DIM == 2) ? 256 : 36, BY = (DIM == 2) ? 1 : 14;
-    TileCand cand[2] = {{AX, AY, tile_occupancy<DIM, AX, AY, Op>()},
-                        {BX, BY, tile_occupancy<DIM, BX, BY, Op>()}};
-    int ncand = 2;
-    if (cand[1].occ == 0) ncand = 1;
-    if (cand[0].occ == 0) return fail("marching kernel does not fit on this device");
-    MarchPlan p = plan_march(c, opkey * 100 + DIM * 10 + Op::NF, cand, ncand, cstage, cemit);
-    if (p.tile < 0) return fail("no marching tile fits");
-    if (p.tile == 0) return launch_tile<DIM, AX, AY, Op>(c, op, p, st);
-    return launch_tile<DIM, BX, BY, Op>(c, op, p, st);
-}
-
-template <int DIM, int NLIG>
-static int launch_residual_march(ksfd_ctx *c, VecRef u, const double *udot,
-                                 const double *src, double *out, cudaStream_t st)
-{
-    ResidualOp<DIM, NLIG> op{u, udot, src, out};
-    return launch_op<DIM>(c, op, 1, 130.0, 25.0 * DIM + 15.0, st);
-}
-
-template <int DIM, int NLIG>
-static int launch_jvp_march(ksfd_ctx *c, VecRef coef, VecRef v, VecRef pc,
-                            bool precond, double *out, cudaStream_t st)
-{
-    double w2c = 0.0;
-    for (int a = 0; a < c->dim; ++a) w2c += c->P.w2[a][2];
-    if (precond) {
-        JvpOp<DIM, NLIG, true> op{coef, v, pc, c->shift, w2c, out};
-        return launch_op<DIM>(c, op, 2, 40.0, 40.0 * DIM + 15.0, st);
-    }
-    JvpOp<DIM, NLIG, false> op{coef, v, pc, c->shift, w2c, out};
-    return launch_op<DIM>(c, op, 3, 25.0, 40.0 * DIM + 15.0, st);
-}
-
-template <int DIM, int NLIG>
-static int launch_velocity_march(ksfd_ctx *c, VecRef u, double *vel, double *vmax,
-                                 cudaStream_t st)
-{
-    VelocityOp<DIM, NLIG> op{u, vel, vmax};
-    return launch_op<DIM>(c, op, 4, 130.0, 6.0 * DIM, st);
-}
-
-#define DISPATCH_DIM_NLIG(FN, ...)                                         \
-    do {                                                                   \
-        const int nl_ = c->dof - 1;                                        \
-        if (c->dim == 2) {                                                 \
-            switch (nl_) {                                                 \
-            case 1: return FN<2, 1>(__VA_ARGS__);                          \
-            case 2: return FN<2, 2>(__VA_ARGS__);                          \
-            case 3: return FN<2, 3>(__VA_ARGS__);                          \
-            case 4: return FN<2, 4>(__VA_ARGS__);                          \
-            }                                                              \
-        } else if (c->dim == 3) {                                          \
-            switch (nl_) {                                                 \
-            case 1: return FN<3, 1>(__VA_ARGS__);                          \
-            case 2: return FN<3, 2>(__VA_ARGS__);                          \
-            case 3: return FN<3, 3>(__VA_ARGS__);                          \
-            case 4: return FN<3, 4>(__VA_ARGS__);                          \
-            }                                                              \
-        }                                                                  \
-        return fail("no marching kernel for this dim/dof");                \
-    } while (0)
 
 static inline unsigned nblk(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
@@ -613,7 +418,8 @@ static int residual_impl(ksfd_ctx *c, const double *u, const double *udot,
     TRY(exchange(c, u, c->dof, 0, st));
     VecRef ur = make_ref(c, u, c->dof, 0);
     if (use_march(c)) {
-        DISPATCH_DIM_NLIG(launch_residual_march, c, ur, udot, src, f, st);
+        return c->dim == 2 ? ksfd_march_residual_d2(c, ur, udot, src, f, st)
+                           : ksfd_march_residual_d3(c, ur, udot, src, f, st);
     }
     k_residual_naive<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, ur, udot,
                                                            src, f);
@@ -636,7 +442,8 @@ static int velocity_impl(ksfd_ctx *c, const double *u, double *vel, double *vmax
     VecRef ur = make_ref(c, u, c->dof, 0);
     if (vmax) CK(cudaMemsetAsync(vmax, 0, sizeof(double) * c->dim, st));
     if (use_march(c)) {
-        DISPATCH_DIM_NLIG(launch_velocity_march, c, ur, vel, vmax, st);
+        return c->dim == 2 ? ksfd_march_velocity_d2(c, ur, vel, vmax, st)
+                           : ksfd_march_velocity_d3(c, ur, vel, vmax, st);
     }
     k_velocity_naive<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, ur, vel, vmax);
     CKL();
@@ -675,19 +482,23 @@ static int jvp_setup_impl(ksfd_ctx *c, const double *u, double shift,
     const Geom &g = c->g;
     const long long gpts = (long long)(g.nloc + 2 * KSFD_SW) * g.plane_pts;
     if (!c->coef) CK(cudaMalloc(&c->coef, sizeof(double) * gpts * (c->dof + 2)));
-    if (!c->pc) CK(cudaMalloc(&c->pc, sizeof(double) * g.npts * c->dof));
+    if (!c->pc) CK(cudaMalloc(&c->pc, sizeof(double) * g.npts));
     c->shift = shift;
+    for (int l = 0; l < c->P.nlig; ++l)
+        c->invd[l] = 1.0 / (shift + c->P.gamma[l] - c->P.D[l] * c->P.w2c);
     if (u) {
         TRY(exchange(c, u, c->dof, 0, st));
         VecRef ur = make_ref(c, u, c->dof, 0);
         k_coef_setup<<<nblk(gpts, 128), 128, 0, st>>>(g, c->P, ur, c->coef);
         CKL();
     }
-    k_pc_setup<<<nblk(g.npts, 128), 128, 0, st>>>(g, c->P, coef_ref(c), shift, c->pc,
+    InvD id;
+    for (int l = 0; l < KSFD_MAX_LIGANDS; ++l) id.v[l] = c->invd[l];
+    k_pc_setup<<<nblk(g.npts, 128), 128, 0, st>>>(g, c->P, coef_ref(c), shift, id, c->pc,
                                                   blocks);
     CKL();
     // ghost planes of the preconditioner field for the fused A*M^{-1} kernel
-    TRY(exchange(c, c->pc, c->dof, 2, st));
+    TRY(exchange(c, c->pc, 1, 2, st));
     c->have_jac = true;
     return 0;
 }
@@ -715,12 +526,15 @@ static int jvp_impl(ksfd_ctx *c, const double *v, double *out, bool precond,
     if (v == out) return fail("ksfd_jvp: in-place application is not supported");
     TRY(exchange(c, v, c->dof, 1, st));
     VecRef vr = make_ref(c, v, c->dof, 1);
-    VecRef pr = make_ref(c, c->pc, c->dof, 2);
+    VecRef pr = make_ref(c, c->pc, 1, 2);
     VecRef cr = coef_ref(c);
     if (use_march(c)) {
-        DISPATCH_DIM_NLIG(launch_jvp_march, c, cr, vr, pr, precond, out, st);
+        return c->dim == 2 ? ksfd_march_jvp_d2(c, cr, vr, pr, precond, out, st)
+                           : ksfd_march_jvp_d3(c, cr, vr, pr, precond, out, st);
     }
-    k_jvp_naive<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, cr, vr, pr,
+    InvD id;
+    for (int l = 0; l < KSFD_MAX_LIGANDS; ++l) id.v[l] = c->invd[l];
+    k_jvp_naive<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, cr, vr, pr, id,
                                                       precond ? 1 : 0, c->shift, out);
     CKL();
     return 0;
@@ -739,15 +553,21 @@ extern "C" int ksfd_jvp_precond(ksfd_ctx *c, const double *v, double *out, void 
     return jvp_impl(c, v, out, true, (cudaStream_t)stream);
 }
 
+static int pc_apply_impl(ksfd_ctx *c, const double *r, double *z, cudaStream_t st)
+{
+    InvD id;
+    for (int l = 0; l < KSFD_MAX_LIGANDS; ++l) id.v[l] = c->invd[l];
+    k_pc_apply<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, coef_ref(c), id, c->pc, r, z);
+    CKL();
+    return 0;
+}
+
 extern "C" int ksfd_pc_apply(ksfd_ctx *c, const double *r, double *z, void *stream)
 {
     TRY(check_ready(c));
     if (!c->have_jac) return fail("ksfd_jvp_setup has not been called");
     if (!r || !z) return fail("ksfd_pc_apply: NULL vector");
-    k_pc_apply<<<nblk(c->g.npts, 128), 128, 0, (cudaStream_t)stream>>>(
-        c->g, c->P, c->shift, c->pc, r, z);
-    CKL();
-    return 0;
+    return pc_apply_impl(c, r, z, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------
@@ -1163,9 +983,7 @@ static int gmres_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x
                 // x += M^{-1} (V y)
                 TRY(ensure_work(c, 1));
                 TRY(maxpy_impl(c, k, y.data(), vp.data(), 0.0, tmp, st));
-                k_pc_apply<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, c->shift,
-                                                                c->pc, tmp, c->work[1]);
-                CKL();
+                TRY(pc_apply_impl(c, tmp, c->work[1], st));
                 const double one = 1.0;
                 const double *wp = c->work[1];
                 TRY(maxpy_impl(c, 1, &one, &wp, 1.0, x, st));

@@ -1,112 +1,301 @@
 // Marching stencil kernels (the performance path, 2-D and 3-D).
 //
-// A CTA owns a tile of TXL x TYL "lanes" (one thread each) in the non-marching
-// axes (x in 2-D, x*y in 3-D; two halo lanes on every side, periodic wrap) and
-// marches along the LAST axis over RZ output planes.  Per plane:
-//   stage: the plane's points (plane-SoA => fully coalesced loads, software-
-//          prefetched one plane ahead) are clamped and turned into the
+// A CTA owns a tile of up to TX x TY output points in the non-marching axes
+// (x in 2-D, x*y in 3-D) plus the two-deep star halo around it (periodic
+// wrap), one LANE per point, one thread per lane, and marches along the LAST
+// axis over `rz` output planes.  Per plane kk:
+//   stage: the plane's points (plane-SoA => coalesced loads, prefetched one
+//          plane ahead into registers) are clamped and turned into the
 //          pointwise fields the stencil needs — for the residual: rho,
-//          G(rho,U) [3 log + 1 tanh, evaluated ONCE per point], U_l.  Each
-//          thread pushes its lane's fields into a 5-deep REGISTER queue (the
-//          marching-axis stencil never touches memory) and into one slot of a
-//          4-slot shared-memory ring (for the cross-axis neighbours);
-//   emit : after ONE __syncthreads, the 4th-order star stencil of the plane two
-//          behind is formed from the queue (marching axis) and from
-//          neighbouring lanes of the ring slot (cross axes: immediate-offset
-//          LDS, strides are compile-time) and the outputs are stored coalesced.
+//          G(rho,U) [3 log + 1 exp, table driven, evaluated ONCE per lane and
+//          plane], U_l — and pushed into a 5-deep REGISTER queue per lane (the
+//          marching-axis stencil costs no memory traffic);
+//   share: the queue's CENTRE plane (kk-2) is written to one of two
+//          shared-memory slots; one __syncthreads per plane (two slots are
+//          enough: a slot is rewritten two barriers after it was read);
+//   emit : interior lanes form the 4th-order star stencil of plane kk-2 from
+//          the queue (marching axis) and from neighbouring lanes of the slot
+//          (cross axes: immediate-offset LDS, strides are compile-time) and
+//          store the outputs coalesced.
+// 3-D lane packing: threads [0, TX*TY) are the interior lanes, the 4*TX + 4*TY
+// halo lanes follow, so the emit phase runs on fully populated warps and halo
+// lanes cost staging work only.
+//
+// Constants: on sm_100 fp64 instructions take constants from the 63 uniform
+// registers only, so constant count is a first-order cost.  The stencils are
+// therefore evaluated in their symmetric form
+//     d/dx   = c1 (8 (f[+1]-f[-1]) - (f[+2]-f[-2]))
+//     d2/dx2 = c2 (16 (f[+1]+f[-1]) - (f[+2]+f[-2]) - 30 f[0])
+// (8, 16, 30 are instruction immediates; one scale per axis instead of ten
+// weights), and log/exp are table driven (fastmath.cuh).
+//
 // The field vector is read once from HBM (halo re-reads hit L2), G is evaluated
-// (TXL*TYL/out) * (RZ+4)/RZ times per output point instead of 1+4*dim times,
+// lanes/outputs * (rz+4)/rz times per output point instead of 1+4*dim times,
 // and no ghosted copy or G array is ever materialised.
 //
 // The skeleton is shared by three operators (Op policies): residual, J.v
 // (optionally fused with the block-Jacobi solve), velocity(-max).
 #pragma once
 #include "device_common.cuh"
-#include "naive_kernels.cuh"   // pc_point
+#include "fastmath.cuh"
 
-// stencil access for one lane at emit time
-template <int DIM, int NF, int TXL, int NT>
-struct RegAcc {
-    const double (*q)[5];       // q[f][0..4] = planes ko-2 .. ko+2 of this lane
-    const double *rc;           // &ring[centre slot][0][tid]
-    __device__ __forceinline__ double c(int f) const { return q[f][2]; }
-    // weighted 5-point sum of field f along axis ax with weights w[5]
-    __device__ __forceinline__ double wsum(int f, int ax, const double *w) const
+// uniform launch parameters (32-bit: a rank-local vector has < 2^31 elements,
+// checked on the host)
+struct MarchArgs {
+    int n0, n1, nloc;       // extents in x, y (1 in 2-D); owned planes
+    int fs;                 // field stride = points per plane
+    int ox, oy;             // outputs per tile in x, y (balanced pitch <= TX, TY)
+    int rz;                 // output planes per CTA
+};
+
+template <int DIM, int TX, int TY>
+struct TileT {
+    static constexpr int NL = (DIM == 2) ? TX + 4 : TX * TY + 4 * TX + 4 * TY;   // lanes
+    static constexpr int NT = (NL + 31) / 32 * 32;                                // threads
+    static constexpr int PX = TX + 4;                               // smem row pitch
+    static constexpr int SP = (DIM == 2) ? TX + 4 : (TX + 4) * (TY + 4);
+    static constexpr int SY = (DIM == 2) ? 0 : PX;
+};
+
+// log / exp tables (fastmath.cuh), staged to shared memory by each CTA
+static __device__ const unsigned long long g_log_tab[256] = KSFD_LOG_TAB_INIT;
+static __device__ const unsigned long long g_exp_tab[64] = KSFD_EXP_TAB_INIT;
+#define KSFD_TAB_DOUBLES 320
+
+// All shared memory is addressed through this symbol with integer indices (a
+// generic pointer into shared memory would make every access recompute the
+// shared window base).  Layout: [2][NF][SP] ring, then the tables.
+extern __shared__ double ksfd_smem[];
+
+// table accessor over the CTA's shared-memory copy; OFF = index of the tables
+template <int OFF>
+struct SmemTabs {
+    __device__ __forceinline__ void log_pair(int i, double &invc, double &logc) const
     {
-        double r;
-        if (ax == DIM - 1) {
-            r = w[0] * q[f][0];
-            r = fma(w[1], q[f][1], r);
-            r = fma(w[2], q[f][2], r);
-            r = fma(w[3], q[f][3], r);
-            r = fma(w[4], q[f][4], r);
-        } else {
-            const int st = (ax == 0) ? 1 : TXL;
-            const double *b = rc + f * NT;
-            r = w[0] * b[-2 * st];
-            r = fma(w[1], b[-st], r);
-            r = fma(w[2], q[f][2], r);
-            r = fma(w[3], b[st], r);
-            r = fma(w[4], b[2 * st], r);
-        }
-        return r;
+        const double2 v = *reinterpret_cast<const double2 *>(&ksfd_smem[OFF + 2 * i]);
+        invc = v.x;
+        logc = v.y;
+    }
+    __device__ __forceinline__ double exp2j(int j) const { return ksfd_smem[OFF + 256 + j]; }
+};
+
+// pointer to plane k of a vector whose planes hold `ps` doubles
+__device__ __forceinline__ const double *plane_of(const VecRef &v, int k, int nloc,
+                                                  int ps)
+{
+    if (k < 0) return v.lo + (k + KSFD_SW) * (long long)ps;
+    if (k >= nloc) return v.hi + (k - nloc) * (long long)ps;
+    return v.base + k * (long long)ps;
+}
+
+// input cursor: per-thread pointer to this lane's point in the next plane to
+// load; planes are contiguous except at the two ghost boundaries
+struct InCursor {
+    const double *p;
+    __device__ __forceinline__ void init(const VecRef &v, int k, int nloc, int ps, int poff)
+    {
+        p = plane_of(v, k, nloc, ps) + poff;
+    }
+    // after plane k was loaded
+    __device__ __forceinline__ void next(const VecRef &v, int k, int nloc, int ps, int poff)
+    {
+        const int kn = k + 1;
+        if (kn == 0 || kn == nloc)              // uniform, at most twice per CTA
+            p = plane_of(v, kn, nloc, ps) + poff;
+        else
+            p += ps;
     }
 };
 
+// stencil access of one interior lane at emit time.  PH = phase of the
+// unrolled plane loop: plane kk (newest) sits in q[.][PH], plane kk-4+s in
+// q[.][(PH+1+s)%5], the centre plane kk-2 in q[.][(PH+3)%5].
+template <int DIM, int NF, int SP, int SY, int PH>
+struct LaneAcc {
+    const double (&q)[NF][5];
+    const int ri;                // index of slot[field 0][this lane] in ksfd_smem
+    __device__ __forceinline__ LaneAcc(const double (&q_)[NF][5], int ri_)
+        : q(q_), ri(ri_) {}
+    __device__ __forceinline__ double c(int f) const { return q[f][(PH + 3) % 5]; }
+    // the four neighbours of field f along axis ax
+    __device__ __forceinline__ void nb(int f, int ax, double &m2, double &m1, double &p1,
+                                       double &p2) const
+    {
+        if (ax == DIM - 1) {
+            m2 = q[f][(PH + 1) % 5];
+            m1 = q[f][(PH + 2) % 5];
+            p1 = q[f][(PH + 4) % 5];
+            p2 = q[f][PH];
+        } else {
+            const int st = (ax == 0) ? 1 : SY;
+            const int b = ri + f * SP;
+            m2 = ksfd_smem[b - 2 * st];
+            m1 = ksfd_smem[b - st];
+            p1 = ksfd_smem[b + st];
+            p2 = ksfd_smem[b + 2 * st];
+        }
+    }
+    // 12h * d/dx:  8 (f[+1]-f[-1]) - (f[+2]-f[-2])
+    __device__ __forceinline__ double D1(int f, int ax) const
+    {
+        double m2, m1, p1, p2;
+        nb(f, ax, m2, m1, p1, p2);
+        return fma(8.0, p1 - m1, m2 - p2);
+    }
+    // 12h^2 * d2/dx2:  16 (f[+1]+f[-1]) - (f[+2]+f[-2]) - 30 f[0]
+    __device__ __forceinline__ double D2(int f, int ax) const
+    {
+        double m2, m1, p1, p2;
+        nb(f, ax, m2, m1, p1, p2);
+        return fma(-30.0, c(f), fma(16.0, p1 + m1, -(p2 + m2)));
+    }
+    // both at once (shares the neighbour loads)
+    __device__ __forceinline__ void D12(int f, int ax, double &d1, double &d2) const
+    {
+        double m2, m1, p1, p2;
+        nb(f, ax, m2, m1, p1, p2);
+        d1 = fma(8.0, p1 - m1, m2 - p2);
+        d2 = fma(-30.0, c(f), fma(16.0, p1 + m1, -(p2 + m2)));
+    }
+};
+
+// the log part of G for arguments outside the fast domain (never taken for
+// physical states; kept out of line, arguments by value)
+static __device__ __noinline__ double G_logs_slow(double s2, double rho, int ng, double b0,
+                                                  double a0, double b1, double a1, double b2,
+                                                  double a2, double b3, double a3)
+{
+    double G = s2 * log(rho);
+    if (ng > 0) G = fma(-b0, log(a0), G);
+    if (ng > 1) G = fma(-b1, log(a1), G);
+    if (ng > 2) G = fma(-b2, log(a2), G);
+    if (ng > 3) G = fma(-b3, log(a3), G);
+    return G;
+}
+
+// Pointwise free energy G(rho, U) = V + s2*log(rho) with the table-driven
+// log / logistic (KSFD/ksfdsym.py:983-990; KSFD/ksfdligand.py:527-547;
+// ksfdsoln.py:147-161)
+template <int NLIG, class TA>
+__device__ __forceinline__ double G_fast(const DevPhys &P, const TA &T, double rho,
+                                         const double *U)
+{
+    // all NLIG group slots are evaluated without tests: slots beyond ngroups
+    // hold alpha = 1, beta = 0, W = 0 (set on the host), i.e. contribute
+    // -0*log(1); straight-line code lets the independent log chains interleave
+    double a[NLIG];
+    bool ok = ksfd_log_domain(rho);
+#pragma unroll
+    for (int g = 0; g < NLIG; ++g) {
+        double t = P.alpha[g];
+#pragma unroll
+        for (int l = 0; l < NLIG; ++l) t = fma(P.Wgl[g][l], U[l], t);
+        a[g] = t;
+        ok = ok && ksfd_log_domain(t);
+    }
+    double G;
+    if (ok) {
+        G = P.s2 * ksfd_log_core(rho, P.mk, T);
+#pragma unroll
+        for (int g = 0; g < NLIG; ++g) G = fma(-P.beta[g], ksfd_log_core(a[g], P.mk, T), G);
+    } else {
+        G = G_logs_slow(P.s2, rho, NLIG, P.beta[0], a[0], P.beta[1], a[NLIG > 1 ? 1 : 0],
+                        P.beta[2], a[NLIG > 2 ? 2 : 0], P.beta[3], a[NLIG > 3 ? 3 : 0]);
+    }
+    // capscale*(tanh(x)+1) = 2*capscale/(1+exp(-2x)),  x = (rho-rhomax)/cushion
+    double cap = P.capscale2 * ksfd_logistic(fma(P.ycap1, rho, P.ycap0), P.mk, T);
+    if (P.cap_type == 1) cap *= rho * P.inv_rhomax;
+    return G + cap;
+}
+
+// z = M^{-1} r for one point of the point-block Jacobi preconditioner.
+//   block = [ a  b_l ; c_l  d_l ],  c_l = -s_l,  d_l = shift + gamma_l - D_l*w2c
+//   b_l = -(rho*w2c) * dG/dU_l   (the w1-centre term of the exact block, zero up
+//   to the last-bit asymmetry of the reference weights, is left to the Krylov
+//   iteration);  pcinv = 1/(a - sum_l b_l c_l / d_l)  is the only stored field.
+template <int NLIG>
+__device__ __forceinline__ void pc_solve(const DevPhys &P, const double *invd,
+                                         double rho, const double *gU, double pcinv,
+                                         const double *r, double *z)
+{
+    const double fac = rho * P.w2c;
+    double t = r[0];
+#pragma unroll
+    for (int l = 0; l < NLIG; ++l) t = fma(fac * gU[l] * invd[l], r[1 + l], t);
+    const double zr = pcinv * t;
+    z[0] = zr;
+#pragma unroll
+    for (int l = 0; l < NLIG; ++l) z[1 + l] = fma(P.s[l], zr, r[1 + l]) * invd[l];
+}
+
 // ---------------------------------------------------------------------------
-// Operator policies
+// Operator policies.  Each owns its per-thread pointers (State): inputs advance
+// plane by plane (InCursor), outputs advance by one plane per emit.
 // ---------------------------------------------------------------------------
 // Residual: F = udot - (f(u)+src)  |  f(u)+src
 // (KSFD/ksfdsym.py:902-940 + KSFD/ksfdts.py:591-592 fused)
-template <int DIM, int NLIG>
+// FIXED = true: udot given, no source (the implicit-step case; no runtime tests)
+template <int DIM, int NLIG, bool FIXED>
 struct ResidualOp {
     static constexpr int NF = NLIG + 2;        // rho, G, U_l
     static constexpr int NPRE = NLIG + 1;
     static constexpr int NAUX = NLIG + 1;      // udot of the output plane
+    static constexpr bool TABS = true;
     VecRef u;
     const double *udot, *src;
     double *out;
-    struct State {};
+    struct State {
+        InCursor in;
+        int e;                                 // element index of the next output
+    };
 
-    __device__ __forceinline__ void load(const Geom &g, int k, long long poff,
+    __device__ __forceinline__ void init(const MarchArgs &g, State &st, int kfirst, int k0,
+                                         int poff) const
+    {
+        st.in.init(u, kfirst, g.nloc, g.fs * (NLIG + 1), poff);
+        st.e = k0 * (NLIG + 1) * g.fs + poff;
+    }
+    __device__ __forceinline__ void load(const MarchArgs &g, State &st, int k, int poff,
                                          double *pre) const
     {
-        const double *p = plane_ptr(u, k, g.nloc, g.plane_pts * (NLIG + 1)) + poff;
 #pragma unroll
-        for (int c = 0; c < NLIG + 1; ++c) pre[c] = __ldg(p + c * g.plane_pts);
+        for (int c = 0; c < NLIG + 1; ++c) pre[c] = __ldg(st.in.p + c * g.fs);
+        st.in.next(u, k, g.nloc, g.fs * (NLIG + 1), poff);
     }
-    __device__ __forceinline__ void load_aux(const Geom &g, int ko, long long poff,
+    __device__ __forceinline__ void load_aux(const MarchArgs &g, const State &st,
                                              double *aux) const
     {
-        if (udot) {
-            const double *p = udot + (long long)ko * (NLIG + 1) * g.plane_pts + poff;
+        if (FIXED || udot) {
 #pragma unroll
-            for (int c = 0; c < NLIG + 1; ++c) aux[c] = __ldg(p + c * g.plane_pts);
+            for (int c = 0; c < NLIG + 1; ++c) aux[c] = __ldg(udot + (st.e + c * g.fs));
         }
     }
-    __device__ __forceinline__ void stage(const DevPhys &P, const double *pre,
+    template <class TA>
+    __device__ __forceinline__ void stage(const DevPhys &P, const TA &T, const double *pre,
                                           double *f) const
     {
-        double rho = clampv(pre[0], P.rhomin);
+        const double rho = clampv(pre[0], P.rhomin);
         double U[NLIG];
 #pragma unroll
         for (int l = 0; l < NLIG; ++l) U[l] = clampv(pre[1 + l], P.Umin);
         f[0] = rho;
-        f[1] = G_point<NLIG>(P, rho, U);
+        f[1] = G_fast<NLIG>(P, T, rho, U);
 #pragma unroll
         for (int l = 0; l < NLIG; ++l) f[2 + l] = U[l];
     }
     template <class Acc>
-    __device__ __forceinline__ void emit(const DevPhys &P, const Geom &g, int ko,
-                                         long long poff, const Acc &a,
-                                         const double *aux, State &) const
+    __device__ __forceinline__ void emit(const DevPhys &P, const MarchArgs &g, const Acc &a,
+                                         const double *aux, State &st) const
     {
+        // f_rho = grad(rho).grad(G) + rho*lap(G)
         const double rho0 = a.c(0);
         double acc = 0.0, lap = 0.0;
 #pragma unroll
         for (int ax = 0; ax < DIM; ++ax) {
-            acc = fma(a.wsum(0, ax, P.w1[ax]), a.wsum(1, ax, P.w1[ax]), acc);
-            lap += a.wsum(1, ax, P.w2[ax]);
+            double d1G, d2G;
+            a.D12(1, ax, d1G, d2G);
+            acc = fma(a.D1(0, ax) * P.c1sq[ax], d1G, acc);
+            lap = fma(P.c2[ax], d2G, lap);
         }
         double f[NLIG + 1];
         f[0] = fma(rho0, lap, acc);
@@ -114,57 +303,77 @@ struct ResidualOp {
         for (int l = 0; l < NLIG; ++l) {
             double lapU = 0.0;
 #pragma unroll
-            for (int ax = 0; ax < DIM; ++ax) lapU += a.wsum(2 + l, ax, P.w2[ax]);
+            for (int ax = 0; ax < DIM; ++ax) lapU = fma(P.c2[ax], a.D2(2 + l, ax), lapU);
             f[1 + l] =
                 fma(P.D[l], lapU, fma(P.s[l], rho0, -P.gamma[l] * a.c(2 + l)));
         }
-        const long long e = (long long)ko * (NLIG + 1) * g.plane_pts + poff;
 #pragma unroll
         for (int c = 0; c < NLIG + 1; ++c) {
             double v = f[c];
-            if (src) v += __ldg(src + e + c * g.plane_pts);
-            out[e + c * g.plane_pts] = udot ? aux[c] - v : v;
+            if (FIXED) {
+                v = aux[c] - v;
+            } else {
+                if (src) v += __ldg(src + (st.e + c * g.fs));
+                if (udot) v = aux[c] - v;
+            }
+            out[st.e + c * g.fs] = v;
         }
+    }
+    // once per emitted plane, by every thread
+    __device__ __forceinline__ void advance_out(const MarchArgs &g, State &st) const
+    {
+        st.e += (NLIG + 1) * g.fs;
     }
     __device__ __forceinline__ void finish(State &) const {}
 };
 
 // J.v: out = (shift*I - J(u_lin)) * z,  z = v or M^{-1} v
 // (replaces the assembled matrix of KSFD/ksfdsym.py:814-886)
+// coef fields per point: rho, G, dG/drho, dG/dU_l  (NLIG+3)
 template <int DIM, int NLIG, bool PRECOND>
 struct JvpOp {
     static constexpr int NF = NLIG + 4;   // z_rho, dG, z_U.., rho, G
-    static constexpr int NPRE = (NLIG + 3) + (NLIG + 1) + (PRECOND ? NLIG + 1 : 0);
+    static constexpr int NPRE = (NLIG + 3) + (NLIG + 1) + (PRECOND ? 1 : 0);
     static constexpr int NAUX = 1;
+    static constexpr bool TABS = false;
     VecRef coef, v, pc;
-    double shift, w2c;
+    double shift;
+    double invd[NLIG];
     double *out;
-    struct State {};
+    struct State {
+        InCursor ic, iv, ip;
+        int e;
+    };
 
-    __device__ __forceinline__ void load(const Geom &g, int k, long long poff,
+    __device__ __forceinline__ void init(const MarchArgs &g, State &st, int kfirst, int k0,
+                                         int poff) const
+    {
+        st.ic.init(coef, kfirst, g.nloc, g.fs * (NLIG + 3), poff);
+        st.iv.init(v, kfirst, g.nloc, g.fs * (NLIG + 1), poff);
+        if (PRECOND) st.ip.init(pc, kfirst, g.nloc, g.fs, poff);
+        st.e = k0 * (NLIG + 1) * g.fs + poff;
+    }
+    __device__ __forceinline__ void load(const MarchArgs &g, State &st, int k, int poff,
                                          double *pre) const
     {
-        const double *pc_ = plane_ptr(coef, k, g.nloc, g.plane_pts * (NLIG + 3)) + poff;
 #pragma unroll
-        for (int c = 0; c < NLIG + 3; ++c) pre[c] = __ldg(pc_ + c * g.plane_pts);
-        const double *pv = plane_ptr(v, k, g.nloc, g.plane_pts * (NLIG + 1)) + poff;
+        for (int c = 0; c < NLIG + 3; ++c) pre[c] = __ldg(st.ic.p + c * g.fs);
 #pragma unroll
-        for (int c = 0; c < NLIG + 1; ++c) pre[NLIG + 3 + c] = __ldg(pv + c * g.plane_pts);
-        if (PRECOND) {
-            const double *pp = plane_ptr(pc, k, g.nloc, g.plane_pts * (NLIG + 1)) + poff;
-#pragma unroll
-            for (int c = 0; c < NLIG + 1; ++c)
-                pre[2 * NLIG + 4 + c] = __ldg(pp + c * g.plane_pts);
-        }
+        for (int c = 0; c < NLIG + 1; ++c) pre[NLIG + 3 + c] = __ldg(st.iv.p + c * g.fs);
+        if (PRECOND) pre[2 * NLIG + 4] = __ldg(st.ip.p);
+        st.ic.next(coef, k, g.nloc, g.fs * (NLIG + 3), poff);
+        st.iv.next(v, k, g.nloc, g.fs * (NLIG + 1), poff);
+        if (PRECOND) st.ip.next(pc, k, g.nloc, g.fs, poff);
     }
-    __device__ __forceinline__ void load_aux(const Geom &, int, long long,
+    __device__ __forceinline__ void load_aux(const MarchArgs &, const State &,
                                              double *) const {}
-    __device__ __forceinline__ void stage(const DevPhys &P, const double *pre,
+    template <class TA>
+    __device__ __forceinline__ void stage(const DevPhys &P, const TA &, const double *pre,
                                           double *f) const
     {
         double z[NLIG + 1];
         if (PRECOND) {
-            pc_point(P, shift, w2c, pre + 2 * NLIG + 4, pre + NLIG + 3, z, NLIG);
+            pc_solve<NLIG>(P, invd, pre[0], pre + 3, pre[2 * NLIG + 4], pre + NLIG + 3, z);
         } else {
 #pragma unroll
             for (int c = 0; c < NLIG + 1; ++c) z[c] = pre[NLIG + 3 + c];
@@ -180,32 +389,39 @@ struct JvpOp {
         f[NLIG + 3] = pre[1];
     }
     template <class Acc>
-    __device__ __forceinline__ void emit(const DevPhys &P, const Geom &g, int ko,
-                                         long long poff, const Acc &a,
-                                         const double *, State &) const
+    __device__ __forceinline__ void emit(const DevPhys &P, const MarchArgs &g, const Acc &a,
+                                         const double *, State &st) const
     {
+        // (J z)_rho = grad(z0).grad(G) + grad(rho).grad(dG) + z0*lap(G) + rho*lap(dG)
         constexpr int FR = NLIG + 2, FG = NLIG + 3;
         double acc = 0.0, lapG = 0.0, lapdG = 0.0;
 #pragma unroll
         for (int ax = 0; ax < DIM; ++ax) {
-            acc = fma(a.wsum(0, ax, P.w1[ax]), a.wsum(FG, ax, P.w1[ax]), acc);
-            acc = fma(a.wsum(FR, ax, P.w1[ax]), a.wsum(1, ax, P.w1[ax]), acc);
-            lapG += a.wsum(FG, ax, P.w2[ax]);
-            lapdG += a.wsum(1, ax, P.w2[ax]);
+            double d1G, d2G, d1dG, d2dG;
+            a.D12(FG, ax, d1G, d2G);
+            a.D12(1, ax, d1dG, d2dG);
+            double t = a.D1(0, ax) * d1G;
+            t = fma(a.D1(FR, ax), d1dG, t);
+            acc = fma(P.c1sq[ax], t, acc);
+            lapG = fma(P.c2[ax], d2G, lapG);
+            lapdG = fma(P.c2[ax], d2dG, lapdG);
         }
         const double z0 = a.c(0);
         const double Jv0 = fma(a.c(FR), lapdG, fma(z0, lapG, acc));
-        const long long e = (long long)ko * (NLIG + 1) * g.plane_pts + poff;
-        out[e] = fma(shift, z0, -Jv0);
+        out[st.e] = fma(shift, z0, -Jv0);
 #pragma unroll
         for (int l = 0; l < NLIG; ++l) {
             double lapV = 0.0;
 #pragma unroll
-            for (int ax = 0; ax < DIM; ++ax) lapV += a.wsum(2 + l, ax, P.w2[ax]);
+            for (int ax = 0; ax < DIM; ++ax) lapV = fma(P.c2[ax], a.D2(2 + l, ax), lapV);
             const double zl = a.c(2 + l);
-            double JvU = fma(P.D[l], lapV, fma(P.s[l], z0, -P.gamma[l] * zl));
-            out[e + (1 + l) * g.plane_pts] = fma(shift, zl, -JvU);
+            const double JvU = fma(P.D[l], lapV, fma(P.s[l], z0, -P.gamma[l] * zl));
+            out[st.e + (1 + l) * g.fs] = fma(shift, zl, -JvU);
         }
+    }
+    __device__ __forceinline__ void advance_out(const MarchArgs &g, State &st) const
+    {
+        st.e += (NLIG + 1) * g.fs;
     }
     __device__ __forceinline__ void finish(State &) const {}
 };
@@ -216,51 +432,64 @@ struct VelocityOp {
     static constexpr int NF = 1;
     static constexpr int NPRE = NLIG + 1;
     static constexpr int NAUX = 1;
+    static constexpr bool TABS = true;
     VecRef u;
     double *vel;        // optional plane-SoA output with DIM fields
     double *vmax;       // optional per-axis max
     struct State {
+        InCursor in;
+        int e;
         double vm[3];
-        __device__ State() { vm[0] = vm[1] = vm[2] = 0.0; }
     };
 
-    __device__ __forceinline__ void load(const Geom &g, int k, long long poff,
+    __device__ __forceinline__ void init(const MarchArgs &g, State &st, int kfirst, int k0,
+                                         int poff) const
+    {
+        st.in.init(u, kfirst, g.nloc, g.fs * (NLIG + 1), poff);
+        st.e = k0 * DIM * g.fs + poff;
+        st.vm[0] = st.vm[1] = st.vm[2] = 0.0;
+    }
+    __device__ __forceinline__ void load(const MarchArgs &g, State &st, int k, int poff,
                                          double *pre) const
     {
-        const double *p = plane_ptr(u, k, g.nloc, g.plane_pts * (NLIG + 1)) + poff;
 #pragma unroll
-        for (int c = 0; c < NLIG + 1; ++c) pre[c] = __ldg(p + c * g.plane_pts);
+        for (int c = 0; c < NLIG + 1; ++c) pre[c] = __ldg(st.in.p + c * g.fs);
+        st.in.next(u, k, g.nloc, g.fs * (NLIG + 1), poff);
     }
-    __device__ __forceinline__ void load_aux(const Geom &, int, long long,
+    __device__ __forceinline__ void load_aux(const MarchArgs &, const State &,
                                              double *) const {}
-    __device__ __forceinline__ void stage(const DevPhys &P, const double *pre,
+    template <class TA>
+    __device__ __forceinline__ void stage(const DevPhys &P, const TA &T, const double *pre,
                                           double *f) const
     {
-        double rho = clampv(pre[0], P.rhomin);
+        const double rho = clampv(pre[0], P.rhomin);
         double U[NLIG];
 #pragma unroll
         for (int l = 0; l < NLIG; ++l) U[l] = clampv(pre[1 + l], P.Umin);
-        f[0] = G_point<NLIG>(P, rho, U);
+        f[0] = G_fast<NLIG>(P, T, rho, U);
     }
     template <class Acc>
-    __device__ __forceinline__ void emit(const DevPhys &P, const Geom &g, int ko,
-                                         long long poff, const Acc &a,
+    __device__ __forceinline__ void emit(const DevPhys &P, const MarchArgs &g, const Acc &a,
                                          const double *, State &st) const
     {
-        const long long e = (long long)ko * DIM * g.plane_pts + poff;
 #pragma unroll
         for (int ax = 0; ax < DIM; ++ax) {
-            double d = a.wsum(0, ax, P.w1[ax]);
-            if (vel) vel[e + ax * g.plane_pts] = d;
+            const double d = P.c1[ax] * a.D1(0, ax);
+            if (vel) vel[st.e + ax * g.fs] = d;
             st.vm[ax] = fmax(st.vm[ax], fabs(d));
         }
     }
+    __device__ __forceinline__ void advance_out(const MarchArgs &g, State &st) const
+    {
+        st.e += DIM * g.fs;
+    }
+    // every thread of the CTA calls this (non-emitting lanes carry zeros)
     __device__ __forceinline__ void finish(State &st) const
     {
         if (!vmax) return;
 #pragma unroll
         for (int ax = 0; ax < DIM; ++ax) {
-            double m = warp_max(st.vm[ax]);
+            const double m = warp_max(st.vm[ax]);
             if ((threadIdx.x & 31) == 0 && m > 0.0) atomic_max_nonneg(vmax + ax, m);
         }
     }
@@ -269,68 +498,154 @@ struct VelocityOp {
 // ---------------------------------------------------------------------------
 // The marching skeleton
 // ---------------------------------------------------------------------------
-template <int DIM, int TXL, int TYL, class Op>
-__global__ void __launch_bounds__(TXL *TYL)
-k_march(const __grid_constant__ Geom g, const __grid_constant__ DevPhys P,
-        const int RZ, Op op)
-{
-    constexpr int NF = Op::NF;
-    constexpr int NPRE = Op::NPRE;
-    constexpr int NAUX = Op::NAUX;
-    constexpr int NT = TXL * TYL;
-    extern __shared__ double ring[];            // [KSFD_RING][NF][NT]
-    const int tid = threadIdx.x;
-    const int lx = (TYL == 1) ? tid : tid % TXL;
-    const int ly = (TYL == 1) ? 0 : tid / TXL;
-    const int i0 = blockIdx.x * (TXL - 2 * KSFD_SW);
-    const int j0 = (DIM == 3) ? blockIdx.y * (TYL - 2 * KSFD_SW) : 0;
-    const int k0 = blockIdx.z * RZ;
-    const int k1 = min(k0 + RZ, g.nloc);
-
-    long long poff = wrapi(i0 - KSFD_SW + lx, g.n0);
-    bool emits = lx >= KSFD_SW && lx < TXL - KSFD_SW && (i0 + lx - KSFD_SW) < g.n0;
-    if (DIM == 3) {
-        poff += (long long)wrapi(j0 - KSFD_SW + ly, g.n1) * g.n0;
-        emits = emits && ly >= KSFD_SW && ly < TYL - KSFD_SW &&
-                (j0 + ly - KSFD_SW) < g.n1;
-    }
-    typename Op::State st;
+// UNR: unroll the plane loop five times (queue rotates by register renaming);
+// otherwise the queue is shifted with moves (smaller code, fewer registers).
+template <int DIM, int TX, int TY, class Op, bool UNR>
+struct Marcher {
+    using T = TileT<DIM, TX, TY>;
+    static constexpr int NF = Op::NF, NPRE = Op::NPRE, NAUX = Op::NAUX;
+    static constexpr int RING = 2 * NF * T::SP;     // doubles; tables follow
+    const MarchArgs &g;
+    const DevPhys &P;
+    const Op &op;
     double q[NF][5];
-#pragma unroll
-    for (int f = 0; f < NF; ++f)
-#pragma unroll
-        for (int s = 0; s < 5; ++s) q[f][s] = 0.0;
+    double pre[NPRE];
+    double aux[NAUX];
+    typename Op::State st;
+    int poff, spos, k0, k1;
+    bool active, emits;
 
-    double pre[NPRE], aux[NAUX];
-    op.load(g, k0 - KSFD_SW, poff, pre);
+    __device__ __forceinline__ Marcher(const MarchArgs &g_, const DevPhys &P_, const Op &op_)
+        : g(g_), P(P_), op(op_)
+    {
+        const int tid = threadIdx.x;
+        if (Op::TABS) {
+            // stage the log / exp tables behind the ring
+            for (int i = tid; i < KSFD_TAB_DOUBLES; i += T::NT)
+                ksfd_smem[RING + i] = __longlong_as_double(
+                    (long long)(i < 256 ? g_log_tab[i] : g_exp_tab[i - 256]));
+            __syncthreads();
+        }
+        const int i0 = blockIdx.x * g.ox;
+        int x, y = 0;               // tile-relative position incl. halo
+        bool interior;
+        if (DIM == 2) {
+            x = tid;
+            active = x < g.ox + 2 * KSFD_SW;
+            interior = x >= KSFD_SW && x < g.ox + KSFD_SW;
+            spos = x;
+            poff = wrapi(i0 - KSFD_SW + x, g.n0);
+            emits = interior && (i0 + x - KSFD_SW) < g.n0;
+        } else {
+            const int j0 = blockIdx.y * g.oy;
+            if (tid < TX * TY) {
+                const int a = tid % TX, b = tid / TX;
+                x = a + KSFD_SW;
+                y = b + KSFD_SW;
+                active = a < g.ox && b < g.oy;
+                interior = active;
+            } else {
+                int h = tid - TX * TY;
+                interior = false;
+                if (h < 4 * TX) {               // two rows below, two above
+                    const int r = h / TX, a = h - r * TX;
+                    x = a + KSFD_SW;
+                    y = r < 2 ? r : g.oy + r;
+                    active = a < g.ox;
+                } else {                        // two columns left, two right
+                    h -= 4 * TX;
+                    const int cc = h & 3, b = h >> 2;
+                    x = cc < 2 ? cc : g.ox + cc;
+                    y = b + KSFD_SW;
+                    active = b < g.oy && b < TY;    // threads padding the last warp
+                }
+            }
+            spos = y * T::PX + x;
+            poff = wrapi(j0 - KSFD_SW + y, g.n1) * g.n0 + wrapi(i0 - KSFD_SW + x, g.n0);
+            emits = interior && (i0 + x - KSFD_SW) < g.n0 && (j0 + y - KSFD_SW) < g.n1;
+        }
+        k0 = blockIdx.z * g.rz;
+        k1 = min(k0 + g.rz, g.nloc);
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int s = 0; s < 5; ++s) q[f][s] = 0.0;
+    }
 
-    int slot = 0;
-    for (int kk = k0 - KSFD_SW; kk < k1 + KSFD_SW; ++kk) {
+    template <int PH>
+    __device__ __forceinline__ void step(int kk)
+    {
         double cur[NPRE];
 #pragma unroll
         for (int c = 0; c < NPRE; ++c) cur[c] = pre[c];
-        if (kk + 1 < k1 + KSFD_SW) op.load(g, kk + 1, poff, pre);
-        const int ko = kk - KSFD_SW;
-        const bool do_emit = emits && ko >= k0;
-        if (do_emit) op.load_aux(g, ko, poff, aux);
-
-        double f[NF];
-        op.stage(P, cur, f);
+        if (active && kk + 1 < k1 + KSFD_SW) op.load(g, st, kk + 1, poff, pre);
+        if (active) {
+            double f[NF];
+            op.stage(P, SmemTabs<RING>(), cur, f);
 #pragma unroll
-        for (int c = 0; c < NF; ++c) {
+            for (int c = 0; c < NF; ++c) q[c][PH] = f[c];
+        }
+        if (kk - KSFD_SW >= k0) {                       // uniform over the CTA
+            // after the register-hungry stage; the barrier wait hides the latency
+            if (emits) op.load_aux(g, st, aux);
+            const int ri = (kk & 1) * (NF * T::SP) + spos;
+            if (active) {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) q[c][s] = q[c][s + 1];
-            q[c][4] = f[c];
-            ring[(slot * NF + c) * NT + tid] = f[c];
+                for (int c = 0; c < NF; ++c) ksfd_smem[ri + c * T::SP] = q[c][(PH + 3) % 5];
+            }
+            __syncthreads();
+            if (emits) {
+                LaneAcc<DIM, NF, T::SP, T::SY, PH> a(q, ri);
+                op.emit(P, g, a, aux, st);
+            }
+            op.advance_out(g, st);
         }
-        __syncthreads();
-        if (do_emit) {
-            RegAcc<DIM, NF, TXL, NT> a;
-            a.q = q;
-            a.rc = ring + ((slot ^ 2) * NF) * NT + tid;   // slot of plane ko
-            op.emit(P, g, ko, poff, a, aux, st);
-        }
-        slot = (slot + 1) & (KSFD_RING - 1);
     }
-    op.finish(st);
+
+    __device__ __forceinline__ void run()
+    {
+        int kk = k0 - KSFD_SW;
+        const int kend = k1 + KSFD_SW;
+        op.init(g, st, kk, k0, poff);
+        if (active) op.load(g, st, kk, poff, pre);
+        if (!UNR) {
+            for (; kk < kend; ++kk) {
+                step<4>(kk);
+#pragma unroll
+                for (int c = 0; c < NF; ++c) {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) q[c][s] = q[c][s + 1];
+                }
+            }
+        } else {
+            for (;;) {
+                step<0>(kk);
+                if (++kk >= kend) break;
+                step<1>(kk);
+                if (++kk >= kend) break;
+                step<2>(kk);
+                if (++kk >= kend) break;
+                step<3>(kk);
+                if (++kk >= kend) break;
+                step<4>(kk);
+                if (++kk >= kend) break;
+            }
+        }
+        op.finish(st);
+    }
+};
+
+template <class Op, int SP>
+constexpr size_t march_smem_bytes()
+{
+    return sizeof(double) * (2 * Op::NF * SP + (Op::TABS ? KSFD_TAB_DOUBLES : 0));
+}
+
+template <int DIM, int TX, int TY, class Op, int MINB, bool UNR>
+__global__ void __launch_bounds__(TileT<DIM, TX, TY>::NT, MINB)
+k_march(const __grid_constant__ MarchArgs g, const __grid_constant__ DevPhys P,
+        const __grid_constant__ Op op)
+{
+    Marcher<DIM, TX, TY, Op, UNR> m(g, P, op);
+    m.run();
 }

@@ -1,0 +1,38 @@
+// Marching residual kernels, one dimension per object file (-DKSFD_MARCH_DIM).
+#include "march_launch.cuh"
+
+#ifndef KSFD_MARCH_DIM
+#error "compile with -DKSFD_MARCH_DIM=2 or 3"
+#endif
+#define DIM KSFD_MARCH_DIM
+
+template <int NLIG, bool FIXED>
+static int launch_residual_f(ksfd_ctx *c, VecRef u, const double *udot, const double *src,
+                             double *out, cudaStream_t st)
+{
+    ResidualOp<DIM, NLIG, FIXED> op{u, udot, src, out};
+#if KSFD_MARCH_DIM == 2
+    return launch_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 124, 1, 6, 252, 1, 3>(
+        c, op, FIXED ? 1 : 5, 150.0, 35.0 * DIM + 30.0, st);
+#else
+    return launch_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 16, 16, 2, 32, 16, 1>(
+        c, op, FIXED ? 1 : 5, 150.0, 35.0 * DIM + 30.0, st);
+#endif
+}
+
+// the implicit-step case (udot given, no sources) has its own instantiation
+// without the runtime tests
+template <int NLIG>
+static int launch_residual(ksfd_ctx *c, VecRef u, const double *udot, const double *src,
+                           double *out, cudaStream_t st)
+{
+    if (udot && !src) return launch_residual_f<NLIG, true>(c, u, udot, src, out, st);
+    return launch_residual_f<NLIG, false>(c, u, udot, src, out, st);
+}
+
+int KSFD_CAT(ksfd_march_residual_d, KSFD_MARCH_DIM)(ksfd_ctx *c, VecRef u,
+                                                    const double *udot, const double *src,
+                                                    double *out, cudaStream_t st)
+{
+    KSFD_DISPATCH_NLIG(launch_residual, c, u, udot, src, out, st);
+}

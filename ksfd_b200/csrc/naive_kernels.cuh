@@ -214,14 +214,22 @@ __global__ void k_coef_setup(Geom g, DevPhys P, VecRef u,
     for (int l = 0; l < P.nlig; ++l) c[(3 + l) * g.plane_pts] = g_U[l];
 }
 
+struct InvD {
+    double v[KSFD_MAX_LIGANDS];          // 1/d_l, d_l = shift + gamma_l - D_l*w2c
+};
+
 // Point-block Jacobi of A = shift*I - J.  The diagonal block is
 //   [ a   b_1 .. b_n ]      a   = shift - dJ_rho/drho0
 //   [ c_1 d_1        ]      b_l = -dJ_rho/dU_l0      c_l = -s_l
 //   [ c_n        d_n ]      d_l = shift + gamma_l - D_l*sum_ax w2c
-// stored (plane-SoA, dof fields) as ( 1/(a - sum b_l c_l/d_l), b_1/d_1, .. ).
-// If blocks != NULL the dense dof x dof blocks are written too (tests;
+// The preconditioner M takes b_l = -(rho0*w2c)*dG/dU_l (the exact b_l has an
+// extra w1-centre term that is zero up to the last-bit asymmetry of the
+// reference weights), so that only ONE field has to be stored per point:
+//   pc = 1/(a - sum_l b_l c_l / d_l)
+// and b_l/d_l is recomputed from the coefficient field (see pc_point_rt).
+// If blocks != NULL the exact dense dof x dof blocks are written too (tests;
 // row-major per point in natural point order).
-__global__ void k_pc_setup(Geom g, DevPhys P, VecRef coef, double shift,
+__global__ void k_pc_setup(Geom g, DevPhys P, VecRef coef, double shift, InvD invd,
                            double *__restrict__ pc, double *__restrict__ blocks)
 {
     long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -230,7 +238,7 @@ __global__ void k_pc_setup(Geom g, DevPhys P, VecRef coef, double shift,
     const int cs = g.dof + 2;
     PtRef c0 = nbr(g, coef, q, 0, 0, cs);
     double rho0 = c0[0];
-    double fac = 0.0, lap = 0.0, dir = 0.0, w2c = 0.0;
+    double fac = 0.0, lap = 0.0, dir = 0.0;
     for (int ax = 0; ax < g.dim; ++ax) {
         double d1r = 0.0, d1G = 0.0, d2G = 0.0;
         for (int s = 0; s < 5; ++s) {
@@ -242,79 +250,64 @@ __global__ void k_pc_setup(Geom g, DevPhys P, VecRef coef, double shift,
         fac += d1r * P.w1[ax][2] + rho0 * P.w2[ax][2];
         dir += P.w1[ax][2] * d1G;
         lap += d2G;
-        w2c += P.w2[ax][2];
     }
-    double Jrr = dir + fac * c0[2] + lap;
-    double a = shift - Jrr;
+    const double Jrr = dir + fac * c0[2] + lap;
+    const double a = shift - Jrr;
+    const double facm = rho0 * P.w2c;            // M's version of fac
     double schur = a;
     for (int l = 0; l < P.nlig; ++l) {
-        double b = -fac * c0[3 + l];
-        double d = shift + P.gamma[l] - P.D[l] * w2c;
-        double bd = b / d;
-        pc[el(g, q, 1 + l, g.dof)] = bd;
+        const double bd = -facm * c0[3 + l] * invd.v[l];
         schur -= bd * (-P.s[l]);
         if (blocks) {
             double *B = blocks + p * g.dof * g.dof;
-            B[0 * g.dof + (1 + l)] = b;
+            B[0 * g.dof + (1 + l)] = -fac * c0[3 + l];
             B[(1 + l) * g.dof + 0] = -P.s[l];
             for (int m = 0; m < P.nlig; ++m)
-                B[(1 + l) * g.dof + (1 + m)] = (m == l) ? d : 0.0;
+                B[(1 + l) * g.dof + (1 + m)] =
+                    (m == l) ? shift + P.gamma[l] - P.D[l] * P.w2c : 0.0;
         }
     }
-    pc[el(g, q, 0, g.dof)] = 1.0 / schur;
+    pc[p] = 1.0 / schur;
     if (blocks) blocks[p * g.dof * g.dof] = a;
 }
 
-// z = M^{-1} r for one point; pcp[0] = 1/schur, pcp[1+l] = b_l/d_l
-__device__ __forceinline__ void pc_point(const DevPhys &P, double shift,
-                                         double w2c_sum, const double *pcp,
-                                         const double *r, double *z, int nlig)
+// z = M^{-1} r for one point (runtime nlig); same arithmetic as pc_solve<NLIG>
+// of the marching kernels
+__device__ __forceinline__ void pc_point_rt(const DevPhys &P, const InvD &invd, double rho,
+                                            const double *gU, double pcinv,
+                                            const double *r, double *z)
 {
+    const double fac = rho * P.w2c;
     double t = r[0];
-#pragma unroll
-    for (int l = 0; l < nlig; ++l) t = fma(-pcp[1 + l], r[1 + l], t);
-    double zr = pcp[0] * t;
+    for (int l = 0; l < P.nlig; ++l) t = fma(fac * gU[l] * invd.v[l], r[1 + l], t);
+    const double zr = pcinv * t;
     z[0] = zr;
-#pragma unroll
-    for (int l = 0; l < nlig; ++l) {
-        double d = shift + P.gamma[l] - P.D[l] * w2c_sum;
-        z[1 + l] = (r[1 + l] + P.s[l] * zr) / d;
-    }
+    for (int l = 0; l < P.nlig; ++l) z[1 + l] = fma(P.s[l], zr, r[1 + l]) * invd.v[l];
 }
 
-__device__ __forceinline__ double w2c_total(const DevPhys &P, int dim)
-{
-    double w = 0.0;
-    for (int ax = 0; ax < dim; ++ax) w += P.w2[ax][2];
-    return w;
-}
-
-__global__ void k_pc_apply(Geom g, DevPhys P, double shift,
+__global__ void k_pc_apply(Geom g, DevPhys P, VecRef coef, InvD invd,
                            const double *__restrict__ pc,
                            const double *__restrict__ r, double *__restrict__ z)
 {
     long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (p >= g.npts) return;
     PointIdx q = decode_point(g, p);
-    double rr[KSFD_MAX_LIGANDS + 1], zz[KSFD_MAX_LIGANDS + 1], pp[KSFD_MAX_LIGANDS + 1];
-    for (int c = 0; c < g.dof; ++c) {
-        const long long e = el(g, q, c, g.dof);
-        rr[c] = r[e];
-        pp[c] = pc[e];
-    }
-    pc_point(P, shift, w2c_total(P, g.dim), pp, rr, zz, P.nlig);
+    PtRef c0 = nbr(g, coef, q, 0, 0, g.dof + 2);
+    double rr[KSFD_MAX_LIGANDS + 1], zz[KSFD_MAX_LIGANDS + 1], gU[KSFD_MAX_LIGANDS];
+    for (int c = 0; c < g.dof; ++c) rr[c] = r[el(g, q, c, g.dof)];
+    for (int l = 0; l < P.nlig; ++l) gU[l] = c0[3 + l];
+    pc_point_rt(P, invd, c0[0], gU, pc[p], rr, zz);
     for (int c = 0; c < g.dof; ++c) z[el(g, q, c, g.dof)] = zz[c];
 }
 
 // out = (shift*I - J(u_lin)) * v   (optionally v := M^{-1} v first)
-__global__ void k_jvp_naive(Geom g, DevPhys P, VecRef coef, VecRef v, VecRef pc,
+__global__ void k_jvp_naive(Geom g, DevPhys P, VecRef coef, VecRef v, VecRef pc, InvD invd,
                             int precond, double shift, double *__restrict__ out)
 {
     long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (p >= g.npts) return;
     PointIdx q = decode_point(g, p);
     const int dof = g.dof, cs = g.dof + 2;
-    const double w2c = w2c_total(P, g.dim);
     double acc = 0.0, lapG = 0.0, lapdG = 0.0, lapV[KSFD_MAX_LIGANDS];
     for (int l = 0; l < P.nlig; ++l) lapV[l] = 0.0;
     double v0[KSFD_MAX_LIGANDS + 1], rho0 = 0.0;
@@ -327,13 +320,11 @@ __global__ void k_jvp_naive(Geom g, DevPhys P, VecRef coef, VecRef v, VecRef pc,
             PtRef vn = nbr(g, v, q, ax, s - 2, dof);
             double vv[KSFD_MAX_LIGANDS + 1];
             if (precond) {
-                double rr[KSFD_MAX_LIGANDS + 1], pp[KSFD_MAX_LIGANDS + 1];
-                PtRef pn = nbr(g, pc, q, ax, s - 2, dof);
-                for (int c = 0; c < dof; ++c) {
-                    rr[c] = vn[c];
-                    pp[c] = pn[c];
-                }
-                pc_point(P, shift, w2c, pp, rr, vv, P.nlig);
+                double rr[KSFD_MAX_LIGANDS + 1], gU[KSFD_MAX_LIGANDS];
+                PtRef pn = nbr(g, pc, q, ax, s - 2, 1);
+                for (int c = 0; c < dof; ++c) rr[c] = vn[c];
+                for (int l = 0; l < P.nlig; ++l) gU[l] = cn[3 + l];
+                pc_point_rt(P, invd, cn[0], gU, pn[0], rr, vv);
             } else {
                 for (int c = 0; c < dof; ++c) vv[c] = vn[c];
             }
