@@ -269,3 +269,328 @@ __global__ void k_scale_dof0(long long npts, long long plane_pts, int dof, doubl
         u[k * dof * plane_pts + (p - k * plane_pts)] *= f;
     }
 }
+
+// ---------------------------------------------------------------------------
+// Pipelined GMRES: the Hessenberg/Givens bookkeeping, the convergence test and
+// the back substitution run on the device; the host only polls a pinned status
+// word (no stream synchronisation inside a solve) and may launch ahead.
+// Every kernel of the pipeline starts with `if (*skip) return`.
+// ---------------------------------------------------------------------------
+#define KSFD_GM_MAXM 64                      // max restart length
+#define KSFD_GM_LD (KSFD_GM_MAXM + 1)
+// double slots of the device state `gm`
+#define GM_H 0                               // H[col*LD + row], rotated in place
+#define GM_CS (GM_H + KSFD_GM_LD * KSFD_GM_MAXM)
+#define GM_SN (GM_CS + KSFD_GM_MAXM)
+#define GM_G (GM_SN + KSFD_GM_MAXM)          // rhs of the least-squares problem
+#define GM_Y (GM_G + KSFD_GM_LD)
+#define GM_HCOL (GM_Y + KSFD_GM_MAXM)        // raw column of the current step (+ <w,w>)
+#define GM_INV (GM_HCOL + KSFD_GM_LD + 1)    // 1/h[j+1,j]
+#define GM_BETA (GM_INV + 1)
+#define GM_TOL (GM_BETA + 1)
+#define GM_CTOL (GM_TOL + 1)
+#define GM_RNORM0 (GM_CTOL + 1)
+#define GM_RNORM (GM_RNORM0 + 1)
+#define GM_DOUBLES (GM_RNORM + 1)
+// int slots of `gmi`
+#define GMI_CYCLE_DONE 0                     // iteration kernels skip
+#define GMI_FINAL 1                          // cycle-start kernels skip
+#define GMI_NOUPD 2                          // x-update skips (nothing to add / NaN)
+#define GMI_K 3                              // columns of the closed cycle
+#define GMI_ITS 4                            // total iterations of the solve
+#define GMI_REASON 5
+#define GMI_INTS 8
+
+// host-visible progress (pinned, mapped): written by the device, polled by the host
+struct GmStatus {
+    volatile int seq;            // 2*cycle+1 once the cycle has begun
+    volatile int iters_done;     // columns finished in the current cycle
+    volatile int cycle_done, final_, reason, its_total;
+    volatile double rnorm, rnorm0;
+};
+
+struct GmOpts {
+    double rtol, atol, dtol;
+    int max_it, m, reorth;
+    double cycle_factor;         // close a cycle after this reduction (0: never early)
+};
+
+__device__ __forceinline__ double block_sum_partials(const double *partial, int nblocks)
+{
+    // all threads of one block; returns the sum in every thread
+    __shared__ double sm_[32];
+    __shared__ double tot_;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += partial[b];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sm_[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int q = 0; q < (blockDim.x + 31) / 32; ++q) t += sm_[q];
+        tot_ = t;
+    }
+    __syncthreads();
+    return tot_;
+}
+
+// Start of a cycle: beta = ||r|| from the partial sums of <r,r> (nblocks of
+// them; 1 when already reduced over ranks), tolerances, convergence of the
+// TRUE residual.
+__global__ void k_gm_cycle_begin(int nblocks, const double *__restrict__ partial,
+                                 double *__restrict__ gm, int *__restrict__ gmi,
+                                 GmStatus *hs, int cycle, GmOpts o)
+{
+    if (gmi[GMI_FINAL]) return;
+    const double s = block_sum_partials(partial, nblocks);
+    if (threadIdx.x != 0) return;
+    const double beta = sqrt(s);
+    if (cycle == 0) {
+        gm[GM_RNORM0] = beta;
+        gm[GM_TOL] = fmax(o.rtol * beta, o.atol);
+        gmi[GMI_ITS] = 0;
+    }
+    const double tol = gm[GM_TOL];
+    gm[GM_BETA] = beta;
+    gm[GM_RNORM] = beta;
+    gm[GM_CTOL] = fmax(tol, o.cycle_factor * beta);
+    for (int i = 0; i <= o.m; ++i) gm[GM_G + i] = 0.0;
+    gm[GM_G] = beta;
+    int fin = 0, reason = 0;
+    if (!(beta == beta)) { fin = 1; reason = -9; }
+    else if (beta == 0.0) { fin = 1; reason = 3; }
+    else if (beta <= tol) { fin = 1; reason = 2; }
+    else if (gmi[GMI_ITS] >= o.max_it) { fin = 1; reason = -3; }
+    gmi[GMI_CYCLE_DONE] = fin;
+    gmi[GMI_FINAL] = fin;
+    gmi[GMI_NOUPD] = 1;          // until a column exists
+    gmi[GMI_K] = 0;
+    gmi[GMI_REASON] = reason;
+    hs->iters_done = 0;
+    hs->cycle_done = fin;
+    hs->final_ = fin;
+    hs->reason = reason;
+    hs->its_total = gmi[GMI_ITS];
+    hs->rnorm = beta;
+    hs->rnorm0 = gm[GM_RNORM0];
+    __threadfence_system();
+    hs->seq = 2 * cycle + 1;
+    __threadfence_system();
+}
+
+// y = x * (sign / gm[GM_BETA])    (first Krylov vector)
+__global__ void k_gm_first_vector(long long n, const double *x, const double *__restrict__ gm,
+                                  const int *__restrict__ gmi, double sign, double *y)
+{
+    if (gmi[GMI_FINAL]) return;
+    const double f = sign / gm[GM_BETA];
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+         e += (long long)gridDim.x * blockDim.x)
+        y[e] = x[e] * f;
+}
+
+// partial[i][block] = <vs[i], w>, skipping when the cycle is closed
+template <int NV>
+__global__ void __launch_bounds__(KSFD_RED_THREADS)
+k_gm_mdot(long long n, VecList vs, const double *__restrict__ w,
+          const int *__restrict__ gmi, double *__restrict__ partial)
+{
+    if (gmi[GMI_CYCLE_DONE]) return;
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+         e += (long long)gridDim.x * blockDim.x) {
+        const double wv = w[e];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] = fma(__ldg(vs.v[i] + e), wv, acc[i]);
+    }
+    block_reduce_store<NV>(acc, partial, KSFD_RED_BLOCKS);
+}
+
+// hcol[off + i] = sum_b partial[i][b], i < nv  (earlier batches of a long column)
+__global__ void k_gm_reduce(int nv, int off, int nblocks, const double *__restrict__ partial,
+                            const int *__restrict__ gmi, double *__restrict__ gm)
+{
+    if (gmi[GMI_CYCLE_DONE]) return;
+    const int i = blockIdx.x;
+    if (i >= nv) return;
+    const double s = block_sum_partials(partial + (size_t)i * KSFD_RED_BLOCKS, nblocks);
+    if (threadIdx.x == 0) gm[GM_HCOL + off + i] = s;
+}
+
+// End of Arnoldi step j (one block).  Reduces the last batch of partial sums
+// (nv_batch rows into hcol[off..]; nv_batch = 0 when hcol is complete already,
+// e.g. after the all-reduce over ranks), forms h[j+1] from <w,w> - sum h_i^2,
+// applies the Givens rotations, updates the residual norm, decides whether the
+// cycle / the solve ends, and if the cycle ends solves the triangular system.
+// The serial part works out of shared memory (every global access of a single
+// thread costs an L2 round trip).
+__global__ void k_gm_finalize(int nv_batch, int off, int j, int nblocks,
+                              const double *__restrict__ partial, double *__restrict__ gm,
+                              int *__restrict__ gmi, GmStatus *hs, GmOpts o)
+{
+    if (gmi[GMI_CYCLE_DONE]) return;
+    __shared__ double h[KSFD_GM_LD + 1], cs[KSFD_GM_MAXM], sn[KSFD_GM_MAXM], y[KSFD_GM_MAXM];
+    __shared__ double sc[6];            // g[j], tol, ctol, rnorm0, its(as double), -
+    __shared__ double Ht[KSFD_GM_MAXM * (KSFD_GM_MAXM + 1) / 2];
+    __shared__ double gs[KSFD_GM_LD];
+    __shared__ int dec[4];              // cyc, fin, reason, noupd
+    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    // columns reduced by earlier batches (or all of them when nv_batch == 0)
+    for (int i = tid; i <= j + 1; i += blockDim.x)
+        if (i < off || nv_batch == 0) h[i] = gm[GM_HCOL + i];
+    for (int i = tid; i < j; i += blockDim.x) {
+        cs[i] = gm[GM_CS + i];
+        sn[i] = gm[GM_SN + i];
+    }
+    if (tid == 0) {
+        sc[0] = gm[GM_G + j];
+        sc[1] = gm[GM_TOL];
+        sc[2] = gm[GM_CTOL];
+        sc[3] = gm[GM_RNORM0];
+        sc[4] = (double)gmi[GMI_ITS];
+    }
+    for (int i = w; i < nv_batch; i += blockDim.x >> 5) {
+        double s = 0.0;
+        for (int b = l; b < nblocks; b += 32) s += partial[(size_t)i * KSFD_RED_BLOCKS + b];
+        s = warp_sum(s);
+        if (l == 0) h[off + i] = s;
+    }
+    __syncthreads();
+    const int k = j + 1;
+    if (tid == 0) {
+        const double ww = h[j + 1];
+        double ss = 0.0;
+        for (int i = 0; i <= j; ++i) ss = fma(h[i], h[i], ss);
+        const double hn2 = ww - ss;
+        // <w,w> - sum h^2 carries an absolute error ~eps*<w,w>: below 1e-8*<w,w>
+        // the norm of the new direction is no longer reliable (it lies,
+        // numerically, inside the current space).  Keep the column with the
+        // best available norm, do not normalise w, and close the cycle: the
+        // next one restarts from the TRUE residual, which also decides
+        // convergence.
+        const bool bad = !(hn2 > 1e-8 * ww);
+        const double hn = hn2 > 0.0 ? sqrt(hn2) : 0.0;
+        gm[GM_INV] = (bad || hn == 0.0) ? 0.0 : 1.0 / hn;
+        // keep the raw column for the orthogonalisation kernel
+        for (int i = 0; i < nv_batch; ++i) gm[GM_HCOL + off + i] = h[off + i];
+        h[j + 1] = hn;
+        for (int i = 0; i < j; ++i) {
+            const double t = cs[i] * h[i] + sn[i] * h[i + 1];
+            h[i + 1] = -sn[i] * h[i] + cs[i] * h[i + 1];
+            h[i] = t;
+        }
+        const double den = hypot(h[j], h[j + 1]);
+        const double c_ = den > 0.0 ? h[j] / den : 1.0, s_ = den > 0.0 ? h[j + 1] / den : 0.0;
+        h[j] = den;
+        h[j + 1] = 0.0;
+        gm[GM_CS + j] = c_;
+        gm[GM_SN + j] = s_;
+        const double gj = sc[0];
+        gm[GM_G + j + 1] = -s_ * gj;
+        gm[GM_G + j] = c_ * gj;
+        const double rnorm = fabs(s_ * gj);
+        gm[GM_RNORM] = rnorm;
+        const int its = (int)sc[4] + 1;
+        gmi[GMI_ITS] = its;
+        const double tol = sc[1], ctol = sc[2];
+        int fin = 0, cyc = 0, reason = 0, noupd = 0;
+        if (!(rnorm == rnorm)) { fin = cyc = 1; reason = -9; noupd = 1; }
+        else if (bad) cyc = 1;
+        else if (rnorm <= tol && ctol <= tol) { fin = cyc = 1; reason = 2; }
+        else if (o.dtol > 0.0 && rnorm > o.dtol * sc[3]) { fin = cyc = 1; reason = -4; }
+        else if (its >= o.max_it) { fin = cyc = 1; reason = -3; }
+        else if (rnorm <= ctol || j == o.m - 1) cyc = 1;
+        dec[0] = cyc;
+        dec[1] = fin;
+        dec[2] = reason;
+        dec[3] = noupd;
+        sc[5] = rnorm;
+        if (!cyc) hs->iters_done = k;       // the common case: one word, no fence
+    }
+    __syncthreads();
+    // rotated column -> H (global), by all threads
+    for (int i = tid; i <= j + 1; i += blockDim.x) gm[GM_H + (size_t)j * KSFD_GM_LD + i] = h[i];
+    if (!dec[0]) return;
+    // the cycle ends: back substitution on the k x k triangle (packed in smem)
+    if (!dec[3]) {
+        __syncthreads();
+        for (int e = tid; e < k * (k + 1) / 2; e += blockDim.x) {
+            // e -> (col q, row i <= q), packed by columns
+            int q = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            while (q * (q + 1) / 2 > e) --q;
+            while ((q + 1) * (q + 2) / 2 <= e) ++q;
+            const int i = e - q * (q + 1) / 2;
+            Ht[e] = (q == j) ? h[i] : gm[GM_H + (size_t)q * KSFD_GM_LD + i];
+        }
+        for (int i = tid; i <= k; i += blockDim.x) gs[i] = gm[GM_G + i];
+        __syncthreads();
+        if (tid == 0) {
+            // g[j], g[j+1] were written above by this thread: use the values
+            gs[j] = gm[GM_G + j];
+            for (int i = k - 1; i >= 0; --i) {
+                double s = gs[i];
+                for (int q = i + 1; q < k; ++q) s -= Ht[q * (q + 1) / 2 + i] * y[q];
+                y[i] = s / Ht[i * (i + 1) / 2 + i];
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < k; i += blockDim.x) gm[GM_Y + i] = y[i];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        gmi[GMI_K] = k;
+        gmi[GMI_NOUPD] = dec[3];
+        gmi[GMI_REASON] = dec[2];
+        gmi[GMI_FINAL] = dec[1];
+        __threadfence();
+        gmi[GMI_CYCLE_DONE] = 1;
+        hs->rnorm = sc[5];
+        hs->its_total = gmi[GMI_ITS];
+        hs->reason = dec[2];
+        hs->final_ = dec[1];
+        hs->iters_done = k;
+        __threadfence_system();
+        hs->cycle_done = 1;
+    }
+}
+
+// w = (w - sum_i h[i]*V_i) * inv   with h, inv from the device state
+template <int NV>
+__global__ void __launch_bounds__(KSFD_RED_THREADS)
+k_gm_orth_scale(long long n, VecList vs, int off, int do_scale,
+                const double *__restrict__ gm, const int *__restrict__ gmi,
+                double *__restrict__ w)
+{
+    // the step that closed the cycle does not need its new basis vector
+    if (gmi[GMI_CYCLE_DONE]) return;
+    double hh[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) hh[i] = gm[GM_HCOL + off + i];
+    const double sc = do_scale ? gm[GM_INV] : 1.0;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+         e += (long long)gridDim.x * blockDim.x) {
+        double s = w[e];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) s = fma(-hh[i], __ldg(vs.v[i] + e), s);
+        w[e] = s * sc;
+    }
+}
+
+// r = sign*rhs - Ax (in place in ax) with the partial sums of <r,r>
+__global__ void __launch_bounds__(KSFD_RED_THREADS)
+k_gm_true_residual(long long n, const double *__restrict__ rhs, double sign,
+                   const int *__restrict__ gmi, double *__restrict__ ax,
+                   double *__restrict__ partial)
+{
+    if (gmi[GMI_FINAL]) return;
+    double acc[1] = {0.0};
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+         e += (long long)gridDim.x * blockDim.x) {
+        const double r = fma(sign, rhs[e], -ax[e]);
+        ax[e] = r;
+        acc[0] = fma(r, r, acc[0]);
+    }
+    block_reduce_store<1>(acc, partial, KSFD_RED_BLOCKS);
+}

@@ -65,6 +65,17 @@ struct ksfd_ctx {
     double *dscal = nullptr;     // device scalars (KSFD_NSCAL)
     double *hscal = nullptr;     // pinned host scalars (KSFD_NSCAL)
     void *plan_cache = nullptr;  // std::map<long long, MarchPlan>*
+    // pipelined GMRES: device state, pinned host-visible status
+    double *gm = nullptr;
+    int *gmi = nullptr;
+    void *gm_status = nullptr, *gm_status_dev = nullptr;   // GmStatus (mapped)
+    int gm_pipeline = 1, gm_runahead = 2;
+    // Single-pass classical Gram-Schmidt loses orthogonality like eps*kappa^2,
+    // kappa ~ the residual reduction inside the cycle, so a cycle is closed
+    // after this reduction and restarted from the TRUE residual (measured on
+    // the benchmark problem: with 1e-9 some stage solves need 20-80 iterations
+    // instead of 6)
+    double gm_cycle_factor = 1e-5;
     // solver workspace
     double *krylov = nullptr;    // (restart+1) vectors
     int krylov_cap = 0;
@@ -79,7 +90,8 @@ struct ksfd_ctx {
     int ksfd_march_residual_d##D(ksfd_ctx *c, VecRef u, const double *udot,           \
                                  const double *src, double *out, cudaStream_t st);    \
     int ksfd_march_jvp_d##D(ksfd_ctx *c, VecRef coef, VecRef v, VecRef pc,            \
-                            bool precond, double *out, cudaStream_t st);              \
+                            bool precond, double *out, const int *skip,           \
+                            cudaStream_t st);                                         \
     int ksfd_march_velocity_d##D(ksfd_ctx *c, VecRef u, double *vel, double *vmax,    \
                                  cudaStream_t st);
 KSFD_DECL_MARCH(2)

@@ -146,6 +146,9 @@ extern "C" int ksfd_ctx_destroy(ksfd_ctx *c)
     cudaFree(c->dscal);
     cudaFreeHost(c->hscal);
     cudaFree(c->krylov);
+    cudaFree(c->gm);
+    cudaFree(c->gmi);
+    if (c->gm_status) cudaFreeHost(c->gm_status);
     for (auto &w : c->work) cudaFree(w);
     ksfd_free_plans(c);
     delete c;
@@ -236,6 +239,9 @@ extern "C" int ksfd_set_option(ksfd_ctx *c, const char *key, int64_t v)
     if (k == "variant") c->variant = (int)v;
     else if (k == "tile") { c->opt_tx = (int)v; c->opt_tile_set = v >= 0; }
     else if (k == "rz") c->opt_rz = (int)v;
+    else if (k == "gmres_pipeline") c->gm_pipeline = (int)v;
+    else if (k == "gmres_cycle_exp") c->gm_cycle_factor = v <= 0 ? 0.0 : std::pow(10.0, -(double)v);
+    else if (k == "gmres_runahead") c->gm_runahead = (int)std::max<int64_t>(0, std::min<int64_t>(v, 8));
     else return fail("unknown option " + k);
     ksfd_invalidate_plans(c);
     return 0;
@@ -520,7 +526,7 @@ extern "C" int ksfd_block_diagonal(ksfd_ctx *c, double *blocks, void *stream)
 }
 
 static int jvp_impl(ksfd_ctx *c, const double *v, double *out, bool precond,
-                    cudaStream_t st)
+                    cudaStream_t st, const int *skip = nullptr)
 {
     if (!c->have_jac) return fail("ksfd_jvp_setup has not been called");
     if (v == out) return fail("ksfd_jvp: in-place application is not supported");
@@ -529,13 +535,13 @@ static int jvp_impl(ksfd_ctx *c, const double *v, double *out, bool precond,
     VecRef pr = make_ref(c, c->pc, 1, 2);
     VecRef cr = coef_ref(c);
     if (use_march(c)) {
-        return c->dim == 2 ? ksfd_march_jvp_d2(c, cr, vr, pr, precond, out, st)
-                           : ksfd_march_jvp_d3(c, cr, vr, pr, precond, out, st);
+        return c->dim == 2 ? ksfd_march_jvp_d2(c, cr, vr, pr, precond, out, skip, st)
+                           : ksfd_march_jvp_d3(c, cr, vr, pr, precond, out, skip, st);
     }
     InvD id;
     for (int l = 0; l < KSFD_MAX_LIGANDS; ++l) id.v[l] = c->invd[l];
     k_jvp_naive<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, cr, vr, pr, id,
-                                                      precond ? 1 : 0, c->shift, out);
+                                                      precond ? 1 : 0, c->shift, skip, out);
     CKL();
     return 0;
 }
@@ -846,8 +852,8 @@ static int cgs_fused_step(ksfd_ctx *c, int j, double *V, double *w, cudaStream_t
     return 0;
 }
 
-static int gmres_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x,
-                      const ksfd_ksp_opts &o, ksfd_ksp_result *res, cudaStream_t st)
+static int gmres_sync_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x,
+                           const ksfd_ksp_opts &o, ksfd_ksp_result *res, cudaStream_t st)
 {
     const long long n = nlocal(c);
     const int m = std::max(1, std::min(o.restart > 0 ? o.restart : 30, 60));
@@ -1000,6 +1006,224 @@ static int gmres_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x
         res->rnorm = rnorm;
     }
     return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Pipelined GMRES(m) (default): same algorithm as gmres_sync_impl (single-pass
+// classical Gram-Schmidt with the norm from <w,w> - |h|^2, cycles closed after
+// a 1e-5 reduction and restarted from the TRUE residual), but the Hessenberg /
+// Givens bookkeeping, the convergence tests and the back substitution run on
+// the device.  The host never synchronises the stream inside a solve: it polls
+// a pinned status word and launches up to `gm_runahead` Arnoldi steps ahead;
+// kernels launched past the end of a cycle return at once (skip flags).
+// With several ranks the run-ahead is 0, so that every rank issues the same
+// sequence of NCCL calls (decisions are taken from all-reduced, identical data).
+// ---------------------------------------------------------------------------
+static int gm_alloc(ksfd_ctx *c)
+{
+    if (c->gm) return 0;
+    CK(cudaMalloc(&c->gm, sizeof(double) * GM_DOUBLES));
+    CK(cudaMalloc(&c->gmi, sizeof(int) * GMI_INTS));
+    CK(cudaHostAlloc(&c->gm_status, sizeof(GmStatus), cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(&c->gm_status_dev, c->gm_status, 0));
+    memset(c->gm_status, 0, sizeof(GmStatus));
+    return 0;
+}
+
+// spin until pred() holds; fails if the stream dies or drains without it
+template <class Pred>
+static int gm_wait(cudaStream_t st, Pred pred, const char *what)
+{
+    for (unsigned long long spins = 0;; ++spins) {
+        if (pred()) return 0;
+        if ((spins & 0x3ff) == 0x3ff) {
+            cudaError_t e = cudaStreamQuery(st);
+            if (e == cudaSuccess) {
+                if (pred()) return 0;
+                return fail(std::string("pipelined GMRES stalled waiting for ") + what);
+            }
+            if (e != cudaErrorNotReady)
+                return fail(std::string("pipelined GMRES: ") + cudaGetErrorString(e));
+        }
+    }
+}
+
+template <int NV>
+static int gm_mdot_launch(ksfd_ctx *c, const VecList &vl, const double *w, cudaStream_t st)
+{
+    k_gm_mdot<NV><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(nlocal(c), vl, w, c->gmi,
+                                                                c->partial);
+    CKL();
+    return 0;
+}
+template <int NV>
+static int gm_orth_launch(ksfd_ctx *c, const VecList &vl, int off, int do_scale, double *w,
+                          cudaStream_t st)
+{
+    k_gm_orth_scale<NV><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(nlocal(c), vl, off,
+                                                                      do_scale, c->gm, c->gmi, w);
+    CKL();
+    return 0;
+}
+#define GM_SWITCH(m_, CALL)                      \
+    switch (m_) {                                \
+    case 1: TRY(CALL(1)); break;                 \
+    case 2: TRY(CALL(2)); break;                 \
+    case 3: TRY(CALL(3)); break;                 \
+    case 4: TRY(CALL(4)); break;                 \
+    case 5: TRY(CALL(5)); break;                 \
+    case 6: TRY(CALL(6)); break;                 \
+    case 7: TRY(CALL(7)); break;                 \
+    default: TRY(CALL(8)); break;                \
+    }
+
+// one Arnoldi step j of the pipeline (all launches, no host wait)
+static int gm_step(ksfd_ctx *c, int j, double *V, bool pre, const GmOpts &go, cudaStream_t st)
+{
+    const long long n = nlocal(c);
+    double *w = V + (long long)(j + 1) * n;
+    GmStatus *hsd = static_cast<GmStatus *>(c->gm_status_dev);
+    TRY(jvp_impl(c, V + (long long)j * n, w, pre, st, c->gmi + GMI_CYCLE_DONE));
+    const int nv = j + 2;                     // V_0..V_j and w itself
+    for (int b = 0; b < nv; b += KSFD_MAXV) {
+        const int m = std::min(KSFD_MAXV, nv - b);
+        const bool last = b + m >= nv;
+        VecList vl;
+        for (int i = 0; i < KSFD_MAXV; ++i) {
+            const int idx = b + std::min(i, m - 1);
+            vl.v[i] = (idx == j + 1) ? w : V + (long long)idx * n;
+        }
+#define GM_CALL_MDOT(N) gm_mdot_launch<N>(c, vl, w, st)
+        GM_SWITCH(m, GM_CALL_MDOT)
+#undef GM_CALL_MDOT
+        if (last && c->nranks == 1) {
+            k_gm_finalize<<<1, 256, 0, st>>>(m, b, j, KSFD_RED_BLOCKS, c->partial, c->gm, c->gmi,
+                                             hsd, go);
+            CKL();
+        } else {
+            k_gm_reduce<<<m, 128, 0, st>>>(m, b, KSFD_RED_BLOCKS, c->partial, c->gmi, c->gm);
+            CKL();
+        }
+    }
+    if (c->nranks > 1) {
+        TRY(allreduce_dev(c, c->gm + GM_HCOL, nv, ncclSum_, st));
+        k_gm_finalize<<<1, 32, 0, st>>>(0, 0, j, 0, c->partial, c->gm, c->gmi, hsd, go);
+        CKL();
+    }
+    const int no = j + 1;
+    for (int b = 0; b < no; b += KSFD_MAXV) {
+        const int m = std::min(KSFD_MAXV, no - b);
+        const bool last = b + m >= no;
+        VecList vl;
+        for (int i = 0; i < KSFD_MAXV; ++i)
+            vl.v[i] = V + (long long)(b + std::min(i, m - 1)) * n;
+#define GM_CALL_ORTH(N) gm_orth_launch<N>(c, vl, b, last ? 1 : 0, w, st)
+        GM_SWITCH(m, GM_CALL_ORTH)
+#undef GM_CALL_ORTH
+    }
+    return 0;
+}
+
+static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x,
+                           const ksfd_ksp_opts &o, ksfd_ksp_result *res, cudaStream_t st)
+{
+    const long long n = nlocal(c);
+    const int m = std::max(1, std::min(o.restart > 0 ? o.restart : 30, 60));
+    const bool pre = o.precond != 0;
+    if (c->krylov_cap < m + 1) {
+        cudaFree(c->krylov);
+        c->krylov = nullptr;
+        CK(cudaMalloc(&c->krylov, sizeof(double) * n * (m + 1)));
+        c->krylov_cap = m + 1;
+    }
+    TRY(ensure_work(c, 0));
+    TRY(gm_alloc(c));
+    double *V = c->krylov;
+    double *tmp = c->work[0];
+    GmStatus *hs = static_cast<GmStatus *>(c->gm_status);
+    GmStatus *hsd = static_cast<GmStatus *>(c->gm_status_dev);
+    GmOpts go{o.rtol, o.atol, o.dtol, o.max_it > 0 ? o.max_it : 10000, m, 0, c->gm_cycle_factor};
+    const int R = c->nranks > 1 ? 0 : c->gm_runahead;
+    InvD id;
+    for (int l = 0; l < KSFD_MAX_LIGANDS; ++l) id.v[l] = c->invd[l];
+
+    // the previous solve on this context has been waited for (see the end of
+    // this function), so the status block is ours
+    hs->seq = 0;
+    hs->iters_done = 0;
+    hs->cycle_done = hs->final_ = hs->reason = hs->its_total = 0;
+    CK(cudaMemsetAsync(c->gmi, 0, sizeof(int) * GMI_INTS, st));
+    CK(cudaMemsetAsync(x, 0, sizeof(double) * n, st));
+    for (int cycle = 0;; ++cycle) {
+        const double *r = rhs;
+        double sign = rhs_sign;
+        if (cycle == 0) {
+            VecList vl;
+            for (int i = 0; i < KSFD_MAXV; ++i) vl.v[i] = rhs;
+            k_mdot<1><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(n, vl, rhs, c->partial);
+            CKL();
+        } else {
+            // r = sign*rhs - A x   (true residual at restart)
+            TRY(jvp_impl(c, x, tmp, false, st, c->gmi + GMI_FINAL));
+            k_gm_true_residual<<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(
+                n, rhs, rhs_sign, c->gmi, tmp, c->partial);
+            CKL();
+            r = tmp;
+            sign = 1.0;
+        }
+        if (c->nranks == 1) {
+            k_gm_cycle_begin<<<1, 256, 0, st>>>(KSFD_RED_BLOCKS, c->partial, c->gm, c->gmi, hsd,
+                                                cycle, go);
+            CKL();
+        } else {
+            k_reduce_partials<<<1, 128, 0, st>>>(1, KSFD_RED_BLOCKS, c->partial,
+                                                 c->dscal + SC_NORM, 0);
+            CKL();
+            TRY(allreduce_dev(c, c->dscal + SC_NORM, 1, ncclSum_, st));
+            k_gm_cycle_begin<<<1, 32, 0, st>>>(1, c->dscal + SC_NORM, c->gm, c->gmi, hsd, cycle,
+                                               go);
+            CKL();
+        }
+        k_gm_first_vector<<<KSFD_RED_BLOCKS, 256, 0, st>>>(n, r, c->gm, c->gmi, sign, V);
+        CKL();
+        const int seq = 2 * cycle + 1;
+        for (int j = 0; j < m; ++j) {
+            // launch step j once step j-R-1 is known not to have closed the
+            // cycle; the first R+1 steps go out before the cycle has even begun
+            // on the device (they skip if it ends at once)
+            TRY(gm_wait(st, [&] {
+                if (hs->seq < seq) return j <= R;
+                return hs->cycle_done != 0 || hs->iters_done >= j - R;
+            }, "an Arnoldi step"));
+            if (hs->seq >= seq && hs->cycle_done) break;
+            TRY(gm_step(c, j, V, pre, go, st));
+        }
+        TRY(gm_wait(st, [&] { return hs->seq >= seq && hs->cycle_done; }, "the end of a cycle"));
+        if (hs->reason != -9 && hs->iters_done > 0) {
+            k_gm_update_x<<<nblk(c->g.npts, 128), 128, 0, st>>>(
+                c->g, c->P, coef_ref(c), id, c->pc, pre ? 1 : 0, n, V, c->gm + GM_Y,
+                c->gmi + GMI_K, c->gmi + GMI_NOUPD, x);
+            CKL();
+        }
+        if (hs->final_) break;
+    }
+    if (getenv("KSFD_DEBUG_GMRES"))
+        fprintf(stderr, "gmres: its %d reason %d rnorm0 %.3e rnorm %.3e\n", hs->its_total,
+                hs->reason, hs->rnorm0, hs->rnorm);
+    if (res) {
+        res->its = hs->its_total;
+        res->reason = hs->reason;
+        res->rnorm0 = hs->rnorm0;
+        res->rnorm = hs->rnorm;
+    }
+    return 0;
+}
+
+static int gmres_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x,
+                      const ksfd_ksp_opts &o, ksfd_ksp_result *res, cudaStream_t st)
+{
+    if (c->gm_pipeline && !o.reorth) return gmres_pipe_impl(c, rhs, rhs_sign, x, o, res, st);
+    return gmres_sync_impl(c, rhs, rhs_sign, x, o, res, st);
 }
 
 extern "C" int ksfd_gmres(ksfd_ctx *c, const double *rhs, double *x,

@@ -8,7 +8,7 @@
 
 template <int NLIG, bool PRECOND>
 static int launch_jvp_p(ksfd_ctx *c, VecRef coef, VecRef v, VecRef pc, double *out,
-                        cudaStream_t st)
+                        const int *skip, cudaStream_t st)
 {
     JvpOp<DIM, NLIG, PRECOND> op;
     op.coef = coef;
@@ -20,23 +20,24 @@ static int launch_jvp_p(ksfd_ctx *c, VecRef coef, VecRef v, VecRef pc, double *o
     const double cstage = PRECOND ? 45.0 : 30.0;
 #if KSFD_MARCH_DIM == 2
     return launch_op<DIM, JvpOp<DIM, NLIG, PRECOND>, true, 124, 1, 4, 252, 1, 2>(
-        c, op, PRECOND ? 2 : 3, cstage, 40.0 * DIM + 30.0, st);
+        c, op, PRECOND ? 2 : 3, cstage, 40.0 * DIM + 30.0, skip, st);
 #else
     return launch_op<DIM, JvpOp<DIM, NLIG, PRECOND>, true, 32, 8, 1, 16, 16, 1>(
-        c, op, PRECOND ? 2 : 3, cstage, 40.0 * DIM + 30.0, st);
+        c, op, PRECOND ? 2 : 3, cstage, 40.0 * DIM + 30.0, skip, st);
 #endif
 }
 
 template <int NLIG>
 static int launch_jvp(ksfd_ctx *c, VecRef coef, VecRef v, VecRef pc, bool precond,
-                      double *out, cudaStream_t st)
+                      double *out, const int *skip, cudaStream_t st)
 {
-    if (precond) return launch_jvp_p<NLIG, true>(c, coef, v, pc, out, st);
-    return launch_jvp_p<NLIG, false>(c, coef, v, pc, out, st);
+    if (precond) return launch_jvp_p<NLIG, true>(c, coef, v, pc, out, skip, st);
+    return launch_jvp_p<NLIG, false>(c, coef, v, pc, out, skip, st);
 }
 
 int KSFD_CAT(ksfd_march_jvp_d, KSFD_MARCH_DIM)(ksfd_ctx *c, VecRef coef, VecRef v, VecRef pc,
-                                               bool precond, double *out, cudaStream_t st)
+                                               bool precond, double *out, const int *skip,
+                                               cudaStream_t st)
 {
-    KSFD_DISPATCH_NLIG(launch_jvp, c, coef, v, pc, precond, out, st);
+    KSFD_DISPATCH_NLIG(launch_jvp, c, coef, v, pc, precond, out, skip, st);
 }

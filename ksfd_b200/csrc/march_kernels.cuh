@@ -644,8 +644,10 @@ constexpr size_t march_smem_bytes()
 template <int DIM, int TX, int TY, class Op, int MINB, bool UNR>
 __global__ void __launch_bounds__(TileT<DIM, TX, TY>::NT, MINB)
 k_march(const __grid_constant__ MarchArgs g, const __grid_constant__ DevPhys P,
-        const __grid_constant__ Op op)
+        const __grid_constant__ Op op, const int *__restrict__ skip)
 {
+    // pipelined Krylov solver: launched ahead of the convergence test
+    if (skip && *skip) return;
     Marcher<DIM, TX, TY, Op, UNR> m(g, P, op);
     m.run();
 }

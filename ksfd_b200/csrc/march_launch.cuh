@@ -117,12 +117,13 @@ static int tile_occupancy()
 }
 
 template <int DIM, int TX, int TY, class Op, int MINB, bool UNR>
-static int launch_tile(const ksfd_ctx *c, const Op &op, const MarchPlan &p, cudaStream_t st)
+static int launch_tile(const ksfd_ctx *c, const Op &op, const MarchPlan &p, const int *skip,
+                       cudaStream_t st)
 {
     using T = TileT<DIM, TX, TY>;
     auto kern = k_march<DIM, TX, TY, Op, MINB, UNR>;
     const size_t smem = march_smem_bytes<Op, T::SP>();
-    kern<<<p.grid, T::NT, smem, st>>>(p.a, c->P, op);
+    kern<<<p.grid, T::NT, smem, st>>>(p.a, c->P, op, skip);
     CKL();
     return 0;
 }
@@ -130,7 +131,7 @@ static int launch_tile(const ksfd_ctx *c, const Op &op, const MarchPlan &p, cuda
 // two tile candidates per operator: (AX, AY, AMINB) and (BX, BY, BMINB)
 template <int DIM, class Op, bool UNR, int AX, int AY, int AMINB, int BX, int BY, int BMINB>
 static int launch_op(ksfd_ctx *c, const Op &op, int opkey, double cstage, double cemit,
-                     cudaStream_t st)
+                     const int *skip, cudaStream_t st)
 {
     const long long maxel = (long long)(c->g.nloc + 2 * KSFD_SW) * c->g.plane_pts * (c->dof + 2);
     if (maxel >= (1LL << 31))
@@ -143,8 +144,8 @@ static int launch_op(ksfd_ctx *c, const Op &op, int opkey, double cstage, double
         return fail("marching kernel does not fit on this device");
     MarchPlan p = plan_march(c, opkey * 100 + DIM * 10 + Op::NF, cand, 2, cstage, cemit);
     if (p.tile < 0) return fail("no marching tile fits");
-    if (p.tile == 0) return launch_tile<DIM, AX, AY, Op, AMINB, UNR>(c, op, p, st);
-    return launch_tile<DIM, BX, BY, Op, BMINB, UNR>(c, op, p, st);
+    if (p.tile == 0) return launch_tile<DIM, AX, AY, Op, AMINB, UNR>(c, op, p, skip, st);
+    return launch_tile<DIM, BX, BY, Op, BMINB, UNR>(c, op, p, skip, st);
 }
 
 #define KSFD_DISPATCH_NLIG(FN, ...)                                        \

@@ -142,14 +142,14 @@ static void run_variant(const char *name, const Problem &pb, const DevPhys &P, O
         for (int i = 0; i < 3; ++i) {
             Op op = op_proto;
             bind(op, pb, i % pb.nrot);
-            kern<<<grid, T::NT, smem>>>(a, P, op);
+            kern<<<grid, T::NT, smem>>>(a, P, op, nullptr);
         }
         CHECK(cudaDeviceSynchronize());
         CHECK(cudaEventRecord(e0));
         for (int i = 0; i < reps; ++i) {
             Op op = op_proto;
             bind(op, pb, i % pb.nrot);
-            kern<<<grid, T::NT, smem>>>(a, P, op);
+            kern<<<grid, T::NT, smem>>>(a, P, op, nullptr);
         }
         CHECK(cudaEventRecord(e1));
         CHECK(cudaDeviceSynchronize());
