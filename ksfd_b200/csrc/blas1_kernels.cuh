@@ -306,6 +306,8 @@ struct GmStatus {
     volatile int seq;            // 2*cycle+1 once the cycle has begun
     volatile int iters_done;     // columns finished in the current cycle
     volatile int cycle_done, final_, reason, its_total;
+    volatile int k_cols;         // columns of the cycle that closed (valid with cycle_done)
+    volatile int pad_;
     volatile double rnorm, rnorm0;
 };
 
@@ -367,6 +369,7 @@ __global__ void k_gm_cycle_begin(int nblocks, const double *__restrict__ partial
     gmi[GMI_K] = 0;
     gmi[GMI_REASON] = reason;
     hs->iters_done = 0;
+    hs->k_cols = 0;
     hs->cycle_done = fin;
     hs->final_ = fin;
     hs->reason = reason;
@@ -546,13 +549,18 @@ __global__ void k_gm_finalize(int nv_batch, int off, int j, int nblocks,
         gmi[GMI_FINAL] = dec[1];
         __threadfence();
         gmi[GMI_CYCLE_DONE] = 1;
+        // order matters: a host that sees iters_done == k must also see
+        // cycle_done (with several ranks a step launched on one rank only
+        // would desynchronise their NCCL call sequences)
         hs->rnorm = sc[5];
         hs->its_total = gmi[GMI_ITS];
         hs->reason = dec[2];
         hs->final_ = dec[1];
-        hs->iters_done = k;
+        hs->k_cols = k;
         __threadfence_system();
         hs->cycle_done = 1;
+        __threadfence_system();
+        hs->iters_done = k;
     }
 }
 

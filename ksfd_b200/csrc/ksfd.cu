@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <dlfcn.h>
 #include <map>
 #include <string>
@@ -1032,11 +1033,22 @@ static int gm_alloc(ksfd_ctx *c)
 
 // spin until pred() holds; fails if the stream dies or drains without it
 template <class Pred>
-static int gm_wait(cudaStream_t st, Pred pred, const char *what)
+static int gm_wait(cudaStream_t st, Pred pred, const char *what, const ksfd_ctx *c = nullptr)
 {
+    time_t t0 = 0;
+    bool warned = false;
     for (unsigned long long spins = 0;; ++spins) {
         if (pred()) return 0;
         if ((spins & 0x3ff) == 0x3ff) {
+            if (!t0) t0 = time(nullptr);
+            if (!warned && time(nullptr) - t0 > 20) {
+                warned = true;
+                const GmStatus *hs = c ? static_cast<const GmStatus *>(c->gm_status) : nullptr;
+                fprintf(stderr, "ksfd_b200[rank %d]: GMRES pipeline waiting >20 s for %s "
+                        "(seq %d iters %d cycle_done %d final %d its %d)\n",
+                        c ? c->rank : -1, what, hs ? hs->seq : -1, hs ? hs->iters_done : -1,
+                        hs ? hs->cycle_done : -1, hs ? hs->final_ : -1, hs ? hs->its_total : -1);
+            }
             cudaError_t e = cudaStreamQuery(st);
             if (e == cudaSuccess) {
                 if (pred()) return 0;
@@ -1152,6 +1164,7 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
     hs->seq = 0;
     hs->iters_done = 0;
     hs->cycle_done = hs->final_ = hs->reason = hs->its_total = 0;
+    hs->k_cols = 0;
     CK(cudaMemsetAsync(c->gmi, 0, sizeof(int) * GMI_INTS, st));
     CK(cudaMemsetAsync(x, 0, sizeof(double) * n, st));
     for (int cycle = 0;; ++cycle) {
@@ -1187,20 +1200,43 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
         k_gm_first_vector<<<KSFD_RED_BLOCKS, 256, 0, st>>>(n, r, c->gm, c->gmi, sign, V);
         CKL();
         const int seq = 2 * cycle + 1;
-        for (int j = 0; j < m; ++j) {
-            // launch step j once step j-R-1 is known not to have closed the
-            // cycle; the first R+1 steps go out before the cycle has even begun
-            // on the device (they skip if it ends at once)
-            TRY(gm_wait(st, [&] {
-                if (hs->seq < seq) return j <= R;
-                return hs->cycle_done != 0 || hs->iters_done >= j - R;
-            }, "an Arnoldi step"));
-            if (hs->seq >= seq && hs->cycle_done) break;
-            TRY(gm_step(c, j, V, pre, go, st));
+        if (c->nranks == 1) {
+            for (int j = 0; j < m; ++j) {
+                // launch step j once step j-R-1 is known not to have closed the
+                // cycle; the first R+1 steps go out before the cycle has even
+                // begun on the device (they skip if it ends at once)
+                TRY(gm_wait(st, [&] {
+                    if (hs->seq < seq) return j <= R;
+                    return hs->cycle_done != 0 || hs->iters_done >= j - R;
+                }, "an Arnoldi step", c));
+                if (hs->seq >= seq && hs->cycle_done) break;
+                TRY(gm_step(c, j, V, pre, go, st));
+            }
+        } else {
+            // several ranks: every launch decision must be taken from the same
+            // data on all ranks, or their NCCL call sequences diverge.  Steps go
+            // out in chunks of `chunk`; the decision to launch the next chunk is
+            // taken only when the previous one has completely finished (its
+            // status is final and identical everywhere); steps of a chunk past
+            // the end of the cycle skip their kernels but still make their
+            // (matching) NCCL calls.
+            const int chunk = std::max(1, c->gm_runahead);
+            for (int j = 0; j < m; j += chunk) {
+                TRY(gm_wait(st, [&] {
+                    return hs->seq >= seq && (hs->cycle_done != 0 || hs->iters_done >= j);
+                }, "an Arnoldi chunk", c));
+                if (hs->cycle_done) break;
+                for (int jj = j; jj < std::min(j + chunk, m); ++jj)
+                    TRY(gm_step(c, jj, V, pre, go, st));
+            }
         }
-        TRY(gm_wait(st, [&] { return hs->seq >= seq && hs->cycle_done; }, "the end of a cycle"));
-        if (hs->reason != -9 && hs->iters_done > 0) {
-            k_gm_update_x<<<nblk(c->g.npts, 128), 128, 0, st>>>(
+        TRY(gm_wait(st, [&] { return hs->seq >= seq && hs->cycle_done; }, "the end of a cycle", c));
+        if (getenv("KSFD_DEBUG_GMRES"))
+            fprintf(stderr, "  cycle %d: seq %d iters %d cycle_done %d final %d reason %d its %d "
+                    "rnorm %.3e\n", cycle, hs->seq, hs->k_cols, hs->cycle_done, hs->final_,
+                    hs->reason, hs->its_total, hs->rnorm);
+        if (hs->reason != -9 && hs->k_cols > 0) {
+            k_gm_update_x<<<std::min(nblk(c->g.npts, 256), 148u * 8u), 256, 0, st>>>(
                 c->g, c->P, coef_ref(c), id, c->pc, pre ? 1 : 0, n, V, c->gm + GM_Y,
                 c->gmi + GMI_K, c->gmi + GMI_NOUPD, x);
             CKL();

@@ -303,36 +303,40 @@ __global__ void k_pc_apply(Geom g, DevPhys P, VecRef coef, InvD invd,
 // GMRES solution update at the end of a cycle (k, y on the device):
 //   x += M^{-1} (sum_{i<k} y_i V_i)   or   x += sum_{i<k} y_i V_i
 // gm_y = y, gmi_k = &k, gmi_skip = &no-update flag
-__global__ void k_gm_update_x(Geom g, DevPhys P, VecRef coef, InvD invd,
-                              const double *__restrict__ pc, int precond, long long n,
-                              const double *__restrict__ V, const double *__restrict__ gm_y,
-                              const int *__restrict__ gmi_k, const int *__restrict__ gmi_skip,
-                              double *__restrict__ x)
+__global__ void __launch_bounds__(256)
+k_gm_update_x(Geom g, DevPhys P, VecRef coef, InvD invd, const double *__restrict__ pc,
+              int precond, long long n, const double *__restrict__ V,
+              const double *__restrict__ gm_y, const int *__restrict__ gmi_k,
+              const int *__restrict__ gmi_skip, double *__restrict__ x)
 {
     if (*gmi_skip) return;
     __shared__ double y[64];
     const int k = *gmi_k;
     for (int i = threadIdx.x; i < k; i += blockDim.x) y[i] = gm_y[i];
     __syncthreads();
-    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (p >= g.npts) return;
-    PointIdx q = decode_point(g, p);
-    double rr[KSFD_MAX_LIGANDS + 1], zz[KSFD_MAX_LIGANDS + 1];
-    for (int c = 0; c < g.dof; ++c) {
-        const long long e = el(g, q, c, g.dof);
-        double s = 0.0;
-        for (int i = 0; i < k; ++i) s = fma(y[i], V[(long long)i * n + e], s);
-        rr[c] = s;
+    const int fs = (int)g.plane_pts, dof = g.dof;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < (int)g.npts;
+         p += gridDim.x * blockDim.x) {
+        const int kp = p / fs, pp = p - kp * fs;
+        const int e0 = kp * dof * fs + pp;          // field c of this point: e0 + c*fs
+        double rr[KSFD_MAX_LIGANDS + 1], zz[KSFD_MAX_LIGANDS + 1];
+        for (int c = 0; c < dof; ++c) rr[c] = 0.0;
+        for (int i = 0; i < k; ++i) {
+            const double *vi = V + (long long)i * n + e0;
+            const double yi = y[i];
+            for (int c = 0; c < dof; ++c) rr[c] = fma(yi, __ldg(vi + c * fs), rr[c]);
+        }
+        if (precond) {
+            // coef is ghosted by KSFD_SW planes along the last axis
+            const double *c0 = coef.base + ((long long)kp * (dof + 2)) * fs + pp;
+            double gU[KSFD_MAX_LIGANDS];
+            for (int l = 0; l < P.nlig; ++l) gU[l] = __ldg(c0 + (3 + l) * fs);
+            pc_point_rt(P, invd, __ldg(c0), gU, __ldg(pc + p), rr, zz);
+        } else {
+            for (int c = 0; c < dof; ++c) zz[c] = rr[c];
+        }
+        for (int c = 0; c < dof; ++c) x[e0 + c * fs] += zz[c];
     }
-    if (precond) {
-        PtRef c0 = nbr(g, coef, q, 0, 0, g.dof + 2);
-        double gU[KSFD_MAX_LIGANDS];
-        for (int l = 0; l < P.nlig; ++l) gU[l] = c0[3 + l];
-        pc_point_rt(P, invd, c0[0], gU, pc[p], rr, zz);
-    } else {
-        for (int c = 0; c < g.dof; ++c) zz[c] = rr[c];
-    }
-    for (int c = 0; c < g.dof; ++c) x[el(g, q, c, g.dof)] += zz[c];
 }
 
 // out = (shift*I - J(u_lin)) * v   (optionally v := M^{-1} v first)

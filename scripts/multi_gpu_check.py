@@ -41,6 +41,7 @@ def main():
         uu = u.clone(); t, h = 0.0, 1e-6
         for k in range(3):
             ctx.groom(uu); r = ctx.ts_step(uu, t, h, opts); t, h = r.t_new, r.h_next
+            assert r.accepted == 1 and r.ksp_fail == 0, ('multi-rank step failed', dim, n, k, r.ksp_its)
         us = ctx.download(uu)
         ctx.close()
         if rank == 0:
@@ -54,6 +55,7 @@ def main():
             uu1 = U.clone(); t1, h1 = 0.0, 1e-6
             for k in range(3):
                 c1.groom(uu1); r1 = c1.ts_step(uu1, t1, h1, opts); t1, h1 = r1.t_new, r1.h_next
+                assert r1.accepted == 1 and r1.ksp_fail == 0, ('single-rank step failed', dim, n, k)
             us1 = c1.download(uu1)
             c1.close()
             def rel(a, b): return float(np.abs(a - b).max() / np.abs(b).max())
