@@ -162,8 +162,11 @@ def reference_arm(args):
                 ms_per_step=1e3 * cb['seconds'] / max(args.steps, 1),
                 higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f64', data='synthetic',
-                config=dict(workload='2-D %dx%d tile per core, dof 3, options84 physics, '
-                                     'h=1/384, dt=1e-3, ROSW ra34pw2 + direct LU' % (n, n)),
+                config=dict(workload='2-D %dx%d tile per GPU (global %dx%d), dof 3, options84 physics, '
+                                     'h=1/384, dt=1e-3, ROSW ra34pw2; CPU arm: direct LU (SuperLU) instead '
+                                     'of GMRES, each step a bounded sample = one %dx%d tile per core'
+                                     % (TILE, TILE, TILE, TILE * max(args.gpus, 1), n, n),
+                            parallelism='%d host cores, independent tiles' % procs),
                 cpu_baseline=dict(value=cb['value'], unit=cb['unit'], cores=procs,
                                   kind='port', sample=cb['sample']),
                 e2e=dict(value=cb['value'], unit='Mpts*steps/s',
@@ -376,7 +379,7 @@ def main():
         faulthandler.dump_traceback_later(float(wd), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--quick', action='store_true', help='skip the 256^3 kernel timings')

@@ -107,6 +107,33 @@ struct InCursor {
     }
 };
 
+// Where the loads of a plane go.  RegSink: straight into registers (__ldg).
+// AsyncSink: cp.async into this lane's column of a shared-memory pipeline slot
+// (several planes in flight per thread without holding registers; the values
+// are read back by the same thread after cp.async.wait_group).
+struct RegSink {
+    double *r;
+    __device__ __forceinline__ void put(int c, const double *p) const { r[c] = __ldg(p); }
+};
+struct AsyncSink {
+    unsigned addr;              // shared-space byte address of field 0 of this lane
+    int stride;                 // bytes between fields
+    __device__ __forceinline__ void put(int c, const double *p) const
+    {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(addr + c * stride), "l"(p)
+                     : "memory");
+    }
+};
+__device__ __forceinline__ void cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // stencil access of one interior lane at emit time.  PH = phase of the
 // unrolled plane loop: plane kk (newest) sits in q[.][PH], plane kk-4+s in
 // q[.][(PH+1+s)%5], the centre plane kk-2 in q[.][(PH+3)%5].
@@ -240,6 +267,7 @@ struct ResidualOp {
     static constexpr int NF = NLIG + 2;        // rho, G, U_l
     static constexpr int NPRE = NLIG + 1;
     static constexpr int NAUX = NLIG + 1;      // udot of the output plane
+    static constexpr bool HAS_AUX = true;
     static constexpr bool TABS = true;
     VecRef u;
     const double *udot, *src;
@@ -248,6 +276,7 @@ struct ResidualOp {
         InCursor in;
         int e;                                 // element index of the next output
     };
+    __device__ static constexpr int out_fields(int) { return NLIG + 1; }
 
     __device__ __forceinline__ void init(const MarchArgs &g, State &st, int kfirst, int k0,
                                          int poff) const
@@ -255,19 +284,22 @@ struct ResidualOp {
         st.in.init(u, kfirst, g.nloc, g.fs * (NLIG + 1), poff);
         st.e = k0 * (NLIG + 1) * g.fs + poff;
     }
+    template <class Sink>
     __device__ __forceinline__ void load(const MarchArgs &g, State &st, int k, int poff,
-                                         double *pre) const
+                                         const Sink &sink) const
     {
 #pragma unroll
-        for (int c = 0; c < NLIG + 1; ++c) pre[c] = __ldg(st.in.p + c * g.fs);
+        for (int c = 0; c < NLIG + 1; ++c) sink.put(c, st.in.p + c * g.fs);
         st.in.next(u, k, g.nloc, g.fs * (NLIG + 1), poff);
     }
-    __device__ __forceinline__ void load_aux(const MarchArgs &g, const State &st,
-                                             double *aux) const
+    // udot of output plane ko (element index e of this lane), fields [off, off+NAUX)
+    template <class Sink>
+    __device__ __forceinline__ void load_aux(const MarchArgs &g, int e, int off,
+                                             const Sink &sink) const
     {
         if (FIXED || udot) {
 #pragma unroll
-            for (int c = 0; c < NLIG + 1; ++c) aux[c] = __ldg(udot + (st.e + c * g.fs));
+            for (int c = 0; c < NLIG + 1; ++c) sink.put(off + c, udot + (e + c * g.fs));
         }
     }
     template <class TA>
@@ -335,6 +367,7 @@ struct JvpOp {
     static constexpr int NF = NLIG + 4;   // z_rho, dG, z_U.., rho, G
     static constexpr int NPRE = (NLIG + 3) + (NLIG + 1) + (PRECOND ? 1 : 0);
     static constexpr int NAUX = 1;
+    static constexpr bool HAS_AUX = false;
     static constexpr bool TABS = false;
     VecRef coef, v, pc;
     double shift;
@@ -344,6 +377,7 @@ struct JvpOp {
         InCursor ic, iv, ip;
         int e;
     };
+    __device__ static constexpr int out_fields(int) { return NLIG + 1; }
 
     __device__ __forceinline__ void init(const MarchArgs &g, State &st, int kfirst, int k0,
                                          int poff) const
@@ -353,20 +387,21 @@ struct JvpOp {
         if (PRECOND) st.ip.init(pc, kfirst, g.nloc, g.fs, poff);
         st.e = k0 * (NLIG + 1) * g.fs + poff;
     }
+    template <class Sink>
     __device__ __forceinline__ void load(const MarchArgs &g, State &st, int k, int poff,
-                                         double *pre) const
+                                         const Sink &sink) const
     {
 #pragma unroll
-        for (int c = 0; c < NLIG + 3; ++c) pre[c] = __ldg(st.ic.p + c * g.fs);
+        for (int c = 0; c < NLIG + 3; ++c) sink.put(c, st.ic.p + c * g.fs);
 #pragma unroll
-        for (int c = 0; c < NLIG + 1; ++c) pre[NLIG + 3 + c] = __ldg(st.iv.p + c * g.fs);
-        if (PRECOND) pre[2 * NLIG + 4] = __ldg(st.ip.p);
+        for (int c = 0; c < NLIG + 1; ++c) sink.put(NLIG + 3 + c, st.iv.p + c * g.fs);
+        if (PRECOND) sink.put(2 * NLIG + 4, st.ip.p);
         st.ic.next(coef, k, g.nloc, g.fs * (NLIG + 3), poff);
         st.iv.next(v, k, g.nloc, g.fs * (NLIG + 1), poff);
         if (PRECOND) st.ip.next(pc, k, g.nloc, g.fs, poff);
     }
-    __device__ __forceinline__ void load_aux(const MarchArgs &, const State &,
-                                             double *) const {}
+    template <class Sink>
+    __device__ __forceinline__ void load_aux(const MarchArgs &, int, int, const Sink &) const {}
     template <class TA>
     __device__ __forceinline__ void stage(const DevPhys &P, const TA &, const double *pre,
                                           double *f) const
@@ -432,6 +467,7 @@ struct VelocityOp {
     static constexpr int NF = 1;
     static constexpr int NPRE = NLIG + 1;
     static constexpr int NAUX = 1;
+    static constexpr bool HAS_AUX = false;
     static constexpr bool TABS = true;
     VecRef u;
     double *vel;        // optional plane-SoA output with DIM fields
@@ -441,6 +477,7 @@ struct VelocityOp {
         int e;
         double vm[3];
     };
+    __device__ static constexpr int out_fields(int dim) { return dim; }
 
     __device__ __forceinline__ void init(const MarchArgs &g, State &st, int kfirst, int k0,
                                          int poff) const
@@ -449,15 +486,16 @@ struct VelocityOp {
         st.e = k0 * DIM * g.fs + poff;
         st.vm[0] = st.vm[1] = st.vm[2] = 0.0;
     }
+    template <class Sink>
     __device__ __forceinline__ void load(const MarchArgs &g, State &st, int k, int poff,
-                                         double *pre) const
+                                         const Sink &sink) const
     {
 #pragma unroll
-        for (int c = 0; c < NLIG + 1; ++c) pre[c] = __ldg(st.in.p + c * g.fs);
+        for (int c = 0; c < NLIG + 1; ++c) sink.put(c, st.in.p + c * g.fs);
         st.in.next(u, k, g.nloc, g.fs * (NLIG + 1), poff);
     }
-    __device__ __forceinline__ void load_aux(const MarchArgs &, const State &,
-                                             double *) const {}
+    template <class Sink>
+    __device__ __forceinline__ void load_aux(const MarchArgs &, int, int, const Sink &) const {}
     template <class TA>
     __device__ __forceinline__ void stage(const DevPhys &P, const TA &T, const double *pre,
                                           double *f) const
@@ -500,19 +538,30 @@ struct VelocityOp {
 // ---------------------------------------------------------------------------
 // UNR: unroll the plane loop five times (queue rotates by register renaming);
 // otherwise the queue is shifted with moves (smaller code, fewer registers).
-template <int DIM, int TX, int TY, class Op, bool UNR>
+// DEPTH: 0 = the next plane is prefetched into registers (one plane in flight);
+// 3 = planes are fetched with cp.async into a 4-slot shared-memory pipeline per
+// lane, three planes in flight and no registers held across iterations (a CTA
+// handling few planes is otherwise bound by one DRAM round trip per plane).
+// The auxiliary fields of the OUTPUT plane (udot of plane kk-2) travel in the
+// group of plane kk.
+template <int DIM, int TX, int TY, class Op, bool UNR, int DEPTH>
 struct Marcher {
     using T = TileT<DIM, TX, TY>;
     static constexpr int NF = Op::NF, NPRE = Op::NPRE, NAUX = Op::NAUX;
-    static constexpr int RING = 2 * NF * T::SP;     // doubles; tables follow
+    static constexpr int RING = 2 * NF * T::SP;     // doubles; tables follow, then the pipeline
+    static constexpr int TABS = Op::TABS ? KSFD_TAB_DOUBLES : 0;
+    static constexpr int NIN = NPRE + (Op::HAS_AUX ? NAUX : 0);
+    static constexpr int NSLOT = DEPTH + 1;
+    static constexpr int PIPE = RING + TABS;        // index of the pipeline in ksfd_smem
     const MarchArgs &g;
     const DevPhys &P;
     const Op &op;
     double q[NF][5];
-    double pre[NPRE];
+    double pre[DEPTH == 0 ? NPRE : 1];
     double aux[NAUX];
     typename Op::State st;
-    int poff, spos, k0, k1;
+    int poff, spos, k0, k1, it, e_aux;
+    unsigned pipe_addr;         // shared byte address of pipeline slot 0, field 0, this lane
     bool active, emits;
 
     __device__ __forceinline__ Marcher(const MarchArgs &g_, const DevPhys &P_, const Op &op_)
@@ -526,6 +575,7 @@ struct Marcher {
                     (long long)(i < 256 ? g_log_tab[i] : g_exp_tab[i - 256]));
             __syncthreads();
         }
+        pipe_addr = (unsigned)__cvta_generic_to_shared(ksfd_smem + PIPE + tid);
         const int i0 = blockIdx.x * g.ox;
         int x, y = 0;               // tile-relative position incl. halo
         bool interior;
@@ -566,19 +616,48 @@ struct Marcher {
         }
         k0 = blockIdx.z * g.rz;
         k1 = min(k0 + g.rz, g.nloc);
+        it = 0;
 #pragma unroll
         for (int f = 0; f < NF; ++f)
 #pragma unroll
             for (int s = 0; s < 5; ++s) q[f][s] = 0.0;
     }
 
+    // fetch plane k (and the aux fields of output plane k-2) into pipeline slot
+    // `slot`; always commits a group so that group counting stays uniform
+    __device__ __forceinline__ void issue(int k, int slot)
+    {
+        if (k < k1 + KSFD_SW) {
+            AsyncSink sink{pipe_addr + (unsigned)(slot * NIN * T::NT * 8), T::NT * 8};
+            if (active) op.load(g, st, k, poff, sink);
+            if (Op::HAS_AUX && emits && k - KSFD_SW >= k0) {
+                op.load_aux(g, e_aux, NPRE, sink);
+                e_aux += Op::out_fields(DIM) * g.fs;
+            }
+        }
+        cp_async_commit();
+    }
+
     template <int PH>
     __device__ __forceinline__ void step(int kk)
     {
         double cur[NPRE];
+        if (DEPTH == 0) {
 #pragma unroll
-        for (int c = 0; c < NPRE; ++c) cur[c] = pre[c];
-        if (active && kk + 1 < k1 + KSFD_SW) op.load(g, st, kk + 1, poff, pre);
+            for (int c = 0; c < NPRE; ++c) cur[c] = pre[c];
+            if (active && kk + 1 < k1 + KSFD_SW) op.load(g, st, kk + 1, poff, RegSink{pre});
+        } else {
+            cp_async_wait<DEPTH - 1>();             // the group of plane kk has landed
+            const int base = PIPE + (it & (NSLOT - 1)) * NIN * T::NT + threadIdx.x;
+#pragma unroll
+            for (int c = 0; c < NPRE; ++c) cur[c] = ksfd_smem[base + c * T::NT];
+            if (Op::HAS_AUX) {
+#pragma unroll
+                for (int c = 0; c < NAUX; ++c) aux[c] = ksfd_smem[base + (NPRE + c) * T::NT];
+            }
+            issue(kk + DEPTH, (it + DEPTH) & (NSLOT - 1));
+            ++it;
+        }
         if (active) {
             double f[NF];
             op.stage(P, SmemTabs<RING>(), cur, f);
@@ -586,8 +665,11 @@ struct Marcher {
             for (int c = 0; c < NF; ++c) q[c][PH] = f[c];
         }
         if (kk - KSFD_SW >= k0) {                       // uniform over the CTA
-            // after the register-hungry stage; the barrier wait hides the latency
-            if (emits) op.load_aux(g, st, aux);
+            if (DEPTH == 0 && Op::HAS_AUX && emits) {
+                // after the register-hungry stage; the barrier wait hides some latency
+                op.load_aux(g, e_aux, 0, RegSink{aux});
+                e_aux += Op::out_fields(DIM) * g.fs;
+            }
             const int ri = (kk & 1) * (NF * T::SP) + spos;
             if (active) {
 #pragma unroll
@@ -604,10 +686,17 @@ struct Marcher {
 
     __device__ __forceinline__ void run()
     {
+        static_assert(DEPTH == 0 || (NSLOT & (NSLOT - 1)) == 0, "pipeline slots: power of two");
         int kk = k0 - KSFD_SW;
         const int kend = k1 + KSFD_SW;
         op.init(g, st, kk, k0, poff);
-        if (active) op.load(g, st, kk, poff, pre);
+        e_aux = k0 * Op::out_fields(DIM) * g.fs + poff;
+        if (DEPTH == 0) {
+            if (active) op.load(g, st, kk, poff, RegSink{pre});
+        } else {
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) issue(kk + d, d);
+        }
         if (!UNR) {
             for (; kk < kend; ++kk) {
                 step<4>(kk);
@@ -631,23 +720,26 @@ struct Marcher {
                 if (++kk >= kend) break;
             }
         }
+        if (DEPTH > 0) cp_async_wait<0>();
         op.finish(st);
     }
 };
 
-template <class Op, int SP>
+template <class Op, int SP, int NT, int DEPTH>
 constexpr size_t march_smem_bytes()
 {
-    return sizeof(double) * (2 * Op::NF * SP + (Op::TABS ? KSFD_TAB_DOUBLES : 0));
+    return sizeof(double) * (2 * Op::NF * SP + (Op::TABS ? KSFD_TAB_DOUBLES : 0) +
+                             (DEPTH > 0 ? (DEPTH + 1) * (Op::NPRE + (Op::HAS_AUX ? Op::NAUX : 0)) * NT
+                                        : 0));
 }
 
-template <int DIM, int TX, int TY, class Op, int MINB, bool UNR>
+template <int DIM, int TX, int TY, class Op, int MINB, bool UNR, int DEPTH>
 __global__ void __launch_bounds__(TileT<DIM, TX, TY>::NT, MINB)
 k_march(const __grid_constant__ MarchArgs g, const __grid_constant__ DevPhys P,
         const __grid_constant__ Op op, const int *__restrict__ skip)
 {
     // pipelined Krylov solver: launched ahead of the convergence test
     if (skip && *skip) return;
-    Marcher<DIM, TX, TY, Op, UNR> m(g, P, op);
+    Marcher<DIM, TX, TY, Op, UNR, DEPTH> m(g, P, op);
     m.run();
 }

@@ -92,14 +92,14 @@ static MarchPlan plan_march(ksfd_ctx *c, long long key, const TileCand *cand, in
     return p;
 }
 
-template <int DIM, int TX, int TY, class Op, int MINB, bool UNR>
+template <int DIM, int TX, int TY, class Op, int MINB, bool UNR, int DEPTH>
 static int tile_occupancy()
 {
     static int occ = -1;
     if (occ >= 0) return occ;
     using T = TileT<DIM, TX, TY>;
-    auto kern = k_march<DIM, TX, TY, Op, MINB, UNR>;
-    const size_t smem = march_smem_bytes<Op, T::SP>();
+    auto kern = k_march<DIM, TX, TY, Op, MINB, UNR, DEPTH>;
+    const size_t smem = march_smem_bytes<Op, T::SP, T::NT, DEPTH>();
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess) {
         cudaGetLastError();
@@ -116,20 +116,21 @@ static int tile_occupancy()
     return occ;
 }
 
-template <int DIM, int TX, int TY, class Op, int MINB, bool UNR>
+template <int DIM, int TX, int TY, class Op, int MINB, bool UNR, int DEPTH>
 static int launch_tile(const ksfd_ctx *c, const Op &op, const MarchPlan &p, const int *skip,
                        cudaStream_t st)
 {
     using T = TileT<DIM, TX, TY>;
-    auto kern = k_march<DIM, TX, TY, Op, MINB, UNR>;
-    const size_t smem = march_smem_bytes<Op, T::SP>();
+    auto kern = k_march<DIM, TX, TY, Op, MINB, UNR, DEPTH>;
+    const size_t smem = march_smem_bytes<Op, T::SP, T::NT, DEPTH>();
     kern<<<p.grid, T::NT, smem, st>>>(p.a, c->P, op, skip);
     CKL();
     return 0;
 }
 
 // two tile candidates per operator: (AX, AY, AMINB) and (BX, BY, BMINB)
-template <int DIM, class Op, bool UNR, int AX, int AY, int AMINB, int BX, int BY, int BMINB>
+template <int DIM, class Op, bool UNR, int DEPTH, int AX, int AY, int AMINB, int BX, int BY,
+          int BMINB>
 static int launch_op(ksfd_ctx *c, const Op &op, int opkey, double cstage, double cemit,
                      const int *skip, cudaStream_t st)
 {
@@ -138,14 +139,14 @@ static int launch_op(ksfd_ctx *c, const Op &op, int opkey, double cstage, double
         return fail("rank-local slab too large for the 32-bit indexed kernels; "
                     "decompose over more ranks");
     TileCand cand[2] = {
-        {AX, AY, TileT<DIM, AX, AY>::NT, tile_occupancy<DIM, AX, AY, Op, AMINB, UNR>()},
-        {BX, BY, TileT<DIM, BX, BY>::NT, tile_occupancy<DIM, BX, BY, Op, BMINB, UNR>()}};
+        {AX, AY, TileT<DIM, AX, AY>::NT, tile_occupancy<DIM, AX, AY, Op, AMINB, UNR, DEPTH>()},
+        {BX, BY, TileT<DIM, BX, BY>::NT, tile_occupancy<DIM, BX, BY, Op, BMINB, UNR, DEPTH>()}};
     if (cand[0].occ == 0 && cand[1].occ == 0)
         return fail("marching kernel does not fit on this device");
     MarchPlan p = plan_march(c, opkey * 100 + DIM * 10 + Op::NF, cand, 2, cstage, cemit);
     if (p.tile < 0) return fail("no marching tile fits");
-    if (p.tile == 0) return launch_tile<DIM, AX, AY, Op, AMINB, UNR>(c, op, p, skip, st);
-    return launch_tile<DIM, BX, BY, Op, BMINB, UNR>(c, op, p, skip, st);
+    if (p.tile == 0) return launch_tile<DIM, AX, AY, Op, AMINB, UNR, DEPTH>(c, op, p, skip, st);
+    return launch_tile<DIM, BX, BY, Op, BMINB, UNR, DEPTH>(c, op, p, skip, st);
 }
 
 #define KSFD_DISPATCH_NLIG(FN, ...)                                        \

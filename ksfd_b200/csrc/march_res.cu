@@ -12,10 +12,10 @@ static int launch_residual_f(ksfd_ctx *c, VecRef u, const double *udot, const do
 {
     ResidualOp<DIM, NLIG, FIXED> op{u, udot, src, out};
 #if KSFD_MARCH_DIM == 2
-    return launch_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 124, 1, 6, 252, 1, 3>(
+    return launch_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 0, 124, 1, 6, 252, 1, 3>(
         c, op, FIXED ? 1 : 5, 150.0, 35.0 * DIM + 30.0, nullptr, st);
 #else
-    return launch_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 16, 16, 2, 32, 16, 1>(
+    return launch_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 0, 16, 16, 2, 32, 16, 1>(
         c, op, FIXED ? 1 : 5, 150.0, 35.0 * DIM + 30.0, nullptr, st);
 #endif
 }

@@ -11,10 +11,10 @@ static int launch_velocity(ksfd_ctx *c, VecRef u, double *vel, double *vmax, cud
 {
     VelocityOp<DIM, NLIG> op{u, vel, vmax};
 #if KSFD_MARCH_DIM == 2
-    return launch_op<DIM, VelocityOp<DIM, NLIG>, false, 124, 1, 6, 252, 1, 3>(
+    return launch_op<DIM, VelocityOp<DIM, NLIG>, false, 0, 124, 1, 6, 252, 1, 3>(
         c, op, 4, 150.0, 8.0 * DIM + 10.0, nullptr, st);
 #else
-    return launch_op<DIM, VelocityOp<DIM, NLIG>, false, 16, 16, 2, 32, 16, 1>(
+    return launch_op<DIM, VelocityOp<DIM, NLIG>, false, 0, 16, 16, 2, 32, 16, 1>(
         c, op, 4, 150.0, 8.0 * DIM + 10.0, nullptr, st);
 #endif
 }

@@ -101,7 +101,7 @@ static bool selected()
     return false;
 }
 
-template <int DIM, int TX, int TY, class Op, int MINB, bool UNR>
+template <int DIM, int TX, int TY, class Op, int MINB, bool UNR, int DEPTH>
 static void run_variant(const char *name, const Problem &pb, const DevPhys &P, Op op_proto,
                         void (*bind)(Op &, const Problem &, int), const int *rzs, int nrz)
 {
@@ -109,8 +109,8 @@ static void run_variant(const char *name, const Problem &pb, const DevPhys &P, O
     const int ord = g_ordinal;
     if (!selected()) return;
     if (getenv("TUNE_ONLY")) nrz = 1;
-    auto kern = k_march<DIM, TX, TY, Op, MINB, UNR>;
-    const size_t smem = march_smem_bytes<Op, T::SP>();
+    auto kern = k_march<DIM, TX, TY, Op, MINB, UNR, DEPTH>;
+    const size_t smem = march_smem_bytes<Op, T::SP, T::NT, DEPTH>();
     CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T::NT, smem));
@@ -157,8 +157,8 @@ static void run_variant(const char *name, const Problem &pb, const DevPhys &P, O
         CHECK(cudaEventElapsedTime(&ms, e0, e1));
         const double us = ms * 1e3 / reps;
         const double gpts = pb.npts / us / 1e3;
-        printf("#%02d %-12s TX%3d TY%2d MINB%d UNR%d regs%3d occ%d rz%4d grid %4dx%3dx%4d  %9.2f us  %6.2f Gpts/s  frac %.3f\n",
-               ord, name, TX, TY, MINB, (int)UNR, fa.numRegs, occ, rz, ntx, nty, nch, us, gpts,
+        printf("#%02d %-12s TX%3d TY%2d MINB%d UNR%d D%d regs%3d occ%d rz%4d grid %4dx%3dx%4d  %9.2f us  %6.2f Gpts/s  frac %.3f\n",
+               ord, name, TX, TY, MINB, (int)UNR, DEPTH, fa.numRegs, occ, rz, ntx, nty, nch, us, gpts,
                gpts * 72.0 / 6544.7);
     }
     fflush(stdout);
@@ -234,14 +234,14 @@ static void free_problem(Problem &pb)
     cudaFree(pb.pc);
 }
 
-#define RES2(TX, MINB, UNR) \
-    run_variant<2, TX, 1, ResidualOp<2, 2, true>, MINB, UNR>("residual2d", pb, P, ResidualOp<2, 2, true>{}, bind_res<2>, rzs, nrz)
-#define JVP2(TX, MINB, UNR, PC) \
-    run_variant<2, TX, 1, JvpOp<2, 2, PC>, MINB, UNR>(PC ? "jvp_pc2d" : "jvp2d", pb, P, JvpOp<2, 2, PC>{}, bind_jvp<2, PC>, rzs, nrz)
-#define RES3(TX, TY, MINB, UNR) \
-    run_variant<3, TX, TY, ResidualOp<3, 2, true>, MINB, UNR>("residual3d", pb, P, ResidualOp<3, 2, true>{}, bind_res<3>, rzs, nrz)
-#define JVP3(TX, TY, MINB, UNR, PC) \
-    run_variant<3, TX, TY, JvpOp<3, 2, PC>, MINB, UNR>(PC ? "jvp_pc3d" : "jvp3d", pb, P, JvpOp<3, 2, PC>{}, bind_jvp<3, PC>, rzs, nrz)
+#define RES2(TX, MINB, UNR, D) \
+    run_variant<2, TX, 1, ResidualOp<2, 2, true>, MINB, UNR, D>("residual2d", pb, P, ResidualOp<2, 2, true>{}, bind_res<2>, rzs, nrz)
+#define JVP2(TX, MINB, UNR, PC, D) \
+    run_variant<2, TX, 1, JvpOp<2, 2, PC>, MINB, UNR, D>(PC ? "jvp_pc2d" : "jvp2d", pb, P, JvpOp<2, 2, PC>{}, bind_jvp<2, PC>, rzs, nrz)
+#define RES3(TX, TY, MINB, UNR, D) \
+    run_variant<3, TX, TY, ResidualOp<3, 2, true>, MINB, UNR, D>("residual3d", pb, P, ResidualOp<3, 2, true>{}, bind_res<3>, rzs, nrz)
+#define JVP3(TX, TY, MINB, UNR, PC, D) \
+    run_variant<3, TX, TY, JvpOp<3, 2, PC>, MINB, UNR, D>(PC ? "jvp_pc3d" : "jvp3d", pb, P, JvpOp<3, 2, PC>{}, bind_jvp<3, PC>, rzs, nrz)
 
 int main(int argc, char **argv)
 {
@@ -254,36 +254,37 @@ int main(int argc, char **argv)
         DevPhys P = make_phys(dim);
         printf("== %dD n=%d  (%lld points, %d buffer sets)\n", dim, n, pb.npts, pb.nrot);
         if (dim == 2) {
-            RES2(124, 6, false);
-            RES2(124, 8, false);
-            RES2(124, 6, true);
-            RES2(252, 3, false);
-            RES2(252, 4, false);
-            RES2(188, 4, false);
-            RES2(60, 12, false);
-            JVP2(124, 4, true, true);
-            JVP2(124, 5, true, true);
-            JVP2(124, 4, false, true);
-            JVP2(252, 2, true, true);
-            JVP2(60, 8, true, true);
-            JVP2(124, 4, true, false);
-            JVP2(252, 2, true, false);
+            RES2(124, 6, false, 0);
+            RES2(124, 6, false, 3);
+            RES2(252, 3, false, 0);
+            RES2(252, 3, false, 3);
+            RES2(124, 6, true, 3);
+            JVP2(124, 4, true, true, 0);
+            JVP2(124, 4, true, true, 3);
+            JVP2(124, 5, true, true, 3);
+            JVP2(124, 6, true, true, 3);
+            JVP2(252, 2, true, true, 3);
+            JVP2(252, 3, true, true, 3);
+            JVP2(124, 4, false, true, 3);
+            JVP2(124, 6, false, true, 3);
+            JVP2(124, 4, true, false, 0);
+            JVP2(124, 4, true, false, 3);
+            JVP2(124, 6, true, false, 3);
         } else {
-            RES3(32, 16, 1, false);
-            RES3(16, 16, 2, false);
-            RES3(16, 16, 3, false);
-            RES3(32, 8, 2, false);
-            RES3(32, 8, 3, false);
-            RES3(16, 8, 4, false);
-            RES3(16, 8, 5, false);
-            JVP3(32, 8, 1, true, true);
-            JVP3(16, 16, 1, true, true);
-            JVP3(16, 16, 2, true, true);
-            JVP3(16, 8, 2, true, true);
-            JVP3(16, 8, 3, true, true);
-            JVP3(32, 8, 2, true, true);
-            JVP3(32, 8, 1, true, false);
-            JVP3(16, 16, 1, true, false);
+            RES3(32, 16, 1, false, 0);
+            RES3(32, 16, 1, false, 3);
+            RES3(16, 16, 2, false, 0);
+            RES3(16, 16, 2, false, 3);
+            JVP3(32, 8, 1, true, true, 0);
+            JVP3(32, 8, 1, true, true, 3);
+            JVP3(32, 8, 2, true, true, 3);
+            JVP3(16, 16, 1, true, true, 3);
+            JVP3(16, 16, 2, true, true, 3);
+            JVP3(32, 16, 1, true, true, 3);
+            JVP3(32, 8, 1, false, true, 3);
+            JVP3(32, 8, 2, false, true, 3);
+            JVP3(32, 8, 1, true, false, 3);
+            JVP3(32, 8, 2, true, false, 3);
         }
         free_problem(pb);
     }
