@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import check_field, cond_scale, load_golden, oracle_physics, relerr
+from helpers import check_field, cond_scale, load_golden, oracle_physics, phys84, relerr
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -183,3 +183,56 @@ def test_solver_main_save_resume_roundtrip(tmp_path, capsys):
     assert np.array_equal(ser2.retrieve_by_time(6.0), last6)
     x = g.coordsNoGhosts[0]
     assert np.abs(ser2.retrieve_by_time(10.0) - exact93(x, 10.0)).max() < 2e-6
+
+
+OPT84_FILE = os.path.join(HERE, 'options', 'options84.args')
+
+
+def opt_with(path, tmp_path, name, **over):
+    lines = []
+    for line in open(path):
+        key = line.split('=', 1)[0].strip()
+        if key.startswith('--save') or key.startswith('--check'):
+            continue
+        if key in over:
+            line = '%s=%s\n' % (key, over.pop(key))
+        lines.append(line)
+    f = tmp_path / name
+    f.write_text(''.join(lines))
+    return '@' + str(f)
+
+
+def test_options84_reduced_adaptive_run_vs_oracle(tmp_path, capsys):
+    """BASELINE configs[1]: the options84 option file (2-D, two ligand groups,
+    TSAdapt basic from dt = 1e-8, '-pc_type lu' mapped to the iterative solve)
+    run through the ksfdsolver2 entry at the SAME grid spacing h = 1/384 on a
+    48x48 tile, 8 accepted steps; the saved trajectory (times and states) must
+    match the oracle's adaptive ROSW with direct solves started from the saved
+    initial state."""
+    from ksfd_b200.grid import Comm, Grid
+    from ksfd_b200.solver import main
+    from ksfd_b200.timeseries import TimeSeries
+    from oracle import ksfd_oracle as O
+    save = str(tmp_path / 'solutions' / 'run84')
+    n = 48
+    args = opt_with(OPT84_FILE, tmp_path, 'opts84', nelements=n, width=n / 384.0,
+                    height=n / 384.0, maxsteps=8)
+    rc = main('ksfdsolver2.py', args, '--save=' + save)
+    assert rc == 0
+    out = capsys.readouterr().out
+    assert 'SNES failures =  0' in out
+    g = Grid(dim=2, nx=n, ny=n, width=n / 384.0, height=n / 384.0, dof=3, comm=Comm(0, 1))
+    ser = TimeSeries(save, grid=g, mode='r')
+    times = list(ser.sorted_times())
+    assert len(times) == 9 and times[0] == 0.0
+    u0 = np.asarray(ser.retrieve_by_time(0.0)).reshape(-1, order='F')
+    p = phys84(2, (n, n))
+    ph = oracle_physics(p)
+    traj = O.integrate(u0, 0.0, 1e-8, 8, ph,
+                       adapt=dict(atol=0.01, rtol=1e-6, clip=(0.1, 5.0), dt_min=1e-20,
+                                  dt_max=1e4))
+    for k, (t, u) in enumerate(traj):
+        assert abs(times[k + 1] - t) <= 1e-9 * t, (k, times[k + 1], t)
+        got = np.asarray(ser.retrieve_by_time(times[k + 1])).reshape(-1, order='F')
+        ref = u.reshape(-1, order='F')
+        assert relerr(got, ref, 3) < 1e-8, (k, relerr(got, ref, 3))
