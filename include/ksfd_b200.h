@@ -80,9 +80,13 @@ int ksfd_ctx_create(ksfd_ctx **out, int dim, const int64_t n_global[3],
                     int device);
 int ksfd_ctx_destroy(ksfd_ctx *ctx);
 int ksfd_set_physics(ksfd_ctx *ctx, const ksfd_physics *phys);
-/* kernel selection / tile tuning: key in {"variant","tile","rz"};
+/* kernel selection / tuning: key in {"variant","tile","rz","gmres_pipeline",
+   "gmres_runahead","gmres_cycle_exp","halo_p2p"};
    variant 0 = auto, 1 = naive direct kernels, 2 = marching kernels;
-   tile = index of the marching tile shape (-1 = auto), rz = planes per CTA */
+   tile = index of the marching tile shape (-1 = auto), rz = planes per CTA;
+   gmres_pipeline 1 = device-decided launch-ahead GMRES (default), 0 = host
+   driven; gmres_runahead = Arnoldi steps launched ahead; gmres_cycle_exp = k:
+   close a cycle after a 1e-k residual reduction; halo_p2p 0/1 */
 int ksfd_set_option(ksfd_ctx *ctx, const char *key, int64_t value);
 int64_t ksfd_local_size(const ksfd_ctx *ctx);   /* dof * owned points */
 
@@ -99,6 +103,15 @@ int ksfd_from_internal(ksfd_ctx *ctx, const double *in_dev, double *ref_dev,
 int ksfd_nccl_unique_id(const char *libnccl_path, char id_out[128]);
 int ksfd_comm_init(ksfd_ctx *ctx, const char *libnccl_path, int nranks,
                    int rank, const char id[128]);
+/* optional: direct peer-to-peer halo push over NVLink instead of ncclSend/Recv.
+   export: allocate this rank's IPC-shared halo buffers and return their CUDA
+   IPC handle (64 bytes); the caller gathers the handles of all ranks (MPI /
+   torch.distributed) and hands the two neighbours' handles to import.  Halo
+   exchanges then run as ONE kernel that stores the boundary planes into the
+   neighbours' buffers and waits on flag words (no NCCL call). */
+int ksfd_p2p_export(ksfd_ctx *ctx, char handle_out[64]);
+int ksfd_p2p_import(ksfd_ctx *ctx, const char dn_handle[64],
+                    const char up_handle[64]);
 /* fill this rank's ghost planes of `vec` (kept inside the context, slot 0..3) */
 int ksfd_halo_exchange(ksfd_ctx *ctx, const double *vec, int slot,
                        void *stream);

@@ -18,7 +18,8 @@ EXPORTS = [
     'ksfd_ctx_create', 'ksfd_ctx_destroy', 'ksfd_set_physics',
     'ksfd_set_option', 'ksfd_local_size',
     'ksfd_to_internal', 'ksfd_from_internal',
-    'ksfd_nccl_unique_id', 'ksfd_comm_init', 'ksfd_halo_exchange',
+    'ksfd_nccl_unique_id', 'ksfd_comm_init', 'ksfd_p2p_export', 'ksfd_p2p_import',
+    'ksfd_halo_exchange',
     'ksfd_groom', 'ksfd_residual', 'ksfd_velocity_max', 'ksfd_velocity',
     'ksfd_jvp_setup', 'ksfd_jvp', 'ksfd_jvp_precond', 'ksfd_pc_apply',
     'ksfd_block_diagonal',
@@ -105,6 +106,8 @@ def load():
     lib.ksfd_from_internal.argtypes = [vp, dp, dp, i32, vp]
     lib.ksfd_nccl_unique_id.argtypes = [C.c_char_p, C.c_char_p]
     lib.ksfd_comm_init.argtypes = [vp, C.c_char_p, i32, i32, C.c_char_p]
+    lib.ksfd_p2p_export.argtypes = [vp, C.c_char_p]
+    lib.ksfd_p2p_import.argtypes = [vp, C.c_char_p, C.c_char_p]
     lib.ksfd_halo_exchange.argtypes = [vp, dp, i32, vp]
     lib.ksfd_groom.argtypes = [vp, dp, vp]
     lib.ksfd_residual.argtypes = [vp, dp, dp, dp, dp, vp]

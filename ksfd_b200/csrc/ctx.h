@@ -54,6 +54,14 @@ struct ksfd_ctx {
     // halo slots: [lo(2 planes) | hi(2 planes)] per slot, sized for dof+2 stride
     double *halo[KSFD_HALO_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
     size_t halo_plane_doubles = 0;
+    // direct peer-to-peer halo push over NVLink (ksfd_p2p_export/import): one
+    // IPC-shared allocation per rank: [64 doubles of flags][slot][parity][lo|hi]
+    double *p2p_mine = nullptr, *p2p_dn = nullptr, *p2p_up = nullptr;
+    bool p2p_on = false;
+    unsigned long long p2p_seq[KSFD_HALO_SLOTS] = {0, 0, 0, 0};
+    double *p2p_lo[KSFD_HALO_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    double *p2p_hi[KSFD_HALO_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned *p2p_done = nullptr;
     // Jacobian state
     double *coef = nullptr;      // ghosted (nloc+4 planes) x (dof+2)
     double *pc = nullptr;        // nloc planes x 1: inverse Schur pivot per point

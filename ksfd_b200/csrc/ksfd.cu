@@ -131,6 +131,7 @@ extern "C" int ksfd_ctx_create(ksfd_ctx **out, int dim, const int64_t n_global[3
     CK(cudaMalloc(&c->dscal, sizeof(double) * KSFD_NSCAL));
     CK(cudaMallocHost(&c->hscal, sizeof(double) * KSFD_NSCAL));
     c->halo_plane_doubles = (size_t)g.plane_pts * (dof + 2);
+    if (const char *e = getenv("KSFD_GM_RUNAHEAD")) c->gm_runahead = std::max(0, std::min(atoi(e), 8));
     *out = c;
     return 0;
 }
@@ -149,6 +150,10 @@ extern "C" int ksfd_ctx_destroy(ksfd_ctx *c)
     cudaFree(c->krylov);
     cudaFree(c->gm);
     cudaFree(c->gmi);
+    if (c->p2p_dn) cudaIpcCloseMemHandle(c->p2p_dn);
+    if (c->p2p_up && c->p2p_up != c->p2p_dn) cudaIpcCloseMemHandle(c->p2p_up);
+    cudaFree(c->p2p_mine);
+    cudaFree(c->p2p_done);
     if (c->gm_status) cudaFreeHost(c->gm_status);
     for (auto &w : c->work) cudaFree(w);
     ksfd_free_plans(c);
@@ -241,6 +246,7 @@ extern "C" int ksfd_set_option(ksfd_ctx *c, const char *key, int64_t v)
     else if (k == "tile") { c->opt_tx = (int)v; c->opt_tile_set = v >= 0; }
     else if (k == "rz") c->opt_rz = (int)v;
     else if (k == "gmres_pipeline") c->gm_pipeline = (int)v;
+    else if (k == "halo_p2p") c->p2p_on = v != 0 && c->p2p_up != nullptr;
     else if (k == "gmres_cycle_exp") c->gm_cycle_factor = v <= 0 ? 0.0 : std::pow(10.0, -(double)v);
     else if (k == "gmres_runahead") c->gm_runahead = (int)std::max<int64_t>(0, std::min<int64_t>(v, 8));
     else return fail("unknown option " + k);
@@ -287,6 +293,9 @@ static VecRef make_ref(const ksfd_ctx *c, const double *base, int stride, int sl
     if (c->nranks == 1) {
         r.lo = base + (long long)(c->g.nloc - KSFD_SW) * ps;
         r.hi = base;
+    } else if (c->p2p_on) {
+        r.lo = c->p2p_lo[slot];
+        r.hi = c->p2p_hi[slot];
     } else {
         r.lo = c->halo[slot];
         r.hi = c->halo[slot] + KSFD_SW * c->halo_plane_doubles;
@@ -294,11 +303,127 @@ static VecRef make_ref(const ksfd_ctx *c, const double *base, int stride, int sl
     return r;
 }
 
+// ---------------------------------------------------------------------------
+// Direct halo push over NVLink peer memory.  Every rank owns one IPC-shared
+// allocation [64 flag words][slot][parity][lo planes | hi planes]; a single
+// kernel writes this rank's top planes into the upper neighbour's lo buffer and
+// its bottom planes into the lower neighbour's hi buffer (stores over NVLink),
+// publishes the exchange number in the neighbours' flag words and waits for its
+// own two flags: no NCCL call, no host involvement, ~one kernel launch of
+// latency.  Buffers are double-buffered on the exchange parity: a neighbour may
+// already push exchange q+1 while this rank still reads exchange q; every use
+// of a slot is separated from its second-next use by a rank-synchronising
+// all-reduce (one per Arnoldi step / norm / error norm), so two buffers suffice.
+// ---------------------------------------------------------------------------
+#define KSFD_P2P_FLAGS 64
+static size_t p2p_buf_doubles(const ksfd_ctx *c) { return 2 * KSFD_SW * c->halo_plane_doubles; }
+static size_t p2p_total_doubles(const ksfd_ctx *c)
+{
+    return KSFD_P2P_FLAGS + (size_t)KSFD_HALO_SLOTS * 2 * p2p_buf_doubles(c);
+}
+static double *p2p_buf(const ksfd_ctx *c, double *base, int slot, int parity)
+{
+    return base + KSFD_P2P_FLAGS + ((size_t)slot * 2 + parity) * p2p_buf_doubles(c);
+}
+
+__global__ void k_halo_xchg(const double *__restrict__ top, const double *__restrict__ bot,
+                            long long cnt, double *__restrict__ up_lo, double *__restrict__ dn_hi,
+                            volatile unsigned long long *up_flag_lo,
+                            volatile unsigned long long *dn_flag_hi,
+                            volatile unsigned long long *my_flag_lo,
+                            volatile unsigned long long *my_flag_hi, unsigned long long q,
+                            unsigned *done)
+{
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < cnt;
+         e += (long long)gridDim.x * blockDim.x) {
+        up_lo[e] = top[e];
+        dn_hi[e] = bot[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(done, 1u);
+        if (t == gridDim.x - 1) {               // last block: all planes are on their way
+            atomicExch(done, 0u);
+            __threadfence_system();
+            *up_flag_lo = q;
+            *dn_flag_hi = q;
+            while (*my_flag_lo < q || *my_flag_hi < q) __nanosleep(64);
+            __threadfence_system();
+        }
+    }
+}
+
+extern "C" int ksfd_p2p_export(ksfd_ctx *c, char handle_out[64])
+{
+    if (!c || !handle_out) return fail("ksfd_p2p_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaSetDevice(c->device));
+    if (!c->p2p_mine) {
+        CK(cudaMalloc(&c->p2p_mine, sizeof(double) * p2p_total_doubles(c)));
+        CK(cudaMemset(c->p2p_mine, 0, sizeof(double) * KSFD_P2P_FLAGS));
+        CK(cudaMalloc(&c->p2p_done, sizeof(unsigned)));
+        CK(cudaMemset(c->p2p_done, 0, sizeof(unsigned)));
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->p2p_mine));
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+
+extern "C" int ksfd_p2p_import(ksfd_ctx *c, const char dn_handle[64], const char up_handle[64])
+{
+    if (!c || !dn_handle || !up_handle) return fail("ksfd_p2p_import: NULL argument");
+    if (!c->p2p_mine) return fail("ksfd_p2p_import: call ksfd_p2p_export first");
+    if (c->nranks < 2) return 0;
+    CK(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t hd, hu;
+    memcpy(&hd, dn_handle, 64);
+    memcpy(&hu, up_handle, 64);
+    void *pd = nullptr, *pu = nullptr;
+    CK(cudaIpcOpenMemHandle(&pd, hd, cudaIpcMemLazyEnablePeerAccess));
+    if (memcmp(dn_handle, up_handle, 64) == 0) {
+        pu = pd;                                 // two ranks: both neighbours are the same peer
+    } else {
+        CK(cudaIpcOpenMemHandle(&pu, hu, cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->p2p_dn = static_cast<double *>(pd);
+    c->p2p_up = static_cast<double *>(pu);
+    c->p2p_on = true;
+    return 0;
+}
+
+static int exchange_p2p(ksfd_ctx *c, const double *vec, int stride, int slot, cudaStream_t st)
+{
+    const unsigned long long q = ++c->p2p_seq[slot];
+    const int par = (int)(q & 1);
+    const size_t cnt = (size_t)KSFD_SW * c->g.plane_pts * stride;
+    const size_t hi_off = KSFD_SW * c->halo_plane_doubles;
+    double *mine = p2p_buf(c, c->p2p_mine, slot, par);
+    c->p2p_lo[slot] = mine;
+    c->p2p_hi[slot] = mine + hi_off;
+    double *up_lo = p2p_buf(c, c->p2p_up, slot, par);               // my top -> up's lo
+    double *dn_hi = p2p_buf(c, c->p2p_dn, slot, par) + hi_off;      // my bottom -> dn's hi
+    const double *top = vec + (size_t)(c->g.nloc - KSFD_SW) * c->g.plane_pts * stride;
+    typedef volatile unsigned long long *flag_t;
+    flag_t up_flag_lo = reinterpret_cast<flag_t>(c->p2p_up) + slot * 2 + 0;
+    flag_t dn_flag_hi = reinterpret_cast<flag_t>(c->p2p_dn) + slot * 2 + 1;
+    flag_t my_flag_lo = reinterpret_cast<flag_t>(c->p2p_mine) + slot * 2 + 0;
+    flag_t my_flag_hi = reinterpret_cast<flag_t>(c->p2p_mine) + slot * 2 + 1;
+    const unsigned blocks = (unsigned)std::min<size_t>((cnt + 255) / 256, 64);
+    k_halo_xchg<<<blocks, 256, 0, st>>>(top, vec, (long long)cnt, up_lo, dn_hi, up_flag_lo,
+                                        dn_flag_hi, my_flag_lo, my_flag_hi, q, c->p2p_done);
+    CKL();
+    return 0;
+}
+
+
 static int exchange(ksfd_ctx *c, const double *vec, int stride, int slot,
                     cudaStream_t st)
 {
     if (c->nranks == 1) return 0;
     if (slot < 0 || slot >= KSFD_HALO_SLOTS) return fail("bad halo slot");
+    if (c->p2p_on) return exchange_p2p(c, vec, stride, slot, st);
     if (!c->halo[slot])
         CK(cudaMalloc(&c->halo[slot],
                       sizeof(double) * 2 * KSFD_SW * c->halo_plane_doubles));

@@ -112,3 +112,29 @@ def init_comm(ctx):
     dist.broadcast(t, src=0)
     uid = bytes(t.cpu().tolist())
     ctx.comm_init(path, uid)
+    if backend == 'nccl' and os.environ.get('KSFD_HALO_P2P', '1') != '0':
+        init_p2p(ctx)
+
+
+def init_p2p(ctx):
+    """Direct NVLink halo push: exchange the CUDA IPC handles of the ranks'
+    halo buffers and open the two neighbours'.  Falls back to ncclSend/Recv
+    (silently, all ranks together) if any rank cannot export/open a handle."""
+    import torch
+    import torch.distributed as dist
+    lib = _lib.load()
+    buf = C.create_string_buffer(64)
+    ok = lib.ksfd_p2p_export(ctx.h, buf) == 0
+    mine = torch.tensor(list(buf.raw) + [1 if ok else 0], dtype=torch.uint8, device=ctx.tdev)
+    allh = [torch.empty_like(mine) for _ in range(ctx.nranks)]
+    dist.all_gather(allh, mine)
+    rows = [bytes(t.cpu().tolist()) for t in allh]
+    good = all(r[64] == 1 for r in rows)
+    dn, up = neighbours(ctx.rank, ctx.nranks)
+    if good:
+        good = lib.ksfd_p2p_import(ctx.h, rows[dn][:64], rows[up][:64]) == 0
+    flag = torch.tensor([1 if good else 0], dtype=torch.int32, device=ctx.tdev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        ctx.set_option('halo_p2p', 0)
+    ctx.halo_p2p = bool(int(flag.item()))
