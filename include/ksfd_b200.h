@@ -103,15 +103,16 @@ int ksfd_from_internal(ksfd_ctx *ctx, const double *in_dev, double *ref_dev,
 int ksfd_nccl_unique_id(const char *libnccl_path, char id_out[128]);
 int ksfd_comm_init(ksfd_ctx *ctx, const char *libnccl_path, int nranks,
                    int rank, const char id[128]);
-/* optional: direct peer-to-peer halo push over NVLink instead of ncclSend/Recv.
-   export: allocate this rank's IPC-shared halo buffers and return their CUDA
-   IPC handle (64 bytes); the caller gathers the handles of all ranks (MPI /
-   torch.distributed) and hands the two neighbours' handles to import.  Halo
-   exchanges then run as ONE kernel that stores the boundary planes into the
-   neighbours' buffers and waits on flag words (no NCCL call). */
+/* optional: direct peer-to-peer exchange over NVLink peer memory instead of
+   NCCL (<= 16 ranks on one node).  export: allocate this rank's IPC-shared
+   buffers and return their CUDA IPC handle (64 bytes); the caller gathers the
+   handles of ALL ranks in rank order (MPI / torch.distributed) and hands them
+   to import (nhandles = number of ranks, 64 bytes each).  Afterwards a halo
+   exchange is ONE kernel that stores the boundary planes into the neighbours'
+   buffers and waits on flag words, and the small all-reduces of the Krylov
+   solver (dot products, norms) run INSIDE its reduction kernels. */
 int ksfd_p2p_export(ksfd_ctx *ctx, char handle_out[64]);
-int ksfd_p2p_import(ksfd_ctx *ctx, const char dn_handle[64],
-                    const char up_handle[64]);
+int ksfd_p2p_import(ksfd_ctx *ctx, const char *handles, int nhandles);
 /* fill this rank's ghost planes of `vec` (kept inside the context, slot 0..3) */
 int ksfd_halo_exchange(ksfd_ctx *ctx, const double *vec, int slot,
                        void *stream);

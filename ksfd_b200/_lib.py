@@ -107,7 +107,7 @@ def load():
     lib.ksfd_nccl_unique_id.argtypes = [C.c_char_p, C.c_char_p]
     lib.ksfd_comm_init.argtypes = [vp, C.c_char_p, i32, i32, C.c_char_p]
     lib.ksfd_p2p_export.argtypes = [vp, C.c_char_p]
-    lib.ksfd_p2p_import.argtypes = [vp, C.c_char_p, C.c_char_p]
+    lib.ksfd_p2p_import.argtypes = [vp, C.c_char_p, i32]
     lib.ksfd_halo_exchange.argtypes = [vp, dp, i32, vp]
     lib.ksfd_groom.argtypes = [vp, dp, vp]
     lib.ksfd_residual.argtypes = [vp, dp, dp, dp, dp, vp]

@@ -271,6 +271,83 @@ __global__ void k_scale_dof0(long long npts, long long plane_pts, int dof, doubl
 }
 
 // ---------------------------------------------------------------------------
+// All-reduce of a few doubles over NVLink peer memory, INSIDE a single-block
+// kernel (fused with the reduction / Givens kernels of the solver: no NCCL call
+// and no extra launch in the Krylov loop).  Every rank writes its values into
+// slot [parity][rank] of every peer's IPC-shared reduce area, publishes the
+// exchange number q in the peers' flag words, waits for the flags of all peers
+// and sums the contributions in rank order (bitwise identical on all ranks).
+// Double-buffered on q&1: exchange q+2 can only start after this rank received
+// q+1 from every peer, which they send after they finished reading q.
+// ---------------------------------------------------------------------------
+#define KSFD_P2P_MAXR 16
+#define KSFD_P2P_RED_MAX 72                 // doubles per contribution
+#define KSFD_P2P_FLAGS 256                  // flag words at the start of the shared allocation
+#define KSFD_P2P_RFLAG0 32                  // reduce flags: word RFLAG0 + source rank
+struct P2PRed {
+    double *base[KSFD_P2P_MAXR];            // shared allocation of every rank (own included)
+    long long red_off;                      // doubles from base to the reduce area
+    unsigned long long *ctr;                // DEVICE-side exchange counter of this rank
+    int nranks, rank;
+};
+
+// vals[0..n) (shared or global memory of this block) <- op over ranks; op 0 = sum, 1 = max
+// The exchange number is a DEVICE-side counter, advanced only by exchanges that
+// are really made: kernels of the pipelined solver that were launched ahead and
+// skip (identically on all ranks: the skip flag is a function of reduced data)
+// make no exchange and leave no gap, so the host may launch ahead by different
+// amounts on different ranks.
+__device__ __forceinline__ void p2p_allreduce(const P2PRed &pr, double *vals, int n, int op)
+{
+    __shared__ unsigned long long q_;
+    if (threadIdx.x == 0) q_ = *pr.ctr + 1;
+    __syncthreads();
+    const unsigned long long q = q_;
+    const int par = (int)(q & 1);
+    const long long slot0 = pr.red_off + (long long)par * pr.nranks * KSFD_P2P_RED_MAX;
+    __syncthreads();                         // vals complete
+    for (int t = threadIdx.x; t < n * pr.nranks; t += blockDim.x) {
+        const int r = t / n, i = t - r * n;
+        pr.base[r][slot0 + (long long)pr.rank * KSFD_P2P_RED_MAX + i] = vals[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < pr.nranks && threadIdx.x != pr.rank) {
+        volatile unsigned long long *f =
+            reinterpret_cast<volatile unsigned long long *>(pr.base[threadIdx.x]) +
+            KSFD_P2P_RFLAG0 + pr.rank;
+        *f = q;
+        volatile unsigned long long *mine =
+            reinterpret_cast<volatile unsigned long long *>(pr.base[pr.rank]) +
+            KSFD_P2P_RFLAG0 + threadIdx.x;
+        while (*mine < q) __nanosleep(32);
+    }
+    __threadfence_system();
+    __syncthreads();
+    const volatile double *area = pr.base[pr.rank] + slot0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double s = area[i];
+        for (int r = 1; r < pr.nranks; ++r) {
+            const double v = area[(long long)r * KSFD_P2P_RED_MAX + i];
+            s = op == 1 ? fmax(s, v) : s + v;
+        }
+        vals[i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *pr.ctr = q;
+}
+
+// stand-alone version for the remaining small reductions (norms, error norm,
+// CFL maxima): buf[0..n) in global memory, one block
+__global__ void k_p2p_allreduce(P2PRed pr, double *buf, int n, int op)
+{
+    __shared__ double v[KSFD_P2P_RED_MAX];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = buf[i];
+    p2p_allreduce(pr, v, n, op);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) buf[i] = v[i];
+}
+
+// ---------------------------------------------------------------------------
 // Pipelined GMRES: the Hessenberg/Givens bookkeeping, the convergence test and
 // the back substitution run on the device; the host only polls a pinned status
 // word (no stream synchronisation inside a solve) and may launch ahead.
@@ -341,10 +418,16 @@ __device__ __forceinline__ double block_sum_partials(const double *partial, int 
 // TRUE residual.
 __global__ void k_gm_cycle_begin(int nblocks, const double *__restrict__ partial,
                                  double *__restrict__ gm, int *__restrict__ gmi,
-                                 GmStatus *hs, int cycle, GmOpts o)
+                                 GmStatus *hs, int cycle, GmOpts o, P2PRed pr)
 {
     if (gmi[GMI_FINAL]) return;
-    const double s = block_sum_partials(partial, nblocks);
+    double s = block_sum_partials(partial, nblocks);
+    if (pr.nranks > 1) {
+        __shared__ double sv[1];
+        if (threadIdx.x == 0) sv[0] = s;
+        p2p_allreduce(pr, sv, 1, 0);
+        s = sv[0];
+    }
     if (threadIdx.x != 0) return;
     const double beta = sqrt(s);
     if (cycle == 0) {
@@ -431,7 +514,7 @@ __global__ void k_gm_reduce(int nv, int off, int nblocks, const double *__restri
 // thread costs an L2 round trip).
 __global__ void k_gm_finalize(int nv_batch, int off, int j, int nblocks,
                               const double *__restrict__ partial, double *__restrict__ gm,
-                              int *__restrict__ gmi, GmStatus *hs, GmOpts o)
+                              int *__restrict__ gmi, GmStatus *hs, GmOpts o, P2PRed pr)
 {
     if (gmi[GMI_CYCLE_DONE]) return;
     __shared__ double h[KSFD_GM_LD + 1], cs[KSFD_GM_MAXM], sn[KSFD_GM_MAXM], y[KSFD_GM_MAXM];
@@ -461,6 +544,7 @@ __global__ void k_gm_finalize(int nv_batch, int off, int j, int nblocks,
         if (l == 0) h[off + i] = s;
     }
     __syncthreads();
+    if (pr.nranks > 1) p2p_allreduce(pr, h, j + 2, 0);      // sum the column over the ranks
     const int k = j + 1;
     if (tid == 0) {
         const double ww = h[j + 1];
@@ -476,8 +560,12 @@ __global__ void k_gm_finalize(int nv_batch, int off, int j, int nblocks,
         const bool bad = !(hn2 > 1e-8 * ww);
         const double hn = hn2 > 0.0 ? sqrt(hn2) : 0.0;
         gm[GM_INV] = (bad || hn == 0.0) ? 0.0 : 1.0 / hn;
-        // keep the raw column for the orthogonalisation kernel
-        for (int i = 0; i < nv_batch; ++i) gm[GM_HCOL + off + i] = h[off + i];
+        // keep the raw (rank-summed) column for the orthogonalisation kernel
+        if (pr.nranks > 1) {
+            for (int i = 0; i <= j + 1; ++i) gm[GM_HCOL + i] = h[i];
+        } else {
+            for (int i = 0; i < nv_batch; ++i) gm[GM_HCOL + off + i] = h[off + i];
+        }
         h[j + 1] = hn;
         for (int i = 0; i < j; ++i) {
             const double t = cs[i] * h[i] + sn[i] * h[i + 1];

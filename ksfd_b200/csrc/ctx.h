@@ -57,10 +57,10 @@ struct ksfd_ctx {
     // direct peer-to-peer halo push over NVLink (ksfd_p2p_export/import): one
     // IPC-shared allocation per rank: [64 doubles of flags][slot][parity][lo|hi]
     double *p2p_mine = nullptr, *p2p_dn = nullptr, *p2p_up = nullptr;
+    double *p2p_peer[16] = {nullptr};       // every rank's allocation (own included), <= 16 ranks
     bool p2p_on = false;
-    unsigned long long p2p_seq[KSFD_HALO_SLOTS] = {0, 0, 0, 0};
-    double *p2p_lo[KSFD_HALO_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
-    double *p2p_hi[KSFD_HALO_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    // device-side exchange counters: [0..3] halo slots, [4] all-reduce
+    unsigned long long *p2p_ctr = nullptr;
     unsigned *p2p_done = nullptr;
     // Jacobian state
     double *coef = nullptr;      // ghosted (nloc+4 planes) x (dof+2)

@@ -61,13 +61,22 @@ struct VecRef {
     const double *base;         // plane 0 .. nloc-1
     const double *lo;           // planes -2, -1
     const double *hi;           // planes nloc, nloc+1
+    // peer-to-peer halos are double-buffered on the parity of a DEVICE-side
+    // exchange counter: the ghost planes live at lo/hi + (*par & 1) * pstride
+    const unsigned long long *par;
+    long long pstride;
 };
+
+__device__ __forceinline__ long long ghost_shift(const VecRef &v)
+{
+    return v.par ? (long long)(*v.par & 1ull) * v.pstride : 0;
+}
 
 __device__ __forceinline__ const double *plane_ptr(const VecRef &v, int k,
                                                    int nloc, long long stride)
 {
-    if (k < 0) return v.lo + (long long)(k + KSFD_SW) * stride;
-    if (k >= nloc) return v.hi + (long long)(k - nloc) * stride;
+    if (k < 0) return v.lo + ghost_shift(v) + (long long)(k + KSFD_SW) * stride;
+    if (k >= nloc) return v.hi + ghost_shift(v) + (long long)(k - nloc) * stride;
     return v.base + (long long)k * stride;
 }
 

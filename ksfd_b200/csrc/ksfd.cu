@@ -150,10 +150,11 @@ extern "C" int ksfd_ctx_destroy(ksfd_ctx *c)
     cudaFree(c->krylov);
     cudaFree(c->gm);
     cudaFree(c->gmi);
-    if (c->p2p_dn) cudaIpcCloseMemHandle(c->p2p_dn);
-    if (c->p2p_up && c->p2p_up != c->p2p_dn) cudaIpcCloseMemHandle(c->p2p_up);
+    for (int r = 0; r < 16; ++r)
+        if (c->p2p_peer[r] && c->p2p_peer[r] != c->p2p_mine) cudaIpcCloseMemHandle(c->p2p_peer[r]);
     cudaFree(c->p2p_mine);
     cudaFree(c->p2p_done);
+    cudaFree(c->p2p_ctr);
     if (c->gm_status) cudaFreeHost(c->gm_status);
     for (auto &w : c->work) cudaFree(w);
     ksfd_free_plans(c);
@@ -246,7 +247,7 @@ extern "C" int ksfd_set_option(ksfd_ctx *c, const char *key, int64_t v)
     else if (k == "tile") { c->opt_tx = (int)v; c->opt_tile_set = v >= 0; }
     else if (k == "rz") c->opt_rz = (int)v;
     else if (k == "gmres_pipeline") c->gm_pipeline = (int)v;
-    else if (k == "halo_p2p") c->p2p_on = v != 0 && c->p2p_up != nullptr;
+    else if (k == "halo_p2p") c->p2p_on = v != 0 && c->p2p_up != nullptr;   // same on all ranks
     else if (k == "gmres_cycle_exp") c->gm_cycle_factor = v <= 0 ? 0.0 : std::pow(10.0, -(double)v);
     else if (k == "gmres_runahead") c->gm_runahead = (int)std::max<int64_t>(0, std::min<int64_t>(v, 8));
     else return fail("unknown option " + k);
@@ -285,17 +286,25 @@ extern "C" int ksfd_comm_init(ksfd_ctx *c, const char *path, int nranks, int ran
 // VecRef for a vector with `stride` doubles per point.  One rank: the ghost
 // planes alias the vector (periodic wrap).  Several ranks: ghost planes live in
 // halo slot `slot`, filled by exchange().
+static size_t p2p_buf_doubles(const ksfd_ctx *c);
+static double *p2p_buf(const ksfd_ctx *c, double *base, int slot, int parity);
+
 static VecRef make_ref(const ksfd_ctx *c, const double *base, int stride, int slot)
 {
     VecRef r;
     r.base = base;
+    r.par = nullptr;
+    r.pstride = 0;
     const long long ps = c->g.plane_pts * stride;
     if (c->nranks == 1) {
         r.lo = base + (long long)(c->g.nloc - KSFD_SW) * ps;
         r.hi = base;
     } else if (c->p2p_on) {
-        r.lo = c->p2p_lo[slot];
-        r.hi = c->p2p_hi[slot];
+        // parity-0 buffer; the kernel adds (*par & 1) * pstride
+        r.lo = p2p_buf(c, c->p2p_mine, slot, 0);
+        r.hi = r.lo + KSFD_SW * c->halo_plane_doubles;
+        r.par = c->p2p_ctr + slot;
+        r.pstride = (long long)p2p_buf_doubles(c);
     } else {
         r.lo = c->halo[slot];
         r.hi = c->halo[slot] + KSFD_SW * c->halo_plane_doubles;
@@ -315,29 +324,51 @@ static VecRef make_ref(const ksfd_ctx *c, const double *base, int stride, int sl
 // of a slot is separated from its second-next use by a rank-synchronising
 // all-reduce (one per Arnoldi step / norm / error norm), so two buffers suffice.
 // ---------------------------------------------------------------------------
-#define KSFD_P2P_FLAGS 64
 static size_t p2p_buf_doubles(const ksfd_ctx *c) { return 2 * KSFD_SW * c->halo_plane_doubles; }
-static size_t p2p_total_doubles(const ksfd_ctx *c)
+static size_t p2p_red_off(const ksfd_ctx *c)
 {
     return KSFD_P2P_FLAGS + (size_t)KSFD_HALO_SLOTS * 2 * p2p_buf_doubles(c);
+}
+static size_t p2p_total_doubles(const ksfd_ctx *c)
+{
+    return p2p_red_off(c) + (size_t)2 * KSFD_P2P_MAXR * KSFD_P2P_RED_MAX;
+}
+static P2PRed p2p_red(const ksfd_ctx *c)
+{
+    P2PRed pr{};
+    pr.nranks = c->p2p_on ? c->nranks : 1;
+    pr.rank = c->rank;
+    pr.red_off = (long long)p2p_red_off(c);
+    pr.ctr = c->p2p_ctr ? c->p2p_ctr + KSFD_HALO_SLOTS : nullptr;
+    for (int r = 0; r < KSFD_P2P_MAXR; ++r) pr.base[r] = r < c->nranks ? c->p2p_peer[r] : nullptr;
+    return pr;
 }
 static double *p2p_buf(const ksfd_ctx *c, double *base, int slot, int parity)
 {
     return base + KSFD_P2P_FLAGS + ((size_t)slot * 2 + parity) * p2p_buf_doubles(c);
 }
 
+// up_lo0 / dn_hi0 / flags: parity-0 destinations in the neighbours' allocations;
+// ctr = this rank's device-side exchange counter of the slot
 __global__ void k_halo_xchg(const double *__restrict__ top, const double *__restrict__ bot,
-                            long long cnt, double *__restrict__ up_lo, double *__restrict__ dn_hi,
+                            long long cnt, double *__restrict__ up_lo0,
+                            double *__restrict__ dn_hi0, long long pstride,
                             volatile unsigned long long *up_flag_lo,
                             volatile unsigned long long *dn_flag_hi,
                             volatile unsigned long long *my_flag_lo,
-                            volatile unsigned long long *my_flag_hi, unsigned long long q,
-                            unsigned *done)
+                            volatile unsigned long long *my_flag_hi, unsigned long long *ctr,
+                            unsigned *done, const int *__restrict__ skip)
 {
+    // launched ahead by the pipelined solver: no exchange once the cycle is closed
+    if (skip && *skip) return;
+    // every block reads the counter before the last one (which only exists
+    // after all blocks have copied) advances it
+    const unsigned long long q = *ctr + 1;
+    const long long sh = (long long)(q & 1ull) * pstride;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < cnt;
          e += (long long)gridDim.x * blockDim.x) {
-        up_lo[e] = top[e];
-        dn_hi[e] = bot[e];
+        up_lo0[sh + e] = top[e];
+        dn_hi0[sh + e] = bot[e];
     }
     __threadfence_system();
     __syncthreads();
@@ -350,6 +381,7 @@ __global__ void k_halo_xchg(const double *__restrict__ top, const double *__rest
             *dn_flag_hi = q;
             while (*my_flag_lo < q || *my_flag_hi < q) __nanosleep(64);
             __threadfence_system();
+            *ctr = q;
         }
     }
 }
@@ -364,6 +396,8 @@ extern "C" int ksfd_p2p_export(ksfd_ctx *c, char handle_out[64])
         CK(cudaMemset(c->p2p_mine, 0, sizeof(double) * KSFD_P2P_FLAGS));
         CK(cudaMalloc(&c->p2p_done, sizeof(unsigned)));
         CK(cudaMemset(c->p2p_done, 0, sizeof(unsigned)));
+        CK(cudaMalloc(&c->p2p_ctr, sizeof(unsigned long long) * (KSFD_HALO_SLOTS + 1)));
+        CK(cudaMemset(c->p2p_ctr, 0, sizeof(unsigned long long) * (KSFD_HALO_SLOTS + 1)));
     }
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, c->p2p_mine));
@@ -371,39 +405,38 @@ extern "C" int ksfd_p2p_export(ksfd_ctx *c, char handle_out[64])
     return 0;
 }
 
-extern "C" int ksfd_p2p_import(ksfd_ctx *c, const char dn_handle[64], const char up_handle[64])
+extern "C" int ksfd_p2p_import(ksfd_ctx *c, const char *handles, int nhandles)
 {
-    if (!c || !dn_handle || !up_handle) return fail("ksfd_p2p_import: NULL argument");
+    if (!c || !handles) return fail("ksfd_p2p_import: NULL argument");
     if (!c->p2p_mine) return fail("ksfd_p2p_import: call ksfd_p2p_export first");
     if (c->nranks < 2) return 0;
+    if (nhandles != c->nranks) return fail("ksfd_p2p_import: one handle per rank expected");
+    if (c->nranks > KSFD_P2P_MAXR) return fail("ksfd_p2p_import: more than 16 ranks");
     CK(cudaSetDevice(c->device));
-    cudaIpcMemHandle_t hd, hu;
-    memcpy(&hd, dn_handle, 64);
-    memcpy(&hu, up_handle, 64);
-    void *pd = nullptr, *pu = nullptr;
-    CK(cudaIpcOpenMemHandle(&pd, hd, cudaIpcMemLazyEnablePeerAccess));
-    if (memcmp(dn_handle, up_handle, 64) == 0) {
-        pu = pd;                                 // two ranks: both neighbours are the same peer
-    } else {
-        CK(cudaIpcOpenMemHandle(&pu, hu, cudaIpcMemLazyEnablePeerAccess));
+    for (int r = 0; r < c->nranks; ++r) {
+        if (r == c->rank) {
+            c->p2p_peer[r] = c->p2p_mine;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->p2p_peer[r] = static_cast<double *>(p);
     }
-    c->p2p_dn = static_cast<double *>(pd);
-    c->p2p_up = static_cast<double *>(pu);
+    c->p2p_dn = c->p2p_peer[(c->rank + c->nranks - 1) % c->nranks];
+    c->p2p_up = c->p2p_peer[(c->rank + 1) % c->nranks];
     c->p2p_on = true;
     return 0;
 }
 
-static int exchange_p2p(ksfd_ctx *c, const double *vec, int stride, int slot, cudaStream_t st)
+static int exchange_p2p(ksfd_ctx *c, const double *vec, int stride, int slot, cudaStream_t st,
+                        const int *skip)
 {
-    const unsigned long long q = ++c->p2p_seq[slot];
-    const int par = (int)(q & 1);
     const size_t cnt = (size_t)KSFD_SW * c->g.plane_pts * stride;
     const size_t hi_off = KSFD_SW * c->halo_plane_doubles;
-    double *mine = p2p_buf(c, c->p2p_mine, slot, par);
-    c->p2p_lo[slot] = mine;
-    c->p2p_hi[slot] = mine + hi_off;
-    double *up_lo = p2p_buf(c, c->p2p_up, slot, par);               // my top -> up's lo
-    double *dn_hi = p2p_buf(c, c->p2p_dn, slot, par) + hi_off;      // my bottom -> dn's hi
+    double *up_lo0 = p2p_buf(c, c->p2p_up, slot, 0);               // my top -> up's lo
+    double *dn_hi0 = p2p_buf(c, c->p2p_dn, slot, 0) + hi_off;      // my bottom -> dn's hi
     const double *top = vec + (size_t)(c->g.nloc - KSFD_SW) * c->g.plane_pts * stride;
     typedef volatile unsigned long long *flag_t;
     flag_t up_flag_lo = reinterpret_cast<flag_t>(c->p2p_up) + slot * 2 + 0;
@@ -411,19 +444,20 @@ static int exchange_p2p(ksfd_ctx *c, const double *vec, int stride, int slot, cu
     flag_t my_flag_lo = reinterpret_cast<flag_t>(c->p2p_mine) + slot * 2 + 0;
     flag_t my_flag_hi = reinterpret_cast<flag_t>(c->p2p_mine) + slot * 2 + 1;
     const unsigned blocks = (unsigned)std::min<size_t>((cnt + 255) / 256, 64);
-    k_halo_xchg<<<blocks, 256, 0, st>>>(top, vec, (long long)cnt, up_lo, dn_hi, up_flag_lo,
-                                        dn_flag_hi, my_flag_lo, my_flag_hi, q, c->p2p_done);
+    k_halo_xchg<<<blocks, 256, 0, st>>>(top, vec, (long long)cnt, up_lo0, dn_hi0,
+                                        (long long)p2p_buf_doubles(c), up_flag_lo, dn_flag_hi,
+                                        my_flag_lo, my_flag_hi, c->p2p_ctr + slot, c->p2p_done,
+                                        skip);
     CKL();
     return 0;
 }
 
-
 static int exchange(ksfd_ctx *c, const double *vec, int stride, int slot,
-                    cudaStream_t st)
+                    cudaStream_t st, const int *skip = nullptr)
 {
     if (c->nranks == 1) return 0;
     if (slot < 0 || slot >= KSFD_HALO_SLOTS) return fail("bad halo slot");
-    if (c->p2p_on) return exchange_p2p(c, vec, stride, slot, st);
+    if (c->p2p_on) return exchange_p2p(c, vec, stride, slot, st, skip);
     if (!c->halo[slot])
         CK(cudaMalloc(&c->halo[slot],
                       sizeof(double) * 2 * KSFD_SW * c->halo_plane_doubles));
@@ -453,6 +487,11 @@ extern "C" int ksfd_halo_exchange(ksfd_ctx *c, const double *vec, int slot,
 static int allreduce_dev(ksfd_ctx *c, double *buf, int n, int op, cudaStream_t st)
 {
     if (c->nranks == 1) return 0;
+    if (c->p2p_on && n <= KSFD_P2P_RED_MAX) {
+        k_p2p_allreduce<<<1, 128, 0, st>>>(p2p_red(c), buf, n, op == ncclMax_ ? 1 : 0);
+        CKL();
+        return 0;
+    }
     NK(g_nccl.AllReduce(buf, buf, n, ncclFloat64_, op, c->comm, st));
     return 0;
 }
@@ -602,6 +641,8 @@ static VecRef coef_ref(const ksfd_ctx *c)
 {
     const long long ps = c->g.plane_pts * (c->dof + 2);
     VecRef r;
+    r.par = nullptr;
+    r.pstride = 0;
     r.lo = c->coef;
     r.base = c->coef + KSFD_SW * ps;
     r.hi = c->coef + (long long)(KSFD_SW + c->g.nloc) * ps;
@@ -656,7 +697,7 @@ static int jvp_impl(ksfd_ctx *c, const double *v, double *out, bool precond,
 {
     if (!c->have_jac) return fail("ksfd_jvp_setup has not been called");
     if (v == out) return fail("ksfd_jvp: in-place application is not supported");
-    TRY(exchange(c, v, c->dof, 1, st));
+    TRY(exchange(c, v, c->dof, 1, st, skip));
     VecRef vr = make_ref(c, v, c->dof, 1);
     VecRef pr = make_ref(c, c->pc, 1, 2);
     VecRef cr = coef_ref(c);
@@ -1233,18 +1274,21 @@ static int gm_step(ksfd_ctx *c, int j, double *V, bool pre, const GmOpts &go, cu
 #define GM_CALL_MDOT(N) gm_mdot_launch<N>(c, vl, w, st)
         GM_SWITCH(m, GM_CALL_MDOT)
 #undef GM_CALL_MDOT
-        if (last && c->nranks == 1) {
+        const bool fused = c->nranks == 1 || c->p2p_on;     // rank sum inside the kernel
+        if (last && fused) {
             k_gm_finalize<<<1, 256, 0, st>>>(m, b, j, KSFD_RED_BLOCKS, c->partial, c->gm, c->gmi,
-                                             hsd, go);
+                                             hsd, go, p2p_red(c));
             CKL();
         } else {
             k_gm_reduce<<<m, 128, 0, st>>>(m, b, KSFD_RED_BLOCKS, c->partial, c->gmi, c->gm);
             CKL();
         }
     }
-    if (c->nranks > 1) {
+    if (c->nranks > 1 && !c->p2p_on) {
+        P2PRed none{};
+        none.nranks = 1;
         TRY(allreduce_dev(c, c->gm + GM_HCOL, nv, ncclSum_, st));
-        k_gm_finalize<<<1, 32, 0, st>>>(0, 0, j, 0, c->partial, c->gm, c->gmi, hsd, go);
+        k_gm_finalize<<<1, 32, 0, st>>>(0, 0, j, 0, c->partial, c->gm, c->gmi, hsd, go, none);
         CKL();
     }
     const int no = j + 1;
@@ -1280,7 +1324,10 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
     GmStatus *hs = static_cast<GmStatus *>(c->gm_status);
     GmStatus *hsd = static_cast<GmStatus *>(c->gm_status_dev);
     GmOpts go{o.rtol, o.atol, o.dtol, o.max_it > 0 ? o.max_it : 10000, m, 0, c->gm_cycle_factor};
-    const int R = c->nranks > 1 ? 0 : c->gm_runahead;
+    const int R = c->gm_runahead;
+    // with the peer-to-peer exchanges (device-side exchange counters) launch
+    // decisions need not be identical on all ranks
+    const bool free_running = c->nranks == 1 || c->p2p_on;
     InvD id;
     for (int l = 0; l < KSFD_MAX_LIGANDS; ++l) id.v[l] = c->invd[l];
 
@@ -1309,23 +1356,25 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
             r = tmp;
             sign = 1.0;
         }
-        if (c->nranks == 1) {
+        if (c->nranks == 1 || c->p2p_on) {
             k_gm_cycle_begin<<<1, 256, 0, st>>>(KSFD_RED_BLOCKS, c->partial, c->gm, c->gmi, hsd,
-                                                cycle, go);
+                                                cycle, go, p2p_red(c));
             CKL();
         } else {
+            P2PRed none{};
+            none.nranks = 1;
             k_reduce_partials<<<1, 128, 0, st>>>(1, KSFD_RED_BLOCKS, c->partial,
                                                  c->dscal + SC_NORM, 0);
             CKL();
             TRY(allreduce_dev(c, c->dscal + SC_NORM, 1, ncclSum_, st));
             k_gm_cycle_begin<<<1, 32, 0, st>>>(1, c->dscal + SC_NORM, c->gm, c->gmi, hsd, cycle,
-                                               go);
+                                               go, none);
             CKL();
         }
         k_gm_first_vector<<<KSFD_RED_BLOCKS, 256, 0, st>>>(n, r, c->gm, c->gmi, sign, V);
         CKL();
         const int seq = 2 * cycle + 1;
-        if (c->nranks == 1) {
+        if (free_running) {
             for (int j = 0; j < m; ++j) {
                 // launch step j once step j-R-1 is known not to have closed the
                 // cycle; the first R+1 steps go out before the cycle has even
@@ -1338,8 +1387,8 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
                 TRY(gm_step(c, j, V, pre, go, st));
             }
         } else {
-            // several ranks: every launch decision must be taken from the same
-            // data on all ranks, or their NCCL call sequences diverge.  Steps go
+            // several ranks over NCCL: every launch decision must be taken from the
+            // same data on all ranks, or their NCCL call sequences diverge.  Steps go
             // out in chunks of `chunk`; the decision to launch the next chunk is
             // taken only when the previous one has completely finished (its
             // status is final and identical everywhere); steps of a chunk past

@@ -83,8 +83,8 @@ struct SmemTabs {
 __device__ __forceinline__ const double *plane_of(const VecRef &v, int k, int nloc,
                                                   int ps)
 {
-    if (k < 0) return v.lo + (k + KSFD_SW) * (long long)ps;
-    if (k >= nloc) return v.hi + (k - nloc) * (long long)ps;
+    if (k < 0) return v.lo + ghost_shift(v) + (k + KSFD_SW) * (long long)ps;
+    if (k >= nloc) return v.hi + ghost_shift(v) + (k - nloc) * (long long)ps;
     return v.base + k * (long long)ps;
 }
 

@@ -170,6 +170,8 @@ static void bind_res(ResidualOp<DIM, 2, true> &op, const Problem &pb, int i)
     op.u.base = pb.u[i];
     op.u.lo = pb.u[i] + (long long)(pb.nloc - 2) * pb.n0 * pb.n1 * 3;
     op.u.hi = pb.u[i];
+    op.u.par = nullptr;
+    op.u.pstride = 0;
     op.udot = pb.v[i];
     op.src = nullptr;
     op.out = pb.out[i];
@@ -181,6 +183,8 @@ static void bind_jvp(JvpOp<DIM, 2, PC> &op, const Problem &pb, int i)
     op.coef.lo = pb.coef;
     op.coef.base = pb.coef + 2 * ps * 5;
     op.coef.hi = pb.coef + (2 + pb.nloc) * ps * 5;
+    op.coef.par = op.v.par = op.pc.par = nullptr;
+    op.coef.pstride = op.v.pstride = op.pc.pstride = 0;
     op.v.base = pb.v[i];
     op.v.lo = pb.v[i] + (long long)(pb.nloc - 2) * ps * 3;
     op.v.hi = pb.v[i];
