@@ -17,7 +17,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     ok_all = True
-    for dim, n in ((2, (96, 64)), (3, (20, 24, 16)), (1, (64,)), (2, (256, 1024))):
+    for dim, n in ((2, (96, 64)), (3, (20, 24, 32)), (1, (64,)), (2, (256, 1024))):   # >= 4 planes per rank at 8 ranks: same kernel family as one rank
         p = phys84(dim, n)
         dof = 3
         u_g = random_state(p, 5)
