@@ -78,6 +78,7 @@ struct ksfd_ctx {
     int *gmi = nullptr;
     void *gm_status = nullptr, *gm_status_dev = nullptr;   // GmStatus (mapped)
     int gm_pipeline = 1, gm_runahead = 2;
+    int gm_pred[2] = {0, 0};     // columns of the last first / later cycle (launch-ahead hint)
     // Single-pass classical Gram-Schmidt loses orthogonality like eps*kappa^2,
     // kappa ~ the residual reduction inside the cycle, so a cycle is closed
     // after this reduction and restarted from the TRUE residual (measured on

@@ -1379,9 +1379,14 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
                 // launch step j once step j-R-1 is known not to have closed the
                 // cycle; the first R+1 steps go out before the cycle has even
                 // begun on the device (they skip if it ends at once)
+                // cycles of consecutive solves have very similar lengths: launch
+                // ahead only while the cycle is expected to go on, so that few
+                // launched-ahead steps are wasted (each costs ~5 skipped kernels)
+                const int pred = c->gm_pred[cycle > 0];
+                const int Rj = (pred == 0 || j + 1 < pred) ? R : 0;
                 TRY(gm_wait(st, [&] {
-                    if (hs->seq < seq) return j <= R;
-                    return hs->cycle_done != 0 || hs->iters_done >= j - R;
+                    if (hs->seq < seq) return j <= Rj;
+                    return hs->cycle_done != 0 || hs->iters_done >= j - Rj;
                 }, "an Arnoldi step", c));
                 if (hs->seq >= seq && hs->cycle_done) break;
                 TRY(gm_step(c, j, V, pre, go, st));
@@ -1409,10 +1414,20 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
             fprintf(stderr, "  cycle %d: seq %d iters %d cycle_done %d final %d reason %d its %d "
                     "rnorm %.3e\n", cycle, hs->seq, hs->k_cols, hs->cycle_done, hs->final_,
                     hs->reason, hs->its_total, hs->rnorm);
+        c->gm_pred[cycle > 0] = hs->k_cols;
         if (hs->reason != -9 && hs->k_cols > 0) {
-            k_gm_update_x<<<std::min(nblk(c->g.npts, 256), 148u * 8u), 256, 0, st>>>(
-                c->g, c->P, coef_ref(c), id, c->pc, pre ? 1 : 0, n, V, c->gm + GM_Y,
-                c->gmi + GMI_K, c->gmi + GMI_NOUPD, x);
+            const unsigned ub = std::min(nblk(c->g.npts, 256), 148u * 8u);
+#define KSFD_UPD(D)                                                                          \
+    k_gm_update_x<D><<<ub, 256, 0, st>>>(c->g, c->P, coef_ref(c), id, c->pc, pre ? 1 : 0, n, V, \
+                                         c->gm + GM_Y, c->gmi + GMI_K, c->gmi + GMI_NOUPD, x)
+            switch (c->dof) {
+            case 2: KSFD_UPD(2); break;
+            case 3: KSFD_UPD(3); break;
+            case 4: KSFD_UPD(4); break;
+            case 5: KSFD_UPD(5); break;
+            default: KSFD_UPD(0); break;
+            }
+#undef KSFD_UPD
             CKL();
         }
         if (hs->final_) break;

@@ -303,6 +303,7 @@ __global__ void k_pc_apply(Geom g, DevPhys P, VecRef coef, InvD invd,
 // GMRES solution update at the end of a cycle (k, y on the device):
 //   x += M^{-1} (sum_{i<k} y_i V_i)   or   x += sum_{i<k} y_i V_i
 // gm_y = y, gmi_k = &k, gmi_skip = &no-update flag
+template <int DOF>          // DOF = 0: runtime dof (any), else compile-time (registers)
 __global__ void __launch_bounds__(256)
 k_gm_update_x(Geom g, DevPhys P, VecRef coef, InvD invd, const double *__restrict__ pc,
               int precond, long long n, const double *__restrict__ V,
@@ -314,28 +315,43 @@ k_gm_update_x(Geom g, DevPhys P, VecRef coef, InvD invd, const double *__restric
     const int k = *gmi_k;
     for (int i = threadIdx.x; i < k; i += blockDim.x) y[i] = gm_y[i];
     __syncthreads();
-    const int fs = (int)g.plane_pts, dof = g.dof;
+    const int fs = (int)g.plane_pts;
+    const int dof = DOF ? DOF : g.dof;
+    constexpr int MD = DOF ? DOF : KSFD_MAX_LIGANDS + 1;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < (int)g.npts;
          p += gridDim.x * blockDim.x) {
         const int kp = p / fs, pp = p - kp * fs;
         const int e0 = kp * dof * fs + pp;          // field c of this point: e0 + c*fs
-        double rr[KSFD_MAX_LIGANDS + 1], zz[KSFD_MAX_LIGANDS + 1];
-        for (int c = 0; c < dof; ++c) rr[c] = 0.0;
+        double rr[MD], zz[MD];
+#pragma unroll
+        for (int c = 0; c < MD; ++c) rr[c] = 0.0;
         for (int i = 0; i < k; ++i) {
             const double *vi = V + (long long)i * n + e0;
             const double yi = y[i];
-            for (int c = 0; c < dof; ++c) rr[c] = fma(yi, __ldg(vi + c * fs), rr[c]);
+#pragma unroll
+            for (int c = 0; c < MD; ++c)
+                if (c < dof) rr[c] = fma(yi, __ldg(vi + c * fs), rr[c]);
         }
         if (precond) {
-            // coef is ghosted by KSFD_SW planes along the last axis
+            // coef is ghosted by KSFD_SW planes along the last axis (coef.base = plane 0)
             const double *c0 = coef.base + ((long long)kp * (dof + 2)) * fs + pp;
-            double gU[KSFD_MAX_LIGANDS];
-            for (int l = 0; l < P.nlig; ++l) gU[l] = __ldg(c0 + (3 + l) * fs);
-            pc_point_rt(P, invd, __ldg(c0), gU, __ldg(pc + p), rr, zz);
+            const double fac = __ldg(c0) * P.w2c;
+            double t = rr[0];
+#pragma unroll
+            for (int l = 0; l < MD - 1; ++l)
+                if (l < dof - 1) t = fma(fac * __ldg(c0 + (3 + l) * fs) * invd.v[l], rr[1 + l], t);
+            const double zr = __ldg(pc + p) * t;
+            zz[0] = zr;
+#pragma unroll
+            for (int l = 0; l < MD - 1; ++l)
+                if (l < dof - 1) zz[1 + l] = fma(P.s[l], zr, rr[1 + l]) * invd.v[l];
         } else {
-            for (int c = 0; c < dof; ++c) zz[c] = rr[c];
+#pragma unroll
+            for (int c = 0; c < MD; ++c) zz[c] = rr[c];
         }
-        for (int c = 0; c < dof; ++c) x[e0 + c * fs] += zz[c];
+#pragma unroll
+        for (int c = 0; c < MD; ++c)
+            if (c < dof) x[e0 + c * fs] += zz[c];
     }
 }
 
