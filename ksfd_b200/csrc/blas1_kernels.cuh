@@ -476,24 +476,6 @@ __global__ void k_gm_first_vector(long long n, const double *x, const double *__
 }
 
 // partial[i][block] = <vs[i], w>, skipping when the cycle is closed
-template <int NV>
-__global__ void __launch_bounds__(KSFD_RED_THREADS)
-k_gm_mdot(long long n, VecList vs, const double *__restrict__ w,
-          const int *__restrict__ gmi, double *__restrict__ partial)
-{
-    if (gmi[GMI_CYCLE_DONE]) return;
-    double acc[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
-         e += (long long)gridDim.x * blockDim.x) {
-        const double wv = w[e];
-#pragma unroll
-        for (int i = 0; i < NV; ++i) acc[i] = fma(__ldg(vs.v[i] + e), wv, acc[i]);
-    }
-    block_reduce_store<NV>(acc, partial, KSFD_RED_BLOCKS);
-}
-
 // hcol[off + i] = sum_b partial[i][b], i < nv  (earlier batches of a long column)
 __global__ void k_gm_reduce(int nv, int off, int nblocks, const double *__restrict__ partial,
                             const int *__restrict__ gmi, double *__restrict__ gm)
@@ -512,11 +494,27 @@ __global__ void k_gm_reduce(int nv, int off, int nblocks, const double *__restri
 // cycle / the solve ends, and if the cycle ends solves the triangular system.
 // The serial part works out of shared memory (every global access of a single
 // thread costs an L2 round trip).
-__global__ void k_gm_finalize(int nv_batch, int off, int j, int nblocks,
-                              const double *__restrict__ partial, double *__restrict__ gm,
-                              int *__restrict__ gmi, GmStatus *hs, GmOpts o, P2PRed pr)
+struct GmFin {                      // arguments of the end-of-step bookkeeping
+    int nv_batch, off, j, nblocks;
+    const double *partial;
+    double *gm;
+    int *gmi;
+    GmStatus *hs;
+    GmOpts o;
+    P2PRed pr;
+    unsigned *done;                 // block counter when fused into the multi-dot kernel
+};
+
+// executed by ONE block of 256 threads
+__device__ __forceinline__ void gm_finalize_body(const GmFin &a)
 {
-    if (gmi[GMI_CYCLE_DONE]) return;
+    const int nv_batch = a.nv_batch, off = a.off, j = a.j, nblocks = a.nblocks;
+    const double *__restrict__ partial = a.partial;
+    double *__restrict__ gm = a.gm;
+    int *__restrict__ gmi = a.gmi;
+    GmStatus *hs = a.hs;
+    const GmOpts &o = a.o;
+    const P2PRed &pr = a.pr;
     __shared__ double h[KSFD_GM_LD + 1], cs[KSFD_GM_MAXM], sn[KSFD_GM_MAXM], y[KSFD_GM_MAXM];
     __shared__ double sc[6];            // g[j], tol, ctol, rnorm0, its(as double), -
     __shared__ double Ht[KSFD_GM_MAXM * (KSFD_GM_MAXM + 1) / 2];
@@ -651,6 +649,47 @@ __global__ void k_gm_finalize(int nv_batch, int off, int j, int nblocks,
         hs->iters_done = k;
     }
 }
+
+__global__ void k_gm_finalize(GmFin a)
+{
+    if (a.gmi[GMI_CYCLE_DONE]) return;
+    gm_finalize_body(a);
+}
+
+// FUSE: the block that finishes last also does the end-of-step bookkeeping
+// (gm_finalize_body): no separate one-block kernel per Arnoldi step.
+template <int NV, bool FUSE>
+__global__ void __launch_bounds__(KSFD_RED_THREADS)
+k_gm_mdot(long long n, VecList vs, const double *__restrict__ w,
+          const int *__restrict__ gmi, double *__restrict__ partial, GmFin fin)
+{
+    if (gmi[GMI_CYCLE_DONE]) return;
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+         e += (long long)gridDim.x * blockDim.x) {
+        const double wv = w[e];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] = fma(__ldg(vs.v[i] + e), wv, acc[i]);
+    }
+    block_reduce_store<NV>(acc, partial, KSFD_RED_BLOCKS);
+    if (FUSE) {
+        __shared__ int last_;
+        __threadfence();                       // this block's partial sums are visible
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned t = atomicAdd(fin.done, 1u);
+            last_ = (t == gridDim.x - 1);
+            if (last_) atomicExch(fin.done, 0u);
+        }
+        __syncthreads();
+        if (!last_) return;
+        __threadfence();                       // see every block's partial sums
+        gm_finalize_body(fin);
+    }
+}
+
 
 // w = (w - sum_i h[i]*V_i) * inv   with h, inv from the device state
 template <int NV>

@@ -77,6 +77,7 @@ struct ksfd_ctx {
     double *gm = nullptr;
     int *gmi = nullptr;
     void *gm_status = nullptr, *gm_status_dev = nullptr;   // GmStatus (mapped)
+    unsigned *gm_done = nullptr;                            // block counter of the fused multi-dot
     int gm_pipeline = 1, gm_runahead = 2;
     int gm_pred[2] = {0, 0};     // columns of the last first / later cycle (launch-ahead hint)
     // Single-pass classical Gram-Schmidt loses orthogonality like eps*kappa^2,

@@ -150,6 +150,7 @@ extern "C" int ksfd_ctx_destroy(ksfd_ctx *c)
     cudaFree(c->krylov);
     cudaFree(c->gm);
     cudaFree(c->gmi);
+    cudaFree(c->gm_done);
     for (int r = 0; r < 16; ++r)
         if (c->p2p_peer[r] && c->p2p_peer[r] != c->p2p_mine) cudaIpcCloseMemHandle(c->p2p_peer[r]);
     cudaFree(c->p2p_mine);
@@ -1191,6 +1192,8 @@ static int gm_alloc(ksfd_ctx *c)
     if (c->gm) return 0;
     CK(cudaMalloc(&c->gm, sizeof(double) * GM_DOUBLES));
     CK(cudaMalloc(&c->gmi, sizeof(int) * GMI_INTS));
+    CK(cudaMalloc(&c->gm_done, sizeof(unsigned)));
+    CK(cudaMemset(c->gm_done, 0, sizeof(unsigned)));
     CK(cudaHostAlloc(&c->gm_status, sizeof(GmStatus), cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer(&c->gm_status_dev, c->gm_status, 0));
     memset(c->gm_status, 0, sizeof(GmStatus));
@@ -1227,10 +1230,17 @@ static int gm_wait(cudaStream_t st, Pred pred, const char *what, const ksfd_ctx 
 }
 
 template <int NV>
-static int gm_mdot_launch(ksfd_ctx *c, const VecList &vl, const double *w, cudaStream_t st)
+static int gm_mdot_launch(ksfd_ctx *c, const VecList &vl, const double *w, const GmFin *fin,
+                          cudaStream_t st)
 {
-    k_gm_mdot<NV><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(nlocal(c), vl, w, c->gmi,
-                                                                c->partial);
+    if (fin) {
+        k_gm_mdot<NV, true><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(nlocal(c), vl, w, c->gmi,
+                                                                          c->partial, *fin);
+    } else {
+        GmFin none{};
+        k_gm_mdot<NV, false><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(nlocal(c), vl, w, c->gmi,
+                                                                           c->partial, none);
+    }
     CKL();
     return 0;
 }
@@ -1271,15 +1281,14 @@ static int gm_step(ksfd_ctx *c, int j, double *V, bool pre, const GmOpts &go, cu
             const int idx = b + std::min(i, m - 1);
             vl.v[i] = (idx == j + 1) ? w : V + (long long)idx * n;
         }
-#define GM_CALL_MDOT(N) gm_mdot_launch<N>(c, vl, w, st)
+        const bool fused = c->nranks == 1 || c->p2p_on;     // rank sum inside the kernel
+        GmFin fin{m, b, j, KSFD_RED_BLOCKS, c->partial, c->gm, c->gmi, hsd, go, p2p_red(c),
+                  c->gm_done};
+        const GmFin *tail = (last && fused) ? &fin : nullptr;   // bookkeeping in the last block
+#define GM_CALL_MDOT(N) gm_mdot_launch<N>(c, vl, w, tail, st)
         GM_SWITCH(m, GM_CALL_MDOT)
 #undef GM_CALL_MDOT
-        const bool fused = c->nranks == 1 || c->p2p_on;     // rank sum inside the kernel
-        if (last && fused) {
-            k_gm_finalize<<<1, 256, 0, st>>>(m, b, j, KSFD_RED_BLOCKS, c->partial, c->gm, c->gmi,
-                                             hsd, go, p2p_red(c));
-            CKL();
-        } else {
+        if (!tail) {
             k_gm_reduce<<<m, 128, 0, st>>>(m, b, KSFD_RED_BLOCKS, c->partial, c->gmi, c->gm);
             CKL();
         }
@@ -1288,7 +1297,8 @@ static int gm_step(ksfd_ctx *c, int j, double *V, bool pre, const GmOpts &go, cu
         P2PRed none{};
         none.nranks = 1;
         TRY(allreduce_dev(c, c->gm + GM_HCOL, nv, ncclSum_, st));
-        k_gm_finalize<<<1, 32, 0, st>>>(0, 0, j, 0, c->partial, c->gm, c->gmi, hsd, go, none);
+        GmFin fin{0, 0, j, 0, c->partial, c->gm, c->gmi, hsd, go, none, c->gm_done};
+        k_gm_finalize<<<1, 256, 0, st>>>(fin);
         CKL();
     }
     const int no = j + 1;
