@@ -67,7 +67,29 @@ class ClockSampler:
         self.stop = threading.Event()
         self.th = None
 
+    def _run_nvml(self):
+        """fast path: NVML in process (nvidia-ml-py), one sample every 10 ms"""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        R = [(nv.nvmlClocksThrottleReasonHwSlowdown, 0), (nv.nvmlClocksThrottleReasonHwThermalSlowdown, 1),
+             (nv.nvmlClocksThrottleReasonSwThermalSlowdown, 2), (nv.nvmlClocksThrottleReasonSwPowerCap, 3)]
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            row = [str(sm), str(mx)] + ['Not Active'] * 4
+            for bit, k in R:
+                if bits & bit:
+                    row[2 + k] = 'Active'
+            self.samples.append(row)
+            self.stop.wait(0.01)
+
     def _run(self):
+        try:
+            return self._run_nvml()
+        except Exception:
+            pass
         while not self.stop.is_set():
             try:
                 o = subprocess.run(
