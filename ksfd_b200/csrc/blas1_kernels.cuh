@@ -13,6 +13,21 @@
 struct VecList {
     const double *v[KSFD_MAXV];
 };
+
+// 16-byte (double2) streaming is used when the length is even and every
+// pointer is 16-byte aligned (more bytes in flight per thread)
+__device__ __forceinline__ bool aligned16(const void *p)
+{
+    return (reinterpret_cast<unsigned long long>(p) & 15ull) == 0;
+}
+template <int NV>
+__device__ __forceinline__ bool all_aligned16(long long n, const VecList &vs, const void *w)
+{
+    bool ok = (n & 1) == 0 && aligned16(w);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) ok = ok && aligned16(vs.v[i]);
+    return ok;
+}
 struct CoefList {
     double c[KSFD_MAXV];
 };
@@ -470,6 +485,18 @@ __global__ void k_gm_first_vector(long long n, const double *x, const double *__
 {
     if (gmi[GMI_FINAL]) return;
     const double f = sign / gm[GM_BETA];
+    if ((n & 1) == 0 && aligned16(x) && aligned16(y)) {
+        const double2 *x2 = reinterpret_cast<const double2 *>(x);
+        double2 *y2 = reinterpret_cast<double2 *>(y);
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (n >> 1);
+             e += (long long)gridDim.x * blockDim.x) {
+            double2 v = x2[e];
+            v.x *= f;
+            v.y *= f;
+            y2[e] = v;
+        }
+        return;
+    }
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
          e += (long long)gridDim.x * blockDim.x)
         y[e] = x[e] * f;
@@ -667,11 +694,24 @@ k_gm_mdot(long long n, VecList vs, const double *__restrict__ w,
     double acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
-         e += (long long)gridDim.x * blockDim.x) {
-        const double wv = w[e];
+    if (all_aligned16<NV>(n, vs, w)) {
+        const double2 *w2 = reinterpret_cast<const double2 *>(w);
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (n >> 1);
+             e += (long long)gridDim.x * blockDim.x) {
+            const double2 wv = w2[e];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) acc[i] = fma(__ldg(vs.v[i] + e), wv, acc[i]);
+            for (int i = 0; i < NV; ++i) {
+                const double2 a = __ldg(reinterpret_cast<const double2 *>(vs.v[i]) + e);
+                acc[i] = fma(a.y, wv.y, fma(a.x, wv.x, acc[i]));
+            }
+        }
+    } else {
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+             e += (long long)gridDim.x * blockDim.x) {
+            const double wv = w[e];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) acc[i] = fma(__ldg(vs.v[i] + e), wv, acc[i]);
+        }
     }
     block_reduce_store<NV>(acc, partial, KSFD_RED_BLOCKS);
     if (FUSE) {
@@ -704,6 +744,23 @@ k_gm_orth_scale(long long n, VecList vs, int off, int do_scale,
 #pragma unroll
     for (int i = 0; i < NV; ++i) hh[i] = gm[GM_HCOL + off + i];
     const double sc = do_scale ? gm[GM_INV] : 1.0;
+    if (all_aligned16<NV>(n, vs, w)) {
+        double2 *w2 = reinterpret_cast<double2 *>(w);
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (n >> 1);
+             e += (long long)gridDim.x * blockDim.x) {
+            double2 s = w2[e];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const double2 a = __ldg(reinterpret_cast<const double2 *>(vs.v[i]) + e);
+                s.x = fma(-hh[i], a.x, s.x);
+                s.y = fma(-hh[i], a.y, s.y);
+            }
+            s.x *= sc;
+            s.y *= sc;
+            w2[e] = s;
+        }
+        return;
+    }
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
          e += (long long)gridDim.x * blockDim.x) {
         double s = w[e];

@@ -1,0 +1,34 @@
+"""
+Multi-GPU parity as a test (needs >= 2 GPUs on the box; skipped otherwise):
+launches scripts/multi_gpu_check.py under torchrun, one rank per GPU.  The
+slab-decomposed operator (halo push over NVLink peer memory, in-kernel
+all-reduce) must reproduce the single-GPU result bit for bit (residual, J.v) /
+to rounding (GMRES, adaptive ROSW steps).
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpus():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize('p2p', ['1', '0'])
+def test_two_rank_parity(p2p):
+    if _ngpus() < 2:
+        pytest.skip('needs 2 GPUs')
+    env = dict(os.environ, KSFD_HALO_P2P=p2p)
+    port = 29600 + int(p2p)
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+                        '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                        '--master-port', str(port),
+                        os.path.join(ROOT, 'scripts', 'multi_gpu_check.py')],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert 'MULTI_GPU_CHECK PASS' in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
