@@ -299,8 +299,26 @@ __global__ void k_scale_dof0(long long npts, long long plane_pts, int dof, doubl
 #define KSFD_P2P_RED_MAX 72                 // doubles per contribution
 #define KSFD_P2P_FLAGS 256                  // flag words at the start of the shared allocation
 #define KSFD_P2P_RFLAG0 32                  // reduce flags: word RFLAG0 + source rank
+// bounded spin on a flag word written by a peer GPU: gives up after ~30 s (a
+// peer died) and raises the host-visible error word instead of hanging the GPU
+__device__ __forceinline__ bool p2p_spin(volatile unsigned long long *flag,
+                                         unsigned long long q, volatile int *err)
+{
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while (*flag < q) {
+        __nanosleep(32);
+        if ((++spins & 0xfff) == 0 && clock64() - t0 > 60000000000ll) {
+            if (err) *err = 1;
+            return false;
+        }
+    }
+    return true;
+}
+
 struct P2PRed {
     double *base[KSFD_P2P_MAXR];            // shared allocation of every rank (own included)
+    volatile int *err;                      // pinned, host-visible: set when a wait timed out
     long long red_off;                      // doubles from base to the reduce area
     unsigned long long *ctr;                // DEVICE-side exchange counter of this rank
     int nranks, rank;
@@ -335,7 +353,7 @@ __device__ __forceinline__ void p2p_allreduce(const P2PRed &pr, double *vals, in
         volatile unsigned long long *mine =
             reinterpret_cast<volatile unsigned long long *>(pr.base[pr.rank]) +
             KSFD_P2P_RFLAG0 + threadIdx.x;
-        while (*mine < q) __nanosleep(32);
+        p2p_spin(mine, q, pr.err);
     }
     __threadfence_system();
     __syncthreads();

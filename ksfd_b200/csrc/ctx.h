@@ -62,6 +62,7 @@ struct ksfd_ctx {
     // device-side exchange counters: [0..3] halo slots, [4] all-reduce
     unsigned long long *p2p_ctr = nullptr;
     unsigned *p2p_done = nullptr;
+    int *p2p_err = nullptr, *p2p_err_dev = nullptr;    // pinned + mapped: a peer wait timed out
     // Jacobian state
     double *coef = nullptr;      // ghosted (nloc+4 planes) x (dof+2)
     double *pc = nullptr;        // nloc planes x 1: inverse Schur pivot per point

@@ -156,6 +156,7 @@ extern "C" int ksfd_ctx_destroy(ksfd_ctx *c)
     cudaFree(c->p2p_mine);
     cudaFree(c->p2p_done);
     cudaFree(c->p2p_ctr);
+    if (c->p2p_err) cudaFreeHost(c->p2p_err);
     if (c->gm_status) cudaFreeHost(c->gm_status);
     for (auto &w : c->work) cudaFree(w);
     ksfd_free_plans(c);
@@ -341,6 +342,7 @@ static P2PRed p2p_red(const ksfd_ctx *c)
     pr.rank = c->rank;
     pr.red_off = (long long)p2p_red_off(c);
     pr.ctr = c->p2p_ctr ? c->p2p_ctr + KSFD_HALO_SLOTS : nullptr;
+    pr.err = c->p2p_err_dev;
     for (int r = 0; r < KSFD_P2P_MAXR; ++r) pr.base[r] = r < c->nranks ? c->p2p_peer[r] : nullptr;
     return pr;
 }
@@ -358,7 +360,7 @@ __global__ void k_halo_xchg(const double *__restrict__ top, const double *__rest
                             volatile unsigned long long *dn_flag_hi,
                             volatile unsigned long long *my_flag_lo,
                             volatile unsigned long long *my_flag_hi, unsigned long long *ctr,
-                            unsigned *done, const int *__restrict__ skip)
+                            unsigned *done, const int *__restrict__ skip, volatile int *err)
 {
     // launched ahead by the pipelined solver: no exchange once the cycle is closed
     if (skip && *skip) return;
@@ -380,7 +382,8 @@ __global__ void k_halo_xchg(const double *__restrict__ top, const double *__rest
             __threadfence_system();
             *up_flag_lo = q;
             *dn_flag_hi = q;
-            while (*my_flag_lo < q || *my_flag_hi < q) __nanosleep(64);
+            p2p_spin(my_flag_lo, q, err);
+            p2p_spin(my_flag_hi, q, err);
             __threadfence_system();
             *ctr = q;
         }
@@ -397,6 +400,9 @@ extern "C" int ksfd_p2p_export(ksfd_ctx *c, char handle_out[64])
         CK(cudaMemset(c->p2p_mine, 0, sizeof(double) * KSFD_P2P_FLAGS));
         CK(cudaMalloc(&c->p2p_done, sizeof(unsigned)));
         CK(cudaMemset(c->p2p_done, 0, sizeof(unsigned)));
+        CK(cudaHostAlloc(&c->p2p_err, sizeof(int), cudaHostAllocMapped));
+        *c->p2p_err = 0;
+        CK(cudaHostGetDevicePointer(&c->p2p_err_dev, c->p2p_err, 0));
         CK(cudaMalloc(&c->p2p_ctr, sizeof(unsigned long long) * (KSFD_HALO_SLOTS + 1)));
         CK(cudaMemset(c->p2p_ctr, 0, sizeof(unsigned long long) * (KSFD_HALO_SLOTS + 1)));
     }
@@ -448,7 +454,7 @@ static int exchange_p2p(ksfd_ctx *c, const double *vec, int stride, int slot, cu
     k_halo_xchg<<<blocks, 256, 0, st>>>(top, vec, (long long)cnt, up_lo0, dn_hi0,
                                         (long long)p2p_buf_doubles(c), up_flag_lo, dn_flag_hi,
                                         my_flag_lo, my_flag_hi, c->p2p_ctr + slot, c->p2p_done,
-                                        skip);
+                                        skip, c->p2p_err_dev);
     CKL();
     return 0;
 }
@@ -863,6 +869,8 @@ static int fetch(ksfd_ctx *c, int slot, int n, cudaStream_t st)
     CK(cudaMemcpyAsync(c->hscal + slot, c->dscal + slot, sizeof(double) * n,
                        cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (c->p2p_err && *c->p2p_err)
+        return fail("peer-to-peer exchange timed out (a neighbouring rank is gone)");
     return 0;
 }
 
@@ -1209,6 +1217,8 @@ static int gm_wait(cudaStream_t st, Pred pred, const char *what, const ksfd_ctx 
     for (unsigned long long spins = 0;; ++spins) {
         if (pred()) return 0;
         if ((spins & 0x3ff) == 0x3ff) {
+            if (c && c->p2p_err && *c->p2p_err)
+                return fail("peer-to-peer exchange timed out (a neighbouring rank is gone)");
             if (!t0) t0 = time(nullptr);
             if (!warned && time(nullptr) - t0 > 20) {
                 warned = true;
