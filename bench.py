@@ -406,7 +406,18 @@ def main():
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--quick', action='store_true', help='skip the 256^3 kernel timings')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline')
+    ap.add_argument('--sweep', action='store_true',
+                    help='kernel rooflines over per-GPU tiles 512^2..4096^2 and 256^3 '
+                         '(BASELINE configs[4]); prints one JSON object, not the bench line')
     args = ap.parse_args()
+    if args.sweep:
+        sys.path.insert(0, os.path.join(ROOT, 'tests'))
+        out = {}
+        for n in (512, 1024, 2048, 4096):
+            out['%dx%d' % (n, n)], peak, _ = kernel_rooflines(2, (n, n))
+        out['256x256x256'], peak, _ = kernel_rooflines(3, (256, 256, 256), reps=10)
+        print(json.dumps(dict(sweep=out, peak_gbs=peak, algorithmic_bytes_per_point=ALG_BYTES_PER_PT)))
+        return
     if args.impl == 'reference':
         reference_arm(args)
     else:
