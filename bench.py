@@ -250,6 +250,44 @@ def kernel_rooflines(dim, n, reps=20):
     return out, peak, src
 
 
+def step_timing_3d(n=256, nsteps=5, warm=2):
+    """implicit ROSW steps of the 3-D n^3 problem on one GPU (BASELINE configs[3] tile):
+    the same step as the headline, reported next to it."""
+    import torch
+    from helpers import product_physics
+    from ksfd_b200 import core
+    p = phys_dict(3, (n, n, n))
+    ctx = core.Context(3, (n, n, n), 3)
+    ctx.set_physics(product_physics(p))
+    rng = np.random.default_rng(np.random.SeedSequence(SEED).spawn(1)[0])
+    rho = 9000.0 + 90.0 * rng.standard_normal(ctx.npts)
+    u = ctx.to_internal(torch.from_numpy(np.repeat(rho, 3)).cuda())
+    opts = core.ts_options(ts_type='rosw', adapt='none', atol=0.01, rtol=1e-6,
+                           ksp_rtol=KSP_RTOL, ksp_max_it=2000, restart=30)
+    t, its = 0.0, 0
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    for k in range(warm + nsteps):
+        if k == warm:
+            torch.cuda.synchronize()
+            e0.record()
+            its = 0
+        ctx.groom(u)
+        r = ctx.ts_step(u, t, DT, opts)
+        if not r.accepted:
+            raise RuntimeError('3-D time step failed')
+        t = r.t_new
+        its += r.ksp_its
+        ctx.velocity_max(u)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / nsteps
+    ctx.close()
+    torch.cuda.empty_cache()
+    return dict(ms_per_step=ms, steps_per_sec=1e3 / ms, mpts_steps_per_s=n ** 3 / ms / 1e3,
+                gmres_its_per_step=its / nsteps, steps=nsteps)
+
+
 def native_arm(args):
     import torch
     import torch.distributed as dist
@@ -354,6 +392,8 @@ def native_arm(args):
         if not args.quick:
             k3, _, _ = kernel_rooflines(3, (256, 256, 256), reps=10)
             extra['kernels_256x256x256'] = k3
+            if world == 1:
+                extra['step_256x256x256'] = step_timing_3d()
         dom = k2['jvp_precond']
         traffic = None
         tp = os.path.join(ROOT, 'profiles', 'traffic.json')
