@@ -172,7 +172,10 @@ def reference_arm(args):
     if rank != 0:
         return
     procs = min(os.cpu_count() or 1, 32)
-    n = 96
+    # bounded sample: one n x n tile per core and step, sized so that K steps
+    # end within a few minutes (SuperLU factorisation dominates: ~2.2 s per
+    # step at 96^2, ~0.8 s at 64^2)
+    n = 96 if args.steps <= 20 else 64
     for _ in range(max(args.warmup, 0) and 1):
         cpu_baseline(1, n, procs)
     t0 = time.perf_counter()
