@@ -70,9 +70,9 @@ k_mdot(long long n, VecList vs, const double *__restrict__ w,
 }
 
 // out[i] (op)= sum_b partial[i][b];  mode 0: store, 1: add, 2: store sqrt
-__global__ void k_reduce_partials(int nv, int nblocks,
-                                  const double *__restrict__ partial,
-                                  double *__restrict__ out, int mode)
+// (partial and out may alias: in-place sqrt of an all-reduced sum)
+__global__ void k_reduce_partials(int nv, int nblocks, const double *partial, double *out,
+                                  int mode)
 {
     const int i = blockIdx.x;
     if (i >= nv) return;
