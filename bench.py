@@ -63,6 +63,7 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index = index
+        self.window = None          # (t0, t1): only samples inside count
         self.samples = []
         self.stop = threading.Event()
         self.th = None
@@ -82,8 +83,8 @@ class ClockSampler:
             for bit, k in R:
                 if bits & bit:
                     row[2 + k] = 'Active'
-            self.samples.append(row)
-            self.stop.wait(0.01)
+            self.samples.append(row + [time.perf_counter()])
+            self.stop.wait(0.005)
 
     def _run(self):
         try:
@@ -97,7 +98,7 @@ class ClockSampler:
                      '--format=csv,noheader,nounits'],
                     capture_output=True, text=True, timeout=5).stdout.strip()
                 if o:
-                    self.samples.append([x.strip() for x in o.split(',')])
+                    self.samples.append([x.strip() for x in o.split(',')] + [time.perf_counter()])
             except Exception:
                 pass
             self.stop.wait(0.2)
@@ -115,7 +116,11 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
                  'sw_power_cap']
-        for s in self.samples:
+        rows = self.samples
+        if self.window:
+            inside = [r for r in rows if self.window[0] <= r[-1] <= self.window[1]]
+            rows = inside or rows
+        for s in rows:
             try:
                 sm.append(float(s[0]))
                 mx.append(float(s[1]))
@@ -337,20 +342,24 @@ def native_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    # ---- device-resident timing -----------------------------------------
-    barrier()
-    state['its'] = 0
-    l0 = _lib.launch_count()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
+    # the clock sampler (NVML, every 5 ms) runs from before the warm-up; only the
+    # samples taken inside the timed region are reported
     with ClockSampler(local) as cs:
+        for _ in range(args.warmup):
+            step()
+        # ---- device-resident timing -------------------------------------
+        barrier()
+        state['its'] = 0
+        l0 = _lib.launch_count()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
             step()
         e1.record()
         barrier()
+        cs.window = (w0, time.perf_counter())
     ms = torch.tensor([e0.elapsed_time(e1)], device='cuda', dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
