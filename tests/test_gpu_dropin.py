@@ -236,3 +236,25 @@ def test_options84_reduced_adaptive_run_vs_oracle(tmp_path, capsys):
         got = np.asarray(ser.retrieve_by_time(times[k + 1])).reshape(-1, order='F')
         ref = u.reshape(-1, order='F')
         assert relerr(got, ref, 3) < 1e-8, (k, relerr(got, ref, 3))
+
+
+@pytest.mark.parametrize('name,over', [
+    ('options80', dict(nelements=96, maxsteps=5)),                  # 1-D adaptive
+    ('options81', dict(nelements=32, maxsteps=4)),                  # 2-D adaptive
+    ('options92', dict(nelements=64, maxsteps=4)),                  # 1-D, expression ICs
+    ('options113a', dict(nelements=96, randgridnw=96, randgridnh=96,
+                         maxsteps=5)),     # noise injection, worm conservation, CFL limiter
+])
+def test_shipped_option_files_run_through_the_solver_entry(name, over, tmp_path, capsys):
+    """every option file shipped with the reference (argument lines unchanged
+    except for the grid size / step count) runs through the ksfdsolver2 entry on
+    the device path: parser, parameters, initial condition, adaptive ROSW,
+    monitors, time series."""
+    from ksfd_b200.solver import main
+    path = os.path.join(HERE, 'options', name + '.args')
+    save = str(tmp_path / 'solutions' / name)
+    rc = main('ksfdsolver2.py', opt_with(path, tmp_path, name, **over), '--save=' + save)
+    assert rc == 0
+    out = capsys.readouterr().out
+    assert 'SNES failures =  0' in out, out[-2000:]
+    assert out.count('clock:') >= over['maxsteps']
