@@ -1,0 +1,28 @@
+"""BASELINE configs[1]: the reference's options84 problem at FULL size (2-D
+1536x1536, two ligand groups, TSAdapt basic from dt = 1e-8) through the
+ksfdsolver2 entry on one GPU, for a limited number of steps.  Prints wall time
+per accepted step (includes monitors; no --save)."""
+import os
+import sys
+import tempfile
+import time
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, R)
+from ksfd_b200.solver import main
+
+nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+lines = []
+for line in open(os.path.join(R, 'tests', 'options', 'options84.args')):
+    key = line.split('=', 1)[0].strip()
+    if key.startswith('--save') or key.startswith('--check'):
+        continue
+    if key == 'maxsteps':
+        line = 'maxsteps=%d\n' % nsteps
+    lines.append(line)
+with tempfile.NamedTemporaryFile('w', suffix='.args', delete=False) as f:
+    f.write(''.join(lines))
+t0 = time.perf_counter()
+rc = main('ksfdsolver2.py', '@' + f.name)
+wall = time.perf_counter() - t0
+print('options84 full size: rc %d, %d steps in %.2f s wall (%.1f ms/step incl. set-up and '
+      'monitors)' % (rc, nsteps, wall, 1e3 * wall / nsteps))
