@@ -87,6 +87,14 @@ struct ksfd_ctx {
     // the benchmark problem: with 1e-9 some stage solves need 20-80 iterations
     // instead of 6)
     double gm_cycle_factor = 1e-5;
+    // spectral (FFT) preconditioner: cuFFT plans, spectra, coefficient means
+    int fft_fwd = -1, fft_inv = -1;
+    void *fft_spec = nullptr;    // double2 [dof][n2][n1][n0/2+1]
+    double *fft_means = nullptr;
+    bool fft_failed = false;
+    bool fft_means_valid = false;   // means belong to the current linearisation
+    bool pc_auto_fft = false;    // precond = 3 (auto): current choice
+    int pc_auto_small = 0;
     // solver workspace
     double *krylov = nullptr;    // (restart+1) vectors
     int krylov_cap = 0;

@@ -14,6 +14,7 @@
 #include "ctx.h"
 #include "march_launch.cuh"
 #include "naive_kernels.cuh"
+#include "fftpc.cuh"
 
 // ---------------------------------------------------------------------------
 // errors
@@ -88,6 +89,8 @@ static int ensure_work(ksfd_ctx *c, int i)
     return 0;
 }
 
+static void fftpc_destroy(ksfd_ctx *c);
+
 extern "C" int ksfd_abi_version(void) { return KSFD_ABI_VERSION; }
 extern "C" const char *ksfd_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t ksfd_launch_count(void) { return g_launches; }
@@ -148,6 +151,9 @@ extern "C" int ksfd_ctx_destroy(ksfd_ctx *c)
     cudaFree(c->dscal);
     cudaFreeHost(c->hscal);
     cudaFree(c->krylov);
+    fftpc_destroy(c);
+    cudaFree(c->fft_spec);
+    cudaFree(c->fft_means);
     cudaFree(c->gm);
     cudaFree(c->gmi);
     cudaFree(c->gm_done);
@@ -680,6 +686,7 @@ static int jvp_setup_impl(ksfd_ctx *c, const double *u, double shift,
     // ghost planes of the preconditioner field for the fused A*M^{-1} kernel
     TRY(exchange(c, c->pc, 1, 2, st));
     c->have_jac = true;
+    c->fft_means_valid = false;
     return 0;
 }
 
@@ -748,6 +755,139 @@ extern "C" int ksfd_pc_apply(ksfd_ctx *c, const double *r, double *z, void *stre
     if (!c->have_jac) return fail("ksfd_jvp_setup has not been called");
     if (!r || !z) return fail("ksfd_pc_apply: NULL vector");
     return pc_apply_impl(c, r, z, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+// spectral preconditioner (fftpc.cuh): cuFFT through dlopen (CUDA toolkit's
+// libcufft.so.11; no link-time dependency), plans created once per context
+// ---------------------------------------------------------------------------
+struct CufftApi {
+    void *h = nullptr;
+    bool tried = false;
+    int (*PlanMany)(int *, int, int *, int *, int, int, int *, int, int, int, int) = nullptr;
+    int (*SetStream)(int, cudaStream_t) = nullptr;
+    int (*ExecD2Z)(int, double *, double2 *) = nullptr;
+    int (*ExecZ2D)(int, double2 *, double *) = nullptr;
+    int (*Destroy)(int) = nullptr;
+};
+static CufftApi g_fft;
+enum { CUFFT_D2Z_ = 0x6a, CUFFT_Z2D_ = 0x6c };
+
+static bool cufft_load()
+{
+    if (g_fft.tried) return g_fft.h != nullptr;
+    g_fft.tried = true;
+    const char *names[] = {"libcufft.so.11", "/usr/local/cuda/lib64/libcufft.so.11", "libcufft.so",
+                           "libcufft.so.12"};
+    void *h = nullptr;
+    for (const char *nm : names)
+        if ((h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!h) return false;
+#define FSYM(n)                                        \
+    *(void **)(&g_fft.n) = dlsym(h, "cufft" #n);       \
+    if (!g_fft.n) return false;
+    FSYM(PlanMany) FSYM(SetStream) FSYM(ExecD2Z) FSYM(ExecZ2D) FSYM(Destroy)
+#undef FSYM
+    g_fft.h = h;
+    return true;
+}
+
+static void fftpc_destroy(ksfd_ctx *c)
+{
+    if (c->fft_fwd >= 0 && g_fft.Destroy) {
+        g_fft.Destroy(c->fft_fwd);
+        g_fft.Destroy(c->fft_inv);
+        c->fft_fwd = c->fft_inv = -1;
+    }
+}
+
+static bool fftpc_available(ksfd_ctx *c)
+{
+    return c->nranks == 1 && !c->fft_failed && cufft_load();
+}
+
+// plans + buffers (first use); returns false (and remembers) if cuFFT refuses
+static bool fftpc_prepare(ksfd_ctx *c)
+{
+    if (c->fft_fwd >= 0) return true;
+    if (!fftpc_available(c)) return false;
+    const int dof = c->dof;
+    const int nx = (int)c->n[0], ny = c->dim >= 2 ? (int)c->n[1] : 1, nz = c->dim >= 3 ? (int)c->n[2] : 1;
+    const int nxh = nx / 2 + 1;
+    int rank = c->dim, n[3], ie[3], oe[3], istride = 1, idist, odist;
+    if (c->dim == 1) {
+        n[0] = nx; ie[0] = nx; oe[0] = nxh; istride = dof; idist = 1; odist = nxh;
+    } else if (c->dim == 2) {
+        n[0] = ny; n[1] = nx; ie[0] = ny; ie[1] = dof * nx; oe[0] = ny; oe[1] = nxh;
+        idist = nx; odist = ny * nxh;
+    } else {
+        n[0] = nz; n[1] = ny; n[2] = nx; ie[0] = nz; ie[1] = dof * ny; ie[2] = nx;
+        oe[0] = nz; oe[1] = ny; oe[2] = nxh; idist = ny * nx; odist = nz * ny * nxh;
+    }
+    int f = -1, b = -1;
+    if (g_fft.PlanMany(&f, rank, n, ie, istride, idist, oe, 1, odist, CUFFT_D2Z_, dof) != 0 ||
+        g_fft.PlanMany(&b, rank, n, oe, 1, odist, ie, istride, idist, CUFFT_Z2D_, dof) != 0) {
+        if (f >= 0) g_fft.Destroy(f);
+        c->fft_failed = true;
+        return false;
+    }
+    const size_t nspec = (size_t)dof * nz * ny * nxh;
+    if (cudaMalloc(&c->fft_spec, sizeof(double2) * nspec) != cudaSuccess ||
+        cudaMalloc(&c->fft_means, sizeof(double) * (KSFD_MAX_LIGANDS + 2) * (FFT_MEAN_BLOCKS + 1)) !=
+            cudaSuccess) {
+        cudaGetLastError();
+        g_fft.Destroy(f);
+        g_fft.Destroy(b);
+        c->fft_failed = true;
+        return false;
+    }
+    c->fft_fwd = f;
+    c->fft_inv = b;
+    return true;
+}
+
+static VecRef coef_ref(const ksfd_ctx *c);
+
+// coefficient means of the current linearisation (after k_coef_setup)
+static int fftpc_setup(ksfd_ctx *c, cudaStream_t st)
+{
+    if (!fftpc_prepare(c)) return 0;
+    double *partial = c->fft_means + (KSFD_MAX_LIGANDS + 2);
+    k_fft_means_partial<<<dim3(c->P.nlig + 2, FFT_MEAN_BLOCKS), 256, 0, st>>>(c->g, coef_ref(c).base,
+                                                                           partial);
+    CKL();
+    k_fft_means_final<<<c->P.nlig + 2, 32, 0, st>>>(c->g, partial, c->fft_means);
+    CKL();
+    return 0;
+}
+
+// out = A0^-1 in   (in, out: distinct plane-SoA vectors)
+static int fftpc_apply(ksfd_ctx *c, const double *in, double *out, cudaStream_t st,
+                       const int *skip)
+{
+    FftSym S{};
+    S.dof = c->dof;
+    S.nlig = c->P.nlig;
+    S.n0 = (int)c->n[0];
+    S.n1 = c->dim >= 2 ? (int)c->n[1] : 1;
+    S.n2 = c->dim >= 3 ? (int)c->n[2] : 1;
+    S.shift = c->shift;
+    for (int a = 0; a < 3; ++a) S.c2[a] = c->P.c2[a];
+    for (int l = 0; l < KSFD_MAX_LIGANDS; ++l) {
+        S.s[l] = c->P.s[l];
+        S.gamma[l] = c->P.gamma[l];
+        S.D[l] = c->P.D[l];
+    }
+    double2 *spec = static_cast<double2 *>(c->fft_spec);
+    if (g_fft.SetStream(c->fft_fwd, st) != 0 || g_fft.SetStream(c->fft_inv, st) != 0)
+        return fail("cufftSetStream failed");
+    if (g_fft.ExecD2Z(c->fft_fwd, const_cast<double *>(in), spec) != 0)
+        return fail("cufftExecD2Z failed");
+    const long long nk = (long long)(S.n0 / 2 + 1) * S.n1 * S.n2;
+    k_fft_symbol_solve<<<nblk(nk, 256), 256, 0, st>>>(S, c->fft_means, spec, skip);
+    CKL();
+    if (g_fft.ExecZ2D(c->fft_inv, spec, out) != 0) return fail("cufftExecZ2D failed");
+    return 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -1276,12 +1416,18 @@ static int gm_orth_launch(ksfd_ctx *c, const VecList &vl, int off, int do_scale,
     }
 
 // one Arnoldi step j of the pipeline (all launches, no host wait)
-static int gm_step(ksfd_ctx *c, int j, double *V, bool pre, const GmOpts &go, cudaStream_t st)
+static int gm_step(ksfd_ctx *c, int j, double *V, int pcm, const GmOpts &go, cudaStream_t st)
 {
     const long long n = nlocal(c);
     double *w = V + (long long)(j + 1) * n;
     GmStatus *hsd = static_cast<GmStatus *>(c->gm_status_dev);
-    TRY(jvp_impl(c, V + (long long)j * n, w, pre, st, c->gmi + GMI_CYCLE_DONE));
+    if (pcm == 2) {
+        // w = A (A0^-1 v_j): spectral preconditioner, then the plain stencil pass
+        TRY(fftpc_apply(c, V + (long long)j * n, c->work[10], st, c->gmi + GMI_CYCLE_DONE));
+        TRY(jvp_impl(c, c->work[10], w, false, st, c->gmi + GMI_CYCLE_DONE));
+    } else {
+        TRY(jvp_impl(c, V + (long long)j * n, w, pcm == 1, st, c->gmi + GMI_CYCLE_DONE));
+    }
     const int nv = j + 2;                     // V_0..V_j and w itself
     for (int b = 0; b < nv; b += KSFD_MAXV) {
         const int m = std::min(KSFD_MAXV, nv - b);
@@ -1330,7 +1476,14 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
 {
     const long long n = nlocal(c);
     const int m = std::max(1, std::min(o.restart > 0 ? o.restart : 30, 60));
-    const bool pre = o.precond != 0;
+    // preconditioner: 0 none, 1 point-block Jacobi (fused into the stencil
+    // kernel), 2 spectral (fftpc.cuh), 3 automatic: block Jacobi until a solve
+    // needs >= 25 steps, then spectral; back after three spectral solves of <= 2
+    // steps.  Spectral needs one rank and cuFFT, else block Jacobi.
+    int pcm = o.precond;
+    if (pcm == 3) pcm = c->pc_auto_fft ? 2 : 1;
+    if (pcm == 2 && !fftpc_prepare(c)) pcm = 1;
+    const bool pre = pcm == 1;
     if (c->krylov_cap < m + 1) {
         cudaFree(c->krylov);
         c->krylov = nullptr;
@@ -1339,6 +1492,14 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
     }
     TRY(ensure_work(c, 0));
     TRY(gm_alloc(c));
+    if (pcm == 2) {
+        TRY(ensure_work(c, 10));
+        TRY(ensure_work(c, 11));
+        if (!c->fft_means_valid) {
+            TRY(fftpc_setup(c, st));
+            c->fft_means_valid = true;
+        }
+    }
     double *V = c->krylov;
     double *tmp = c->work[0];
     GmStatus *hs = static_cast<GmStatus *>(c->gm_status);
@@ -1409,7 +1570,7 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
                     return hs->cycle_done != 0 || hs->iters_done >= j - Rj;
                 }, "an Arnoldi step", c));
                 if (hs->seq >= seq && hs->cycle_done) break;
-                TRY(gm_step(c, j, V, pre, go, st));
+                TRY(gm_step(c, j, V, pcm, go, st));
             }
         } else {
             // several ranks over NCCL: every launch decision must be taken from the
@@ -1426,7 +1587,7 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
                 }, "an Arnoldi chunk", c));
                 if (hs->cycle_done) break;
                 for (int jj = j; jj < std::min(j + chunk, m); ++jj)
-                    TRY(gm_step(c, jj, V, pre, go, st));
+                    TRY(gm_step(c, jj, V, pcm, go, st));
             }
         }
         TRY(gm_wait(st, [&] { return hs->seq >= seq && hs->cycle_done; }, "the end of a cycle", c));
@@ -1437,16 +1598,29 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
         c->gm_pred[cycle > 0] = hs->k_cols;
         if (hs->reason != -9 && hs->k_cols > 0) {
             const unsigned ub = std::min(nblk(c->g.npts, 256), 148u * 8u);
-#define KSFD_UPD(D)                                                                          \
-    k_gm_update_x<D><<<ub, 256, 0, st>>>(c->g, c->P, coef_ref(c), id, c->pc, pre ? 1 : 0, n, V, \
-                                         c->gm + GM_Y, c->gmi + GMI_K, c->gmi + GMI_NOUPD, x)
-            switch (c->dof) {
-            case 2: KSFD_UPD(2); break;
-            case 3: KSFD_UPD(3); break;
-            case 4: KSFD_UPD(4); break;
-            case 5: KSFD_UPD(5); break;
-            default: KSFD_UPD(0); break;
+#define KSFD_UPD(D, PCF, VV, YY, KK, XX)                                                     \
+    k_gm_update_x<D><<<ub, 256, 0, st>>>(c->g, c->P, coef_ref(c), id, c->pc, PCF, n, VV, YY, KK, \
+                                         c->gmi + GMI_NOUPD, XX)
+#define KSFD_UPD_DOF(PCF, VV, YY, KK, XX)                                                    \
+    switch (c->dof) {                                                                        \
+    case 2: KSFD_UPD(2, PCF, VV, YY, KK, XX); break;                                         \
+    case 3: KSFD_UPD(3, PCF, VV, YY, KK, XX); break;                                         \
+    case 4: KSFD_UPD(4, PCF, VV, YY, KK, XX); break;                                         \
+    case 5: KSFD_UPD(5, PCF, VV, YY, KK, XX); break;                                         \
+    default: KSFD_UPD(0, PCF, VV, YY, KK, XX); break;                                        \
+    }
+            if (pcm == 2) {
+                // x += A0^-1 (V y)
+                double *z = c->work[10], *s2 = c->work[11];
+                CK(cudaMemsetAsync(z, 0, sizeof(double) * n, st));
+                KSFD_UPD_DOF(0, V, c->gm + GM_Y, c->gmi + GMI_K, z)
+                CKL();
+                TRY(fftpc_apply(c, z, s2, st, c->gmi + GMI_NOUPD));
+                KSFD_UPD_DOF(0, s2, nullptr, nullptr, x)
+            } else {
+                KSFD_UPD_DOF(pre ? 1 : 0, V, c->gm + GM_Y, c->gmi + GMI_K, x)
             }
+#undef KSFD_UPD_DOF
 #undef KSFD_UPD
             CKL();
         }
@@ -1455,6 +1629,15 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
     if (getenv("KSFD_DEBUG_GMRES"))
         fprintf(stderr, "gmres: its %d reason %d rnorm0 %.3e rnorm %.3e\n", hs->its_total,
                 hs->reason, hs->rnorm0, hs->rnorm);
+    if (o.precond == 3 && hs->reason > 0) {
+        if (pcm == 1 && hs->its_total >= 25 && fftpc_available(c)) {
+            c->pc_auto_fft = true;
+            c->pc_auto_small = 0;
+        } else if (pcm == 2) {
+            c->pc_auto_small = hs->its_total <= 2 ? c->pc_auto_small + 1 : 0;
+            if (c->pc_auto_small >= 3) c->pc_auto_fft = false;
+        }
+    }
     if (res) {
         res->its = hs->its_total;
         res->reason = hs->reason;
@@ -1468,7 +1651,9 @@ static int gmres_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x
                       const ksfd_ksp_opts &o, ksfd_ksp_result *res, cudaStream_t st)
 {
     if (c->gm_pipeline && !o.reorth) return gmres_pipe_impl(c, rhs, rhs_sign, x, o, res, st);
-    return gmres_sync_impl(c, rhs, rhs_sign, x, o, res, st);
+    ksfd_ksp_opts o1 = o;                   // the host-driven variant knows block Jacobi only
+    if (o1.precond > 1) o1.precond = 1;
+    return gmres_sync_impl(c, rhs, rhs_sign, x, o1, res, st);
 }
 
 extern "C" int ksfd_gmres(ksfd_ctx *c, const double *rhs, double *x,

@@ -312,8 +312,8 @@ k_gm_update_x(Geom g, DevPhys P, VecRef coef, InvD invd, const double *__restric
 {
     if (*gmi_skip) return;
     __shared__ double y[64];
-    const int k = *gmi_k;
-    for (int i = threadIdx.x; i < k; i += blockDim.x) y[i] = gm_y[i];
+    const int k = gmi_k ? *gmi_k : 1;               // no k / y: x += [M^-1] V_0
+    for (int i = threadIdx.x; i < k; i += blockDim.x) y[i] = gm_y ? gm_y[i] : 1.0;
     __syncthreads();
     const int fs = (int)g.plane_pts;
     const int dof = DOF ? DOF : g.dof;

@@ -14,8 +14,9 @@ PETSc options understood (from the '--petsc' block of the option files):
   -ts_adapt_safety / -ts_adapt_reject_safety / -ts_adapt_scale_solve_failed
   -ksp_rtol / -ksp_atol / -ksp_divtol / -ksp_max_it / -ksp_gmres_restart
   -ksp_gmres_cgs_refinement_type refine_never|refine_always
-  -pc_type none|pbjacobi (lu, as shipped in the option files, is mapped to the
-   iterative solve with a tight default tolerance: there is no LU on the device)
+  -pc_type none|pbjacobi|fft (lu, as shipped in the option files, is mapped to the
+   iterative solve with a tight default tolerance and the automatic choice between
+   block Jacobi and the spectral preconditioner: there is no LU on the device)
 Anything else in the block is accepted and ignored, as PETSc would do for
 options it has no consumer for (-options_left would list them).
 """
@@ -161,7 +162,9 @@ class KSFDTS:
             ksp_max_it=max(po.getInt('ksp_max_it', 10000), 1),
             restart=po.getInt('ksp_gmres_restart', 30),
             reorth=0 if refine == 'refine_never' else 1,
-            precond=0 if pc == 'none' else 1)
+            # lu/cholesky (the shipped option files): automatic choice between the
+            # fused block-Jacobi and the spectral preconditioner; 'fft' forces the latter
+            precond={'none': 0, 'pbjacobi': 1, 'bjacobi': 1, 'jacobi': 1, 'fft': 2}.get(pc, 3))
         return self._opts
 
     # -- the step -------------------------------------------------------------

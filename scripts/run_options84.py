@@ -11,6 +11,7 @@ sys.path.insert(0, R)
 from ksfd_b200.solver import main
 
 nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+pc_type = sys.argv[2] if len(sys.argv) > 2 else None     # pbjacobi | fft | (default: lu -> automatic)
 lines = []
 for line in open(os.path.join(R, 'tests', 'options', 'options84.args')):
     key = line.split('=', 1)[0].strip()
@@ -18,11 +19,13 @@ for line in open(os.path.join(R, 'tests', 'options', 'options84.args')):
         continue
     if key == 'maxsteps':
         line = 'maxsteps=%d\n' % nsteps
+    if pc_type and line.startswith('-pc_type'):
+        line = '-pc_type %s\n' % pc_type
     lines.append(line)
 with tempfile.NamedTemporaryFile('w', suffix='.args', delete=False) as f:
     f.write(''.join(lines))
 t0 = time.perf_counter()
 rc = main('ksfdsolver2.py', '@' + f.name)
 wall = time.perf_counter() - t0
-print('options84 full size: rc %d, %d steps in %.2f s wall (%.1f ms/step incl. set-up and '
-      'monitors)' % (rc, nsteps, wall, 1e3 * wall / nsteps))
+print('options84 full size (pc %s): rc %d, %d steps in %.2f s wall (%.1f ms/step incl. set-up and '
+      'monitors)' % (pc_type or 'auto', rc, nsteps, wall, 1e3 * wall / nsteps))

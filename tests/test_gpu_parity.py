@@ -375,3 +375,32 @@ def test_full_size_properties(label, p):
     r = udot - ctx.jvp(x)
     assert ctx.norm2(r) <= 1.5e-8 * ctx.norm2(udot)
     ctx.close()
+
+
+@pytest.mark.parametrize('label,p', [('1d', phys84(1, (128,), h=1.0 / 128)),
+                                     ('2d', phys84(2, (40, 32))),
+                                     ('3d', phys84(3, (12, 10, 14)))])
+def test_gmres_spectral_preconditioner(label, p):
+    """precond=2: FFT inverse of the frozen-coefficient operator.  Same solution
+    as the direct solve for small and large time steps, and far fewer Arnoldi
+    steps than point-block Jacobi once the step is large (the regime options84
+    reaches after its start-up phase)."""
+    import scipy.sparse.linalg as spla
+    from oracle import ksfd_oracle as O
+    ph = oracle_physics(p)
+    u = random_state(p, 21)
+    rng = np.random.default_rng(22)
+    b = rng.standard_normal(u.size)
+    ctx = make_ctx(p)
+    for dt in (1e-3, 1.0, 100.0):
+        shift = 1.0 / (O.ROSW_GAMMA * dt)
+        x_ref = spla.splu(O.ijacobian(u, shift, ph).tocsc()).solve(b)
+        ctx.jvp_setup(ctx.upload(u), shift)
+        x2, r2 = ctx.gmres(ctx.upload(b), rtol=1e-12, max_it=2000, precond=2)
+        assert r2.reason > 0, (label, dt, r2.reason, r2.its)
+        assert relerr(ctx.download(x2), x_ref) < 1e-8, (label, dt, r2.its)
+        x1, r1 = ctx.gmres(ctx.upload(b), rtol=1e-12, max_it=2000, precond=1)
+        assert r2.its <= r1.its + 2, (label, dt, r1.its, r2.its)
+        if dt >= 1.0:
+            assert r2.its <= max(30, r1.its // 4), (label, dt, r1.its, r2.its)
+    ctx.close()
