@@ -167,7 +167,7 @@ typedef struct ksfd_ksp_opts {
     int32_t precond;           /* 0 = none, 1 = point-block Jacobi, 2 = spectral
                                   (FFT inverse of the frozen-coefficient operator;
                                   one rank, needs cuFFT, else 1), 3 = automatic:
-                                  1 until a solve needs >= 25 steps, then 2 */
+                                  1 until a solve needs >= 16 steps, then 2 */
 } ksfd_ksp_opts;
 typedef struct ksfd_ksp_result {
     int32_t its, reason;       /* reason > 0 converged, < 0 diverged      */

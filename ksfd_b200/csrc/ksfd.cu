@@ -1478,7 +1478,7 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
     const int m = std::max(1, std::min(o.restart > 0 ? o.restart : 30, 60));
     // preconditioner: 0 none, 1 point-block Jacobi (fused into the stencil
     // kernel), 2 spectral (fftpc.cuh), 3 automatic: block Jacobi until a solve
-    // needs >= 25 steps, then spectral; back after three spectral solves of <= 2
+    // needs >= 16 steps, then spectral; back after three spectral solves of <= 2
     // steps.  Spectral needs one rank and cuFFT, else block Jacobi.
     int pcm = o.precond;
     if (pcm == 3) pcm = c->pc_auto_fft ? 2 : 1;
@@ -1630,7 +1630,7 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
         fprintf(stderr, "gmres: its %d reason %d rnorm0 %.3e rnorm %.3e\n", hs->its_total,
                 hs->reason, hs->rnorm0, hs->rnorm);
     if (o.precond == 3 && hs->reason > 0) {
-        if (pcm == 1 && hs->its_total >= 25 && fftpc_available(c)) {
+        if (pcm == 1 && hs->its_total >= 16 && fftpc_available(c)) {
             c->pc_auto_fft = true;
             c->pc_auto_small = 0;
         } else if (pcm == 2) {
