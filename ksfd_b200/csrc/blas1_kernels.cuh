@@ -449,11 +449,28 @@ __device__ __forceinline__ double block_sum_partials(const double *partial, int 
 // Start of a cycle: beta = ||r|| from the partial sums of <r,r> (nblocks of
 // them; 1 when already reduced over ranks), tolerances, convergence of the
 // TRUE residual.
-__global__ void k_gm_cycle_begin(int nblocks, const double *__restrict__ partial,
-                                 double *__restrict__ gm, int *__restrict__ gmi,
-                                 GmStatus *hs, int cycle, GmOpts o, P2PRed pr)
+struct GmBegin {
+    int nblocks;                 // partial sums of <r,r>
+    const double *partial;
+    double *gm;
+    int *gmi;
+    GmStatus *hs;
+    int cycle;
+    GmOpts o;
+    P2PRed pr;
+    unsigned *done;              // block counter of the fused variants
+};
+
+// all threads of ONE block
+__device__ __forceinline__ void gm_cycle_begin_body(const GmBegin &a)
 {
-    if (gmi[GMI_FINAL]) return;
+    const double *partial = a.partial;
+    double *gm = a.gm;
+    int *gmi = a.gmi;
+    GmStatus *hs = a.hs;
+    const int nblocks = a.nblocks, cycle = a.cycle;
+    const GmOpts &o = a.o;
+    const P2PRed &pr = a.pr;
     double s = block_sum_partials(partial, nblocks);
     if (pr.nranks > 1) {
         __shared__ double sv[1];
@@ -495,6 +512,54 @@ __global__ void k_gm_cycle_begin(int nblocks, const double *__restrict__ partial
     __threadfence_system();
     hs->seq = 2 * cycle + 1;
     __threadfence_system();
+}
+
+__global__ void k_gm_cycle_begin(GmBegin a)
+{
+    if (a.gmi[GMI_FINAL]) return;
+    gm_cycle_begin_body(a);
+}
+
+// the block that finishes last runs gm_cycle_begin_body (same pattern as the
+// fused bookkeeping of k_gm_mdot); every thread of the block calls this
+__device__ __forceinline__ void gm_begin_in_last_block(const GmBegin &a)
+{
+    __shared__ int last_;
+    __threadfence();                           // this block's partial sum is visible
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(a.done, 1u);
+        last_ = (t == gridDim.x - 1);
+        if (last_) atomicExch(a.done, 0u);
+    }
+    __syncthreads();
+    if (!last_) return;
+    __threadfence();                           // see every block's partial sum
+    gm_cycle_begin_body(a);
+}
+
+// <r,r> of the right-hand side and the start of cycle 0 in one launch
+__global__ void __launch_bounds__(KSFD_RED_THREADS)
+k_gm_norm_begin(long long n, const double *__restrict__ r, double *__restrict__ partial,
+                GmBegin a)
+{
+    double acc[1] = {0.0};
+    if ((n & 1) == 0 && aligned16(r)) {
+        const double2 *r2 = reinterpret_cast<const double2 *>(r);
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (n >> 1);
+             e += (long long)gridDim.x * blockDim.x) {
+            const double2 v = r2[e];
+            acc[0] = fma(v.y, v.y, fma(v.x, v.x, acc[0]));
+        }
+    } else {
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+             e += (long long)gridDim.x * blockDim.x) {
+            const double v = r[e];
+            acc[0] = fma(v, v, acc[0]);
+        }
+    }
+    block_reduce_store<1>(acc, partial, KSFD_RED_BLOCKS);
+    gm_begin_in_last_block(a);
 }
 
 // y = x * (sign / gm[GM_BETA])    (first Krylov vector)
@@ -789,10 +854,12 @@ k_gm_orth_scale(long long n, VecList vs, int off, int do_scale,
 }
 
 // r = sign*rhs - Ax (in place in ax) with the partial sums of <r,r>
+// FUSE: the last block also starts the cycle (gm_cycle_begin_body)
+template <bool FUSE>
 __global__ void __launch_bounds__(KSFD_RED_THREADS)
 k_gm_true_residual(long long n, const double *__restrict__ rhs, double sign,
                    const int *__restrict__ gmi, double *__restrict__ ax,
-                   double *__restrict__ partial)
+                   double *__restrict__ partial, GmBegin a)
 {
     if (gmi[GMI_FINAL]) return;
     double acc[1] = {0.0};
@@ -803,4 +870,5 @@ k_gm_true_residual(long long n, const double *__restrict__ rhs, double sign,
         acc[0] = fma(r, r, acc[0]);
     }
     block_reduce_store<1>(acc, partial, KSFD_RED_BLOCKS);
+    if (FUSE) gm_begin_in_last_block(a);
 }

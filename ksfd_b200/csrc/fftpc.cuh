@@ -1,16 +1,27 @@
-// Spectral preconditioner: exact inverse (by FFT) of the CONSTANT-COEFFICIENT
-// operator obtained by freezing the Jacobian coefficients at their grid means,
-//   (A0 v)_rho = shift v_rho - rho0 * Lap(g_rho v_rho + sum_l g_l v_l)
-//   (A0 v)_l   = (shift + gamma_l - D_l Lap) v_l - s_l v_rho
-// On the periodic uniform grid A0 is block circulant: in Fourier space it is one
-// small "arrow" matrix per wave number (Lap -> lambda(k), the symbol of the
-// 4th-order stencil), solved by a Schur step on rho exactly like the point
-// block.  It captures the stiff cross-diffusion coupling that point-block
-// Jacobi misses: at dt ~ 1 (options84 after the start-up phase) GMRES needs
-// hundreds of steps with block Jacobi and a handful with this.
+// Spectral preconditioner: exact inverse (by FFT) of a CONSTANT-COEFFICIENT
+// operator A0 close to the Jacobian A = shift*I - J.  The stiff part of A is
+//   (A v)_rho = shift v_rho - rho * Lap(g_rho v_rho + sum_l g_l v_l) - (first-order terms)
+//   (A v)_l   = (shift + gamma_l - D_l Lap) v_l - s_l v_rho
+// with g_rho = dG/drho, g_l = dG/dU_l.  Two diagonal scalings remove most of the
+// coefficient variation before anything is frozen: the rho row is divided by
+// rho (left scaling) and the rho unknown becomes y_0 = g_rho v_rho (right
+// scaling), which turns the row into
+//   (shift / k) y_0 - Lap(y_0 + sum_l g_l y_l),      k = rho g_rho
+// (k = s2 wherever the density cap is inactive: log-entropy diffusion is
+// LINEAR diffusion of v_rho/rho), and the ligand rows into
+//   (shift + gamma_l - D_l Lap) y_l - s_l (1/g_rho) y_0.
+// A0 freezes k, g_l and 1/g_rho at their grid means.  On the periodic uniform
+// grid it is block circulant: in Fourier space one small "arrow" matrix per
+// wave number (Lap -> lambda(k), the symbol of the 4th-order stencil), solved
+// by a Schur step on rho exactly like the point block.  M^-1 = S_R A0^-1 S_L.
+// It captures the stiff cross-diffusion coupling that point-block Jacobi
+// misses (at dt ~ 1 GMRES needs hundreds of steps with block Jacobi and a
+// handful with this) and, through the scalings, stays effective when rho
+// varies over two orders of magnitude (pattern phase of options84: half the
+// Arnoldi steps of the unscaled frozen-coefficient inverse).
 // The transforms are cuFFT calls (library code, dlopen'ed: one batched D2Z and
 // one batched Z2D per application, strided straight from / into the plane-SoA
-// vectors); the symbol solve and the coefficient means are our kernels.
+// vectors); scalings, symbol solve and coefficient means are our kernels.
 // One rank only (a slab-decomposed FFT needs all-to-all transposes).
 #pragma once
 #include "blas1_kernels.cuh"
@@ -22,23 +33,28 @@ struct FftSym {                 // what the symbol kernel needs
     double s[KSFD_MAX_LIGANDS], gamma[KSFD_MAX_LIGANDS], D[KSFD_MAX_LIGANDS];
 };
 
-// means of the coefficient fields rho (0), dG/drho (2), dG/dU_l (3+l) over the
-// owned points -> out[0], out[1], out[2+l].  Two deterministic stages:
-// grid (fields, FFT_MEAN_BLOCKS) partial sums, then one warp per field.
+// grid means over the owned points of k = rho*dG/drho -> out[0], 1/(dG/drho) ->
+// out[1], dG/dU_l -> out[2+l].  Two deterministic stages: grid (fields,
+// FFT_MEAN_BLOCKS) partial sums, then one warp per field.
 #define FFT_MEAN_BLOCKS 128
 __global__ void k_fft_means_partial(Geom g, const double *__restrict__ coef_base,
                                     double *__restrict__ partial)
 {
     // coef_base = plane 0 of the ghosted coefficient array, dof+2 fields per plane
     const int nf = g.dof + 2;
-    const int which = blockIdx.x;                   // 0: rho, 1: g_rho, 2+l: g_l
-    const int field = which == 0 ? 0 : which + 1;
+    const int which = blockIdx.x;                   // 0: rho*g_rho, 1: 1/g_rho, 2+l: g_l
     __shared__ double sm[32];
     double s = 0.0;
     for (long long p = blockIdx.y * (long long)blockDim.x + threadIdx.x; p < g.npts;
          p += (long long)gridDim.y * blockDim.x) {
         const long long k = p / g.plane_pts, pp = p - k * g.plane_pts;
-        s += coef_base[(k * nf + field) * g.plane_pts + pp];
+        const double *cp = coef_base + (k * nf) * g.plane_pts + pp;
+        if (which == 0)
+            s += cp[0] * cp[2 * g.plane_pts];
+        else if (which == 1)
+            s += 1.0 / cp[2 * g.plane_pts];
+        else
+            s += cp[(which + 1) * g.plane_pts];
     }
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
@@ -57,6 +73,31 @@ __global__ void k_fft_means_final(Geom g, const double *__restrict__ partial,
     for (int q = threadIdx.x; q < FFT_MEAN_BLOCKS; q += 32) s += partial[blockIdx.x * FFT_MEAN_BLOCKS + q];
     s = warp_sum(s);
     if (threadIdx.x == 0) out[blockIdx.x] = s / (double)g.npts;
+}
+
+// left scaling S_L: out = in with the rho field divided by rho (in == out allowed)
+__global__ void k_fft_prescale(Geom g, const double *__restrict__ coef_base, const double *in,
+                               double *out, const int *__restrict__ skip)
+{
+    if (skip && *skip) return;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= g.npts * g.dof) return;
+    const long long ps = g.plane_pts * g.dof;
+    const long long k = e / ps, r = e - k * ps;
+    double v = in[e];
+    if (r < g.plane_pts) v /= coef_base[(k * (g.dof + 2)) * g.plane_pts + r];
+    out[e] = v;
+}
+
+// right scaling S_R, in place: v_rho = y_0 / g_rho
+__global__ void k_fft_postscale(Geom g, const double *__restrict__ coef_base, double *v,
+                                const int *__restrict__ skip)
+{
+    if (skip && *skip) return;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= g.npts) return;
+    const long long k = e / g.plane_pts, pp = e - k * g.plane_pts;
+    v[k * g.dof * g.plane_pts + pp] /= coef_base[(k * (g.dof + 2) + 2) * g.plane_pts + pp];
 }
 
 // in place on the spectra: z^ = A0^(k)^-1 r^ / N   (N = number of grid points:
@@ -86,17 +127,17 @@ __global__ void k_fft_symbol_solve(FftSym S, const double *__restrict__ means, d
         const double c = cospi(2.0 * k2 / S.n2);
         lam += S.c2[2] * (32.0 * c - 2.0 * (2.0 * c * c - 1.0) - 30.0);
     }
-    const double rho0 = means[0], grho = means[1];
+    const double kbar = means[0], cbar = means[1];   // mean rho*g_rho, mean 1/g_rho
     const double inv_n = 1.0 / ((double)S.n0 * S.n1 * S.n2);
     double2 r[KSFD_MAX_LIGANDS + 1];
     for (int c = 0; c < S.dof; ++c) r[c] = spec[(long long)c * nk + e];
-    double schur = S.shift - rho0 * grho * lam;
+    double schur = S.shift / kbar - lam;
     double2 t = r[0];
     double bd[KSFD_MAX_LIGANDS], invd[KSFD_MAX_LIGANDS];
     for (int l = 0; l < S.nlig; ++l) {
         invd[l] = 1.0 / (S.shift + S.gamma[l] - S.D[l] * lam);
-        bd[l] = -rho0 * means[2 + l] * lam * invd[l];       // b_l / d_l
-        schur += bd[l] * S.s[l];                            // - b_l c_l / d_l, c_l = -s_l
+        bd[l] = -means[2 + l] * lam * invd[l];              // b_l / d_l
+        schur += bd[l] * S.s[l] * cbar;                     // - b_l c_l / d_l, c_l = -s_l*cbar
         t.x -= bd[l] * r[1 + l].x;
         t.y -= bd[l] * r[1 + l].y;
     }
@@ -107,9 +148,9 @@ __global__ void k_fft_symbol_solve(FftSym S, const double *__restrict__ means, d
     spec[e] = z0;
     for (int l = 0; l < S.nlig; ++l) {
         double2 z;
-        // z_l = (r_l/N + s_l z_rho) / d_l
-        z.x = (r[1 + l].x * inv_n + S.s[l] * z0.x) * invd[l];
-        z.y = (r[1 + l].y * inv_n + S.s[l] * z0.y) * invd[l];
+        // y_l = (r_l/N + s_l cbar y_0) / d_l
+        z.x = (r[1 + l].x * inv_n + S.s[l] * cbar * z0.x) * invd[l];
+        z.y = (r[1 + l].y * inv_n + S.s[l] * cbar * z0.y) * invd[l];
         spec[(long long)(1 + l) * nk + e] = z;
     }
 }

@@ -861,9 +861,10 @@ static int fftpc_setup(ksfd_ctx *c, cudaStream_t st)
     return 0;
 }
 
-// out = A0^-1 in   (in, out: distinct plane-SoA vectors)
-static int fftpc_apply(ksfd_ctx *c, const double *in, double *out, cudaStream_t st,
-                       const int *skip)
+// out = S_R A0^-1 S_L in   (in, out: distinct plane-SoA vectors; scratch holds the
+// row-scaled copy of `in` and may be `in` itself if that may be overwritten)
+static int fftpc_apply(ksfd_ctx *c, const double *in, double *scratch, double *out,
+                       cudaStream_t st, const int *skip)
 {
     FftSym S{};
     S.dof = c->dof;
@@ -881,12 +882,15 @@ static int fftpc_apply(ksfd_ctx *c, const double *in, double *out, cudaStream_t 
     double2 *spec = static_cast<double2 *>(c->fft_spec);
     if (g_fft.SetStream(c->fft_fwd, st) != 0 || g_fft.SetStream(c->fft_inv, st) != 0)
         return fail("cufftSetStream failed");
-    if (g_fft.ExecD2Z(c->fft_fwd, const_cast<double *>(in), spec) != 0)
-        return fail("cufftExecD2Z failed");
+    k_fft_prescale<<<nblk(nlocal(c), 256), 256, 0, st>>>(c->g, coef_ref(c).base, in, scratch, skip);
+    CKL();
+    if (g_fft.ExecD2Z(c->fft_fwd, scratch, spec) != 0) return fail("cufftExecD2Z failed");
     const long long nk = (long long)(S.n0 / 2 + 1) * S.n1 * S.n2;
     k_fft_symbol_solve<<<nblk(nk, 256), 256, 0, st>>>(S, c->fft_means, spec, skip);
     CKL();
     if (g_fft.ExecZ2D(c->fft_inv, spec, out) != 0) return fail("cufftExecZ2D failed");
+    k_fft_postscale<<<nblk(c->g.npts, 256), 256, 0, st>>>(c->g, coef_ref(c).base, out, skip);
+    CKL();
     return 0;
 }
 
@@ -1423,7 +1427,8 @@ static int gm_step(ksfd_ctx *c, int j, double *V, int pcm, const GmOpts &go, cud
     GmStatus *hsd = static_cast<GmStatus *>(c->gm_status_dev);
     if (pcm == 2) {
         // w = A (A0^-1 v_j): spectral preconditioner, then the plain stencil pass
-        TRY(fftpc_apply(c, V + (long long)j * n, c->work[10], st, c->gmi + GMI_CYCLE_DONE));
+        TRY(fftpc_apply(c, V + (long long)j * n, c->work[11], c->work[10], st,
+                        c->gmi + GMI_CYCLE_DONE));
         TRY(jvp_impl(c, c->work[10], w, false, st, c->gmi + GMI_CYCLE_DONE));
     } else {
         TRY(jvp_impl(c, V + (long long)j * n, w, pcm == 1, st, c->gmi + GMI_CYCLE_DONE));
@@ -1519,27 +1524,41 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
     hs->cycle_done = hs->final_ = hs->reason = hs->its_total = 0;
     hs->k_cols = 0;
     CK(cudaMemsetAsync(c->gmi, 0, sizeof(int) * GMI_INTS, st));
-    CK(cudaMemsetAsync(x, 0, sizeof(double) * n, st));
+    // x = 0 is not stored: the first cycle's update WRITES x (x_zero below)
     for (int cycle = 0;; ++cycle) {
         const double *r = rhs;
         double sign = rhs_sign;
+        // one rank: the block that finishes the <r,r> reduction last also starts
+        // the cycle (no separate one-block launch)
+        const bool fuse_begin = c->nranks == 1;
+        GmBegin gb{KSFD_RED_BLOCKS, c->partial, c->gm, c->gmi, hsd, cycle, go, p2p_red(c),
+                   c->gm_done};
         if (cycle == 0) {
-            VecList vl;
-            for (int i = 0; i < KSFD_MAXV; ++i) vl.v[i] = rhs;
-            k_mdot<1><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(n, vl, rhs, c->partial);
+            if (fuse_begin) {
+                k_gm_norm_begin<<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(n, rhs, c->partial, gb);
+            } else {
+                VecList vl;
+                for (int i = 0; i < KSFD_MAXV; ++i) vl.v[i] = rhs;
+                k_mdot<1><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(n, vl, rhs, c->partial);
+            }
             CKL();
         } else {
             // r = sign*rhs - A x   (true residual at restart)
             TRY(jvp_impl(c, x, tmp, false, st, c->gmi + GMI_FINAL));
-            k_gm_true_residual<<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(
-                n, rhs, rhs_sign, c->gmi, tmp, c->partial);
+            if (fuse_begin)
+                k_gm_true_residual<true><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(
+                    n, rhs, rhs_sign, c->gmi, tmp, c->partial, gb);
+            else
+                k_gm_true_residual<false><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(
+                    n, rhs, rhs_sign, c->gmi, tmp, c->partial, gb);
             CKL();
             r = tmp;
             sign = 1.0;
         }
-        if (c->nranks == 1 || c->p2p_on) {
-            k_gm_cycle_begin<<<1, 256, 0, st>>>(KSFD_RED_BLOCKS, c->partial, c->gm, c->gmi, hsd,
-                                                cycle, go, p2p_red(c));
+        if (fuse_begin) {
+            // done above
+        } else if (c->p2p_on) {
+            k_gm_cycle_begin<<<1, 256, 0, st>>>(gb);
             CKL();
         } else {
             P2PRed none{};
@@ -1548,8 +1567,8 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
                                                  c->dscal + SC_NORM, 0);
             CKL();
             TRY(allreduce_dev(c, c->dscal + SC_NORM, 1, ncclSum_, st));
-            k_gm_cycle_begin<<<1, 32, 0, st>>>(1, c->dscal + SC_NORM, c->gm, c->gmi, hsd, cycle,
-                                               go, none);
+            GmBegin g1{1, c->dscal + SC_NORM, c->gm, c->gmi, hsd, cycle, go, none, c->gm_done};
+            k_gm_cycle_begin<<<1, 32, 0, st>>>(g1);
             CKL();
         }
         k_gm_first_vector<<<KSFD_RED_BLOCKS, 256, 0, st>>>(n, r, c->gm, c->gmi, sign, V);
@@ -1598,31 +1617,33 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
         c->gm_pred[cycle > 0] = hs->k_cols;
         if (hs->reason != -9 && hs->k_cols > 0) {
             const unsigned ub = std::min(nblk(c->g.npts, 256), 148u * 8u);
-#define KSFD_UPD(D, PCF, VV, YY, KK, XX)                                                     \
+#define KSFD_UPD(D, PCF, VV, YY, KK, XZ, XX)                                                 \
     k_gm_update_x<D><<<ub, 256, 0, st>>>(c->g, c->P, coef_ref(c), id, c->pc, PCF, n, VV, YY, KK, \
-                                         c->gmi + GMI_NOUPD, XX)
-#define KSFD_UPD_DOF(PCF, VV, YY, KK, XX)                                                    \
+                                         c->gmi + GMI_NOUPD, XZ, XX)
+#define KSFD_UPD_DOF(PCF, VV, YY, KK, XZ, XX)                                                \
     switch (c->dof) {                                                                        \
-    case 2: KSFD_UPD(2, PCF, VV, YY, KK, XX); break;                                         \
-    case 3: KSFD_UPD(3, PCF, VV, YY, KK, XX); break;                                         \
-    case 4: KSFD_UPD(4, PCF, VV, YY, KK, XX); break;                                         \
-    case 5: KSFD_UPD(5, PCF, VV, YY, KK, XX); break;                                         \
-    default: KSFD_UPD(0, PCF, VV, YY, KK, XX); break;                                        \
+    case 2: KSFD_UPD(2, PCF, VV, YY, KK, XZ, XX); break;                                     \
+    case 3: KSFD_UPD(3, PCF, VV, YY, KK, XZ, XX); break;                                     \
+    case 4: KSFD_UPD(4, PCF, VV, YY, KK, XZ, XX); break;                                     \
+    case 5: KSFD_UPD(5, PCF, VV, YY, KK, XZ, XX); break;                                     \
+    default: KSFD_UPD(0, PCF, VV, YY, KK, XZ, XX); break;                                    \
     }
+            const int xz = cycle == 0 ? 1 : 0;
             if (pcm == 2) {
                 // x += A0^-1 (V y)
                 double *z = c->work[10], *s2 = c->work[11];
-                CK(cudaMemsetAsync(z, 0, sizeof(double) * n, st));
-                KSFD_UPD_DOF(0, V, c->gm + GM_Y, c->gmi + GMI_K, z)
+                KSFD_UPD_DOF(0, V, c->gm + GM_Y, c->gmi + GMI_K, 1, z)
                 CKL();
-                TRY(fftpc_apply(c, z, s2, st, c->gmi + GMI_NOUPD));
-                KSFD_UPD_DOF(0, s2, nullptr, nullptr, x)
+                TRY(fftpc_apply(c, z, z, s2, st, c->gmi + GMI_NOUPD));
+                KSFD_UPD_DOF(0, s2, nullptr, nullptr, xz, x)
             } else {
-                KSFD_UPD_DOF(pre ? 1 : 0, V, c->gm + GM_Y, c->gmi + GMI_K, x)
+                KSFD_UPD_DOF(pre ? 1 : 0, V, c->gm + GM_Y, c->gmi + GMI_K, xz, x)
             }
 #undef KSFD_UPD_DOF
 #undef KSFD_UPD
             CKL();
+        } else if (cycle == 0) {
+            CK(cudaMemsetAsync(x, 0, sizeof(double) * n, st));     // nothing to add: x = 0
         }
         if (hs->final_) break;
     }

@@ -303,14 +303,22 @@ __global__ void k_pc_apply(Geom g, DevPhys P, VecRef coef, InvD invd,
 // GMRES solution update at the end of a cycle (k, y on the device):
 //   x += M^{-1} (sum_{i<k} y_i V_i)   or   x += sum_{i<k} y_i V_i
 // gm_y = y, gmi_k = &k, gmi_skip = &no-update flag
+// x_zero: x is known to be zero on entry (first cycle) and holds garbage: it is
+// written, not read (x = ..., or x = 0 when the update is skipped)
 template <int DOF>          // DOF = 0: runtime dof (any), else compile-time (registers)
 __global__ void __launch_bounds__(256)
 k_gm_update_x(Geom g, DevPhys P, VecRef coef, InvD invd, const double *__restrict__ pc,
               int precond, long long n, const double *__restrict__ V,
               const double *__restrict__ gm_y, const int *__restrict__ gmi_k,
-              const int *__restrict__ gmi_skip, double *__restrict__ x)
+              const int *__restrict__ gmi_skip, int x_zero, double *__restrict__ x)
 {
-    if (*gmi_skip) return;
+    if (*gmi_skip) {
+        if (x_zero)
+            for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+                 e += (long long)gridDim.x * blockDim.x)
+                x[e] = 0.0;
+        return;
+    }
     __shared__ double y[64];
     const int k = gmi_k ? *gmi_k : 1;               // no k / y: x += [M^-1] V_0
     for (int i = threadIdx.x; i < k; i += blockDim.x) y[i] = gm_y ? gm_y[i] : 1.0;
@@ -351,7 +359,7 @@ k_gm_update_x(Geom g, DevPhys P, VecRef coef, InvD invd, const double *__restric
         }
 #pragma unroll
         for (int c = 0; c < MD; ++c)
-            if (c < dof) x[e0 + c * fs] += zz[c];
+            if (c < dof) x[e0 + c * fs] = x_zero ? zz[c] : x[e0 + c * fs] + zz[c];
     }
 }
 

@@ -10,10 +10,12 @@ Tolerances (fp64, max-norm relative to the largest entry of each dof):
   J.v vs assembled J@v  1e-11
   block-Jacobi blocks   1e-11
 """
+import os
+
 import numpy as np
 import pytest
 
-from helpers import (check_field, cond_scale, golden_names, load_golden,
+from helpers import (GOLD, check_field, cond_scale, golden_names, load_golden,
                      oracle_physics, phys84, product_physics, random_state,
                      relerr)
 
@@ -403,4 +405,27 @@ def test_gmres_spectral_preconditioner(label, p):
         assert r2.its <= r1.its + 2, (label, dt, r1.its, r2.its)
         if dt >= 1.0:
             assert r2.its <= max(30, r1.its // 4), (label, dt, r1.its, r2.its)
+    ctx.close()
+
+
+def test_gmres_spectral_preconditioner_on_patterned_state():
+    """The pattern phase of options84 (fixture from oracle/make_pattern_state.py:
+    rho between 5e2 and 2.6e4).  The scaled spectral preconditioner converges to
+    the direct solution in a few dozen Arnoldi steps (numpy restatement:
+    23 / 43, tests/test_spectral_pc_cpu.py)."""
+    import scipy.sparse.linalg as spla
+    from oracle import ksfd_oracle as O
+    g = np.load(os.path.join(GOLD, 'host_pattern96.npz'))
+    u, n = g['u'], tuple(int(x) for x in g['n'])
+    p = phys84(2, n)
+    ph = oracle_physics(p)
+    b = O.dfdt(u, ph).reshape(-1, order='F')
+    ctx = make_ctx(p)
+    for dt, most in ((5.0, 40), (20.0, 70)):
+        shift = 1.0 / (O.ROSW_GAMMA * dt)
+        x_ref = spla.splu(O.ijacobian(u, shift, ph).tocsc()).solve(b)
+        ctx.jvp_setup(ctx.upload(u), shift)
+        x2, r2 = ctx.gmres(ctx.upload(b), rtol=1e-11, max_it=2000, precond=2)
+        assert r2.reason > 0 and r2.its <= most * 11 // 8, (dt, r2.reason, r2.its)
+        assert relerr(ctx.download(x2), x_ref) < 1e-7, (dt, r2.its)
     ctx.close()
