@@ -1,3 +1,6 @@
+"""Arnoldi steps and wall time of one linear solve with point-block Jacobi (pc 1) and the
+spectral preconditioner (pc 2) over dt = 1e-3 .. 100, 2-D 1024^2 and 3-D 128^3 (run on a GPU box;
+output kept in profiles/r01_spectral_pc_timing.txt)."""
 import os, sys, time
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, 'tests'))
