@@ -39,6 +39,13 @@
 #include "device_common.cuh"
 #include "fastmath.cuh"
 
+// Experimental code paths, compiled in only by the stand-alone tuner
+// (scripts/tune_march.cu -DKSFD_MARCH_VARIANT=bits); the library builds with 0.
+//   bit 0: stage from the prefetch registers before refilling them (see Marcher::step)
+#ifndef KSFD_MARCH_VARIANT
+#define KSFD_MARCH_VARIANT 0
+#endif
+
 // uniform launch parameters (32-bit: a rank-local vector has < 2^31 elements,
 // checked on the host)
 struct MarchArgs {
@@ -642,7 +649,18 @@ struct Marcher {
     __device__ __forceinline__ void step(int kk)
     {
         double cur[NPRE];
-        if (DEPTH == 0) {
+        if (DEPTH == 0 && (KSFD_MARCH_VARIANT & 1)) {
+            // experimental (tuner only): stage straight from the prefetch registers,
+            // then refill them — no register copy of the plane (18 moves per plane in
+            // the 2-D J.v kernel), the prefetch goes out one stage later
+            if (active) {
+                double f[NF];
+                op.stage(P, SmemTabs<RING>(), pre, f);
+#pragma unroll
+                for (int c = 0; c < NF; ++c) q[c][PH] = f[c];
+                if (kk + 1 < k1 + KSFD_SW) op.load(g, st, kk + 1, poff, RegSink{pre});
+            }
+        } else if (DEPTH == 0) {
 #pragma unroll
             for (int c = 0; c < NPRE; ++c) cur[c] = pre[c];
             if (active && kk + 1 < k1 + KSFD_SW) op.load(g, st, kk + 1, poff, RegSink{pre});
@@ -658,7 +676,7 @@ struct Marcher {
             issue(kk + DEPTH, (it + DEPTH) & (NSLOT - 1));
             ++it;
         }
-        if (active) {
+        if (active && !(DEPTH == 0 && (KSFD_MARCH_VARIANT & 1))) {
             double f[NF];
             op.stage(P, SmemTabs<RING>(), cur, f);
 #pragma unroll

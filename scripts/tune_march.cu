@@ -4,6 +4,10 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo
 //        -I ksfd_b200/csrc scripts/tune_march.cu -o gpurun_out/tune_march
 //   ./tune_march [2d N | 3d N] ...
+// -DKSFD_MARCH_VARIANT=bits compiles the experimental code paths of
+// march_kernels.cuh (build one binary per variant; the checksums of the outputs
+// must agree bit for bit between them).  TUNE_ALL=1 adds the rejected variants
+// (cp.async pipeline, other min-blocks) to the library's own configurations.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -76,6 +80,16 @@ __global__ void k_fill(double *p, long long n, double base, double amp, unsigned
     x *= 0xBF58476D1CE4E5B9ull;
     x ^= x >> 32;
     p[i] = base + amp * ((double)(x & 0xFFFFFF) / 16777216.0 - 0.5);
+}
+
+// order-independent checksum of an output vector (integer sum of the bit patterns)
+__global__ void k_cks(const double *p, long long n, unsigned long long *out)
+{
+    unsigned long long s = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        s += (unsigned long long)__double_as_longlong(p[i]) * 0x9E3779B97F4A7C15ull + (unsigned long long)i;
+    atomicAdd(out, s);
 }
 
 struct Problem {
@@ -157,9 +171,21 @@ static void run_variant(const char *name, const Problem &pb, const DevPhys &P, O
         CHECK(cudaEventElapsedTime(&ms, e0, e1));
         const double us = ms * 1e3 / reps;
         const double gpts = pb.npts / us / 1e3;
-        printf("#%02d %-12s TX%3d TY%2d MINB%d UNR%d D%d regs%3d occ%d rz%4d grid %4dx%3dx%4d  %9.2f us  %6.2f Gpts/s  frac %.3f\n",
-               ord, name, TX, TY, MINB, (int)UNR, DEPTH, fa.numRegs, occ, rz, ntx, nty, nch, us, gpts,
-               gpts * 72.0 / 6544.7);
+        // checksum of one launch on buffer set 0
+        unsigned long long *dck, hck = 0;
+        CHECK(cudaMalloc(&dck, 8));
+        CHECK(cudaMemset(dck, 0, 8));
+        {
+            Op op = op_proto;
+            bind(op, pb, 0);
+            kern<<<grid, T::NT, smem>>>(a, P, op, nullptr);
+            k_cks<<<592, 256>>>(pb.out[0], pb.npts * 3, dck);
+        }
+        CHECK(cudaMemcpy(&hck, dck, 8, cudaMemcpyDeviceToHost));
+        CHECK(cudaFree(dck));
+        printf("#%02d %-12s V%d TX%3d TY%2d MINB%d UNR%d D%d regs%3d occ%d rz%4d grid %4dx%3dx%4d  %9.2f us  %6.2f Gpts/s  frac %.3f  cks %016llx\n",
+               ord, name, KSFD_MARCH_VARIANT, TX, TY, MINB, (int)UNR, DEPTH, fa.numRegs, occ, rz, ntx,
+               nty, nch, us, gpts, gpts * 72.0 / 6544.7, hck);
     }
     fflush(stdout);
 }
@@ -257,38 +283,38 @@ int main(int argc, char **argv)
         Problem pb = make_problem(dim, n);
         DevPhys P = make_phys(dim);
         printf("== %dD n=%d  (%lld points, %d buffer sets)\n", dim, n, pb.npts, pb.nrot);
+        const bool all = getenv("TUNE_ALL") != nullptr;
         if (dim == 2) {
+            // the library's configurations (march_res.cu / march_jvp.cu)
             RES2(124, 6, false, 0);
-            RES2(124, 6, false, 3);
             RES2(252, 3, false, 0);
-            RES2(252, 3, false, 3);
-            RES2(124, 6, true, 3);
             JVP2(124, 4, true, true, 0);
-            JVP2(124, 4, true, true, 3);
-            JVP2(124, 5, true, true, 3);
-            JVP2(124, 6, true, true, 3);
-            JVP2(252, 2, true, true, 3);
-            JVP2(252, 3, true, true, 3);
-            JVP2(124, 4, false, true, 3);
-            JVP2(124, 6, false, true, 3);
+            JVP2(252, 2, true, true, 0);
             JVP2(124, 4, true, false, 0);
-            JVP2(124, 4, true, false, 3);
-            JVP2(124, 6, true, false, 3);
+            JVP2(252, 2, true, false, 0);
+            if (all) {
+                RES2(124, 6, false, 3);
+                RES2(252, 3, false, 3);
+                JVP2(124, 4, true, true, 3);
+                JVP2(124, 5, true, true, 3);
+                JVP2(124, 6, true, true, 3);
+                JVP2(252, 3, true, true, 3);
+                JVP2(124, 4, false, true, 0);
+            }
         } else {
-            RES3(32, 16, 1, false, 0);
-            RES3(32, 16, 1, false, 3);
             RES3(16, 16, 2, false, 0);
-            RES3(16, 16, 2, false, 3);
+            RES3(32, 16, 1, false, 0);
             JVP3(32, 8, 1, true, true, 0);
-            JVP3(32, 8, 1, true, true, 3);
-            JVP3(32, 8, 2, true, true, 3);
-            JVP3(16, 16, 1, true, true, 3);
-            JVP3(16, 16, 2, true, true, 3);
-            JVP3(32, 16, 1, true, true, 3);
-            JVP3(32, 8, 1, false, true, 3);
-            JVP3(32, 8, 2, false, true, 3);
-            JVP3(32, 8, 1, true, false, 3);
-            JVP3(32, 8, 2, true, false, 3);
+            JVP3(16, 16, 1, true, true, 0);
+            JVP3(32, 8, 1, true, false, 0);
+            JVP3(16, 16, 1, true, false, 0);
+            if (all) {
+                RES3(32, 16, 1, false, 3);
+                RES3(16, 16, 2, false, 3);
+                JVP3(32, 8, 1, true, true, 3);
+                JVP3(32, 8, 2, true, true, 3);
+                JVP3(32, 16, 1, true, true, 3);
+            }
         }
         free_problem(pb);
     }
