@@ -310,9 +310,19 @@ def native_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    n = (TILE, TILE * world)
-    p = phys_dict(2, n)
-    ctx = core.Context(2, n, 3, device=local, rank=rank, nranks=world)
+    # default: weak scaling, one 1024^2 tile per GPU; --workload selects the
+    # strong-scaling cases of BASELINE configs[2] / configs[3] (fixed global grid)
+    if args.workload == 'strong-1024':
+        dim, n, scaling = 2, (TILE, TILE), 'strong'
+        wl = '2-D 1024x1024 GLOBAL grid split into %d slab(s)' % world
+    elif args.workload == 'strong-256':
+        dim, n, scaling = 3, (256, 256, 256), 'strong'
+        wl = '3-D 256^3 GLOBAL grid split into %d slab(s) along z' % world
+    else:
+        dim, n, scaling = 2, (TILE, TILE * world), 'weak'
+        wl = '2-D 1024x1024 tile per GPU (global 1024x%d)' % n[1]
+    p = phys_dict(dim, n)
+    ctx = core.Context(dim, n, 3, device=local, rank=rank, nranks=world)
     ctx.set_physics(product_physics(p))
     if world > 1:
         from ksfd_b200 import parallel
@@ -366,7 +376,7 @@ def native_arm(args):
     ms = float(ms.item())
     launches = _lib.launch_count() - l0
     its_per_step = state['its'] / max(args.steps, 1)
-    gpts = n[0] * n[1]
+    gpts = int(np.prod(n))
     value = gpts * args.steps / (ms * 1e-3) / 1e6
     # ---- end-to-end through host buffers --------------------------------
     # two pinned host buffers, ping-pong: each step reads its input from one
@@ -426,12 +436,12 @@ def native_arm(args):
     line = dict(metric='implicit TS throughput (ROSW steps x grid points)',
                 value=value, unit='Mpts*steps/s', n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms / args.steps,
-                higher_is_better=True, scaling='weak', vs_baseline=None,
+                higher_is_better=True, scaling=scaling, vs_baseline=None,
                 dtype='f64', data='synthetic',
                 steps_per_sec=args.steps / (ms * 1e-3),
-                config=dict(workload='2-D 1024x1024 tile per GPU (global 1024x%d), dof 3, '
+                config=dict(workload='%s, dof 3, '
                                      'options84 physics, h=1/384, dt=1e-3, ROSW ra34pw2, '
-                                     'GMRES(30)+point-block-Jacobi rtol %.0e' % (n[1], KSP_RTOL),
+                                     'GMRES(30)+point-block-Jacobi rtol %.0e' % (wl, KSP_RTOL),
                             parallelism='slab%d' % world,
                             l2='step working set ~1 GB (31 Krylov + 10 stage vectors of '
                                '25 MB) exceeds the 126 MB L2; kernel-only timings rotate '
@@ -456,6 +466,11 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--workload', default='weak-1024',
+                    choices=['weak-1024', 'strong-1024', 'strong-256'],
+                    help='weak-1024 (default, the headline): one 1024^2 tile per GPU; '
+                         'strong-1024 / strong-256: BASELINE configs[2] / configs[3], the '
+                         'global 1024^2 / 256^3 grid split over the GPUs')
     ap.add_argument('--quick', action='store_true', help='skip the 256^3 kernel timings')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline')
     ap.add_argument('--sweep', action='store_true',
