@@ -41,7 +41,9 @@
 
 // Experimental code paths, compiled in only by the stand-alone tuner
 // (scripts/tune_march.cu -DKSFD_MARCH_VARIANT=bits); the library builds with 0.
-//   bit 0: stage from the prefetch registers before refilling them (see Marcher::step)
+//   bit 0: policies with STAGE_FIRST stage from the prefetch registers before refilling
+//          them (see Marcher::step).  Measured (profiles/r01_tuner_variant_stage_first.txt,
+//          bit-identical outputs): residual +3 %, J.v -2 % => residual / velocity only.
 #ifndef KSFD_MARCH_VARIANT
 #define KSFD_MARCH_VARIANT 0
 #endif
@@ -276,6 +278,7 @@ struct ResidualOp {
     static constexpr int NAUX = NLIG + 1;      // udot of the output plane
     static constexpr bool HAS_AUX = true;
     static constexpr bool TABS = true;
+    static constexpr bool STAGE_FIRST = (KSFD_MARCH_VARIANT & 1) != 0;
     VecRef u;
     const double *udot, *src;
     double *out;
@@ -376,6 +379,7 @@ struct JvpOp {
     static constexpr int NAUX = 1;
     static constexpr bool HAS_AUX = false;
     static constexpr bool TABS = false;
+    static constexpr bool STAGE_FIRST = false;
     VecRef coef, v, pc;
     double shift;
     double invd[NLIG];
@@ -476,6 +480,7 @@ struct VelocityOp {
     static constexpr int NAUX = 1;
     static constexpr bool HAS_AUX = false;
     static constexpr bool TABS = true;
+    static constexpr bool STAGE_FIRST = (KSFD_MARCH_VARIANT & 1) != 0;
     VecRef u;
     double *vel;        // optional plane-SoA output with DIM fields
     double *vmax;       // optional per-axis max
@@ -649,7 +654,7 @@ struct Marcher {
     __device__ __forceinline__ void step(int kk)
     {
         double cur[NPRE];
-        if (DEPTH == 0 && (KSFD_MARCH_VARIANT & 1)) {
+        if (DEPTH == 0 && Op::STAGE_FIRST) {
             // experimental (tuner only): stage straight from the prefetch registers,
             // then refill them — no register copy of the plane (18 moves per plane in
             // the 2-D J.v kernel), the prefetch goes out one stage later
@@ -676,7 +681,7 @@ struct Marcher {
             issue(kk + DEPTH, (it + DEPTH) & (NSLOT - 1));
             ++it;
         }
-        if (active && !(DEPTH == 0 && (KSFD_MARCH_VARIANT & 1))) {
+        if (active && !(DEPTH == 0 && Op::STAGE_FIRST)) {
             double f[NF];
             op.stage(P, SmemTabs<RING>(), cur, f);
 #pragma unroll
