@@ -297,6 +297,9 @@ def step_timing_3d(n=256, nsteps=5, warm=2):
 
 
 def native_arm(args):
+    # stdout carries the ONE JSON line: NCCL's own log lines ("NCCL version ...",
+    # NCCL_DEBUG=INFO output) go to stderr instead of their default, stdout
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     import torch
     import torch.distributed as dist
     from helpers import product_physics
