@@ -302,6 +302,18 @@ struct ResidualOp {
         for (int c = 0; c < NLIG + 1; ++c) sink.put(c, st.in.p + c * g.fs);
         st.in.next(u, k, g.nloc, g.fs * (NLIG + 1), poff);
     }
+    // (cluster variant) load the plane under the cursor without moving it; move it by d planes
+    template <class Sink>
+    __device__ __forceinline__ void load_here(const MarchArgs &g, const State &st,
+                                              const Sink &sink) const
+    {
+#pragma unroll
+        for (int c = 0; c < NLIG + 1; ++c) sink.put(c, st.in.p + c * g.fs);
+    }
+    __device__ __forceinline__ void move_by(const MarchArgs &g, State &st, int d) const
+    {
+        st.in.p += (long long)d * (g.fs * (NLIG + 1));
+    }
     // udot of output plane ko (element index e of this lane), fields [off, off+NAUX)
     template <class Sink>
     __device__ __forceinline__ void load_aux(const MarchArgs &g, int e, int off,
@@ -410,6 +422,23 @@ struct JvpOp {
         st.ic.next(coef, k, g.nloc, g.fs * (NLIG + 3), poff);
         st.iv.next(v, k, g.nloc, g.fs * (NLIG + 1), poff);
         if (PRECOND) st.ip.next(pc, k, g.nloc, g.fs, poff);
+    }
+    // (cluster variant) load the plane under the cursors without moving them; move them
+    template <class Sink>
+    __device__ __forceinline__ void load_here(const MarchArgs &g, const State &st,
+                                              const Sink &sink) const
+    {
+#pragma unroll
+        for (int c = 0; c < NLIG + 3; ++c) sink.put(c, st.ic.p + c * g.fs);
+#pragma unroll
+        for (int c = 0; c < NLIG + 1; ++c) sink.put(NLIG + 3 + c, st.iv.p + c * g.fs);
+        if (PRECOND) sink.put(2 * NLIG + 4, st.ip.p);
+    }
+    __device__ __forceinline__ void move_by(const MarchArgs &g, State &st, int d) const
+    {
+        st.ic.p += (long long)d * (g.fs * (NLIG + 3));
+        st.iv.p += (long long)d * (g.fs * (NLIG + 1));
+        if (PRECOND) st.ip.p += (long long)d * g.fs;
     }
     template <class Sink>
     __device__ __forceinline__ void load_aux(const MarchArgs &, int, int, const Sink &) const {}
@@ -766,3 +795,209 @@ k_march(const __grid_constant__ MarchArgs g, const __grid_constant__ DevPhys P,
     Marcher<DIM, TX, TY, Op, UNR, DEPTH> m(g, P, op);
     m.run();
 }
+
+
+#if KSFD_MARCH_VARIANT & 2
+// ---------------------------------------------------------------------------
+// Experimental (tuner only): column clusters.  The CTAs that own consecutive
+// chunks of the marching axis form a thread-block cluster (1,1,CZ), CZ even.
+// Neighbouring chunks march in OPPOSITE directions (even cluster rank: down,
+// odd: up), so that two neighbours either both START or both END at their
+// common boundary, and the two staged planes each needs from beyond that
+// boundary are read from the neighbour's shared memory (distributed shared
+// memory) instead of being staged a second time: a CTA stages rz planes, not
+// rz+4 (the two CTAs at the ends of a cluster: rz+2).  The stencil code is
+// untouched: the queue is kept in MARCH order, and first derivatives along the
+// marching axis only enter the residual and J.v as products of two of them
+// (grad a . grad b), which are invariant — bit for bit — under the reversal.
+// (VelocityOp needs the sign and is not supported.)
+//   prologue : stage own planes 0,1 (march order), export them, cluster.sync,
+//              import the start partner's planes 0,1 as my planes -1,-2
+//   steps    : own planes 2 .. n-1 as in Marcher::step (prefetch one ahead)
+//   epilogue : export my planes n-1,n-2, cluster.sync, my planes n,n+1 are the
+//              end partner's n'-1,n'-2 (or, at a cluster end, two real halo
+//              planes staged from global memory); final cluster.sync before exit.
+// Shared memory: ring, tables, then two export areas [2][NF][NT].
+// ---------------------------------------------------------------------------
+#include <cooperative_groups.h>
+namespace ksfd_cg = cooperative_groups;
+
+template <int DIM, int TX, int TY, class Op, bool UNR>
+struct ClusterMarcher : Marcher<DIM, TX, TY, Op, UNR, 0> {
+    using B = Marcher<DIM, TX, TY, Op, UNR, 0>;
+    using T = typename B::T;
+    static constexpr int NF = Op::NF, NPRE = Op::NPRE;
+    static constexpr int EXPS = B::RING + B::TABS;              // start export
+    static constexpr int EXPE = EXPS + 2 * NF * T::NT;          // end export
+    int n_own, dir;
+    const double *rem_end;          // the end partner's export area (nullptr at a cluster end)
+
+    __device__ __forceinline__ ClusterMarcher(const MarchArgs &g_, const DevPhys &P_, const Op &op_)
+        : B(g_, P_, op_) {}
+
+    template <int PH>
+    __device__ __forceinline__ void emit_plane(int i)
+    {
+        // the centre plane (march index i-2) goes to a ring slot, then the stencil
+        const int ri = (i & 1) * (NF * T::SP) + this->spos;
+        if (Op::HAS_AUX && this->emits) {
+            this->op.load_aux(this->g, this->e_aux, 0, RegSink{this->aux});
+            this->e_aux += dir * (Op::out_fields(DIM) * this->g.fs);
+        }
+        if (this->active) {
+#pragma unroll
+            for (int c = 0; c < NF; ++c) ksfd_smem[ri + c * T::SP] = this->q[c][(PH + 3) % 5];
+        }
+        __syncthreads();
+        if (this->emits) {
+            LaneAcc<DIM, NF, T::SP, T::SY, PH> a(this->q, ri);
+            this->op.emit(this->P, this->g, a, this->aux, this->st);
+        }
+        this->st.e += dir * (Op::out_fields(DIM) * this->g.fs);
+    }
+
+    // march index i >= 2: plane i enters the queue at phase PH, plane i-2 is emitted
+    template <int PH>
+    __device__ __forceinline__ void step(int i)
+    {
+        auto cluster = ksfd_cg::this_cluster();
+        if (i < n_own) {
+            double cur[NPRE];
+#pragma unroll
+            for (int c = 0; c < NPRE; ++c) cur[c] = this->pre[c];
+            if (this->active && i + 1 < n_own) {
+                this->op.load_here(this->g, this->st, RegSink{this->pre});
+                this->op.move_by(this->g, this->st, dir);
+            }
+            if (this->active) {
+                double f[NF];
+                this->op.stage(this->P, SmemTabs<B::RING>(), cur, f);
+#pragma unroll
+                for (int c = 0; c < NF; ++c) this->q[c][PH] = f[c];
+            }
+        } else {
+            const int j = i - n_own;                    // 0 or 1
+            if (j == 0) {
+                // my two newest planes (n-1 at phase PH-1, n-2 at PH-2) for the end partner
+                if (this->active) {
+#pragma unroll
+                    for (int c = 0; c < NF; ++c) {
+                        ksfd_smem[EXPE + (0 * NF + c) * T::NT + threadIdx.x] = this->q[c][(PH + 4) % 5];
+                        ksfd_smem[EXPE + (1 * NF + c) * T::NT + threadIdx.x] = this->q[c][(PH + 3) % 5];
+                    }
+                }
+                cluster.sync();
+            }
+            if (rem_end) {
+                if (this->active) {
+#pragma unroll
+                    for (int c = 0; c < NF; ++c)
+                        this->q[c][PH] = rem_end[(j * NF + c) * T::NT + threadIdx.x];
+                }
+            } else if (this->active) {
+                // end of the cluster: a real halo plane (periodic wrap / ghost planes)
+                typename Op::State s2;
+                const int kstart = dir > 0 ? this->k0 : this->k1 - 1;
+                this->op.init(this->g, s2, kstart + dir * i, 0, this->poff);
+                double cur[NPRE], f[NF];
+                this->op.load_here(this->g, s2, RegSink{cur});
+                this->op.stage(this->P, SmemTabs<B::RING>(), cur, f);
+#pragma unroll
+                for (int c = 0; c < NF; ++c) this->q[c][PH] = f[c];
+            }
+        }
+        emit_plane<PH>(i);
+    }
+
+    __device__ __forceinline__ void run()
+    {
+        auto cluster = ksfd_cg::this_cluster();
+        const unsigned rank = cluster.block_rank(), csize = cluster.num_blocks();
+        const bool up = (rank & 1u) != 0;
+        dir = up ? 1 : -1;
+        n_own = this->k1 - this->k0;                    // >= 2 (host)
+        const int kstart = up ? this->k0 : this->k1 - 1;
+        const unsigned start_partner = up ? rank - 1 : rank + 1;
+        const int end_partner = up ? (int)rank + 1 : (int)rank - 1;
+        const bool has_end = end_partner >= 0 && end_partner < (int)csize;
+        this->op.init(this->g, this->st, kstart, kstart, this->poff);
+        this->e_aux = kstart * Op::out_fields(DIM) * this->g.fs + this->poff;
+        // own planes 0 and 1 -> queue phases 2, 3 and the start export
+        if (this->active) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                double cur[NPRE], f[NF];
+                this->op.load_here(this->g, this->st, RegSink{cur});
+                this->op.move_by(this->g, this->st, dir);
+                this->op.stage(this->P, SmemTabs<B::RING>(), cur, f);
+#pragma unroll
+                for (int c = 0; c < NF; ++c) {
+                    this->q[c][2 + j] = f[c];
+                    ksfd_smem[EXPS + (j * NF + c) * T::NT + threadIdx.x] = f[c];
+                }
+            }
+            if (n_own > 2) {                            // prefetch own plane 2
+                this->op.load_here(this->g, this->st, RegSink{this->pre});
+                this->op.move_by(this->g, this->st, dir);
+            }
+        }
+        cluster.sync();
+        {
+            const double *rem = cluster.map_shared_rank(&ksfd_smem[EXPS], start_partner);
+            if (this->active) {
+#pragma unroll
+                for (int c = 0; c < NF; ++c) {
+                    this->q[c][1] = rem[(0 * NF + c) * T::NT + threadIdx.x];    // my plane -1
+                    this->q[c][0] = rem[(1 * NF + c) * T::NT + threadIdx.x];    // my plane -2
+                }
+            }
+        }
+        rem_end = has_end ? cluster.map_shared_rank(&ksfd_smem[EXPE], (unsigned)end_partner)
+                          : nullptr;
+        int i = 2;
+        const int iend = n_own + 2;
+        step<4>(i);
+        ++i;
+        if (!UNR) {
+            // (the shifting-queue form keeps every new plane at phase 4)
+            for (; i < iend; ++i) {
+#pragma unroll
+                for (int c = 0; c < NF; ++c) {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) this->q[c][s] = this->q[c][s + 1];
+                }
+                step<4>(i);
+            }
+        } else {
+            for (; i < iend;) {
+                step<0>(i);
+                if (++i >= iend) break;
+                step<1>(i);
+                if (++i >= iend) break;
+                step<2>(i);
+                if (++i >= iend) break;
+                step<3>(i);
+                if (++i >= iend) break;
+                step<4>(i);
+                if (++i >= iend) break;
+            }
+        }
+        cluster.sync();         // nobody leaves while a neighbour may still read its exports
+    }
+};
+
+template <class Op, int SP, int NT>
+constexpr size_t march_cl_smem_bytes()
+{
+    return sizeof(double) * (2 * Op::NF * SP + (Op::TABS ? KSFD_TAB_DOUBLES : 0) + 4 * Op::NF * NT);
+}
+
+template <int DIM, int TX, int TY, class Op, int MINB, bool UNR>
+__global__ void __launch_bounds__(TileT<DIM, TX, TY>::NT, MINB)
+k_march_cl(const __grid_constant__ MarchArgs g, const __grid_constant__ DevPhys P,
+           const __grid_constant__ Op op)
+{
+    ClusterMarcher<DIM, TX, TY, Op, UNR> m(g, P, op);
+    m.run();
+}
+#endif

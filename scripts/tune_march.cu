@@ -4,7 +4,8 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo
 //        -I ksfd_b200/csrc scripts/tune_march.cu -o gpurun_out/tune_march
 //   ./tune_march [2d N | 3d N] ...
-// -DKSFD_MARCH_VARIANT=bits compiles the experimental code paths of
+// -DKSFD_MARCH_VARIANT=bits (1: stage first, 2: column clusters with distributed shared
+// memory, CLn lines) compiles the experimental code paths of
 // march_kernels.cuh (build one binary per variant; the checksums of the outputs
 // must agree bit for bit between them).  TUNE_ALL=1 adds the rejected variants
 // (cp.async pipeline, other min-blocks) to the library's own configurations.
@@ -190,6 +191,87 @@ static void run_variant(const char *name, const Problem &pb, const DevPhys &P, O
     fflush(stdout);
 }
 
+#if KSFD_MARCH_VARIANT & 2
+// column-cluster variant (march_kernels.cuh: ClusterMarcher): grid.z is a multiple of CZ,
+// every chunk holds the same number of planes
+template <int DIM, int TX, int TY, class Op, int MINB, bool UNR>
+static void run_variant_cl(const char *name, const Problem &pb, const DevPhys &P, Op op_proto,
+                           void (*bind)(Op &, const Problem &, int), int CZ)
+{
+    using T = TileT<DIM, TX, TY>;
+    const int ord = g_ordinal;
+    if (!selected()) return;
+    auto kern = k_march_cl<DIM, TX, TY, Op, MINB, UNR>;
+    const size_t smem = march_cl_smem_bytes<Op, T::SP, T::NT>();
+    CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T::NT, smem));
+    cudaFuncAttributes fa;
+    CHECK(cudaFuncGetAttributes(&fa, kern));
+    const int ntx = (pb.n0 + TX - 1) / TX, ox = (pb.n0 + ntx - 1) / ntx;
+    const int nty = DIM == 3 ? (pb.n1 + TY - 1) / TY : 1, oy = DIM == 3 ? (pb.n1 + nty - 1) / nty : 1;
+    cudaEvent_t e0, e1;
+    CHECK(cudaEventCreate(&e0));
+    CHECK(cudaEventCreate(&e1));
+    for (int waves = 1; waves <= 2; ++waves) {
+        // chunks: fill occ*148 slots `waves` times, rounded to a multiple of CZ that divides nloc
+        const long long cols = (long long)ntx * nty;
+        int nch = (int)((long long)waves * 148 * occ / cols);
+        nch = nch / CZ * CZ;
+        while (nch >= CZ && pb.nloc % nch != 0) nch -= CZ;
+        if (nch < CZ) continue;
+        const int rz = pb.nloc / nch;
+        if (rz < 2) continue;
+        MarchArgs a{pb.n0, pb.n1, pb.nloc, pb.n0 * pb.n1, ox, oy, rz};
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ntx, nty, nch);
+        cfg.blockDim = dim3(T::NT);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = CZ;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const int reps = getenv("TUNE_ONLY") ? 2 : 20;
+        for (int i = 0; i < 3; ++i) {
+            Op op = op_proto;
+            bind(op, pb, i % pb.nrot);
+            CHECK(cudaLaunchKernelEx(&cfg, kern, a, P, op));
+        }
+        CHECK(cudaDeviceSynchronize());
+        CHECK(cudaEventRecord(e0));
+        for (int i = 0; i < reps; ++i) {
+            Op op = op_proto;
+            bind(op, pb, i % pb.nrot);
+            CHECK(cudaLaunchKernelEx(&cfg, kern, a, P, op));
+        }
+        CHECK(cudaEventRecord(e1));
+        CHECK(cudaDeviceSynchronize());
+        float ms = 0;
+        CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        const double us = ms * 1e3 / reps;
+        const double gpts = pb.npts / us / 1e3;
+        unsigned long long *dck, hck = 0;
+        CHECK(cudaMalloc(&dck, 8));
+        CHECK(cudaMemset(dck, 0, 8));
+        {
+            Op op = op_proto;
+            bind(op, pb, 0);
+            CHECK(cudaLaunchKernelEx(&cfg, kern, a, P, op));
+            k_cks<<<592, 256>>>(pb.out[0], pb.npts * 3, dck);
+        }
+        CHECK(cudaMemcpy(&hck, dck, 8, cudaMemcpyDeviceToHost));
+        CHECK(cudaFree(dck));
+        printf("#%02d %-12s CL%d TX%3d TY%2d MINB%d UNR%d regs%3d occ%d rz%4d grid %4dx%3dx%4d  %9.2f us  %6.2f Gpts/s  frac %.3f  cks %016llx\n",
+               ord, name, CZ, TX, TY, MINB, (int)UNR, fa.numRegs, occ, rz, ntx, nty, nch, us, gpts,
+               gpts * 72.0 / 6544.7, hck);
+    }
+    fflush(stdout);
+}
+#endif
+
 template <int DIM>
 static void bind_res(ResidualOp<DIM, 2, true> &op, const Problem &pb, int i)
 {
@@ -273,6 +355,11 @@ static void free_problem(Problem &pb)
 #define JVP3(TX, TY, MINB, UNR, PC, D) \
     run_variant<3, TX, TY, JvpOp<3, 2, PC>, MINB, UNR, D>(PC ? "jvp_pc3d" : "jvp3d", pb, P, JvpOp<3, 2, PC>{}, bind_jvp<3, PC>, rzs, nrz)
 
+#define RES2CL(TX, MINB, CZ) \
+    run_variant_cl<2, TX, 1, ResidualOp<2, 2, true>, MINB, false>("residual2d", pb, P, ResidualOp<2, 2, true>{}, bind_res<2>, CZ)
+#define JVP2CL(TX, MINB, PC, CZ) \
+    run_variant_cl<2, TX, 1, JvpOp<2, 2, PC>, MINB, true>(PC ? "jvp_pc2d" : "jvp2d", pb, P, JvpOp<2, 2, PC>{}, bind_jvp<2, PC>, CZ)
+
 int main(int argc, char **argv)
 {
     const int rzs[] = {0, -2, -3};     // 1, 2, 3 waves of CTAs
@@ -292,6 +379,16 @@ int main(int argc, char **argv)
             JVP2(252, 2, true, true, 0);
             JVP2(124, 4, true, false, 0);
             JVP2(252, 2, true, false, 0);
+#if KSFD_MARCH_VARIANT & 2
+            for (int cz = 2; cz <= 8; cz *= 2) {
+                RES2CL(124, 6, cz);
+                RES2CL(124, 5, cz);
+                JVP2CL(124, 4, true, cz);
+                JVP2CL(124, 4, false, cz);
+            }
+            RES2CL(252, 3, 8);
+            JVP2CL(252, 2, true, 8);
+#endif
             if (all) {
                 RES2(124, 6, false, 3);
                 RES2(252, 3, false, 3);
