@@ -44,6 +44,9 @@
 //   bit 0: policies with STAGE_FIRST stage from the prefetch registers before refilling
 //          them (see Marcher::step).  Measured (profiles/r01_tuner_variant_stage_first.txt,
 //          bit-identical outputs): residual +3 %, J.v -2 % => residual / velocity only.
+//   bit 1: column clusters (ClusterMarcher at the end of this file)
+//   bit 2: register prefetch TWO planes deep (pre, pre2): twice the bytes in flight per
+//          thread for NPRE more doubles of registers (pair with a lower MINB)
 #ifndef KSFD_MARCH_VARIANT
 #define KSFD_MARCH_VARIANT 0
 #endif
@@ -599,6 +602,7 @@ struct Marcher {
     const Op &op;
     double q[NF][5];
     double pre[DEPTH == 0 ? NPRE : 1];
+    double pre2[(DEPTH == 0 && (KSFD_MARCH_VARIANT & 4)) ? NPRE : 1];
     double aux[NAUX];
     typename Op::State st;
     int poff, spos, k0, k1, it, e_aux;
@@ -683,7 +687,18 @@ struct Marcher {
     __device__ __forceinline__ void step(int kk)
     {
         double cur[NPRE];
-        if (DEPTH == 0 && Op::STAGE_FIRST) {
+        if (DEPTH == 0 && (KSFD_MARCH_VARIANT & 4)) {
+            // stage from pre, pre <- pre2, refill pre2 with plane kk+2
+            if (active) {
+                double f[NF];
+                op.stage(P, SmemTabs<RING>(), pre, f);
+#pragma unroll
+                for (int c = 0; c < NF; ++c) q[c][PH] = f[c];
+#pragma unroll
+                for (int c = 0; c < NPRE; ++c) pre[c] = pre2[c];
+                if (kk + 2 < k1 + KSFD_SW) op.load(g, st, kk + 2, poff, RegSink{pre2});
+            }
+        } else if (DEPTH == 0 && Op::STAGE_FIRST) {
             // experimental (tuner only): stage straight from the prefetch registers,
             // then refill them — no register copy of the plane (18 moves per plane in
             // the 2-D J.v kernel), the prefetch goes out one stage later
@@ -710,7 +725,7 @@ struct Marcher {
             issue(kk + DEPTH, (it + DEPTH) & (NSLOT - 1));
             ++it;
         }
-        if (active && !(DEPTH == 0 && Op::STAGE_FIRST)) {
+        if (active && !(DEPTH == 0 && (Op::STAGE_FIRST || (KSFD_MARCH_VARIANT & 4)))) {
             double f[NF];
             op.stage(P, SmemTabs<RING>(), cur, f);
 #pragma unroll
@@ -745,6 +760,8 @@ struct Marcher {
         e_aux = k0 * Op::out_fields(DIM) * g.fs + poff;
         if (DEPTH == 0) {
             if (active) op.load(g, st, kk, poff, RegSink{pre});
+            if ((KSFD_MARCH_VARIANT & 4) && active && kk + 1 < kend)
+                op.load(g, st, kk + 1, poff, RegSink{pre2});
         } else {
 #pragma unroll
             for (int d = 0; d < DEPTH; ++d) issue(kk + d, d);

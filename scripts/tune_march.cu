@@ -5,7 +5,7 @@
 //        -I ksfd_b200/csrc scripts/tune_march.cu -o gpurun_out/tune_march
 //   ./tune_march [2d N | 3d N] ...
 // -DKSFD_MARCH_VARIANT=bits (1: stage first, 2: column clusters with distributed shared
-// memory, CLn lines) compiles the experimental code paths of
+// memory, CLn lines, 4: register prefetch two planes deep) compiles the experimental code paths of
 // march_kernels.cuh (build one binary per variant; the checksums of the outputs
 // must agree bit for bit between them).  TUNE_ALL=1 adds the rejected variants
 // (cp.async pipeline, other min-blocks) to the library's own configurations.
@@ -379,6 +379,12 @@ int main(int argc, char **argv)
             JVP2(252, 2, true, true, 0);
             JVP2(124, 4, true, false, 0);
             JVP2(252, 2, true, false, 0);
+#if KSFD_MARCH_VARIANT & 4
+            // two planes of register prefetch: more registers, fewer CTAs per SM
+            RES2(124, 5, false, 0);
+            JVP2(124, 3, true, true, 0);
+            JVP2(124, 3, true, false, 0);
+#endif
 #if KSFD_MARCH_VARIANT & 2
             for (int cz = 2; cz <= 8; cz *= 2) {
                 RES2CL(124, 6, cz);
