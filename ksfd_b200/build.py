@@ -19,7 +19,8 @@ UNITS = [('ksfd.cu', [], 'ksfd.o')] + [
     (src, ['-DKSFD_MARCH_DIM=%d' % d], '%s_d%d.o' % (src[:-3], d))
     for src in ('march_res.cu', 'march_jvp.cu', 'march_vel.cu') for d in (2, 3)]
 HEADERS = ['device_common.cuh', 'naive_kernels.cuh', 'march_kernels.cuh',
-           'march_launch.cuh', 'ctx.h', 'blas1_kernels.cuh',
+           'march_launch.cuh', 'ctx.h', 'blas1_kernels.cuh', 'fftpc.cuh', 'fastmath.cuh',
+           'fastmath_tables.h',
            os.path.join('..', '..', 'include', 'ksfd_b200.h')]
 OBJDIR = os.path.join(HERE, 'build')
 
@@ -27,6 +28,8 @@ NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
     '-std=c++17', '-Xcompiler', '-fPIC',
 ]
+# experiments: e.g. KSFD_NVCC_EXTRA="-DKSFD_PDL=1" python -m ksfd_b200.build --force
+NVCC_FLAGS += os.environ.get('KSFD_NVCC_EXTRA', '').split()
 
 
 def nvcc_path():

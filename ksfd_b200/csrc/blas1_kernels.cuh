@@ -543,6 +543,7 @@ __global__ void __launch_bounds__(KSFD_RED_THREADS)
 k_gm_norm_begin(long long n, const double *__restrict__ r, double *__restrict__ partial,
                 GmBegin a)
 {
+    KSFD_PDL_ENTER();
     double acc[1] = {0.0};
     if ((n & 1) == 0 && aligned16(r)) {
         const double2 *r2 = reinterpret_cast<const double2 *>(r);
@@ -566,8 +567,9 @@ k_gm_norm_begin(long long n, const double *__restrict__ r, double *__restrict__ 
 __global__ void k_gm_first_vector(long long n, const double *x, const double *__restrict__ gm,
                                   const int *__restrict__ gmi, double sign, double *y)
 {
-    if (gmi[GMI_FINAL]) return;
-    const double f = sign / gm[GM_BETA];
+    KSFD_PDL_ENTER();
+    if (KSFD_FLAG(gmi + GMI_FINAL)) return;
+    const double f = sign / KSFD_FLAG(gm + GM_BETA);
     if ((n & 1) == 0 && aligned16(x) && aligned16(y)) {
         const double2 *x2 = reinterpret_cast<const double2 *>(x);
         double2 *y2 = reinterpret_cast<double2 *>(y);
@@ -773,7 +775,8 @@ __global__ void __launch_bounds__(KSFD_RED_THREADS)
 k_gm_mdot(long long n, VecList vs, const double *__restrict__ w,
           const int *__restrict__ gmi, double *__restrict__ partial, GmFin fin)
 {
-    if (gmi[GMI_CYCLE_DONE]) return;
+    KSFD_PDL_ENTER();
+    if (KSFD_FLAG(gmi + GMI_CYCLE_DONE)) return;
     double acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = 0.0;
@@ -822,11 +825,12 @@ k_gm_orth_scale(long long n, VecList vs, int off, int do_scale,
                 double *__restrict__ w)
 {
     // the step that closed the cycle does not need its new basis vector
-    if (gmi[GMI_CYCLE_DONE]) return;
+    KSFD_PDL_ENTER();
+    if (KSFD_FLAG(gmi + GMI_CYCLE_DONE)) return;
     double hh[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) hh[i] = gm[GM_HCOL + off + i];
-    const double sc = do_scale ? gm[GM_INV] : 1.0;
+    for (int i = 0; i < NV; ++i) hh[i] = KSFD_FLAG(gm + GM_HCOL + off + i);
+    const double sc = do_scale ? KSFD_FLAG(gm + GM_INV) : 1.0;
     if (all_aligned16<NV>(n, vs, w)) {
         double2 *w2 = reinterpret_cast<double2 *>(w);
         for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (n >> 1);
@@ -861,7 +865,8 @@ k_gm_true_residual(long long n, const double *__restrict__ rhs, double sign,
                    const int *__restrict__ gmi, double *__restrict__ ax,
                    double *__restrict__ partial, GmBegin a)
 {
-    if (gmi[GMI_FINAL]) return;
+    KSFD_PDL_ENTER();
+    if (KSFD_FLAG(gmi + GMI_FINAL)) return;
     double acc[1] = {0.0};
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
          e += (long long)gridDim.x * blockDim.x) {

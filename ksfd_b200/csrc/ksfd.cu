@@ -21,6 +21,9 @@
 // ---------------------------------------------------------------------------
 static thread_local std::string g_err;
 static int64_t g_launches = 0;
+#if KSFD_PDL
+bool g_ksfd_pdl = false;        // KSFD_PDL=1 in the environment (read at context creation)
+#endif
 
 int ksfd_fail(const std::string &m)
 {
@@ -135,6 +138,9 @@ extern "C" int ksfd_ctx_create(ksfd_ctx **out, int dim, const int64_t n_global[3
     CK(cudaMallocHost(&c->hscal, sizeof(double) * KSFD_NSCAL));
     c->halo_plane_doubles = (size_t)g.plane_pts * (dof + 2);
     if (const char *e = getenv("KSFD_GM_RUNAHEAD")) c->gm_runahead = std::max(0, std::min(atoi(e), 8));
+#if KSFD_PDL
+    if (const char *e = getenv("KSFD_PDL")) g_ksfd_pdl = atoi(e) != 0;
+#endif
     *out = c;
     return 0;
 }
@@ -1388,12 +1394,12 @@ static int gm_mdot_launch(ksfd_ctx *c, const VecList &vl, const double *w, const
                           cudaStream_t st)
 {
     if (fin) {
-        k_gm_mdot<NV, true><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(nlocal(c), vl, w, c->gmi,
-                                                                          c->partial, *fin);
+        KSFD_KLAUNCH((k_gm_mdot<NV, true>), KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st, nlocal(c), vl, w,
+                     c->gmi, c->partial, *fin);
     } else {
         GmFin none{};
-        k_gm_mdot<NV, false><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(nlocal(c), vl, w, c->gmi,
-                                                                           c->partial, none);
+        KSFD_KLAUNCH((k_gm_mdot<NV, false>), KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st, nlocal(c), vl, w,
+                     c->gmi, c->partial, none);
     }
     CKL();
     return 0;
@@ -1402,8 +1408,8 @@ template <int NV>
 static int gm_orth_launch(ksfd_ctx *c, const VecList &vl, int off, int do_scale, double *w,
                           cudaStream_t st)
 {
-    k_gm_orth_scale<NV><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(nlocal(c), vl, off,
-                                                                      do_scale, c->gm, c->gmi, w);
+    KSFD_KLAUNCH((k_gm_orth_scale<NV>), KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st, nlocal(c), vl, off,
+                 do_scale, c->gm, c->gmi, w);
     CKL();
     return 0;
 }
@@ -1535,7 +1541,8 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
                    c->gm_done};
         if (cycle == 0) {
             if (fuse_begin) {
-                k_gm_norm_begin<<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(n, rhs, c->partial, gb);
+                KSFD_KLAUNCH(k_gm_norm_begin, KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st, n, rhs,
+                             c->partial, gb);
             } else {
                 VecList vl;
                 for (int i = 0; i < KSFD_MAXV; ++i) vl.v[i] = rhs;
@@ -1546,11 +1553,11 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
             // r = sign*rhs - A x   (true residual at restart)
             TRY(jvp_impl(c, x, tmp, false, st, c->gmi + GMI_FINAL));
             if (fuse_begin)
-                k_gm_true_residual<true><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(
-                    n, rhs, rhs_sign, c->gmi, tmp, c->partial, gb);
+                KSFD_KLAUNCH((k_gm_true_residual<true>), KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st, n,
+                             rhs, rhs_sign, c->gmi, tmp, c->partial, gb);
             else
-                k_gm_true_residual<false><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(
-                    n, rhs, rhs_sign, c->gmi, tmp, c->partial, gb);
+                KSFD_KLAUNCH((k_gm_true_residual<false>), KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st, n,
+                             rhs, rhs_sign, c->gmi, tmp, c->partial, gb);
             CKL();
             r = tmp;
             sign = 1.0;
@@ -1571,7 +1578,7 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
             k_gm_cycle_begin<<<1, 32, 0, st>>>(g1);
             CKL();
         }
-        k_gm_first_vector<<<KSFD_RED_BLOCKS, 256, 0, st>>>(n, r, c->gm, c->gmi, sign, V);
+        KSFD_KLAUNCH(k_gm_first_vector, KSFD_RED_BLOCKS, 256, 0, st, n, r, c->gm, c->gmi, sign, V);
         CKL();
         const int seq = 2 * cycle + 1;
         if (free_running) {
@@ -1618,8 +1625,8 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
         if (hs->reason != -9 && hs->k_cols > 0) {
             const unsigned ub = std::min(nblk(c->g.npts, 256), 148u * 8u);
 #define KSFD_UPD(D, PCF, VV, YY, KK, XZ, XX)                                                 \
-    k_gm_update_x<D><<<ub, 256, 0, st>>>(c->g, c->P, coef_ref(c), id, c->pc, PCF, n, VV, YY, KK, \
-                                         c->gmi + GMI_NOUPD, XZ, XX)
+    KSFD_KLAUNCH((k_gm_update_x<D>), ub, 256, 0, st, c->g, c->P, coef_ref(c), id, c->pc, PCF, n, VV, \
+                 YY, KK, c->gmi + GMI_NOUPD, XZ, XX)
 #define KSFD_UPD_DOF(PCF, VV, YY, KK, XZ, XX)                                                \
     switch (c->dof) {                                                                        \
     case 2: KSFD_UPD(2, PCF, VV, YY, KK, XZ, XX); break;                                     \

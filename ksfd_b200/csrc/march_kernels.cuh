@@ -807,8 +807,9 @@ __global__ void __launch_bounds__(TileT<DIM, TX, TY>::NT, MINB)
 k_march(const __grid_constant__ MarchArgs g, const __grid_constant__ DevPhys P,
         const __grid_constant__ Op op, const int *__restrict__ skip)
 {
+    KSFD_PDL_ENTER();
     // pipelined Krylov solver: launched ahead of the convergence test
-    if (skip && *skip) return;
+    if (skip && KSFD_FLAG(skip)) return;
     Marcher<DIM, TX, TY, Op, UNR, DEPTH> m(g, P, op);
     m.run();
 }

@@ -123,7 +123,7 @@ static int launch_tile(const ksfd_ctx *c, const Op &op, const MarchPlan &p, cons
     using T = TileT<DIM, TX, TY>;
     auto kern = k_march<DIM, TX, TY, Op, MINB, UNR, DEPTH>;
     const size_t smem = march_smem_bytes<Op, T::SP, T::NT, DEPTH>();
-    kern<<<p.grid, T::NT, smem, st>>>(p.a, c->P, op, skip);
+    KSFD_KLAUNCH(kern, p.grid, T::NT, smem, st, p.a, c->P, op, skip);
     CKL();
     return 0;
 }

@@ -312,7 +312,8 @@ k_gm_update_x(Geom g, DevPhys P, VecRef coef, InvD invd, const double *__restric
               const double *__restrict__ gm_y, const int *__restrict__ gmi_k,
               const int *__restrict__ gmi_skip, int x_zero, double *__restrict__ x)
 {
-    if (*gmi_skip) {
+    KSFD_PDL_ENTER();
+    if (KSFD_FLAG(gmi_skip)) {
         if (x_zero)
             for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
                  e += (long long)gridDim.x * blockDim.x)
@@ -320,8 +321,8 @@ k_gm_update_x(Geom g, DevPhys P, VecRef coef, InvD invd, const double *__restric
         return;
     }
     __shared__ double y[64];
-    const int k = gmi_k ? *gmi_k : 1;               // no k / y: x += [M^-1] V_0
-    for (int i = threadIdx.x; i < k; i += blockDim.x) y[i] = gm_y ? gm_y[i] : 1.0;
+    const int k = gmi_k ? KSFD_FLAG(gmi_k) : 1;     // no k / y: x += [M^-1] V_0
+    for (int i = threadIdx.x; i < k; i += blockDim.x) y[i] = gm_y ? KSFD_FLAG(gm_y + i) : 1.0;
     __syncthreads();
     const int fs = (int)g.plane_pts;
     const int dof = DOF ? DOF : g.dof;
