@@ -116,6 +116,12 @@ struct ksfd_ctx {
     int fft_fwd = -1, fft_inv = -1;
     void *fft_spec = nullptr;    // double2 [dof][n2][n1][n0/2+1]
     double *fft_means = nullptr;
+    // slab-distributed variant (several ranks, KSFD_FFT_MULTI=1): plane transforms,
+    // last-axis transform, two spectrum buffers (fft_spec, fft_spec2)
+    int fft_z = -1;
+    void *fft_spec2 = nullptr;
+    bool fft_dist = false;
+    long long fft_ps = 0;        // plane wave numbers (n0/2+1, times n1 in 3-D)
     bool fft_failed = false;
     bool fft_means_valid = false;   // means belong to the current linearisation
     bool pc_auto_fft = false;    // precond = 3 (auto): current choice

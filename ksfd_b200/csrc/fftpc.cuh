@@ -29,6 +29,10 @@
 
 struct FftSym {                 // what the symbol kernel needs
     int dof, nlig, n0, n1, n2;  // real extents x, y, z (1 when unused); n0h = n0/2+1 complex
+    // slab-distributed transform (several ranks): this rank holds the plane wave numbers
+    // s in [s0, s0+nsq) (s = kx in 2-D, ky*n0h + kx in 3-D) for ALL NL wave numbers of the
+    // last axis, layout [field][s_loc][k]
+    int dist, s0, nsq, NL;
     double shift, c2[3];
     double s[KSFD_MAX_LIGANDS], gamma[KSFD_MAX_LIGANDS], D[KSFD_MAX_LIGANDS];
 };
@@ -66,13 +70,15 @@ __global__ void k_fft_means_partial(Geom g, const double *__restrict__ coef_base
     }
 }
 
-__global__ void k_fft_means_final(Geom g, const double *__restrict__ partial,
+// inv_count = 1 / (GLOBAL number of grid points): with several ranks the per-rank
+// results are summed afterwards
+__global__ void k_fft_means_final(double inv_count, const double *__restrict__ partial,
                                   double *__restrict__ out)
 {
     double s = 0.0;
     for (int q = threadIdx.x; q < FFT_MEAN_BLOCKS; q += 32) s += partial[blockIdx.x * FFT_MEAN_BLOCKS + q];
     s = warp_sum(s);
-    if (threadIdx.x == 0) out[blockIdx.x] = s / (double)g.npts;
+    if (threadIdx.x == 0) out[blockIdx.x] = s * inv_count;
 }
 
 // left scaling S_L: out = in with the rho field divided by rho (in == out allowed)
@@ -107,12 +113,26 @@ __global__ void k_fft_symbol_solve(FftSym S, const double *__restrict__ means, d
 {
     if (skip && *skip) return;
     const int n0h = S.n0 / 2 + 1;
-    const long long nk = (long long)n0h * S.n1 * S.n2;
+    const long long nk = S.dist ? (long long)S.nsq * S.NL : (long long)n0h * S.n1 * S.n2;
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= nk) return;
-    const int k0 = (int)(e % n0h);
-    const int k1 = (int)((e / n0h) % S.n1);
-    const int k2 = (int)(e / ((long long)n0h * S.n1));
+    int k0, k1, k2;
+    if (S.dist) {
+        const int sg = S.s0 + (int)(e / S.NL), kl = (int)(e % S.NL);
+        if (S.n2 > 1) {
+            k0 = sg % n0h;
+            k1 = sg / n0h;
+            k2 = kl;
+        } else {
+            k0 = sg;
+            k1 = kl;
+            k2 = 0;
+        }
+    } else {
+        k0 = (int)(e % n0h);
+        k1 = (int)((e / n0h) % S.n1);
+        k2 = (int)(e / ((long long)n0h * S.n1));
+    }
     // symbol of the 4th-order Laplacian: sum_ax c2 (32 cos t - 2 cos 2t - 30)
     double lam = 0.0;
     {
@@ -153,4 +173,61 @@ __global__ void k_fft_symbol_solve(FftSym S, const double *__restrict__ means, d
         z.y = (r[1 + l].y * inv_n + S.s[l] * cbar * z0.y) * invd[l];
         spec[(long long)(1 + l) * nk + e] = z;
     }
+}
+
+
+// ---------------------------------------------------------------------------
+// Slab-distributed transform (several ranks; experimental, KSFD_FFT_MULTI=1):
+// local transforms over the plane axes, an all-to-all that gives every rank a
+// share [s0_q, s0_q + nsq_q) of the plane wave numbers for ALL planes, a 1-D
+// transform along the last axis, and the way back.  s0_q = floor(PS*q/P).
+//   A  [(k_loc*dof + c)*PS + s]                     plane spectra of the own planes
+//   B  [nloc*dof*s0_q + (k_loc*dof + c)*nsq_q + s-s0_q]   packed per destination q
+//   R  [(k*dof + c)*nsq + s_loc]   (k global)       what the all-to-all delivers
+//   T  [(c*nsq + s_loc)*NL + k]                     last axis contiguous
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ long long fft_share_start(long long PS, int q, int P)
+{
+    return PS * q / P;
+}
+__host__ __device__ __forceinline__ int fft_share_owner(long long PS, long long s, int P)
+{
+    int q = (int)(((s + 1) * P - 1) / PS);
+    // (floor rounding: correct the estimate by at most one)
+    while (q > 0 && fft_share_start(PS, q, P) > s) --q;
+    while (q + 1 < P && fft_share_start(PS, q + 1, P) <= s) ++q;
+    return q;
+}
+
+// to_packed = 1: B <- A;  0: A <- B   (same index map both ways)
+__global__ void k_fft_pack(int nloc, int dof, long long PS, int P, int to_packed, double2 *A,
+                           double2 *B, const int *__restrict__ skip)
+{
+    if (skip && *skip) return;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)nloc * dof * PS) return;
+    const long long kc = e / PS, s = e - kc * PS;
+    const int q = fft_share_owner(PS, s, P);
+    const long long s0 = fft_share_start(PS, q, P), nsq = fft_share_start(PS, q + 1, P) - s0;
+    const long long b = (long long)nloc * dof * s0 + kc * nsq + (s - s0);
+    if (to_packed)
+        B[b] = A[e];
+    else
+        A[e] = B[b];
+}
+
+// to_T = 1: T[(c*nsq + s)*NL + k] <- R[(k*dof + c)*nsq + s];  0: the way back
+__global__ void k_fft_transpose(int NL, int dof, long long nsq, int to_T, double2 *R, double2 *T,
+                                const int *__restrict__ skip)
+{
+    if (skip && *skip) return;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= (long long)NL * dof * nsq) return;
+    const long long kc = e / nsq, s = e - kc * nsq;
+    const long long k = kc / dof, c = kc - k * dof;
+    const long long t = (c * nsq + s) * NL + k;
+    if (to_T)
+        T[t] = R[e];
+    else
+        R[e] = T[t];
 }

@@ -159,6 +159,7 @@ extern "C" int ksfd_ctx_destroy(ksfd_ctx *c)
     cudaFree(c->krylov);
     fftpc_destroy(c);
     cudaFree(c->fft_spec);
+    cudaFree(c->fft_spec2);
     cudaFree(c->fft_means);
     cudaFree(c->gm);
     cudaFree(c->gmi);
@@ -774,10 +775,11 @@ struct CufftApi {
     int (*SetStream)(int, cudaStream_t) = nullptr;
     int (*ExecD2Z)(int, double *, double2 *) = nullptr;
     int (*ExecZ2D)(int, double2 *, double *) = nullptr;
+    int (*ExecZ2Z)(int, double2 *, double2 *, int) = nullptr;
     int (*Destroy)(int) = nullptr;
 };
 static CufftApi g_fft;
-enum { CUFFT_D2Z_ = 0x6a, CUFFT_Z2D_ = 0x6c };
+enum { CUFFT_D2Z_ = 0x6a, CUFFT_Z2D_ = 0x6c, CUFFT_Z2Z_ = 0x69 };
 
 static bool cufft_load()
 {
@@ -792,7 +794,7 @@ static bool cufft_load()
 #define FSYM(n)                                        \
     *(void **)(&g_fft.n) = dlsym(h, "cufft" #n);       \
     if (!g_fft.n) return false;
-    FSYM(PlanMany) FSYM(SetStream) FSYM(ExecD2Z) FSYM(ExecZ2D) FSYM(Destroy)
+    FSYM(PlanMany) FSYM(SetStream) FSYM(ExecD2Z) FSYM(ExecZ2D) FSYM(ExecZ2Z) FSYM(Destroy)
 #undef FSYM
     g_fft.h = h;
     return true;
@@ -803,13 +805,28 @@ static void fftpc_destroy(ksfd_ctx *c)
     if (c->fft_fwd >= 0 && g_fft.Destroy) {
         g_fft.Destroy(c->fft_fwd);
         g_fft.Destroy(c->fft_inv);
-        c->fft_fwd = c->fft_inv = -1;
+        if (c->fft_z >= 0) g_fft.Destroy(c->fft_z);
+        c->fft_fwd = c->fft_inv = c->fft_z = -1;
     }
+}
+
+// one rank; several ranks only on request (KSFD_FFT_MULTI=1: slab-distributed
+// transform over NCCL send/recv, not yet validated on hardware), 2-D / 3-D, with the
+// DMDA ownership ranges (every rank must be able to compute every other rank's)
+static bool fftpc_dist_wanted(const ksfd_ctx *c)
+{
+    if (c->nranks == 1) return false;
+    const char *e = getenv("KSFD_FFT_MULTI");
+    if (!e || atoi(e) == 0 || !c->comm || c->dim < 2) return false;
+    const long long M = c->last_global, P = c->nranks, r = c->rank;
+    const long long cnt = M / P + (M % P > r ? 1 : 0);
+    const long long start = r * (M / P) + std::min(r, M % P);
+    return cnt == c->last_count && start == c->last_start;
 }
 
 static bool fftpc_available(ksfd_ctx *c)
 {
-    return c->nranks == 1 && !c->fft_failed && cufft_load();
+    return (c->nranks == 1 || fftpc_dist_wanted(c)) && !c->fft_failed && cufft_load();
 }
 
 // plans + buffers (first use); returns false (and remembers) if cuFFT refuses
@@ -820,6 +837,44 @@ static bool fftpc_prepare(ksfd_ctx *c)
     const int dof = c->dof;
     const int nx = (int)c->n[0], ny = c->dim >= 2 ? (int)c->n[1] : 1, nz = c->dim >= 3 ? (int)c->n[2] : 1;
     const int nxh = nx / 2 + 1;
+    if (c->nranks > 1) {
+        // plane transforms over the own planes, 1-D transform along the last axis
+        const int nloc = c->g.nloc, NL = (int)c->last_global, P = c->nranks;
+        const long long PS = c->dim == 2 ? nxh : (long long)ny * nxh;
+        const long long nsq = fft_share_start(PS, c->rank + 1, P) - fft_share_start(PS, c->rank, P);
+        int f = -1, b = -1, z = -1;
+        int np[2], ie[2], oe[2], prank;
+        if (c->dim == 2) {
+            prank = 1; np[0] = nx; ie[0] = nx; oe[0] = nxh;
+        } else {
+            prank = 2; np[0] = ny; np[1] = nx; ie[0] = ny; ie[1] = nx; oe[0] = ny; oe[1] = nxh;
+        }
+        const int pp = (int)c->g.plane_pts;
+        int nz1[1] = {NL}, ez[1] = {NL};
+        bool ok = nsq > 0 &&
+                  g_fft.PlanMany(&f, prank, np, ie, 1, pp, oe, 1, (int)PS, CUFFT_D2Z_, nloc * dof) == 0 &&
+                  g_fft.PlanMany(&b, prank, np, oe, 1, (int)PS, ie, 1, pp, CUFFT_Z2D_, nloc * dof) == 0 &&
+                  g_fft.PlanMany(&z, 1, nz1, ez, 1, NL, ez, 1, NL, CUFFT_Z2Z_, (int)(dof * nsq)) == 0;
+        const size_t cap = (size_t)std::max((long long)nloc * dof * PS, (long long)dof * nsq * NL);
+        ok = ok && cudaMalloc(&c->fft_spec, sizeof(double2) * cap) == cudaSuccess &&
+             cudaMalloc(&c->fft_spec2, sizeof(double2) * cap) == cudaSuccess &&
+             cudaMalloc(&c->fft_means,
+                        sizeof(double) * (KSFD_MAX_LIGANDS + 2) * (FFT_MEAN_BLOCKS + 1)) == cudaSuccess;
+        if (!ok) {
+            cudaGetLastError();
+            if (f >= 0) g_fft.Destroy(f);
+            if (b >= 0) g_fft.Destroy(b);
+            if (z >= 0) g_fft.Destroy(z);
+            c->fft_failed = true;
+            return false;
+        }
+        c->fft_fwd = f;
+        c->fft_inv = b;
+        c->fft_z = z;
+        c->fft_dist = true;
+        c->fft_ps = PS;
+        return true;
+    }
     int rank = c->dim, n[3], ie[3], oe[3], istride = 1, idist, odist;
     if (c->dim == 1) {
         n[0] = nx; ie[0] = nx; oe[0] = nxh; istride = dof; idist = 1; odist = nxh;
@@ -862,8 +917,11 @@ static int fftpc_setup(ksfd_ctx *c, cudaStream_t st)
     k_fft_means_partial<<<dim3(c->P.nlig + 2, FFT_MEAN_BLOCKS), 256, 0, st>>>(c->g, coef_ref(c).base,
                                                                            partial);
     CKL();
-    k_fft_means_final<<<c->P.nlig + 2, 32, 0, st>>>(c->g, partial, c->fft_means);
+    double gcount = 1.0;
+    for (int a = 0; a < c->dim; ++a) gcount *= (double)c->n[a];
+    k_fft_means_final<<<c->P.nlig + 2, 32, 0, st>>>(1.0 / gcount, partial, c->fft_means);
     CKL();
+    if (c->nranks > 1) TRY(allreduce_dev(c, c->fft_means, c->P.nlig + 2, ncclSum_, st));
     return 0;
 }
 
@@ -890,6 +948,62 @@ static int fftpc_apply(ksfd_ctx *c, const double *in, double *scratch, double *o
         return fail("cufftSetStream failed");
     k_fft_prescale<<<nblk(nlocal(c), 256), 256, 0, st>>>(c->g, coef_ref(c).base, in, scratch, skip);
     CKL();
+    if (c->fft_dist) {
+        // slab-distributed transform (fftpc.cuh): A = plane spectra / receive buffer,
+        // B = packed send buffer / last-axis-contiguous spectra.  Every rank makes the
+        // same NCCL calls whether or not the kernels skip.
+        double2 *A = spec, *B = static_cast<double2 *>(c->fft_spec2);
+        const int P = c->nranks, nloc = c->g.nloc, dof = c->dof, NL = (int)c->last_global;
+        const long long PS = c->fft_ps;
+        const long long s0 = fft_share_start(PS, c->rank, P);
+        const long long nsq = fft_share_start(PS, c->rank + 1, P) - s0;
+        auto k0_of = [&](int r) { return (long long)r * (NL / P) + std::min<long long>(r, NL % P); };
+        auto all_to_all = [&](double2 *send, double2 *recv, bool fwd) -> int {
+            // fwd: my planes' share q -> rank q;  back: rank p's planes of my share -> rank p
+            NK(g_nccl.GroupStart());
+            for (int r = 0; r < P; ++r) {
+                const long long sr = fft_share_start(PS, r, P);
+                const long long nsr = fft_share_start(PS, r + 1, P) - sr;
+                const long long kr = k0_of(r), nlr = k0_of(r + 1) - kr;
+                const long long by_share = (long long)nloc * dof * sr, n_share = (long long)nloc * dof * nsr;
+                const long long by_plane = (long long)dof * nsq * kr, n_plane = nlr * dof * nsq;
+                if (fwd) {
+                    NK(g_nccl.Send(send + by_share, 2 * n_share, ncclFloat64_, r, c->comm, st));
+                    NK(g_nccl.Recv(recv + by_plane, 2 * n_plane, ncclFloat64_, r, c->comm, st));
+                } else {
+                    NK(g_nccl.Send(send + by_plane, 2 * n_plane, ncclFloat64_, r, c->comm, st));
+                    NK(g_nccl.Recv(recv + by_share, 2 * n_share, ncclFloat64_, r, c->comm, st));
+                }
+            }
+            NK(g_nccl.GroupEnd());
+            return 0;
+        };
+        if (g_fft.SetStream(c->fft_z, st) != 0) return fail("cufftSetStream failed");
+        if (g_fft.ExecD2Z(c->fft_fwd, scratch, A) != 0) return fail("cufftExecD2Z failed");
+        const long long nA = (long long)nloc * dof * PS, nT = (long long)NL * dof * nsq;
+        k_fft_pack<<<nblk(nA, 256), 256, 0, st>>>(nloc, dof, PS, P, 1, A, B, skip);
+        CKL();
+        TRY(all_to_all(B, A, true));
+        k_fft_transpose<<<nblk(nT, 256), 256, 0, st>>>(NL, dof, nsq, 1, A, B, skip);
+        CKL();
+        if (g_fft.ExecZ2Z(c->fft_z, B, B, -1) != 0) return fail("cufftExecZ2Z failed");
+        S.dist = 1;
+        S.s0 = (int)s0;
+        S.nsq = (int)nsq;
+        S.NL = NL;
+        k_fft_symbol_solve<<<nblk(nsq * NL, 256), 256, 0, st>>>(S, c->fft_means, B, skip);
+        CKL();
+        if (g_fft.ExecZ2Z(c->fft_z, B, B, 1) != 0) return fail("cufftExecZ2Z failed");
+        k_fft_transpose<<<nblk(nT, 256), 256, 0, st>>>(NL, dof, nsq, 0, A, B, skip);
+        CKL();
+        TRY(all_to_all(A, B, false));
+        k_fft_pack<<<nblk(nA, 256), 256, 0, st>>>(nloc, dof, PS, P, 0, A, B, skip);
+        CKL();
+        if (g_fft.ExecZ2D(c->fft_inv, A, out) != 0) return fail("cufftExecZ2D failed");
+        k_fft_postscale<<<nblk(c->g.npts, 256), 256, 0, st>>>(c->g, coef_ref(c).base, out, skip);
+        CKL();
+        return 0;
+    }
     if (g_fft.ExecD2Z(c->fft_fwd, scratch, spec) != 0) return fail("cufftExecD2Z failed");
     const long long nk = (long long)(S.n0 / 2 + 1) * S.n1 * S.n2;
     k_fft_symbol_solve<<<nblk(nk, 256), 256, 0, st>>>(S, c->fft_means, spec, skip);
@@ -1519,7 +1633,9 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
     const int R = c->gm_runahead;
     // with the peer-to-peer exchanges (device-side exchange counters) launch
     // decisions need not be identical on all ranks
-    const bool free_running = c->nranks == 1 || c->p2p_on;
+    // (the slab-distributed spectral preconditioner makes NCCL calls in every step:
+    // identical launch sequences on all ranks are required, as in the NCCL fallback)
+    const bool free_running = c->nranks == 1 || (c->p2p_on && !(pcm == 2 && c->nranks > 1));
     InvD id;
     for (int l = 0; l < KSFD_MAX_LIGANDS; ++l) id.v[l] = c->invd[l];
 

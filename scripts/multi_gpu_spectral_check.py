@@ -1,0 +1,64 @@
+"""
+Check of the slab-distributed spectral preconditioner (experimental, NOT yet run on hardware):
+GMRES with precond=2 over N ranks must converge to the single-GPU solution of the same global
+problem in (nearly) the same number of Arnoldi steps, for small and large time steps.
+
+    KSFD_FFT_MULTI=1 torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \\
+        scripts/multi_gpu_spectral_check.py
+"""
+import os, sys
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, 'tests'))
+import numpy as np, torch, torch.distributed as dist
+from helpers import phys84, product_physics, random_state
+from ksfd_b200 import core, parallel
+
+
+def main():
+    os.environ.setdefault('KSFD_FFT_MULTI', '1')
+    rank = int(os.environ['RANK']); world = int(os.environ['WORLD_SIZE']); local = int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    ok_all = True
+    for dim, n in ((2, (96, 64)), (2, (250, 130)), (3, (20, 24, 32))):
+        p = phys84(dim, n)
+        dof = 3
+        u_g = random_state(p, 5)
+        b_g = np.random.default_rng(6).standard_normal(u_g.size)
+        ctx = core.Context(dim, n, dof, device=local, rank=rank, nranks=world)
+        ctx.set_physics(product_physics(p))
+        parallel.init_comm(ctx)
+        plane = dof * int(np.prod(n[:-1]))
+        sl = slice(ctx.last_start * plane, (ctx.last_start + ctx.last_count) * plane)
+        u, b = ctx.upload(u_g[sl]), ctx.upload(b_g[sl])
+        c1 = None
+        if rank == 0:
+            c1 = core.Context(dim, n, dof, device=local)
+            c1.set_physics(product_physics(p))
+            U, B = c1.upload(u_g), c1.upload(b_g)
+        for dt in (1e-3, 1.0, 100.0):
+            shift = 1.0 / (0.435866521508459 * dt)
+            ctx.jvp_setup(u, shift)
+            x, res = ctx.gmres(b, rtol=1e-10, max_it=500, precond=2)
+            xs = ctx.download(x)
+            true = ctx.norm2(b - ctx.jvp(x)) / ctx.norm2(b)
+            if rank == 0:
+                c1.jvp_setup(U, shift)
+                x1, res1 = c1.gmres(B, rtol=1e-10, max_it=500, precond=2)
+                xs1 = c1.download(x1)
+                err = float(np.abs(xs - xs1[sl]).max() / np.abs(xs1).max())
+                ok = res.reason > 0 and true < 1e-9 and err < 1e-7 and abs(res.its - res1.its) <= 2
+                ok_all = ok_all and ok
+                print('dim', dim, n, 'ranks', world, 'dt', dt, 'OK' if ok else 'FAIL',
+                      dict(err=err, true=true, its=(res.its, res1.its), reason=res.reason), flush=True)
+            dist.barrier()
+        ctx.close()
+        if c1 is not None:
+            c1.close()
+    if rank == 0:
+        print('MULTI_GPU_SPECTRAL_CHECK', 'PASS' if ok_all else 'FAIL', flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -128,3 +128,101 @@ def test_scalings_keep_step_counts_low_on_a_patterned_state():
         y, info = spla.gmres(op, b, rtol=1e-8, restart=30, maxiter=4, callback=cb,
                              callback_type='pr_norm')
         assert info == 0 and count[0] <= most, (dt, count[0])
+
+
+# ---------------------------------------------------------------------------
+# slab-distributed transform (fftpc.cuh: k_fft_pack, k_fft_transpose, the
+# all-to-all of fftpc_apply): the index maps restated in numpy for P emulated
+# ranks must reproduce the global FFT and invert exactly
+# ---------------------------------------------------------------------------
+def _share_start(PS, q, P):
+    return PS * q // P
+
+
+def _share_owner(PS, s, P):
+    q = ((s + 1) * P - 1) // PS
+    while q > 0 and _share_start(PS, q, P) > s:
+        q -= 1
+    while q + 1 < P and _share_start(PS, q + 1, P) <= s:
+        q += 1
+    return q
+
+
+@pytest.mark.parametrize('dim,n,P', [(2, (10, 13), 3), (2, (8, 8), 4), (3, (6, 5, 7), 2),
+                                     (3, (4, 6, 9), 4)])
+def test_slab_transform_index_maps(dim, n, P):
+    rng = np.random.default_rng(7)
+    dof = 3
+    NL = n[-1]
+    plane = n[:-1]                                   # (nx,) or (nx, ny)
+    nxh = n[0] // 2 + 1
+    PS = nxh if dim == 2 else n[1] * nxh
+    # global field [k][c][plane in (y, x) order]
+    X = rng.standard_normal((NL, dof) + tuple(reversed(plane)))
+    k0 = [r * (NL // P) + min(r, NL % P) for r in range(P + 1)]
+    assert k0[P] == NL
+    for s in range(PS):                              # the owner formula inverts the share starts
+        q = _share_owner(PS, s, P)
+        assert _share_start(PS, q, P) <= s < _share_start(PS, q + 1, P)
+    # plane transforms of the own planes: A[(k*dof + c)*PS + s]
+    A = []
+    for r in range(P):
+        loc = X[k0[r]:k0[r + 1]]
+        spec = np.fft.rfft(loc, axis=-1) if dim == 2 else np.fft.rfft2(loc, axes=(-2, -1))
+        A.append(spec.reshape(-1))
+    # pack per destination (k_fft_pack), all-to-all, R[(k*dof + c)*nsq + s_loc] with k global
+    R = []
+    for q in range(P):
+        s0, s1 = _share_start(PS, q, P), _share_start(PS, q + 1, P)
+        nsq = s1 - s0
+        Rq = np.empty(NL * dof * nsq, dtype=complex)
+        for p in range(P):
+            nloc = k0[p + 1] - k0[p]
+            B = np.empty(nloc * dof * PS, dtype=complex)
+            for e in range(nloc * dof * PS):
+                kc, s = divmod(e, PS)
+                d = _share_owner(PS, s, P)
+                ds0 = _share_start(PS, d, P)
+                dn = _share_start(PS, d + 1, P) - ds0
+                B[nloc * dof * ds0 + kc * dn + (s - ds0)] = A[p][e]
+            blk = B[nloc * dof * s0: nloc * dof * s0 + nloc * dof * nsq]     # what p sends to q
+            Rq[dof * nsq * k0[p]: dof * nsq * k0[p] + blk.size] = blk        # where q receives it
+        R.append((Rq, s0, nsq))
+    # transpose (k_fft_transpose), transform along the last axis, compare with the global FFT
+    G = np.fft.rfft(X, axis=-1) if dim == 2 else np.fft.rfft2(X, axes=(-2, -1))
+    G = np.fft.fft(G.reshape(NL, dof, PS), axis=0)                           # [k][c][s]
+    back = [None] * P
+    for q, (Rq, s0, nsq) in enumerate(R):
+        T = np.empty(dof * nsq * NL, dtype=complex)
+        for e in range(NL * dof * nsq):
+            kc, s = divmod(e, nsq)
+            k, c = divmod(kc, dof)
+            T[(c * nsq + s) * NL + k] = Rq[e]
+        T = np.fft.fft(T.reshape(dof, nsq, NL), axis=-1)
+        assert np.allclose(T, np.transpose(G[:, :, s0:s0 + nsq], (1, 2, 0)), atol=1e-10)
+        T = np.fft.ifft(T, axis=-1).reshape(-1)
+        Rb = np.empty_like(Rq)
+        for e in range(NL * dof * nsq):
+            kc, s = divmod(e, nsq)
+            k, c = divmod(kc, dof)
+            Rb[e] = T[(c * nsq + s) * NL + k]
+        back[q] = Rb
+    # the way back: share q of rank p's planes returns to rank p, unpack, inverse plane transform
+    for p in range(P):
+        nloc = k0[p + 1] - k0[p]
+        B = np.empty(nloc * dof * PS, dtype=complex)
+        for q in range(P):
+            s0, nsq = R[q][1], R[q][2]
+            blk = back[q][dof * nsq * k0[p]: dof * nsq * k0[p] + nloc * dof * nsq]
+            B[nloc * dof * s0: nloc * dof * s0 + blk.size] = blk
+        Ab = np.empty_like(B)
+        for e in range(nloc * dof * PS):
+            kc, s = divmod(e, PS)
+            d = _share_owner(PS, s, P)
+            ds0 = _share_start(PS, d, P)
+            dn = _share_start(PS, d + 1, P) - ds0
+            Ab[e] = B[nloc * dof * ds0 + kc * dn + (s - ds0)]
+        shape = (nloc, dof) + ((nxh,) if dim == 2 else (n[1], nxh))
+        loc = (np.fft.irfft(Ab.reshape(shape), n=n[0], axis=-1) if dim == 2
+               else np.fft.irfft2(Ab.reshape(shape), s=(n[1], n[0]), axes=(-2, -1)))
+        assert np.allclose(loc, X[k0[p]:k0[p + 1]], atol=1e-12)
