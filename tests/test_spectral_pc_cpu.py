@@ -226,3 +226,23 @@ def test_slab_transform_index_maps(dim, n, P):
         loc = (np.fft.irfft(Ab.reshape(shape), n=n[0], axis=-1) if dim == 2
                else np.fft.irfft2(Ab.reshape(shape), s=(n[1], n[0]), axes=(-2, -1)))
         assert np.allclose(loc, X[k0[p]:k0[p + 1]], atol=1e-12)
+
+
+def test_share_functions_as_compiled(tmp_path):
+    """fft_share_start / fft_share_owner of fftpc.cuh (host side of the __host__
+    __device__ functions, built with nvcc; no GPU needed): every plane wave number
+    has exactly one owner and the shares tile [0, PS)."""
+    import os
+    import shutil
+    import subprocess
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('needs nvcc')
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / 'share_check')
+    subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-std=c++17',
+                    '-I', os.path.join(os.path.dirname(here), 'ksfd_b200', 'csrc'),
+                    os.path.join(here, 'fft_share_check.cu'), '-o', exe], check=True,
+                   capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and 'bad 0' in out.stdout, out.stdout
