@@ -199,6 +199,25 @@ __host__ __device__ __forceinline__ int fft_share_owner(long long PS, long long 
     return q;
 }
 
+// index maps (host + device: tests/fft_share_check.cu dumps them for the numpy emulation)
+// A element e = (k_loc*dof + c)*PS + s  ->  its place in the packed buffer B
+__host__ __device__ __forceinline__ long long fft_pack_index(int nloc, int dof, long long PS, int P,
+                                                             long long e)
+{
+    const long long kc = e / PS, s = e - kc * PS;
+    const int q = fft_share_owner(PS, s, P);
+    const long long s0 = fft_share_start(PS, q, P), nsq = fft_share_start(PS, q + 1, P) - s0;
+    return (long long)nloc * dof * s0 + kc * nsq + (s - s0);
+}
+// R element e = (k*dof + c)*nsq + s  ->  its place (c*nsq + s)*NL + k in T
+__host__ __device__ __forceinline__ long long fft_transpose_index(int NL, int dof, long long nsq,
+                                                                  long long e)
+{
+    const long long kc = e / nsq, s = e - kc * nsq;
+    const long long k = kc / dof, c = kc - k * dof;
+    return (c * nsq + s) * NL + k;
+}
+
 // to_packed = 1: B <- A;  0: A <- B   (same index map both ways)
 __global__ void k_fft_pack(int nloc, int dof, long long PS, int P, int to_packed, double2 *A,
                            double2 *B, const int *__restrict__ skip)
@@ -206,10 +225,7 @@ __global__ void k_fft_pack(int nloc, int dof, long long PS, int P, int to_packed
     if (skip && *skip) return;
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= (long long)nloc * dof * PS) return;
-    const long long kc = e / PS, s = e - kc * PS;
-    const int q = fft_share_owner(PS, s, P);
-    const long long s0 = fft_share_start(PS, q, P), nsq = fft_share_start(PS, q + 1, P) - s0;
-    const long long b = (long long)nloc * dof * s0 + kc * nsq + (s - s0);
+    const long long b = fft_pack_index(nloc, dof, PS, P, e);
     if (to_packed)
         B[b] = A[e];
     else
@@ -223,9 +239,7 @@ __global__ void k_fft_transpose(int NL, int dof, long long nsq, int to_T, double
     if (skip && *skip) return;
     const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (e >= (long long)NL * dof * nsq) return;
-    const long long kc = e / nsq, s = e - kc * nsq;
-    const long long k = kc / dof, c = kc - k * dof;
-    const long long t = (c * nsq + s) * NL + k;
+    const long long t = fft_transpose_index(NL, dof, nsq, e);
     if (to_T)
         T[t] = R[e];
     else

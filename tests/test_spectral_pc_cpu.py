@@ -246,3 +246,24 @@ def test_share_functions_as_compiled(tmp_path):
                    capture_output=True)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and 'bad 0' in out.stdout, out.stdout
+    # the compiled index maps of k_fft_pack / k_fft_transpose against the formulas the
+    # emulation above (test_slab_transform_index_maps) uses
+    for nloc, dof, PS, P in ((5, 3, 13, 3), (4, 2, 40, 4), (7, 3, 9, 2)):
+        got = [int(x) for x in subprocess.run([exe, 'pack', str(nloc), str(dof), str(PS), str(P)],
+                                              capture_output=True, text=True).stdout.split()]
+        want = []
+        for e in range(nloc * dof * PS):
+            kc, sw = divmod(e, PS)
+            d = _share_owner(PS, sw, P)
+            ds0 = _share_start(PS, d, P)
+            want.append(nloc * dof * ds0 + kc * (_share_start(PS, d + 1, P) - ds0) + (sw - ds0))
+        assert got == want and sorted(got) == list(range(nloc * dof * PS))
+    for NL, dof, nsq in ((9, 3, 4), (16, 2, 7)):
+        got = [int(x) for x in subprocess.run([exe, 'transpose', str(NL), str(dof), str(nsq)],
+                                              capture_output=True, text=True).stdout.split()]
+        want = []
+        for e in range(NL * dof * nsq):
+            kc, sw = divmod(e, nsq)
+            k, c = divmod(kc, dof)
+            want.append((c * nsq + sw) * NL + k)
+        assert got == want and sorted(got) == list(range(NL * dof * nsq))
