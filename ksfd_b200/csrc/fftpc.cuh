@@ -108,14 +108,19 @@ __global__ void k_fft_postscale(Geom g, const double *__restrict__ coef_base, do
 
 // in place on the spectra: z^ = A0^(k)^-1 r^ / N   (N = number of grid points:
 // cuFFT transforms are unnormalised).  spec layout: [field][k2][k1][k0 < n0/2+1]
-__global__ void k_fft_symbol_solve(FftSym S, const double *__restrict__ means, double2 *spec,
-                                   const int *__restrict__ skip)
+// number of wave numbers this rank solves
+__host__ __device__ __forceinline__ long long fft_symbol_count(const FftSym &S)
 {
-    if (skip && *skip) return;
+    return S.dist ? (long long)S.nsq * S.NL : (long long)(S.n0 / 2 + 1) * S.n1 * S.n2;
+}
+
+// one wave number e (host + device: tests/fft_share_check.cu runs it on the host
+// against the numpy restatement)
+__host__ __device__ __forceinline__ void fft_symbol_elem(const FftSym &S, const double *means,
+                                                         double2 *spec, long long e)
+{
     const int n0h = S.n0 / 2 + 1;
-    const long long nk = S.dist ? (long long)S.nsq * S.NL : (long long)n0h * S.n1 * S.n2;
-    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (e >= nk) return;
+    const long long nk = fft_symbol_count(S);
     int k0, k1, k2;
     if (S.dist) {
         const int sg = S.s0 + (int)(e / S.NL), kl = (int)(e % S.NL);
@@ -173,6 +178,15 @@ __global__ void k_fft_symbol_solve(FftSym S, const double *__restrict__ means, d
         z.y = (r[1 + l].y * inv_n + S.s[l] * cbar * z0.y) * invd[l];
         spec[(long long)(1 + l) * nk + e] = z;
     }
+}
+
+__global__ void k_fft_symbol_solve(FftSym S, const double *__restrict__ means, double2 *spec,
+                                   const int *__restrict__ skip)
+{
+    if (skip && *skip) return;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= fft_symbol_count(S)) return;
+    fft_symbol_elem(S, means, spec, e);
 }
 
 

@@ -267,3 +267,89 @@ def test_share_functions_as_compiled(tmp_path):
             k, c = divmod(kc, dof)
             want.append((c * nsq + sw) * NL + k)
         assert got == want and sorted(got) == list(range(NL * dof * nsq))
+
+
+def _numpy_symbol_solve(R, shift, c2, s, gamma, D, means, n):
+    """the per-wave-number solve of spectral_inverse on spectra R[c][k_last..k_0h]
+    (unnormalised transforms: the 1/N is folded in, as in the kernel)"""
+    dim = len(n)
+    nxh = n[0] // 2 + 1
+    lam = 0.0
+    for ax in range(dim):
+        m = nxh if ax == 0 else n[ax]
+        c = np.cos(2 * np.pi * np.arange(m) / n[ax])
+        sh = [1] * dim
+        sh[dim - 1 - ax] = m
+        lam = lam + (c2[ax] * (32 * c - 2 * (2 * c * c - 1) - 30)).reshape(sh)
+    N = float(np.prod(n))
+    kbar, cbar = means[0], means[1]
+    nlig = R.shape[0] - 1
+    schur = shift / kbar - lam
+    t = R[0].copy()
+    invd = []
+    for l in range(nlig):
+        invd.append(1.0 / (shift + gamma[l] - D[l] * lam))
+        bd = -means[2 + l] * lam * invd[l]
+        schur = schur + bd * s[l] * cbar
+        t = t - bd * R[1 + l]
+    Z = np.empty_like(R)
+    Z[0] = t / schur / N
+    for l in range(nlig):
+        Z[1 + l] = (R[1 + l] / N + s[l] * cbar * Z[0]) * invd[l]
+    return Z
+
+
+@pytest.mark.parametrize('n', [(16,), (10, 7), (6, 5, 4)])
+def test_symbol_solve_as_compiled(n, tmp_path):
+    """fft_symbol_elem of fftpc.cuh built for the host (nvcc, no GPU) against the numpy
+    restatement, in the single-rank layout [c][k2][k1][k0] and in the slab-distributed
+    layout [c][s_loc][k] of every rank of a 3-rank split."""
+    import os
+    import shutil
+    import subprocess
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('needs nvcc')
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / 'share_check')
+    subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-std=c++17',
+                    '-I', os.path.join(os.path.dirname(here), 'ksfd_b200', 'csrc'),
+                    os.path.join(here, 'fft_share_check.cu'), '-o', exe], check=True,
+                   capture_output=True)
+    rng = np.random.default_rng(11)
+    dim, dof, ML = len(n), 3, 7
+    nxh = n[0] // 2 + 1
+    shape = tuple(reversed(n[1:])) + (nxh,)                 # [k2][k1][k0h]
+    R = rng.standard_normal((dof,) + shape) + 1j * rng.standard_normal((dof,) + shape)
+    shift = 0.37
+    c2 = [1.0 / (12 * 0.01 ** 2)] * 3
+    s = [0.01, 0.001] + [0.0] * 5
+    gamma = [0.01, 0.001] + [0.0] * 5
+    D = [1e-6, 1e-5] + [0.0] * 5
+    means = [2.9e-4, 3.1e7, -5.2e-8, 5.1e-8] + [0.0] * 5
+    want = _numpy_symbol_solve(R, shift, c2, s, gamma, D, means, n)
+
+    def run(hd, spec):
+        fin, fout = str(tmp_path / 'in.bin'), str(tmp_path / 'out.bin')
+        with open(fin, 'wb') as f:
+            np.array(hd, dtype=np.int32).tofile(f)
+            np.array([shift] + c2 + s + gamma + D + means, dtype=np.float64).tofile(f)
+            np.ascontiguousarray(spec, dtype=np.complex128).tofile(f)
+        subprocess.run([exe, 'symbol', fin, fout], check=True)
+        return np.fromfile(fout, dtype=np.complex128).reshape(spec.shape)
+
+    n3 = list(n) + [1] * (3 - dim)
+    got = run([dof, dof - 1] + n3 + [0, 0, 0, 0], R)
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+    if dim >= 2:
+        # distributed: plane index s = k0 (2-D) or k1*nxh + k0 (3-D), last axis k
+        NL = n[-1]
+        PS = nxh if dim == 2 else n[1] * nxh
+        Rp = R.reshape(dof, NL, PS)                        # [c][k][s]
+        Wp = want.reshape(dof, NL, PS)
+        P = 3
+        for q in range(P):
+            s0, s1 = _share_start(PS, q, P), _share_start(PS, q + 1, P)
+            T = np.transpose(Rp[:, :, s0:s1], (0, 2, 1))   # [c][s_loc][k]
+            got = run([dof, dof - 1] + n3 + [1, s0, s1 - s0, NL], T)
+            assert np.allclose(got, np.transpose(Wp[:, :, s0:s1], (0, 2, 1)), rtol=1e-12, atol=0)
