@@ -310,6 +310,10 @@ static VecRef make_ref(const ksfd_ctx *c, const double *base, int stride, int sl
     r.base = base;
     r.par = nullptr;
     r.pstride = 0;
+#if KSFD_HALO_DEFER
+    r.flag_lo = r.flag_hi = nullptr;
+    r.err = nullptr;
+#endif
     const long long ps = c->g.plane_pts * stride;
     if (c->nranks == 1) {
         r.lo = base + (long long)(c->g.nloc - KSFD_SW) * ps;
@@ -403,6 +407,38 @@ __global__ void k_halo_xchg(const double *__restrict__ top, const double *__rest
     }
 }
 
+#if KSFD_HALO_DEFER
+// push-only variant: the consumer (k_march, halo_wait in plane_of) waits for the flags
+__global__ void k_halo_push(const double *__restrict__ top, const double *__restrict__ bot,
+                            long long cnt, double *__restrict__ up_lo0,
+                            double *__restrict__ dn_hi0, long long pstride,
+                            volatile unsigned long long *up_flag_lo,
+                            volatile unsigned long long *dn_flag_hi, unsigned long long *ctr,
+                            unsigned *done, const int *__restrict__ skip)
+{
+    if (skip && *skip) return;
+    const unsigned long long q = *ctr + 1;
+    const long long sh = (long long)(q & 1ull) * pstride;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < cnt;
+         e += (long long)gridDim.x * blockDim.x) {
+        up_lo0[sh + e] = top[e];
+        dn_hi0[sh + e] = bot[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(done, 1u);
+        if (t == gridDim.x - 1) {
+            atomicExch(done, 0u);
+            __threadfence_system();
+            *up_flag_lo = q;
+            *dn_flag_hi = q;
+            *ctr = q;
+        }
+    }
+}
+#endif
+
 extern "C" int ksfd_p2p_export(ksfd_ctx *c, char handle_out[64])
 {
     if (!c || !handle_out) return fail("ksfd_p2p_export: NULL argument");
@@ -451,7 +487,7 @@ extern "C" int ksfd_p2p_import(ksfd_ctx *c, const char *handles, int nhandles)
 }
 
 static int exchange_p2p(ksfd_ctx *c, const double *vec, int stride, int slot, cudaStream_t st,
-                        const int *skip)
+                        const int *skip, bool defer)
 {
     const size_t cnt = (size_t)KSFD_SW * c->g.plane_pts * stride;
     const size_t hi_off = KSFD_SW * c->halo_plane_doubles;
@@ -464,6 +500,16 @@ static int exchange_p2p(ksfd_ctx *c, const double *vec, int stride, int slot, cu
     flag_t my_flag_lo = reinterpret_cast<flag_t>(c->p2p_mine) + slot * 2 + 0;
     flag_t my_flag_hi = reinterpret_cast<flag_t>(c->p2p_mine) + slot * 2 + 1;
     const unsigned blocks = (unsigned)std::min<size_t>((cnt + 255) / 256, 64);
+#if KSFD_HALO_DEFER
+    if (defer) {
+        k_halo_push<<<blocks, 256, 0, st>>>(top, vec, (long long)cnt, up_lo0, dn_hi0,
+                                            (long long)p2p_buf_doubles(c), up_flag_lo, dn_flag_hi,
+                                            c->p2p_ctr + slot, c->p2p_done, skip);
+        CKL();
+        return 0;
+    }
+#endif
+    (void)defer;
     k_halo_xchg<<<blocks, 256, 0, st>>>(top, vec, (long long)cnt, up_lo0, dn_hi0,
                                         (long long)p2p_buf_doubles(c), up_flag_lo, dn_flag_hi,
                                         my_flag_lo, my_flag_hi, c->p2p_ctr + slot, c->p2p_done,
@@ -473,11 +519,11 @@ static int exchange_p2p(ksfd_ctx *c, const double *vec, int stride, int slot, cu
 }
 
 static int exchange(ksfd_ctx *c, const double *vec, int stride, int slot,
-                    cudaStream_t st, const int *skip = nullptr)
+                    cudaStream_t st, const int *skip = nullptr, bool defer = false)
 {
     if (c->nranks == 1) return 0;
     if (slot < 0 || slot >= KSFD_HALO_SLOTS) return fail("bad halo slot");
-    if (c->p2p_on) return exchange_p2p(c, vec, stride, slot, st, skip);
+    if (c->p2p_on) return exchange_p2p(c, vec, stride, slot, st, skip, defer);
     if (!c->halo[slot])
         CK(cudaMalloc(&c->halo[slot],
                       sizeof(double) * 2 * KSFD_SW * c->halo_plane_doubles));
@@ -663,6 +709,10 @@ static VecRef coef_ref(const ksfd_ctx *c)
     VecRef r;
     r.par = nullptr;
     r.pstride = 0;
+#if KSFD_HALO_DEFER
+    r.flag_lo = r.flag_hi = nullptr;
+    r.err = nullptr;
+#endif
     r.lo = c->coef;
     r.base = c->coef + KSFD_SW * ps;
     r.hi = c->coef + (long long)(KSFD_SW + c->g.nloc) * ps;
@@ -718,10 +768,25 @@ static int jvp_impl(ksfd_ctx *c, const double *v, double *out, bool precond,
 {
     if (!c->have_jac) return fail("ksfd_jvp_setup has not been called");
     if (v == out) return fail("ksfd_jvp: in-place application is not supported");
-    TRY(exchange(c, v, c->dof, 1, st, skip));
+#if KSFD_HALO_DEFER
+    // experimental: push only; the marching kernel waits where it reads ghost planes
+    static const bool defer_env = getenv("KSFD_HALO_DEFER") && atoi(getenv("KSFD_HALO_DEFER")) != 0;
+    const bool defer = defer_env && c->p2p_on && c->nranks > 1 && use_march(c);
+#else
+    const bool defer = false;
+#endif
+    TRY(exchange(c, v, c->dof, 1, st, skip, defer));
     VecRef vr = make_ref(c, v, c->dof, 1);
     VecRef pr = make_ref(c, c->pc, 1, 2);
     VecRef cr = coef_ref(c);
+#if KSFD_HALO_DEFER
+    if (defer) {
+        typedef const volatile unsigned long long *cflag_t;
+        vr.flag_lo = reinterpret_cast<cflag_t>(c->p2p_mine) + 1 * 2 + 0;     // slot 1
+        vr.flag_hi = reinterpret_cast<cflag_t>(c->p2p_mine) + 1 * 2 + 1;
+        vr.err = c->p2p_err_dev;
+    }
+#endif
     if (use_march(c)) {
         return c->dim == 2 ? ksfd_march_jvp_d2(c, cr, vr, pr, precond, out, skip, st)
                            : ksfd_march_jvp_d3(c, cr, vr, pr, precond, out, skip, st);

@@ -95,6 +95,10 @@ struct SmemTabs {
 __device__ __forceinline__ const double *plane_of(const VecRef &v, int k, int nloc,
                                                   int ps)
 {
+#if KSFD_HALO_DEFER
+    if (k < 0) halo_wait(v.flag_lo, v);
+    if (k >= nloc) halo_wait(v.flag_hi, v);
+#endif
     if (k < 0) return v.lo + ghost_shift(v) + (k + KSFD_SW) * (long long)ps;
     if (k >= nloc) return v.hi + ghost_shift(v) + (k - nloc) * (long long)ps;
     return v.base + k * (long long)ps;
