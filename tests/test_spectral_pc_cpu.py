@@ -228,10 +228,12 @@ def test_slab_transform_index_maps(dim, n, P):
         assert np.allclose(loc, X[k0[p]:k0[p + 1]], atol=1e-12)
 
 
-def test_share_functions_as_compiled(tmp_path):
-    """fft_share_start / fft_share_owner of fftpc.cuh (host side of the __host__
-    __device__ functions, built with nvcc; no GPU needed): every plane wave number
-    has exactly one owner and the shares tile [0, PS)."""
+
+
+@pytest.fixture(scope='module')
+def share_check_exe(tmp_path_factory):
+    """tests/fft_share_check.cu (host build of the __host__ __device__ functions of
+    fftpc.cuh) compiled once with nvcc; no GPU needed to run it."""
     import os
     import shutil
     import subprocess
@@ -239,11 +241,19 @@ def test_share_functions_as_compiled(tmp_path):
     if not os.path.exists(nvcc):
         pytest.skip('needs nvcc')
     here = os.path.dirname(os.path.abspath(__file__))
-    exe = str(tmp_path / 'share_check')
+    exe = str(tmp_path_factory.mktemp('fftchk') / 'share_check')
     subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-std=c++17',
                     '-I', os.path.join(os.path.dirname(here), 'ksfd_b200', 'csrc'),
                     os.path.join(here, 'fft_share_check.cu'), '-o', exe], check=True,
                    capture_output=True)
+    return exe
+
+def test_share_functions_as_compiled(share_check_exe):
+    """fft_share_start / fft_share_owner of fftpc.cuh (host side of the __host__
+    __device__ functions, built with nvcc; no GPU needed): every plane wave number
+    has exactly one owner and the shares tile [0, PS)."""
+    import subprocess
+    exe = share_check_exe
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and 'bad 0' in out.stdout, out.stdout
     # the compiled index maps of k_fft_pack / k_fft_transpose against the formulas the
@@ -300,22 +310,12 @@ def _numpy_symbol_solve(R, shift, c2, s, gamma, D, means, n):
 
 
 @pytest.mark.parametrize('n', [(16,), (10, 7), (6, 5, 4)])
-def test_symbol_solve_as_compiled(n, tmp_path):
+def test_symbol_solve_as_compiled(n, tmp_path, share_check_exe):
     """fft_symbol_elem of fftpc.cuh built for the host (nvcc, no GPU) against the numpy
     restatement, in the single-rank layout [c][k2][k1][k0] and in the slab-distributed
     layout [c][s_loc][k] of every rank of a 3-rank split."""
-    import os
-    import shutil
     import subprocess
-    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
-    if not os.path.exists(nvcc):
-        pytest.skip('needs nvcc')
-    here = os.path.dirname(os.path.abspath(__file__))
-    exe = str(tmp_path / 'share_check')
-    subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-std=c++17',
-                    '-I', os.path.join(os.path.dirname(here), 'ksfd_b200', 'csrc'),
-                    os.path.join(here, 'fft_share_check.cu'), '-o', exe], check=True,
-                   capture_output=True)
+    exe = share_check_exe
     rng = np.random.default_rng(11)
     dim, dof, ML = len(n), 3, 7
     nxh = n[0] // 2 + 1
