@@ -7,8 +7,8 @@ implicitTS, ksfdTS, TimeSeries, Generator, random_function, dillnp/dillunp.
 Compute happens in libksfd_b200.so (CUDA, sm_100a) through ksfd_b200._lib.
 """
 from ._lib import KSFDError  # noqa: F401
-from .params import (KSFDException, Ligand, LigandGroup, LigandGroups, Parser,  # noqa: F401
-                     SolutionParameters, default_parameters, find_duplicates,
+from .params import (KSFDException, Ligand, LigandGroup, LigandGroups, Parameter,  # noqa: F401
+                     ParameterList, Parser, SolutionParameters, default_parameters, find_duplicates,
                      parse_commandline, petsc_init, safe_sympify)
 
 

@@ -77,7 +77,7 @@ static __device__ const unsigned long long g_exp_tab[64] = KSFD_EXP_TAB_INIT;
 // All shared memory is addressed through this symbol with integer indices (a
 // generic pointer into shared memory would make every access recompute the
 // shared window base).  Layout: [2][NF][SP] ring, then the tables.
-extern __shared__ double ksfd_smem[];
+extern __shared__ __align__(128) double ksfd_smem[];
 
 // table accessor over the CTA's shared-memory copy; OFF = index of the tables
 template <int OFF>
@@ -286,6 +286,10 @@ struct ResidualOp {
     static constexpr bool HAS_AUX = true;
     static constexpr bool TABS = true;
     static constexpr bool STAGE_FIRST = (KSFD_MARCH_VARIANT & 1) != 0;
+    // input vectors of the TMA-fed marcher (tma_march.cuh): u
+    static constexpr int NIN = 1;
+    __host__ __device__ static constexpr int nc(int) { return NLIG + 1; }
+    __host__ __device__ static constexpr int coff(int) { return 0; }
     VecRef u;
     const double *udot, *src;
     double *out;
@@ -294,6 +298,10 @@ struct ResidualOp {
         int e;                                 // element index of the next output
     };
     __device__ static constexpr int out_fields(int) { return NLIG + 1; }
+    __device__ __forceinline__ void init_out(const MarchArgs &g, State &st, int k0, int poff) const
+    {
+        st.e = k0 * (NLIG + 1) * g.fs + poff;
+    }
 
     __device__ __forceinline__ void init(const MarchArgs &g, State &st, int kfirst, int k0,
                                          int poff) const
@@ -399,6 +407,10 @@ struct JvpOp {
     static constexpr bool HAS_AUX = false;
     static constexpr bool TABS = false;
     static constexpr bool STAGE_FIRST = false;
+    // input vectors of the TMA-fed marcher (tma_march.cuh): coef, v, pc
+    static constexpr int NIN = PRECOND ? 3 : 2;
+    __host__ __device__ static constexpr int nc(int i) { return i == 0 ? NLIG + 3 : i == 1 ? NLIG + 1 : 1; }
+    __host__ __device__ static constexpr int coff(int i) { return i == 0 ? 0 : i == 1 ? NLIG + 3 : 2 * NLIG + 4; }
     VecRef coef, v, pc;
     double shift;
     double invd[NLIG];
@@ -408,6 +420,10 @@ struct JvpOp {
         int e;
     };
     __device__ static constexpr int out_fields(int) { return NLIG + 1; }
+    __device__ __forceinline__ void init_out(const MarchArgs &g, State &st, int k0, int poff) const
+    {
+        st.e = k0 * (NLIG + 1) * g.fs + poff;
+    }
 
     __device__ __forceinline__ void init(const MarchArgs &g, State &st, int kfirst, int k0,
                                          int poff) const
@@ -517,6 +533,9 @@ struct VelocityOp {
     static constexpr bool HAS_AUX = false;
     static constexpr bool TABS = true;
     static constexpr bool STAGE_FIRST = (KSFD_MARCH_VARIANT & 1) != 0;
+    static constexpr int NIN = 1;
+    __host__ __device__ static constexpr int nc(int) { return NLIG + 1; }
+    __host__ __device__ static constexpr int coff(int) { return 0; }
     VecRef u;
     double *vel;        // optional plane-SoA output with DIM fields
     double *vmax;       // optional per-axis max
@@ -526,6 +545,11 @@ struct VelocityOp {
         double vm[3];
     };
     __device__ static constexpr int out_fields(int dim) { return dim; }
+    __device__ __forceinline__ void init_out(const MarchArgs &g, State &st, int k0, int poff) const
+    {
+        st.e = k0 * DIM * g.fs + poff;
+        st.vm[0] = st.vm[1] = st.vm[2] = 0.0;
+    }
 
     __device__ __forceinline__ void init(const MarchArgs &g, State &st, int kfirst, int k0,
                                          int poff) const

@@ -1,0 +1,404 @@
+// TMA-fed marching stencil kernels (sm_100a): the data movement of the marching
+// skeleton of march_kernels.cuh re-done around the Blackwell copy engine.
+//
+// What changes against k_march (the operator policies — stage / emit arithmetic —
+// are shared, results are bit-identical):
+//   * raw input planes arrive in shared memory by cp.async.bulk.tensor (TMA, SASS
+//     UTMALDG) issued by ONE elected thread and completed on mbarriers: no
+//     per-thread address arithmetic, no prefetch registers, SC planes in flight
+//     per CTA independent of the warps' progress;
+//   * there are no halo-lane threads.  A CTA has exactly one thread per OUTPUT
+//     point of its TX x TY tile; the 4*TX + 4*TY halo points of the centre plane
+//     (the x/y neighbours of the tile edge) are staged by the first warps in an
+//     extra pass from their own TMA boxes, which lag the centre boxes by the two
+//     planes of the register queue.  Threads that only ever staged (1/3 of a
+//     16x16 CTA, each holding a full register queue) are gone: twice as many
+//     output points are resident per SM;
+//   * the tile is fetched as 5 boxes per input vector and plane — centre TX x TY,
+//     two y strips TX x 2, two x strips 2 x TY — each with its start coordinate
+//     wrapped periodically, so no box straddles the periodic boundary and the
+//     same code serves every tile (corners are never needed: star stencil);
+//   * the last tile of an axis is CLAMPED to end at the boundary instead of being
+//     partial (it recomputes a few outputs of its neighbour, writing identical
+//     values), so every tile is full and lies inside the domain.
+//
+// Tensor maps (host: tma_host.h): every input vector is described as a rank-3
+// tensor (x, y, plane*nc + field) over its plane-SoA storage; coordinate 2 of a
+// box = kofs + k*nc selects the nc fields of plane k at once.
+//
+// Shared memory (doubles): [staged ring 2 x NF x SP][log/exp tables]
+//   [centre ring SC x NPRE x TX*TY][halo ring SH x NPRE x NH][mbarriers SC + SH]
+#pragma once
+#include <cuda.h>
+
+#include "march_kernels.cuh"
+
+struct TmaVecIn {
+    int kofs[3];    // coordinate 2 of plane 0 of: [0] owned planes, [1] ghost lo (planes -2,-1),
+                    // [2] ghost hi (planes nloc, nloc+1)
+    int wrap;       // 1: ghost planes are periodic images of the owned planes (one rank)
+};
+struct TmaIn {
+    const CUtensorMap *maps;    // [input vector][buffer 0..2][box shape: centre, y strip, x strip]
+    TmaVecIn v[3];
+};
+
+namespace ktma {
+__device__ __forceinline__ unsigned s32(const void *p)
+{
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "KSFD_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra KSFD_DONE;\n"
+        "bra KSFD_WAIT;\n"
+        "KSFD_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// one box of a rank-3 tensor -> shared memory, completion on an mbarrier
+__device__ __forceinline__ void load3(unsigned dst, const CUtensorMap *m, int c0, int c1, int c2,
+                                      unsigned bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+}   // namespace ktma
+
+template <int DIM, int TX, int TY, class Op, bool UNR, int SC, int SH>
+struct TmaMarcher {
+    using T = TileT<DIM, TX, TY>;
+    static constexpr int NTH = (DIM == 2) ? TX : TX * TY;           // threads = outputs
+    static constexpr int NH = (DIM == 2) ? 4 : 4 * TX + 4 * TY;     // halo points per plane
+    static constexpr int NF = Op::NF, NPRE = Op::NPRE, NAUX = Op::NAUX, NIN = Op::NIN;
+    static constexpr int r16(int x) { return (x + 15) / 16 * 16; }
+    static constexpr int RING = r16(2 * NF * T::SP);
+    static constexpr int TABS = Op::TABS ? KSFD_TAB_DOUBLES : 0;
+    static constexpr int CRING = RING + TABS;
+    static constexpr int CSLOT = NPRE * NTH;
+    static constexpr int HRING = CRING + SC * CSLOT;
+    static constexpr int HVEC2 = 16;        // 2-D: doubles reserved per (vector, side) box
+    static constexpr int HSLOT = (DIM == 2) ? NIN * 2 * HVEC2 : NPRE * NH;
+    static constexpr int HBYTES = (DIM == 2) ? NPRE * 4 * 8 : NPRE * NH * 8;
+    static constexpr int BAR = HRING + SH * HSLOT;
+    static constexpr int SMEM_DOUBLES = BAR + SC + SH;
+    static_assert(NTH % 32 == 0 && TABS % 16 == 0, "alignment of the TMA destinations");
+    static_assert(DIM == 2 || (TX % 8 == 0 && TY % 8 == 0), "3-D tiles: multiples of 8");
+    static_assert(NH <= NTH, "halo pass: one halo point per thread");
+
+    // halo slot: offset of the box of (vector i, piece p); field stride of piece p
+    //   3-D pieces: 0 bottom rows, 1 top rows, 2 left columns, 3 right columns
+    //   2-D pieces: 0 left, 1 right
+    __device__ static constexpr int hbox(int i, int p)
+    {
+        if (DIM == 2) return (2 * i + p) * HVEC2;
+        const int po = p == 0 ? 0 : p == 1 ? 2 * TX : p == 2 ? 4 * TX : 4 * TX + 2 * TY;
+        return Op::coff(i) * NH + Op::nc(i) * po;
+    }
+
+    const MarchArgs &g;
+    const DevPhys &P;
+    const Op &op;
+    const TmaIn &tin;
+    double q[NF][5];
+    double aux[NAUX];
+    typename Op::State st;
+    int spos, k0, k1;
+    int hspos, hfs, hoff[NIN];
+    int cs, hs;                 // ring slots of the next centre / halo plane to consume
+    unsigned cph, hph;          // their mbarrier phase parities
+    unsigned bar0;              // shared address of the first mbarrier
+    bool active, hact;
+
+    __device__ __forceinline__ int tile_x0() const { return min((int)blockIdx.x * g.ox, g.n0 - g.ox); }
+    __device__ __forceinline__ int tile_y0() const
+    {
+        return DIM == 2 ? 0 : min((int)blockIdx.y * g.oy, g.n1 - g.oy);
+    }
+
+    __device__ __forceinline__ TmaMarcher(const MarchArgs &g_, const DevPhys &P_, const Op &op_,
+                                          const TmaIn &tin_)
+        : g(g_), P(P_), op(op_), tin(tin_)
+    {
+        const int tid = threadIdx.x;
+        bar0 = ktma::s32(ksfd_smem + BAR);
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < SC + SH; ++s) ktma::mbar_init(bar0 + 8 * s, 1);
+            ktma::mbar_fence_init();
+        }
+        if (Op::TABS) {
+            for (int i = tid; i < KSFD_TAB_DOUBLES; i += NTH)
+                ksfd_smem[RING + i] = __longlong_as_double(
+                    (long long)(i < 256 ? g_log_tab[i] : g_exp_tab[i - 256]));
+        }
+        const int i0 = tile_x0(), j0 = tile_y0();
+        int poff;
+        hact = false;
+        hspos = 0;
+        hfs = 2;
+#pragma unroll
+        for (int i = 0; i < NIN; ++i) hoff[i] = 0;
+        if (DIM == 2) {
+            active = tid < g.ox;
+            spos = tid + KSFD_SW;
+            poff = i0 + tid;
+            if (tid < 4) {
+                const int p = tid >> 1, cc = tid & 1;
+                hact = true;
+                hspos = p ? g.ox + KSFD_SW + cc : cc;
+#pragma unroll
+                for (int i = 0; i < NIN; ++i) hoff[i] = (p ? hbox(i, 1) : hbox(i, 0)) + cc;
+            }
+        } else {
+            const int a = tid % TX, b = tid / TX;
+            active = a < g.ox && b < g.oy;
+            spos = (b + KSFD_SW) * T::PX + a + KSFD_SW;
+            poff = (j0 + b) * g.n0 + i0 + a;
+            if (tid < NH) {
+                int p, idx;
+                if (tid < 4 * TX) {                     // rows below (p 0) / above (p 1) the tile
+                    p = tid >= 2 * TX;
+                    idx = tid - p * 2 * TX;
+                    const int r = idx / TX, aa = idx - r * TX;
+                    hspos = (p ? g.oy + KSFD_SW + r : r) * T::PX + aa + KSFD_SW;
+                    hact = aa < g.ox;
+                    hfs = 2 * TX;
+                } else {                                // columns left (p 2) / right (p 3)
+                    const int h = tid - 4 * TX;
+                    p = 2 + (h >= 2 * TY);
+                    idx = h - (p - 2) * 2 * TY;
+                    const int bb = idx >> 1, cc = idx & 1;
+                    hspos = (bb + KSFD_SW) * T::PX + (p == 3 ? g.ox + KSFD_SW + cc : cc);
+                    hact = bb < g.oy;
+                    hfs = 2 * TY;
+                }
+#pragma unroll
+                for (int i = 0; i < NIN; ++i)
+                    hoff[i] = (p == 0 ? hbox(i, 0) : p == 1 ? hbox(i, 1) : p == 2 ? hbox(i, 2)
+                                                                                 : hbox(i, 3)) +
+                              idx;
+            }
+        }
+        k0 = blockIdx.z * g.rz;
+        k1 = min(k0 + g.rz, g.nloc);
+        op.init_out(g, st, k0, poff);
+        cs = hs = 0;
+        cph = hph = 0;
+#pragma unroll
+        for (int f = 0; f < NF; ++f)
+#pragma unroll
+            for (int s = 0; s < 5; ++s) q[f][s] = 0.0;
+        __syncthreads();                    // barriers initialised, tables staged
+        if (tid == 0) {
+            const int np = k1 - k0 + 2 * KSFD_SW;
+#pragma unroll
+            for (int s = 0; s < SC; ++s)
+                if (s < np) issue_centre(k0 - KSFD_SW + s, s);
+#pragma unroll
+            for (int s = 0; s < SH; ++s)
+                if (s < k1 - k0) issue_halo(k0 + s, s);
+        }
+    }
+
+    // coordinate 2 of plane k of input vector i; buf = which of its three buffers
+    __device__ __forceinline__ int plane_coord(int i, int k, int &buf) const
+    {
+        const TmaVecIn &v = tin.v[i];
+        const int nc = Op::nc(i);
+        buf = 0;
+        if (k < 0) {
+            if (v.wrap) return v.kofs[0] + (k + g.nloc) * nc;
+            buf = 1;
+            return v.kofs[1] + (k + KSFD_SW) * nc;
+        }
+        if (k >= g.nloc) {
+            if (v.wrap) return v.kofs[0] + (k - g.nloc) * nc;
+            buf = 2;
+            return v.kofs[2] + (k - g.nloc) * nc;
+        }
+        return v.kofs[0] + k * nc;
+    }
+
+    // (elected thread) fetch the centre boxes of plane k into centre slot `slot`
+    __device__ __forceinline__ void issue_centre(int k, int slot) const
+    {
+        const unsigned bar = bar0 + 8 * slot;
+        ktma::mbar_expect(bar, CSLOT * 8);
+        const int i0 = tile_x0(), j0 = tile_y0();
+#pragma unroll
+        for (int i = 0; i < NIN; ++i) {
+            int buf;
+            const int kc = plane_coord(i, k, buf);
+            ktma::load3(ktma::s32(ksfd_smem + CRING + slot * CSLOT + Op::coff(i) * NTH),
+                        tin.maps + (i * 3 + buf) * 3, i0, j0, kc, bar);
+        }
+    }
+    // (elected thread) fetch the halo boxes of plane k into halo slot `slot`
+    __device__ __forceinline__ void issue_halo(int k, int slot) const
+    {
+        const unsigned bar = bar0 + 8 * (SC + slot);
+        ktma::mbar_expect(bar, HBYTES);
+        const int i0 = tile_x0(), j0 = tile_y0();
+        const int xl = i0 >= KSFD_SW ? i0 - KSFD_SW : i0 - KSFD_SW + g.n0;
+        const int xr = i0 + g.ox < g.n0 ? i0 + g.ox : i0 + g.ox - g.n0;
+        const double *base = ksfd_smem + HRING + slot * HSLOT;
+#pragma unroll
+        for (int i = 0; i < NIN; ++i) {
+            int buf;
+            const int kc = plane_coord(i, k, buf);
+            const CUtensorMap *m = tin.maps + (i * 3 + buf) * 3;
+            if (DIM == 2) {
+                ktma::load3(ktma::s32(base + hbox(i, 0)), m + 2, xl, 0, kc, bar);
+                ktma::load3(ktma::s32(base + hbox(i, 1)), m + 2, xr, 0, kc, bar);
+            } else {
+                const int yl = j0 >= KSFD_SW ? j0 - KSFD_SW : j0 - KSFD_SW + g.n1;
+                const int yr = j0 + g.oy < g.n1 ? j0 + g.oy : j0 + g.oy - g.n1;
+                ktma::load3(ktma::s32(base + hbox(i, 0)), m + 1, i0, yl, kc, bar);
+                ktma::load3(ktma::s32(base + hbox(i, 1)), m + 1, i0, yr, kc, bar);
+                ktma::load3(ktma::s32(base + hbox(i, 2)), m + 2, xl, j0, kc, bar);
+                ktma::load3(ktma::s32(base + hbox(i, 3)), m + 2, xr, j0, kc, bar);
+            }
+        }
+    }
+
+    // iteration `it` of the CTA: plane kk = k0 - 2 + it enters the queue at phase PH,
+    // plane kk - 2 (if owned) is emitted
+    template <int PH>
+    __device__ __forceinline__ void step(int it)
+    {
+        const int tid = threadIdx.x;
+        const bool emitting = it >= 2 * KSFD_SW;        // kk - 2 >= k0: five planes are queued
+        // 1. the centre box of plane kk: raw values -> pointwise fields -> queue
+        ktma::mbar_wait(bar0 + 8 * cs, cph);
+        if (active) {
+            double cur[NPRE], f[NF];
+            const int b = CRING + cs * CSLOT + tid;
+#pragma unroll
+            for (int c = 0; c < NPRE; ++c) cur[c] = ksfd_smem[b + c * NTH];
+            op.stage(P, SmemTabs<RING>(), cur, f);
+#pragma unroll
+            for (int c = 0; c < NF; ++c) q[c][PH] = f[c];
+        }
+        const int cs_used = cs, hs_used = hs;
+        if (++cs == SC) {
+            cs = 0;
+            cph ^= 1u;
+        }
+        const int ri = (it & 1) * (NF * T::SP);
+        if (emitting) {
+            if (Op::HAS_AUX && active) op.load_aux(g, st.e, 0, RegSink{aux});
+            // 2. the halo points of the centre plane kk - 2, staged by the first warps
+            if (tid < NH) {
+                ktma::mbar_wait(bar0 + 8 * (SC + hs), hph);
+                if (hact) {
+                    double cur[NPRE], f[NF];
+                    const int hb = HRING + hs * HSLOT;
+#pragma unroll
+                    for (int i = 0; i < NIN; ++i)
+#pragma unroll
+                        for (int c = 0; c < Op::nc(i); ++c)
+                            cur[Op::coff(i) + c] = ksfd_smem[hb + hoff[i] + c * hfs];
+                    op.stage(P, SmemTabs<RING>(), cur, f);
+#pragma unroll
+                    for (int c = 0; c < NF; ++c) ksfd_smem[ri + hspos + c * T::SP] = f[c];
+                }
+            }
+            if (++hs == SH) {
+                hs = 0;
+                hph ^= 1u;
+            }
+            // 3. share the centre plane
+            if (active) {
+#pragma unroll
+                for (int c = 0; c < NF; ++c) ksfd_smem[ri + spos + c * T::SP] = q[c][(PH + 3) % 5];
+            }
+        }
+        __syncthreads();
+        // 4. refill the slots that every thread has finished reading
+        if (tid == 0) {
+            const int np = k1 - k0 + 2 * KSFD_SW;
+            if (it + SC < np) issue_centre(k0 - KSFD_SW + it + SC, cs_used);
+            if (emitting && it - 2 * KSFD_SW + SH < k1 - k0)
+                issue_halo(k0 + it - 2 * KSFD_SW + SH, hs_used);
+        }
+        // 5. the stencil of plane kk - 2
+        if (emitting) {
+            if (active) {
+                LaneAcc<DIM, NF, T::SP, T::SY, PH> a(q, ri + spos);
+                op.emit(P, g, a, aux, st);
+            }
+            op.advance_out(g, st);
+        }
+    }
+
+    __device__ __forceinline__ void run()
+    {
+        const int np = k1 - k0 + 2 * KSFD_SW;
+        int it = 0;
+        if (!UNR) {
+            for (; it < np; ++it) {
+                step<4>(it);
+#pragma unroll
+                for (int c = 0; c < NF; ++c) {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) q[c][s] = q[c][s + 1];
+                }
+            }
+        } else {
+            for (;;) {
+                step<0>(it);
+                if (++it >= np) break;
+                step<1>(it);
+                if (++it >= np) break;
+                step<2>(it);
+                if (++it >= np) break;
+                step<3>(it);
+                if (++it >= np) break;
+                step<4>(it);
+                if (++it >= np) break;
+            }
+        }
+        op.finish(st);
+    }
+};
+
+template <int DIM, int TX, int TY, class Op, int MINB, bool UNR, int SC, int SH>
+__global__ void __launch_bounds__((DIM == 2 ? TX : TX * TY), MINB)
+k_tma_march(const __grid_constant__ MarchArgs g, const __grid_constant__ DevPhys P,
+            const __grid_constant__ Op op, const __grid_constant__ TmaIn tin,
+            const int *__restrict__ skip)
+{
+    KSFD_PDL_ENTER();
+    if (skip && KSFD_FLAG(skip)) return;
+    TmaMarcher<DIM, TX, TY, Op, UNR, SC, SH> m(g, P, op, tin);
+    m.run();
+}
+
+template <int DIM, int TX, int TY, class Op, bool UNR, int SC, int SH>
+constexpr size_t tma_march_smem_bytes()
+{
+    return sizeof(double) * TmaMarcher<DIM, TX, TY, Op, UNR, SC, SH>::SMEM_DOUBLES;
+}

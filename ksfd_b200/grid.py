@@ -63,6 +63,14 @@ class Comm:
         dist.broadcast_object_list(box, src=root)
         return box[0]
 
+    def allgather(self, x):
+        if self.size == 1:
+            return [x]
+        import torch.distributed as dist
+        out = [None] * self.size
+        dist.all_gather_object(out, x)
+        return out
+
     def Barrier(self):
         if self.size > 1:
             import torch.distributed as dist
@@ -238,6 +246,14 @@ class Grid:
 
     def make_dmda(self, dof=1):
         return DMDA(self, dof)
+
+    def serial(self):
+        """The same grid owned by a single rank (global shapes)."""
+        if self._comm.size == 1:
+            return self
+        st = self.__getstate__()
+        st['comm'] = Comm(0, 1)
+        return Grid(**st)
 
     def stencil_slice(self, stencil, array, G=None, requireF=True):
         """Shifted interior view of a ghosted array (reference

@@ -246,6 +246,102 @@ def petsc_options():
 
 
 # ---------------------------------------------------------------------------
+# Parameter / ParameterList (names kept for `from KSFD import ParameterList`,
+# reference KSFD/ksfdligand.py:14-63, 65-240): an ordered name -> value table
+# whose entries may live elsewhere (accessor pairs)
+# ---------------------------------------------------------------------------
+class Parameter:
+    """Accessor pair: p() / p.val / p.get() read, p(v) / p.val = v / p.set(v) write."""
+
+    def __init__(self, getter, setter):
+        self.get, self.set = getter, setter
+
+    def __call__(self, val=None):
+        if val is not None:
+            self.set(val)
+        return self.get()
+
+    val = property(lambda self: self.get(), lambda self, v: self.set(v))
+
+
+class ParameterList:
+    """[(key, default[, help]) | (key, Parameter, default, help), ...]"""
+
+    def __init__(self, parameters=()):
+        self.values = collections.OrderedDict()
+        self.ps = collections.OrderedDict()
+        self.defaults = collections.OrderedDict()
+        self.helps = collections.OrderedDict()
+        self.keys = self.ps.keys
+        self.add(parameters)
+
+    def _own(self, key):
+        store = self.values
+        return Parameter(lambda: store[key], lambda v: store.__setitem__(key, v))
+
+    def add(self, parameters):
+        for item in parameters:
+            if len(item) in (2, 3):
+                key, default = item[0], item[1]
+                doc = item[2] if len(item) == 3 else None
+                acc = self.ps[key] if key in self.ps else self._own(key)
+                acc.set(default)
+            elif len(item) == 4:
+                key, acc, default, doc = item
+            else:
+                raise ValueError('parameter element has length %d, 2, 3 or 4 is required'
+                                 % len(item))
+            self.ps[key], self.defaults[key], self.helps[key] = acc, default, doc
+
+    def update(self, parameters):
+        pairs = parameters.items() if callable(getattr(parameters, 'items', None)) else parameters
+        for key, value in pairs:
+            self[key] = value
+
+    def items(self):
+        return ((k, acc()) for k, acc in self.ps.items())
+
+    __iter__ = items
+
+    def __contains__(self, key):
+        return key in self.ps
+
+    def __getitem__(self, key):
+        return self.ps[key]()
+
+    def __setitem__(self, key, value):
+        if key not in self.ps:
+            self.ps[key] = self._own(key)
+            self.defaults.setdefault(key, value)
+            self.helps.setdefault(key, None)
+        self.ps[key].set(value)
+
+    def __delitem__(self, key):
+        del self.ps[key]
+        self.values.pop(key, None)
+        self.defaults.pop(key, None)
+        self.helps.pop(key, None)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def decode(self, params, allow_new=False):
+        """apply 'key=value' strings (values decoded as on the command line)"""
+        keys = [a.split('=', 1)[0] for a in params]
+        dups = find_duplicates(keys)
+        if dups:
+            raise KSFDException('duplicated parameters: ' + ', '.join(dups))
+        for a in params:
+            key, _, text = a.partition('=')
+            if key not in self and not allow_new:
+                raise KSFDException('unknown parameter ' + key)
+            self[key] = decode_value(text)
+
+    def str(self):
+        return '\n'.join('%s = %s' % kv for kv in self.items())
+
+
+# ---------------------------------------------------------------------------
 # ligands
 # ---------------------------------------------------------------------------
 class Ligand(collections.OrderedDict):

@@ -20,6 +20,8 @@ from numpy.random import SeedSequence, default_rng
 class Generator:
     _rng = None
     _seeds = None
+    _seed = None
+    _global = None
 
     def __init__(self, seed=None, comm=None):
         if seed is None and type(self)._rng is not None:
@@ -28,7 +30,23 @@ class Generator:
         size = comm.size if comm is not None else 1
         seeds = SeedSequence(seed).spawn(size)
         type(self)._seeds = seeds
+        type(self)._seed = seed
+        type(self)._global = None
         type(self)._rng = default_rng(seeds[rank])
+
+    @classmethod
+    def global_rng(cls):
+        """The stream a single-rank run of the same seed draws from, identical on
+        every rank: used for fields every rank generates in full and then slices
+        (initial condition), so that a run does not depend on the number of GPUs.
+        With one rank this IS the rank stream."""
+        if cls._rng is None:
+            cls()
+        if cls._seeds is not None and len(cls._seeds) == 1:
+            return cls._rng
+        if cls._global is None:
+            cls._global = default_rng(SeedSequence(cls._seed).spawn(1)[0])
+        return cls._global
 
     def __call__(self):
         return self.get_rng()
@@ -46,14 +64,41 @@ def _hat(x):
 
 def random_function(grid, randgrid=None, vals=None, mu=0.0, sigma=0.01, tol=1e-10,
                     seed=None):
-    """Scalar random field on `grid` (single rank); returns a Vec (dof 1)."""
-    from .grid import DMDA
+    """Scalar random field on `grid`; returns a Vec (dof 1).
+
+    Several ranks: every rank evaluates the GLOBAL field from the single-rank
+    stream (Generator.global_rng) and keeps its own slab, so the field equals the
+    one a single-rank run of the same seed produces.  (The reference draws
+    per-rank streams on a block-partitioned coarse grid, KSFD/ksfdrandom.py:
+    150-220, so its field depends on the rank count; there is nothing to match.)
+    `vals` given on a distributed randgrid are gathered first."""
     if randgrid is None:
         randgrid = grid
     if grid.dim != randgrid.dim:
         raise ValueError('randgrid and grid must have the same dimension')
     if grid.comm.size != 1:
-        raise NotImplementedError('random_function: generate on one rank and scatter')
+        g1, r1 = grid.serial(), randgrid.serial()
+        v1 = None
+        if vals is not None:
+            if randgrid.comm.size == 1:
+                v1 = vals
+            else:
+                parts = grid.comm.allgather(np.asarray(vals.array).reshape(
+                    randgrid.Slshape, order='F'))
+                v1 = r1.Sdmda.createGlobalVec()
+                v1.array = np.concatenate(parts, axis=-1).reshape(-1, order='F')
+        elif seed is not None:
+            Generator(seed=seed, comm=grid.comm)
+        if v1 is None:
+            v1 = r1.Sdmda.createGlobalVec()
+            v1.array = Generator.global_rng().normal(loc=mu, scale=sigma,
+                                                     size=v1.array.shape)
+        full = random_function(g1, randgrid=r1, vals=v1, tol=tol)
+        lo, hi = grid.ranges[-1]
+        out = grid.Sdmda.createGlobalVec()
+        out.array = np.asarray(full.array).reshape(g1.Slshape, order='F')[
+            ..., lo:hi].reshape(-1, order='F')
+        return out
     if vals is None:
         vals = randgrid.Sdmda.createGlobalVec()
         vals.array = Generator(seed=seed, comm=grid.comm)().normal(

@@ -43,9 +43,14 @@ def start_values(clargs, grid, ps):
     p0, v0 = ps.params0, ps.values0
     rn = [p0['randgridnw'] or ps.nwidth // 4, p0['randgridnh'] or ps.nheight // 4,
           p0['randgridnd'] or ps.ndepth // 4]
+    # the coarse random grid is always built whole (size-1 comm): on several ranks
+    # every rank draws the same global sample from the single-rank stream and
+    # random_function keeps the rank's slab (the coarse grid may have fewer planes
+    # than ranks * stencil_width, and the field must not depend on the GPU count)
+    from .grid import Comm
     rgrid = Grid(dim=ps.dim, width=ps.width, height=ps.height, depth=ps.depth,
                  nx=max(rn[0], 1), ny=max(rn[1], 1), nz=max(rn[2], 1), dof=1,
-                 comm=grid.comm)
+                 comm=Comm(0, 1))
     murho0 = v0['Nworms'] / (ps.width ** ps.dim)
     sigma = v0['srho0']
     rvals = rgrid.Sdmda.createGlobalVec()
@@ -53,7 +58,7 @@ def start_values(clargs, grid, ps):
         rvals.array[:] = murho0
     else:
         sig = SpatialExpression(ps, rgrid, sigma)()
-        sample = Generator.get_rng().normal(size=rgrid.Slshape)
+        sample = Generator.global_rng().normal(size=rgrid.Slshape)
         rvals.array = (sig * sample + murho0).reshape(-1, order='F')
     rra = random_function(grid, randgrid=rgrid, vals=rvals).array.reshape(
         grid.Slshape, order='F')

@@ -94,8 +94,11 @@ class TimeSeries:
         self.ks = np.array([], dtype=int)
         self.lastk = -1
         self._open(mode)
+        self.file_size = self.size
         if not self.creating:
             self._read_index()
+            if self._has('size'):
+                self.file_size = int(np.asarray(self._get('size')).reshape(-1)[0])
         else:
             self._set('size', self.size)
             self._set('rank', self.rank)
@@ -220,7 +223,18 @@ class TimeSeries:
         return np.sort(self.ts)
 
     def retrieve_by_number(self, k):
-        return np.array(self._get('data' + str(int(k))))
+        """Values of step k on THIS rank's part of the grid.  A file written by a
+        different number of ranks (the sequential <prefix>s1r0 file of a merged or
+        single-rank run) holds the global array: the rank keeps its own slab, as the
+        reference does with `myslice` (KSFD/ksfdtimeseries.py:560-600)."""
+        a = np.array(self._get('data' + str(int(k))))
+        g = self.grid
+        if (g is not None and self.file_size != self.size
+                and tuple(a.shape[1:]) == tuple(g.globalSshape)
+                and tuple(g.Slshape) != tuple(g.globalSshape)):
+            lo, hi = g.ranges[-1]
+            a = np.ascontiguousarray(a[..., lo:hi])
+        return a
 
     def retrieve_by_time(self, t):
         order = np.argsort(self.ts, kind='stable')

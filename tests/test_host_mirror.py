@@ -172,3 +172,24 @@ def test_timeseries_roundtrip(tmp_path):
     mid = rd.retrieve_by_time(1.0)
     want = 0.5 * (snaps[1] + snaps[2]).reshape(g.Vlshape, order='F')
     assert np.allclose(mid, want)
+
+
+def test_ksfd_import_name_resolves_to_this_package():
+    """existing user scripts do `from KSFD import ...` (reference ksfdsolver2.py:354-360)"""
+    import KSFD
+    from KSFD import (KSFDException, LigandGroups, ParameterList, Parser,  # noqa: F401
+                      SolutionParameters, default_parameters)
+    from KSFD.ksfddebug import log
+    import ksfd_b200
+    assert KSFD.Parser is ksfd_b200.Parser
+    assert KSFD.implicitTS is ksfd_b200.implicitTS and KSFD.Grid is ksfd_b200.Grid
+    assert KSFD.TimeSeries is ksfd_b200.TimeSeries and KSFD.dillnp is ksfd_b200.dillnp
+    log('quiet unless KSFDDEBUG names the system', system='TEST')
+    pl = ParameterList([('a', 1, 'first'), ('b', 2.5)])
+    pl['c'] = 7
+    pl.update({'a': 3})
+    assert dict(pl.items()) == {'a': 3, 'b': 2.5, 'c': 7} and pl.get('zz', 9) == 9
+    pl.decode(['b=4.5'])
+    assert pl['b'] == 4.5 and pl.defaults['b'] == 2.5 and pl.helps['a'] == 'first'
+    with pytest.raises(KSFDException):
+        pl.decode(['a=1', 'a=2'])

@@ -88,3 +88,90 @@ def test_exchange_plan_and_ring():
     assert lo == [1022, 1023] and hi == [128, 129]
     lo, hi = parallel.ghost_sources(10, 3, 2)       # 4,3,3 split
     assert lo == [5, 6] and hi == [0, 1]
+
+
+def _ic_worker(rank, world, port, tmp, q):
+    """start_values / resume_values on `world` ranks against the single-rank run
+    (the advertised torchrun command could not start a fresh run)."""
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from ksfd_b200 import solver
+        from ksfd_b200.grid import Comm, Grid
+        from ksfd_b200.params import SolutionParameters, parse_commandline
+        from ksfd_b200.random import Generator
+        from ksfd_b200.timeseries import TimeSeries
+        here = os.path.dirname(os.path.abspath(__file__))
+        argv = ['@' + os.path.join(here, 'options', 'options84.args'), '--seed', '793817931',
+                'nwidth=32', 'nheight=24']
+        cl = parse_commandline(argv)
+        ps = SolutionParameters(cl)
+
+        def grid_for(comm):
+            return Grid(dim=ps.dim, dof=ps.nligands + 1, width=ps.width, height=ps.height,
+                        depth=ps.depth, nx=ps.nwidth, ny=ps.nheight, nz=ps.ndepth, comm=comm)
+
+        # the single-rank field, computed on every rank
+        Generator(seed=cl.seed, comm=Comm(0, 1))
+        g1 = grid_for(Comm(0, 1))
+        v1, _ = solver.start_values(cl, g1, ps)
+        full = np.asarray(v1.array).reshape(g1.Vlshape, order='F')
+        # the distributed field
+        comm = Comm(rank, world)
+        Generator(seed=cl.seed, comm=comm)
+        g = grid_for(comm)
+        v, t0 = solver.start_values(cl, g, ps)
+        lo, hi = g.ranges[-1]
+        mine = np.asarray(v.array).reshape(g.Vlshape, order='F')
+        ok = np.array_equal(mine, full[..., lo:hi]) and mine.shape[-1] == hi - lo
+        # resume from a sequential (s1r0) file: every rank keeps its slab
+        prefix = os.path.join(tmp, 'seq')
+        if rank == 0:
+            ts = TimeSeries(prefix, grid=g1, mode='w', comm=Comm(0, 1))
+            ts.store(v1, 0.5)
+            ts.store(v1, 1.5)
+            ts.close()
+        comm.Barrier()
+        cl2 = parse_commandline(argv + ['--resume', prefix])
+        ps2 = SolutionParameters(cl2)
+        rv, t = solver.resume_values(cl2, g, ps2)
+        ok = ok and t == 1.5 and np.array_equal(
+            np.asarray(rv.array).reshape(g.Vlshape, order='F'), full[..., lo:hi])
+        # vals given on a distributed coarse grid are gathered
+        from ksfd_b200.random import random_function
+        rg = Grid(dim=2, nx=8, ny=8, dof=1, comm=comm)
+        rg1 = rg.serial()
+        gv = rg1.Sdmda.createGlobalVec()
+        gv.array = np.arange(64, dtype=float)
+        lv = rg.Sdmda.createGlobalVec()
+        l0, l1 = rg.ranges[-1]
+        lv.array = np.asarray(gv.array).reshape(rg1.Slshape, order='F')[..., l0:l1].reshape(
+            -1, order='F')
+        fine = Grid(dim=2, nx=32, ny=16, dof=1, comm=comm)
+        a = random_function(fine, randgrid=rg, vals=lv)
+        b = random_function(fine.serial(), randgrid=rg1, vals=gv)
+        f0, f1 = fine.ranges[-1]
+        ok = ok and np.array_equal(
+            np.asarray(a.array).reshape(fine.Slshape, order='F'),
+            np.asarray(b.array).reshape(fine.serial().Slshape, order='F')[..., f0:f1])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_start_and_resume_values_on_two_ranks(tmp_path):
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ic_worker, args=(r, world, port, str(tmp_path), q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, True) for r in range(world)]
