@@ -36,7 +36,7 @@ extern "C" {
 
 #define KSFD_MAX_LIGANDS 7      /* dof <= 8 */
 #define KSFD_MAX_GROUPS 7
-#define KSFD_ABI_VERSION 1
+#define KSFD_ABI_VERSION 2      /* 2: stream argument on norm2 / sum_dof0 / allreduce_* */
 
 typedef struct ksfd_ctx ksfd_ctx;
 
@@ -153,8 +153,11 @@ int ksfd_mdot(ksfd_ctx *ctx, int nv, const double *const *vs, const double *w,
               double *out_dev, void *stream);   /* out[i] = <vs[i], w> global */
 int ksfd_maxpy(ksfd_ctx *ctx, int nv, const double *coef_host,
                const double *const *vs, double *y, void *stream);
-int ksfd_norm2(ksfd_ctx *ctx, const double *x, double *out_host);
-int ksfd_sum_dof0(ksfd_ctx *ctx, const double *u, double *out_host);
+/* global reductions to a HOST scalar: enqueued on `stream`, which is synchronised before
+   returning.  All reductions of a context share scratch buffers and the peer-to-peer
+   sequence counter: issue them on the stream the context's other work runs on. */
+int ksfd_norm2(ksfd_ctx *ctx, const double *x, double *out_host, void *stream);
+int ksfd_sum_dof0(ksfd_ctx *ctx, const double *u, double *out_host, void *stream);
 int ksfd_scale_dof0(ksfd_ctx *ctx, double *u, double factor, void *stream);
 
 /* ---- linear solve: replaces KSP preonly + PC LU (MUMPS) with a
@@ -201,8 +204,8 @@ int ksfd_ts_step(ksfd_ctx *ctx, double *u, double t, double h,
                  void *user, ksfd_ts_result *res, void *stream);
 
 /* scalar all-reduce helpers over the context communicator (host values) */
-int ksfd_allreduce_max(ksfd_ctx *ctx, double *vals_host, int n);
-int ksfd_allreduce_sum(ksfd_ctx *ctx, double *vals_host, int n);
+int ksfd_allreduce_max(ksfd_ctx *ctx, double *vals_host, int n, void *stream);   /* 0 <= n <= 64 */
+int ksfd_allreduce_sum(ksfd_ctx *ctx, double *vals_host, int n, void *stream);
 
 #ifdef __cplusplus
 }

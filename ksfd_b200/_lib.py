@@ -121,16 +121,16 @@ def load():
     lib.ksfd_mdot.argtypes = [vp, i32, C.POINTER(C.c_void_p), dp, dp, vp]
     lib.ksfd_maxpy.argtypes = [vp, i32, C.POINTER(C.c_double),
                                C.POINTER(C.c_void_p), dp, vp]
-    lib.ksfd_norm2.argtypes = [vp, dp, C.POINTER(C.c_double)]
-    lib.ksfd_sum_dof0.argtypes = [vp, dp, C.POINTER(C.c_double)]
+    lib.ksfd_norm2.argtypes = [vp, dp, C.POINTER(C.c_double), vp]
+    lib.ksfd_sum_dof0.argtypes = [vp, dp, C.POINTER(C.c_double), vp]
     lib.ksfd_scale_dof0.argtypes = [vp, dp, C.c_double, vp]
     lib.ksfd_gmres.argtypes = [vp, dp, dp, C.POINTER(KspOpts),
                                C.POINTER(KspResult), vp]
     lib.ksfd_ts_step.argtypes = [vp, dp, C.c_double, C.c_double,
                                  C.POINTER(TsOpts), dp, TIME_CB, vp,
                                  C.POINTER(TsResult), vp]
-    lib.ksfd_allreduce_max.argtypes = [vp, C.POINTER(C.c_double), i32]
-    lib.ksfd_allreduce_sum.argtypes = [vp, C.POINTER(C.c_double), i32]
+    lib.ksfd_allreduce_max.argtypes = [vp, C.POINTER(C.c_double), i32, vp]
+    lib.ksfd_allreduce_sum.argtypes = [vp, C.POINTER(C.c_double), i32, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ('ksfd_abi_version', 'ksfd_last_error',

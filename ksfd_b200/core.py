@@ -212,7 +212,7 @@ class Context:
         v = vm.cpu().numpy()[:self.dim].copy()
         if self.nranks > 1:
             arr = (C.c_double * self.dim)(*v)
-            _lib.check(self.lib.ksfd_allreduce_max(self.h, arr, self.dim))
+            _lib.check(self.lib.ksfd_allreduce_max(self.h, arr, self.dim, _stream()))
             v = np.array(list(arr))
         return v
 
@@ -265,13 +265,13 @@ class Context:
 
     def norm2(self, x):
         out = C.c_double()
-        _lib.check(self.lib.ksfd_norm2(self.h, _ptr(self._chk(x)), C.byref(out)))
+        _lib.check(self.lib.ksfd_norm2(self.h, _ptr(self._chk(x)), C.byref(out), _stream()))
         return out.value
 
     def sum_dof0(self, u):
         out = C.c_double()
         _lib.check(self.lib.ksfd_sum_dof0(self.h, _ptr(self._chk(u)),
-                                          C.byref(out)))
+                                          C.byref(out), _stream()))
         return out.value
 
     def scale_dof0(self, u, f):
@@ -291,15 +291,28 @@ class Context:
     def ts_step(self, u, t, h, opts, src=None, time_cb=None):
         """One accepted step (or a failure report); u is advanced in place."""
         res = TsResult()
+        raised = []
         if time_cb is not None:
-            cb = _lib.TIME_CB(lambda tt, user: time_cb(tt))
+            def guarded(tt, user):
+                # ctypes swallows exceptions raised inside a callback: keep the first
+                # one and re-raise it once the C call has returned
+                if raised:
+                    return
+                try:
+                    time_cb(tt)
+                except BaseException as e:          # noqa: BLE001
+                    raised.append(e)
+            cb = _lib.TIME_CB(guarded)
         else:
             cb = C.cast(None, _lib.TIME_CB)
         self._cb_keep = cb
-        _lib.check(self.lib.ksfd_ts_step(
+        rc = self.lib.ksfd_ts_step(
             self.h, _ptr(self._chk(u)), float(t), float(h), C.byref(opts),
             _ptr(self._chk(src) if src is not None else None), cb, None,
-            C.byref(res), _stream()))
+            C.byref(res), _stream())
+        if raised:
+            raise raised[0]
+        _lib.check(rc)
         return res
 
 

@@ -299,17 +299,30 @@ __global__ void k_scale_dof0(long long npts, long long plane_pts, int dof, doubl
 #define KSFD_P2P_RED_MAX 72                 // doubles per contribution
 #define KSFD_P2P_FLAGS 256                  // flag words at the start of the shared allocation
 #define KSFD_P2P_RFLAG0 32                  // reduce flags: word RFLAG0 + source rank
-// bounded spin on a flag word written by a peer GPU: gives up after ~30 s (a
-// peer died) and raises the host-visible error word instead of hanging the GPU
+// bounded spin on a flag word written by a peer GPU: gives up after
+// KSFD_P2P_TIMEOUT_CYCLES (~2 min at 1.9 GHz: a peer died; ranks that merely skew on
+// the host, e.g. while one writes a checkpoint, stay far below it) and raises the
+// host-visible error word AND the device-side sticky word `dead` instead of hanging
+// the GPU.  Callers do not advance their exchange counter after a failed wait, and
+// every later exchange of the context returns at once (`dead`), so no kernel consumes
+// a half-received buffer as if it were complete; the host reports the failure at its
+// next entry point (ksfd.cu: p2p_check).
+#ifndef KSFD_P2P_TIMEOUT_CYCLES
+#define KSFD_P2P_TIMEOUT_CYCLES 240000000000ll
+#endif
 __device__ __forceinline__ bool p2p_spin(volatile unsigned long long *flag,
-                                         unsigned long long q, volatile int *err)
+                                         unsigned long long q, volatile int *err,
+                                         volatile unsigned long long *dead = nullptr)
 {
     const long long t0 = clock64();
     unsigned spins = 0;
     while (*flag < q) {
         __nanosleep(32);
-        if ((++spins & 0xfff) == 0 && clock64() - t0 > 60000000000ll) {
+        if ((++spins & 0xfff) == 0 &&
+            (clock64() - t0 > KSFD_P2P_TIMEOUT_CYCLES || (dead && *dead))) {
+            if (dead) *dead = 1ull;
             if (err) *err = 1;
+            __threadfence_system();
             return false;
         }
     }
@@ -321,6 +334,7 @@ struct P2PRed {
     volatile int *err;                      // pinned, host-visible: set when a wait timed out
     long long red_off;                      // doubles from base to the reduce area
     unsigned long long *ctr;                // DEVICE-side exchange counter of this rank
+    volatile unsigned long long *dead;      // DEVICE-side sticky word: a peer wait timed out
     int nranks, rank;
 };
 
@@ -333,8 +347,13 @@ struct P2PRed {
 __device__ __forceinline__ void p2p_allreduce(const P2PRed &pr, double *vals, int n, int op)
 {
     __shared__ unsigned long long q_;
-    if (threadIdx.x == 0) q_ = *pr.ctr + 1;
+    __shared__ int ok_;
+    if (threadIdx.x == 0) {
+        q_ = *pr.ctr + 1;
+        ok_ = !(pr.dead && *pr.dead);
+    }
     __syncthreads();
+    if (!ok_) return;                        // uniform: a peer is gone, the host will report it
     const unsigned long long q = q_;
     const int par = (int)(q & 1);
     const long long slot0 = pr.red_off + (long long)par * pr.nranks * KSFD_P2P_RED_MAX;
@@ -353,10 +372,11 @@ __device__ __forceinline__ void p2p_allreduce(const P2PRed &pr, double *vals, in
         volatile unsigned long long *mine =
             reinterpret_cast<volatile unsigned long long *>(pr.base[pr.rank]) +
             KSFD_P2P_RFLAG0 + threadIdx.x;
-        p2p_spin(mine, q, pr.err);
+        if (!p2p_spin(mine, q, pr.err, pr.dead)) ok_ = 0;
     }
     __threadfence_system();
     __syncthreads();
+    if (!ok_) return;                        // counter not advanced, contributions not summed
     const volatile double *area = pr.base[pr.rank] + slot0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double s = area[i];

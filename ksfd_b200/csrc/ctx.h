@@ -69,6 +69,12 @@ struct ksfd_ctx {
     long long last_start = 0, last_count = 0, last_global = 0;
     Geom g{};
     DevPhys P{};
+    // physics of the current LINEARISATION: snapshot taken by ksfd_jvp_setup and used by
+    // every Jacobian-side kernel (J.v, preconditioners, solution update), so that
+    // time-dependent parameters refreshed at the later ROSW stages (stage callback ->
+    // ksfd_set_physics) change the residual only — PETSc's ROSW keeps the stage-0
+    // Jacobian for the whole step
+    DevPhys Pjac{};
     bool have_phys = false;
     // options
     int variant = 0, opt_tx = -1, opt_rz = 0;
@@ -99,6 +105,7 @@ struct ksfd_ctx {
     double *dscal = nullptr;     // device scalars (KSFD_NSCAL)
     double *hscal = nullptr;     // pinned host scalars (KSFD_NSCAL)
     void *plan_cache = nullptr;  // std::map<long long, MarchPlan>*
+    void *tmap_cache = nullptr;  // TmapCache* (march_launch.cuh): encoded tensor maps
     // pipelined GMRES: device state, pinned host-visible status
     double *gm = nullptr;
     int *gmi = nullptr;
@@ -134,16 +141,34 @@ struct ksfd_ctx {
     int max_smem = 232448;
 };
 
+// Host description of one input vector of the TMA-fed marcher (tma_march.cuh), built next
+// to its VecRef (ksfd.cu: make_hvec): which buffers hold the owned and the ghost planes
+struct TmaSrc {
+    const double *base = nullptr;   // buffer of the owned planes
+    long long base_fields = 0;      // fields (plane_pts doubles each) in that buffer
+    int k0 = 0;                     // field index of plane 0
+    const double *halo = nullptr;   // buffer of the ghost planes (nullptr: wrap, or in `base`)
+    long long halo_fields = 0;
+    int klo = 0, khi = 0;           // field index of plane -2 / plane nloc in the ghost buffer
+    int wrap = 1;
+    const unsigned long long *par = nullptr;    // device-side exchange counter (parity)
+    int parshift = 0;               // fields between the two parity buffers
+};
+struct HostVec {
+    VecRef r;
+    TmaSrc t;
+};
+
 // marching-kernel launchers (march_res.cu, march_jvp.cu, march_vel.cu); each is
 // compiled once per dimension (-DKSFD_MARCH_DIM=2|3)
 #define KSFD_DECL_MARCH(D)                                                            \
-    int ksfd_march_residual_d##D(ksfd_ctx *c, VecRef u, const double *udot,           \
+    int ksfd_march_residual_d##D(ksfd_ctx *c, const HostVec &u, const double *udot,   \
                                  const double *src, double *out, cudaStream_t st);    \
-    int ksfd_march_jvp_d##D(ksfd_ctx *c, VecRef coef, VecRef v, VecRef pc,            \
-                            bool precond, double *out, const int *skip,           \
-                            cudaStream_t st);                                         \
-    int ksfd_march_velocity_d##D(ksfd_ctx *c, VecRef u, double *vel, double *vmax,    \
-                                 cudaStream_t st);
+    int ksfd_march_jvp_d##D(ksfd_ctx *c, const HostVec &coef, const HostVec &v,       \
+                            const HostVec &pc, bool precond, double *out,             \
+                            const int *skip, cudaStream_t st);                        \
+    int ksfd_march_velocity_d##D(ksfd_ctx *c, const HostVec &u, double *vel,          \
+                                 double *vmax, cudaStream_t st);
 KSFD_DECL_MARCH(2)
 KSFD_DECL_MARCH(3)
 void ksfd_free_plans(ksfd_ctx *c);

@@ -7,6 +7,7 @@
 #include <ctime>
 #include <dlfcn.h>
 #include <map>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -20,7 +21,7 @@
 // errors
 // ---------------------------------------------------------------------------
 static thread_local std::string g_err;
-static int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};
 #if KSFD_PDL
 bool g_ksfd_pdl = false;        // KSFD_PDL=1 in the environment (read at context creation)
 #endif
@@ -30,7 +31,7 @@ int ksfd_fail(const std::string &m)
     g_err = m;
     return 1;
 }
-void ksfd_count_launch() { ++g_launches; }
+void ksfd_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------------------
 // NCCL through dlopen (torch ships libnccl.so.2; no header needed)
@@ -79,6 +80,11 @@ static int nccl_load(const char *path)
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
+// largest GMRES restart length: the Arnoldi column + its extras must fit one
+// peer-to-peer reduce contribution (KSFD_P2P_RED_MAX) and the shared-memory
+// Hessenberg of k_gm_finalize (KSFD_GM_MAXM)
+#define KSFD_MAX_RESTART 60
+#define SC_USER 440              // ksfd_norm2 / ksfd_sum_dof0 results (clear of the solver's slots)
 #define SC_H 0                  // Hessenberg column (<= 128)
 #define SC_H2 128               // second Gram-Schmidt pass
 #define SC_NORM 300
@@ -96,7 +102,7 @@ static void fftpc_destroy(ksfd_ctx *c);
 
 extern "C" int ksfd_abi_version(void) { return KSFD_ABI_VERSION; }
 extern "C" const char *ksfd_last_error(void) { return g_err.c_str(); }
-extern "C" int64_t ksfd_launch_count(void) { return g_launches; }
+extern "C" int64_t ksfd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int ksfd_ctx_create(ksfd_ctx **out, int dim, const int64_t n_global[3],
                                int64_t last_start, int64_t last_count, int dof,
@@ -331,6 +337,37 @@ static VecRef make_ref(const ksfd_ctx *c, const double *base, int stride, int sl
     return r;
 }
 
+// VecRef + the buffer description the TMA-fed marcher needs (ctx.h: TmaSrc)
+static HostVec make_hvec(const ksfd_ctx *c, const double *base, int stride, int slot)
+{
+    HostVec h;
+    h.r = make_ref(c, base, stride, slot);
+    TmaSrc &t = h.t;
+    t.base = base;
+    t.base_fields = (long long)c->g.nloc * stride;
+    t.k0 = 0;
+    const long long hp = (long long)(c->halo_plane_doubles / c->g.plane_pts);   // fields per ghost plane
+    if (c->nranks == 1) {
+        t.wrap = 1;
+    } else if (c->p2p_on) {
+        // [parity 0: lo | hi][parity 1: lo | hi], planes packed with the vector's stride
+        t.wrap = 0;
+        t.halo = p2p_buf(c, c->p2p_mine, slot, 0);
+        t.halo_fields = 2 * 2 * KSFD_SW * hp;
+        t.klo = 0;
+        t.khi = (int)(KSFD_SW * hp);
+        t.par = c->p2p_ctr + slot;
+        t.parshift = (int)(2 * KSFD_SW * hp);
+    } else {
+        t.wrap = 0;
+        t.halo = c->halo[slot];
+        t.halo_fields = 2 * KSFD_SW * hp;
+        t.klo = 0;
+        t.khi = (int)(KSFD_SW * hp);
+    }
+    return h;
+}
+
 // ---------------------------------------------------------------------------
 // Direct halo push over NVLink peer memory.  Every rank owns one IPC-shared
 // allocation [64 flag words][slot][parity][lo planes | hi planes]; a single
@@ -359,6 +396,7 @@ static P2PRed p2p_red(const ksfd_ctx *c)
     pr.rank = c->rank;
     pr.red_off = (long long)p2p_red_off(c);
     pr.ctr = c->p2p_ctr ? c->p2p_ctr + KSFD_HALO_SLOTS : nullptr;
+    pr.dead = c->p2p_ctr ? c->p2p_ctr + KSFD_HALO_SLOTS + 1 : nullptr;
     pr.err = c->p2p_err_dev;
     for (int r = 0; r < KSFD_P2P_MAXR; ++r) pr.base[r] = r < c->nranks ? c->p2p_peer[r] : nullptr;
     return pr;
@@ -377,10 +415,12 @@ __global__ void k_halo_xchg(const double *__restrict__ top, const double *__rest
                             volatile unsigned long long *dn_flag_hi,
                             volatile unsigned long long *my_flag_lo,
                             volatile unsigned long long *my_flag_hi, unsigned long long *ctr,
-                            unsigned *done, const int *__restrict__ skip, volatile int *err)
+                            unsigned *done, const int *__restrict__ skip, volatile int *err,
+                            volatile unsigned long long *dead)
 {
     // launched ahead by the pipelined solver: no exchange once the cycle is closed
     if (skip && *skip) return;
+    if (*dead) return;                          // an earlier wait timed out: the host reports it
     // every block reads the counter before the last one (which only exists
     // after all blocks have copied) advances it
     const unsigned long long q = *ctr + 1;
@@ -399,10 +439,9 @@ __global__ void k_halo_xchg(const double *__restrict__ top, const double *__rest
             __threadfence_system();
             *up_flag_lo = q;
             *dn_flag_hi = q;
-            p2p_spin(my_flag_lo, q, err);
-            p2p_spin(my_flag_hi, q, err);
+            const bool ok = p2p_spin(my_flag_lo, q, err, dead) && p2p_spin(my_flag_hi, q, err, dead);
             __threadfence_system();
-            *ctr = q;
+            if (ok) *ctr = q;                   // a failed wait does not complete the exchange
         }
     }
 }
@@ -452,8 +491,9 @@ extern "C" int ksfd_p2p_export(ksfd_ctx *c, char handle_out[64])
         CK(cudaHostAlloc(&c->p2p_err, sizeof(int), cudaHostAllocMapped));
         *c->p2p_err = 0;
         CK(cudaHostGetDevicePointer(&c->p2p_err_dev, c->p2p_err, 0));
-        CK(cudaMalloc(&c->p2p_ctr, sizeof(unsigned long long) * (KSFD_HALO_SLOTS + 1)));
-        CK(cudaMemset(c->p2p_ctr, 0, sizeof(unsigned long long) * (KSFD_HALO_SLOTS + 1)));
+        // [0..3] halo slots, [4] all-reduce, [5] sticky "a peer wait timed out"
+        CK(cudaMalloc(&c->p2p_ctr, sizeof(unsigned long long) * (KSFD_HALO_SLOTS + 2)));
+        CK(cudaMemset(c->p2p_ctr, 0, sizeof(unsigned long long) * (KSFD_HALO_SLOTS + 2)));
     }
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, c->p2p_mine));
@@ -513,7 +553,7 @@ static int exchange_p2p(ksfd_ctx *c, const double *vec, int stride, int slot, cu
     k_halo_xchg<<<blocks, 256, 0, st>>>(top, vec, (long long)cnt, up_lo0, dn_hi0,
                                         (long long)p2p_buf_doubles(c), up_flag_lo, dn_flag_hi,
                                         my_flag_lo, my_flag_hi, c->p2p_ctr + slot, c->p2p_done,
-                                        skip, c->p2p_err_dev);
+                                        skip, c->p2p_err_dev, c->p2p_ctr + KSFD_HALO_SLOTS + 1);
     CKL();
     return 0;
 }
@@ -523,6 +563,10 @@ static int exchange(ksfd_ctx *c, const double *vec, int stride, int slot,
 {
     if (c->nranks == 1) return 0;
     if (slot < 0 || slot >= KSFD_HALO_SLOTS) return fail("bad halo slot");
+    // every public entry point that exchanges halos comes through here: a peer wait
+    // that timed out earlier (pinned word written by the device) is reported now
+    if (c->p2p_err && *c->p2p_err)
+        return fail("peer-to-peer exchange timed out (a neighbouring rank is gone)");
     if (c->p2p_on) return exchange_p2p(c, vec, stride, slot, st, skip, defer);
     if (!c->halo[slot])
         CK(cudaMalloc(&c->halo[slot],
@@ -562,23 +606,30 @@ static int allreduce_dev(ksfd_ctx *c, double *buf, int n, int op, cudaStream_t s
     return 0;
 }
 
-extern "C" int ksfd_allreduce_max(ksfd_ctx *c, double *vals, int n)
+// host scalars -> all-reduce on `stream` -> host scalars.  The staging buffers (dscal, the
+// peer-to-peer reduce area and its sequence counter) are shared by every reduction of the
+// context, so all of them must be issued on ONE stream: the caller's.
+static int allreduce_host(ksfd_ctx *c, double *vals, int n, int op, cudaStream_t st,
+                          const char *who)
 {
-    if (!c || n > 64 || n < 0) return fail("ksfd_allreduce_max: bad argument");
-    if (c->nranks == 1) return 0;
-    CK(cudaMemcpy(c->dscal, vals, sizeof(double) * n, cudaMemcpyHostToDevice));
-    TRY(allreduce_dev(c, c->dscal, n, ncclMax_, 0));
-    CK(cudaMemcpy(vals, c->dscal, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (!c || !vals || n > 64 || n < 0) return fail(std::string(who) + ": bad argument");
+    if (c->nranks == 1 || n == 0) return 0;
+    double *stage = c->dscal + KSFD_NSCAL - 64;         // the tail of the scalar scratch
+    CK(cudaMemcpyAsync(stage, vals, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    TRY(allreduce_dev(c, stage, n, op, st));
+    CK(cudaMemcpyAsync(vals, stage, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (c->p2p_err && *c->p2p_err)
+        return fail("peer-to-peer exchange timed out (a neighbouring rank is gone)");
     return 0;
 }
-extern "C" int ksfd_allreduce_sum(ksfd_ctx *c, double *vals, int n)
+extern "C" int ksfd_allreduce_max(ksfd_ctx *c, double *vals, int n, void *stream)
 {
-    if (!c || n > 64) return fail("ksfd_allreduce_sum: bad argument");
-    if (c->nranks == 1) return 0;
-    CK(cudaMemcpy(c->dscal, vals, sizeof(double) * n, cudaMemcpyHostToDevice));
-    TRY(allreduce_dev(c, c->dscal, n, ncclSum_, 0));
-    CK(cudaMemcpy(vals, c->dscal, sizeof(double) * n, cudaMemcpyDeviceToHost));
-    return 0;
+    return allreduce_host(c, vals, n, ncclMax_, (cudaStream_t)stream, "ksfd_allreduce_max");
+}
+extern "C" int ksfd_allreduce_sum(ksfd_ctx *c, double *vals, int n, void *stream)
+{
+    return allreduce_host(c, vals, n, ncclSum_, (cudaStream_t)stream, "ksfd_allreduce_sum");
 }
 
 // ---------------------------------------------------------------------------
@@ -589,6 +640,8 @@ void ksfd_free_plans(ksfd_ctx *c)
 {
     delete static_cast<PlanMap *>(c->plan_cache);
     c->plan_cache = nullptr;
+    delete static_cast<TmapCache *>(c->tmap_cache);
+    c->tmap_cache = nullptr;
 }
 void ksfd_invalidate_plans(ksfd_ctx *c)
 {
@@ -653,12 +706,12 @@ static int residual_impl(ksfd_ctx *c, const double *u, const double *udot,
                          const double *src, double *f, cudaStream_t st)
 {
     TRY(exchange(c, u, c->dof, 0, st));
-    VecRef ur = make_ref(c, u, c->dof, 0);
+    const HostVec uh = make_hvec(c, u, c->dof, 0);
     if (use_march(c)) {
-        return c->dim == 2 ? ksfd_march_residual_d2(c, ur, udot, src, f, st)
-                           : ksfd_march_residual_d3(c, ur, udot, src, f, st);
+        return c->dim == 2 ? ksfd_march_residual_d2(c, uh, udot, src, f, st)
+                           : ksfd_march_residual_d3(c, uh, udot, src, f, st);
     }
-    k_residual_naive<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, ur, udot,
+    k_residual_naive<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, uh.r, udot,
                                                            src, f);
     CKL();
     return 0;
@@ -676,13 +729,13 @@ static int velocity_impl(ksfd_ctx *c, const double *u, double *vel, double *vmax
                          cudaStream_t st)
 {
     TRY(exchange(c, u, c->dof, 0, st));
-    VecRef ur = make_ref(c, u, c->dof, 0);
+    const HostVec uh = make_hvec(c, u, c->dof, 0);
     if (vmax) CK(cudaMemsetAsync(vmax, 0, sizeof(double) * c->dim, st));
     if (use_march(c)) {
-        return c->dim == 2 ? ksfd_march_velocity_d2(c, ur, vel, vmax, st)
-                           : ksfd_march_velocity_d3(c, ur, vel, vmax, st);
+        return c->dim == 2 ? ksfd_march_velocity_d2(c, uh, vel, vmax, st)
+                           : ksfd_march_velocity_d3(c, uh, vel, vmax, st);
     }
-    k_velocity_naive<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, ur, vel, vmax);
+    k_velocity_naive<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, uh.r, vel, vmax);
     CKL();
     return 0;
 }
@@ -719,6 +772,22 @@ static VecRef coef_ref(const ksfd_ctx *c)
     return r;
 }
 
+// the coefficient field for the TMA-fed marcher: one ghosted buffer, ghost planes in place
+static HostVec coef_hvec(const ksfd_ctx *c)
+{
+    HostVec h;
+    h.r = coef_ref(c);
+    const int nf = c->dof + 2;
+    h.t.base = c->coef;
+    h.t.base_fields = (long long)(c->g.nloc + 2 * KSFD_SW) * nf;
+    h.t.k0 = KSFD_SW * nf;
+    h.t.halo = nullptr;
+    h.t.wrap = 0;
+    h.t.klo = 0;
+    h.t.khi = (KSFD_SW + c->g.nloc) * nf;
+    return h;
+}
+
 static int jvp_setup_impl(ksfd_ctx *c, const double *u, double shift,
                           double *blocks, cudaStream_t st)
 {
@@ -727,6 +796,7 @@ static int jvp_setup_impl(ksfd_ctx *c, const double *u, double shift,
     if (!c->coef) CK(cudaMalloc(&c->coef, sizeof(double) * gpts * (c->dof + 2)));
     if (!c->pc) CK(cudaMalloc(&c->pc, sizeof(double) * g.npts));
     c->shift = shift;
+    c->Pjac = c->P;
     for (int l = 0; l < c->P.nlig; ++l)
         c->invd[l] = 1.0 / (shift + c->P.gamma[l] - c->P.D[l] * c->P.w2c);
     if (u) {
@@ -776,9 +846,11 @@ static int jvp_impl(ksfd_ctx *c, const double *v, double *out, bool precond,
     const bool defer = false;
 #endif
     TRY(exchange(c, v, c->dof, 1, st, skip, defer));
-    VecRef vr = make_ref(c, v, c->dof, 1);
-    VecRef pr = make_ref(c, c->pc, 1, 2);
-    VecRef cr = coef_ref(c);
+    HostVec vh = make_hvec(c, v, c->dof, 1);
+    const HostVec ph = make_hvec(c, c->pc, 1, 2);
+    const HostVec ch = coef_hvec(c);
+    VecRef &vr = vh.r;
+    const VecRef &pr = ph.r, &cr = ch.r;
 #if KSFD_HALO_DEFER
     if (defer) {
         typedef const volatile unsigned long long *cflag_t;
@@ -788,12 +860,12 @@ static int jvp_impl(ksfd_ctx *c, const double *v, double *out, bool precond,
     }
 #endif
     if (use_march(c)) {
-        return c->dim == 2 ? ksfd_march_jvp_d2(c, cr, vr, pr, precond, out, skip, st)
-                           : ksfd_march_jvp_d3(c, cr, vr, pr, precond, out, skip, st);
+        return c->dim == 2 ? ksfd_march_jvp_d2(c, ch, vh, ph, precond, out, skip, st)
+                           : ksfd_march_jvp_d3(c, ch, vh, ph, precond, out, skip, st);
     }
     InvD id;
     for (int l = 0; l < KSFD_MAX_LIGANDS; ++l) id.v[l] = c->invd[l];
-    k_jvp_naive<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, cr, vr, pr, id,
+    k_jvp_naive<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->Pjac, cr, vr, pr, id,
                                                       precond ? 1 : 0, c->shift, skip, out);
     CKL();
     return 0;
@@ -816,7 +888,7 @@ static int pc_apply_impl(ksfd_ctx *c, const double *r, double *z, cudaStream_t s
 {
     InvD id;
     for (int l = 0; l < KSFD_MAX_LIGANDS; ++l) id.v[l] = c->invd[l];
-    k_pc_apply<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, coef_ref(c), id, c->pc, r, z);
+    k_pc_apply<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->Pjac, coef_ref(c), id, c->pc, r, z);
     CKL();
     return 0;
 }
@@ -997,16 +1069,16 @@ static int fftpc_apply(ksfd_ctx *c, const double *in, double *scratch, double *o
 {
     FftSym S{};
     S.dof = c->dof;
-    S.nlig = c->P.nlig;
+    S.nlig = c->Pjac.nlig;
     S.n0 = (int)c->n[0];
     S.n1 = c->dim >= 2 ? (int)c->n[1] : 1;
     S.n2 = c->dim >= 3 ? (int)c->n[2] : 1;
     S.shift = c->shift;
-    for (int a = 0; a < 3; ++a) S.c2[a] = c->P.c2[a];
+    for (int a = 0; a < 3; ++a) S.c2[a] = c->Pjac.c2[a];
     for (int l = 0; l < KSFD_MAX_LIGANDS; ++l) {
-        S.s[l] = c->P.s[l];
-        S.gamma[l] = c->P.gamma[l];
-        S.D[l] = c->P.D[l];
+        S.s[l] = c->Pjac.s[l];
+        S.gamma[l] = c->Pjac.gamma[l];
+        S.D[l] = c->Pjac.D[l];
     }
     double2 *spec = static_cast<double2 *>(c->fft_spec);
     if (g_fft.SetStream(c->fft_fwd, st) != 0 || g_fft.SetStream(c->fft_inv, st) != 0)
@@ -1203,25 +1275,28 @@ static int fetch(ksfd_ctx *c, int slot, int n, cudaStream_t st)
     return 0;
 }
 
-extern "C" int ksfd_norm2(ksfd_ctx *c, const double *x, double *out)
+extern "C" int ksfd_norm2(ksfd_ctx *c, const double *x, double *out, void *stream)
 {
     if (!c || !x || !out) return fail("ksfd_norm2: bad argument");
-    TRY(norm2_dev(c, x, 0, 0));
-    TRY(fetch(c, 0, 1, 0));
-    *out = c->hscal[0];
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(norm2_dev(c, x, SC_USER, st));
+    TRY(fetch(c, SC_USER, 1, st));
+    *out = c->hscal[SC_USER];
     return 0;
 }
 
-extern "C" int ksfd_sum_dof0(ksfd_ctx *c, const double *u, double *out)
+extern "C" int ksfd_sum_dof0(ksfd_ctx *c, const double *u, double *out, void *stream)
 {
     if (!c || !u || !out) return fail("ksfd_sum_dof0: bad argument");
-    k_sum_dof0<<<KSFD_RED_BLOCKS, KSFD_RED_THREADS>>>(c->g.npts, c->g.plane_pts, c->dof, u, c->partial);
+    cudaStream_t st = (cudaStream_t)stream;
+    k_sum_dof0<<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(c->g.npts, c->g.plane_pts, c->dof, u,
+                                                             c->partial);
     CKL();
-    k_reduce_partials<<<1, 128>>>(1, KSFD_RED_BLOCKS, c->partial, c->dscal, 0);
+    k_reduce_partials<<<1, 128, 0, st>>>(1, KSFD_RED_BLOCKS, c->partial, c->dscal + SC_USER + 1, 0);
     CKL();
-    TRY(allreduce_dev(c, c->dscal, 1, ncclSum_, 0));
-    TRY(fetch(c, 0, 1, 0));
-    *out = c->hscal[0];
+    TRY(allreduce_dev(c, c->dscal + SC_USER + 1, 1, ncclSum_, st));
+    TRY(fetch(c, SC_USER + 1, 1, st));
+    *out = c->hscal[SC_USER + 1];
     return 0;
 }
 
@@ -1361,7 +1436,10 @@ static int gmres_sync_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
                            const ksfd_ksp_opts &o, ksfd_ksp_result *res, cudaStream_t st)
 {
     const long long n = nlocal(c);
-    const int m = std::max(1, std::min(o.restart > 0 ? o.restart : 30, 60));
+    if (o.restart > KSFD_MAX_RESTART)
+        return fail("ksfd_gmres: restart " + std::to_string(o.restart) + " exceeds the supported maximum of " +
+                    std::to_string(KSFD_MAX_RESTART) + " (the device-side Hessenberg lives in shared memory)");
+    const int m = std::max(1, o.restart > 0 ? o.restart : 30);
     const int max_it = o.max_it > 0 ? o.max_it : 10000;
     const bool pre = o.precond != 0;
     if (c->krylov_cap < m + 1) {
@@ -1665,7 +1743,10 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
                            const ksfd_ksp_opts &o, ksfd_ksp_result *res, cudaStream_t st)
 {
     const long long n = nlocal(c);
-    const int m = std::max(1, std::min(o.restart > 0 ? o.restart : 30, 60));
+    if (o.restart > KSFD_MAX_RESTART)
+        return fail("ksfd_gmres: restart " + std::to_string(o.restart) + " exceeds the supported maximum of " +
+                    std::to_string(KSFD_MAX_RESTART) + " (the device-side Hessenberg lives in shared memory)");
+    const int m = std::max(1, o.restart > 0 ? o.restart : 30);
     // preconditioner: 0 none, 1 point-block Jacobi (fused into the stencil
     // kernel), 2 spectral (fftpc.cuh), 3 automatic: block Jacobi until a solve
     // needs >= 16 steps, then spectral; back after three spectral solves of <= 2
@@ -1806,7 +1887,7 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
         if (hs->reason != -9 && hs->k_cols > 0) {
             const unsigned ub = std::min(nblk(c->g.npts, 256), 148u * 8u);
 #define KSFD_UPD(D, PCF, VV, YY, KK, XZ, XX)                                                 \
-    KSFD_KLAUNCH((k_gm_update_x<D>), ub, 256, 0, st, c->g, c->P, coef_ref(c), id, c->pc, PCF, n, VV, \
+    KSFD_KLAUNCH((k_gm_update_x<D>), ub, 256, 0, st, c->g, c->Pjac, coef_ref(c), id, c->pc, PCF, n, VV, \
                  YY, KK, c->gmi + GMI_NOUPD, XZ, XX)
 #define KSFD_UPD_DOF(PCF, VV, YY, KK, XZ, XX)                                                \
     switch (c->dof) {                                                                        \

@@ -7,37 +7,47 @@
 #define DIM KSFD_MARCH_DIM
 
 template <int NLIG, bool PRECOND>
-static int launch_jvp_p(ksfd_ctx *c, VecRef coef, VecRef v, VecRef pc, double *out,
-                        const int *skip, cudaStream_t st)
+static int launch_jvp_p(ksfd_ctx *c, const HostVec &coef, const HostVec &v, const HostVec &pc,
+                        double *out, const int *skip, cudaStream_t st)
 {
     JvpOp<DIM, NLIG, PRECOND> op;
-    op.coef = coef;
-    op.v = v;
-    op.pc = pc;
+    op.coef = coef.r;
+    op.v = v.r;
+    op.pc = pc.r;
     op.shift = c->shift;
     for (int l = 0; l < NLIG; ++l) op.invd[l] = c->invd[l];
     op.out = out;
-    const double cstage = PRECOND ? 45.0 : 30.0;
+    const double cstage = PRECOND ? 45.0 : 30.0, cemit = 40.0 * DIM + 30.0;
+    if (ksfd_use_tma(c)) {
+        const TmaSrc src[3] = {coef.t, v.t, pc.t};
+#if KSFD_MARCH_DIM == 2
+        return launch_tma_op<DIM, JvpOp<DIM, NLIG, PRECOND>, true, 128, 1, 4, 3, 256, 1, 2, 3>(
+            c, op, src, PRECOND ? 2 : 3, cstage, cemit, skip, st);
+#else
+        return launch_tma_op<DIM, JvpOp<DIM, NLIG, PRECOND>, true, 16, 16, 2, 2, 32, 8, 2, 2>(
+            c, op, src, PRECOND ? 2 : 3, cstage, cemit, skip, st);
+#endif
+    }
 #if KSFD_MARCH_DIM == 2
     return launch_op<DIM, JvpOp<DIM, NLIG, PRECOND>, true, 0, 124, 1, 4, 252, 1, 2>(
-        c, op, PRECOND ? 2 : 3, cstage, 40.0 * DIM + 30.0, skip, st);
+        c, op, PRECOND ? 2 : 3, cstage, cemit, skip, st);
 #else
     return launch_op<DIM, JvpOp<DIM, NLIG, PRECOND>, true, 0, 32, 8, 1, 16, 16, 1>(
-        c, op, PRECOND ? 2 : 3, cstage, 40.0 * DIM + 30.0, skip, st);
+        c, op, PRECOND ? 2 : 3, cstage, cemit, skip, st);
 #endif
 }
 
 template <int NLIG>
-static int launch_jvp(ksfd_ctx *c, VecRef coef, VecRef v, VecRef pc, bool precond,
-                      double *out, const int *skip, cudaStream_t st)
+static int launch_jvp(ksfd_ctx *c, const HostVec &coef, const HostVec &v, const HostVec &pc,
+                      bool precond, double *out, const int *skip, cudaStream_t st)
 {
     if (precond) return launch_jvp_p<NLIG, true>(c, coef, v, pc, out, skip, st);
     return launch_jvp_p<NLIG, false>(c, coef, v, pc, out, skip, st);
 }
 
-int KSFD_CAT(ksfd_march_jvp_d, KSFD_MARCH_DIM)(ksfd_ctx *c, VecRef coef, VecRef v, VecRef pc,
-                                               bool precond, double *out, const int *skip,
-                                               cudaStream_t st)
+int KSFD_CAT(ksfd_march_jvp_d, KSFD_MARCH_DIM)(ksfd_ctx *c, const HostVec &coef, const HostVec &v,
+                                               const HostVec &pc, bool precond, double *out,
+                                               const int *skip, cudaStream_t st)
 {
     KSFD_DISPATCH_NLIG(launch_jvp, c, coef, v, pc, precond, out, skip, st);
 }

@@ -286,6 +286,7 @@ struct ResidualOp {
     static constexpr bool HAS_AUX = true;
     static constexpr bool TABS = true;
     static constexpr bool STAGE_FIRST = (KSFD_MARCH_VARIANT & 1) != 0;
+    static constexpr bool JACOBIAN = false;     // runs on the current physics (ctx.P)
     // input vectors of the TMA-fed marcher (tma_march.cuh): u
     static constexpr int NIN = 1;
     __host__ __device__ static constexpr int nc(int) { return NLIG + 1; }
@@ -407,6 +408,7 @@ struct JvpOp {
     static constexpr bool HAS_AUX = false;
     static constexpr bool TABS = false;
     static constexpr bool STAGE_FIRST = false;
+    static constexpr bool JACOBIAN = true;      // runs on the physics of the linearisation (ctx.Pjac)
     // input vectors of the TMA-fed marcher (tma_march.cuh): coef, v, pc
     static constexpr int NIN = PRECOND ? 3 : 2;
     __host__ __device__ static constexpr int nc(int i) { return i == 0 ? NLIG + 3 : i == 1 ? NLIG + 1 : 1; }
@@ -533,6 +535,7 @@ struct VelocityOp {
     static constexpr bool HAS_AUX = false;
     static constexpr bool TABS = true;
     static constexpr bool STAGE_FIRST = (KSFD_MARCH_VARIANT & 1) != 0;
+    static constexpr bool JACOBIAN = false;
     static constexpr int NIN = 1;
     __host__ __device__ static constexpr int nc(int) { return NLIG + 1; }
     __host__ __device__ static constexpr int coff(int) { return 0; }

@@ -5,8 +5,13 @@
 #include <cmath>
 #include <map>
 
+#include <array>
+#include <tuple>
+
 #include "ctx.h"
 #include "march_kernels.cuh"
+#include "tma_host.h"
+#include "tma_march.cuh"
 
 struct MarchPlan {
     int tile = -1;              // index into the candidate list
@@ -21,8 +26,10 @@ typedef std::map<long long, MarchPlan> PlanMap;
 // Cost model: waves of CTAs over the SMs times the work of one CTA (stage cost
 // on every active lane of rz+4 planes + emit cost on the outputs of rz planes +
 // a fixed start-up cost); work is counted in whole warps.
+// tma: tiles of the TMA-fed marcher (tma_march.cuh): even pitches, one thread per output,
+// the halo points staged in an extra pass of the first warps
 static MarchPlan plan_search(const ksfd_ctx *c, const TileCand *cand, int ncand,
-                             double cstage, double cemit)
+                             double cstage, double cemit, bool tma = false)
 {
     const Geom &g = c->g;
     MarchPlan best;
@@ -32,13 +39,20 @@ static MarchPlan plan_search(const ksfd_ctx *c, const TileCand *cand, int ncand,
         if (c->opt_tile_set && c->opt_tx >= 0 && c->opt_tx < ncand && t != c->opt_tx)
             continue;
         const int ntx = (g.n0 + cand[t].TX - 1) / cand[t].TX;
-        const int ox = (g.n0 + ntx - 1) / ntx;
+        int ox = (g.n0 + ntx - 1) / ntx;
         const int nty = c->dim == 3 ? (g.n1 + cand[t].TY - 1) / cand[t].TY : 1;
-        const int oy = c->dim == 3 ? (g.n1 + nty - 1) / nty : 1;
+        int oy = c->dim == 3 ? (g.n1 + nty - 1) / nty : 1;
+        if (tma) {
+            ox += ox & 1;
+            if (c->dim == 3) oy += oy & 1;
+        }
         const long long cols = (long long)ntx * nty;
         // active warps of the stage / emit phases
         double wstage, wemit;
-        if (c->dim == 2) {
+        if (tma) {
+            wemit = cand[t].NT / 32.0;
+            wstage = wemit + (c->dim == 2 ? 1.0 : std::ceil((4.0 * cand[t].TX + 4.0 * cand[t].TY) / 32.0));
+        } else if (c->dim == 2) {
             wstage = std::ceil((ox + 4) / 32.0);
             wemit = wstage;
         } else {
@@ -81,30 +95,33 @@ static MarchPlan plan_search(const ksfd_ctx *c, const TileCand *cand, int ncand,
 }
 
 static MarchPlan plan_march(ksfd_ctx *c, long long key, const TileCand *cand, int ncand,
-                            double cstage, double cemit)
+                            double cstage, double cemit, bool tma = false)
 {
     if (!c->plan_cache) c->plan_cache = new PlanMap();
     PlanMap &pm = *static_cast<PlanMap *>(c->plan_cache);
     auto it = pm.find(key);
     if (it != pm.end()) return it->second;
-    MarchPlan p = plan_search(c, cand, ncand, cstage, cemit);
+    MarchPlan p = plan_search(c, cand, ncand, cstage, cemit, tma);
     pm[key] = p;
     return p;
 }
 
 template <int DIM, int TX, int TY, class Op, int MINB, bool UNR, int DEPTH>
-static int tile_occupancy()
+static int tile_occupancy(int device)
 {
-    static int occ = -1;
-    if (occ >= 0) return occ;
+    // per device: the dynamic-shared-memory opt-in below is a per-device attribute
+    static std::map<int, int> occ_of;
+    auto it = occ_of.find(device);
+    if (it != occ_of.end()) return it->second;
+    int occ;
     using T = TileT<DIM, TX, TY>;
     auto kern = k_march<DIM, TX, TY, Op, MINB, UNR, DEPTH>;
     const size_t smem = march_smem_bytes<Op, T::SP, T::NT, DEPTH>();
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess) {
         cudaGetLastError();
-        occ = 0;
-        return occ;
+        occ_of[device] = 0;
+        return 0;
     }
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, T::NT, smem) !=
@@ -113,6 +130,7 @@ static int tile_occupancy()
         nb = 0;
     }
     occ = nb;
+    occ_of[device] = occ;
     return occ;
 }
 
@@ -123,7 +141,9 @@ static int launch_tile(const ksfd_ctx *c, const Op &op, const MarchPlan &p, cons
     using T = TileT<DIM, TX, TY>;
     auto kern = k_march<DIM, TX, TY, Op, MINB, UNR, DEPTH>;
     const size_t smem = march_smem_bytes<Op, T::SP, T::NT, DEPTH>();
-    KSFD_KLAUNCH(kern, p.grid, T::NT, smem, st, p.a, c->P, op, skip);
+    // Jacobian-side operators run on the physics of the linearisation (ctx.h: Pjac)
+    const DevPhys &P = Op::JACOBIAN ? c->Pjac : c->P;
+    KSFD_KLAUNCH(kern, p.grid, T::NT, smem, st, p.a, P, op, skip);
     CKL();
     return 0;
 }
@@ -139,14 +159,129 @@ static int launch_op(ksfd_ctx *c, const Op &op, int opkey, double cstage, double
         return fail("rank-local slab too large for the 32-bit indexed kernels; "
                     "decompose over more ranks");
     TileCand cand[2] = {
-        {AX, AY, TileT<DIM, AX, AY>::NT, tile_occupancy<DIM, AX, AY, Op, AMINB, UNR, DEPTH>()},
-        {BX, BY, TileT<DIM, BX, BY>::NT, tile_occupancy<DIM, BX, BY, Op, BMINB, UNR, DEPTH>()}};
+        {AX, AY, TileT<DIM, AX, AY>::NT, tile_occupancy<DIM, AX, AY, Op, AMINB, UNR, DEPTH>(c->device)},
+        {BX, BY, TileT<DIM, BX, BY>::NT, tile_occupancy<DIM, BX, BY, Op, BMINB, UNR, DEPTH>(c->device)}};
     if (cand[0].occ == 0 && cand[1].occ == 0)
         return fail("marching kernel does not fit on this device");
     MarchPlan p = plan_march(c, opkey * 100 + DIM * 10 + Op::NF, cand, 2, cstage, cemit);
     if (p.tile < 0) return fail("no marching tile fits");
     if (p.tile == 0) return launch_tile<DIM, AX, AY, Op, AMINB, UNR, DEPTH>(c, op, p, skip, st);
     return launch_tile<DIM, BX, BY, Op, BMINB, UNR, DEPTH>(c, op, p, skip, st);
+}
+
+// ---------------------------------------------------------------------------
+// TMA-fed marcher (tma_march.cuh)
+// ---------------------------------------------------------------------------
+// encoded tensor maps are cached per (buffer, extent, fields per plane, tile)
+typedef std::tuple<const void *, long long, int, int, int> TmapKey;
+typedef std::map<TmapKey, std::array<CUtensorMap, 3>> TmapCache;
+
+// option `variant`: 0 auto, 1 direct kernels, 2 marching (TMA-fed where eligible),
+// 3 marching with the register-prefetch kernels (k_march) only
+static bool ksfd_use_tma(const ksfd_ctx *c)
+{
+    if (c->variant == 3) return false;
+    // rows must be multiples of 16 bytes (tensor-map strides) and tile pitches even
+    if (c->g.n0 % 2 != 0 || (c->dim == 3 && c->g.n1 % 2 != 0)) return false;
+    return ksfd_tmap_encoder() != nullptr;
+}
+
+static int tma_maps(ksfd_ctx *c, CUtensorMap out[3], const double *buf, long long fields, int nc,
+                    int TX, int TY)
+{
+    if (!c->tmap_cache) c->tmap_cache = new TmapCache();
+    TmapCache &tc = *static_cast<TmapCache *>(c->tmap_cache);
+    const TmapKey key(buf, fields, nc, TX, TY);
+    auto it = tc.find(key);
+    if (it == tc.end()) {
+        std::array<CUtensorMap, 3> m;
+        const std::string e = ksfd_make_tmaps(m.data(), buf, c->g.n0, c->g.n1, fields, nc, TX, TY);
+        if (!e.empty()) return fail("tensor map: " + e);
+        if (tc.size() > 4096) tc.clear();
+        it = tc.emplace(key, m).first;
+    }
+    for (int s = 0; s < 3; ++s) out[s] = it->second[s];
+    return 0;
+}
+
+template <class Op>
+static int tma_bind(ksfd_ctx *c, TmaInT<Op::NIN> &tin, const TmaSrc *src, int TX, int TY)
+{
+    for (int i = 0; i < Op::NIN; ++i) {
+        const TmaSrc &t = src[i];
+        const int nc = Op::nc(i);
+        TRY(tma_maps(c, tin.m[i][0], t.base, t.base_fields, nc, TX, TY));
+        if (t.halo)
+            TRY(tma_maps(c, tin.m[i][1], t.halo, t.halo_fields, nc, TX, TY));
+        else
+            for (int s = 0; s < 3; ++s) tin.m[i][1][s] = tin.m[i][0][s];
+        tin.v[i].kofs[0] = t.k0;
+        tin.v[i].kofs[1] = t.klo;
+        tin.v[i].kofs[2] = t.khi;
+        tin.v[i].wrap = t.wrap;
+        tin.v[i].par = t.par;
+        tin.v[i].parshift = t.parshift;
+        tin.v[i].pad_ = 0;
+    }
+    return 0;
+}
+
+template <int DIM, int TX, int TY, class Op, int MINB, bool UNR, int SC, int SH>
+static int tma_tile_occupancy(const ksfd_ctx *c)
+{
+    static std::map<int, int> occ_of;           // per device (the opt-in is per device too)
+    auto it = occ_of.find(c->device);
+    if (it != occ_of.end()) return it->second;
+    using M = TmaMarcher<DIM, TX, TY, Op, UNR, SC, SH>;
+    auto kern = k_tma_march<DIM, TX, TY, Op, MINB, UNR, SC, SH>;
+    const size_t smem = tma_march_smem_bytes<DIM, TX, TY, Op, UNR, SC, SH>();
+    int nb = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+            cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, M::NTH, smem) != cudaSuccess) {
+        cudaGetLastError();
+        nb = 0;
+    }
+    occ_of[c->device] = nb;
+    return nb;
+}
+
+template <int DIM, int TX, int TY, class Op, int MINB, bool UNR, int SC, int SH>
+static int launch_tma_tile(ksfd_ctx *c, const Op &op, const TmaSrc *src, const MarchPlan &p,
+                           const int *skip, cudaStream_t st)
+{
+    using M = TmaMarcher<DIM, TX, TY, Op, UNR, SC, SH>;
+    auto kern = k_tma_march<DIM, TX, TY, Op, MINB, UNR, SC, SH>;
+    const size_t smem = tma_march_smem_bytes<DIM, TX, TY, Op, UNR, SC, SH>();
+    TmaInT<Op::NIN> tin;
+    TRY(tma_bind<Op>(c, tin, src, TX, TY));
+    const DevPhys &P = Op::JACOBIAN ? c->Pjac : c->P;
+    KSFD_KLAUNCH(kern, p.grid, M::NTH, smem, st, p.a, P, op, tin, skip);
+    CKL();
+    return 0;
+}
+
+// two tile candidates per operator: (AX, AY, AMINB, ASC) and (BX, BY, BMINB, BSC)
+template <int DIM, class Op, bool UNR, int AX, int AY, int AMINB, int ASC, int BX, int BY,
+          int BMINB, int BSC>
+static int launch_tma_op(ksfd_ctx *c, const Op &op, const TmaSrc *src, int opkey, double cstage,
+                         double cemit, const int *skip, cudaStream_t st)
+{
+    const long long maxel = (long long)(c->g.nloc + 2 * KSFD_SW) * c->g.plane_pts * (c->dof + 2);
+    if (maxel >= (1LL << 31))
+        return fail("rank-local slab too large for the 32-bit indexed kernels; "
+                    "decompose over more ranks");
+    constexpr int ANT = DIM == 2 ? AX : AX * AY, BNT = DIM == 2 ? BX : BX * BY;
+    TileCand cand[2] = {
+        {AX, AY, ANT, tma_tile_occupancy<DIM, AX, AY, Op, AMINB, UNR, ASC, ASC>(c)},
+        {BX, BY, BNT, tma_tile_occupancy<DIM, BX, BY, Op, BMINB, UNR, BSC, BSC>(c)}};
+    if (cand[0].occ == 0 && cand[1].occ == 0)
+        return fail("TMA marching kernel does not fit on this device");
+    MarchPlan p = plan_march(c, 1000 + opkey * 100 + DIM * 10 + Op::NF, cand, 2, cstage, cemit, true);
+    if (p.tile < 0) return fail("no marching tile fits");
+    if (p.tile == 0)
+        return launch_tma_tile<DIM, AX, AY, Op, AMINB, UNR, ASC, ASC>(c, op, src, p, skip, st);
+    return launch_tma_tile<DIM, BX, BY, Op, BMINB, UNR, BSC, BSC>(c, op, src, p, skip, st);
 }
 
 #define KSFD_DISPATCH_NLIG(FN, ...)                                        \

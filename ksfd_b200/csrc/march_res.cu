@@ -7,30 +7,40 @@
 #define DIM KSFD_MARCH_DIM
 
 template <int NLIG, bool FIXED>
-static int launch_residual_f(ksfd_ctx *c, VecRef u, const double *udot, const double *src,
+static int launch_residual_f(ksfd_ctx *c, const HostVec &u, const double *udot, const double *src,
                              double *out, cudaStream_t st)
 {
-    ResidualOp<DIM, NLIG, FIXED> op{u, udot, src, out};
+    ResidualOp<DIM, NLIG, FIXED> op{u.r, udot, src, out};
+    const double cemit = 35.0 * DIM + 30.0;
+    if (ksfd_use_tma(c)) {
+#if KSFD_MARCH_DIM == 2
+        return launch_tma_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 128, 1, 6, 3, 256, 1, 3, 3>(
+            c, op, &u.t, FIXED ? 1 : 5, 150.0, cemit, nullptr, st);
+#else
+        return launch_tma_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 16, 16, 3, 3, 32, 8, 3, 3>(
+            c, op, &u.t, FIXED ? 1 : 5, 150.0, cemit, nullptr, st);
+#endif
+    }
 #if KSFD_MARCH_DIM == 2
     return launch_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 0, 124, 1, 6, 252, 1, 3>(
-        c, op, FIXED ? 1 : 5, 150.0, 35.0 * DIM + 30.0, nullptr, st);
+        c, op, FIXED ? 1 : 5, 150.0, cemit, nullptr, st);
 #else
     return launch_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 0, 16, 16, 2, 32, 16, 1>(
-        c, op, FIXED ? 1 : 5, 150.0, 35.0 * DIM + 30.0, nullptr, st);
+        c, op, FIXED ? 1 : 5, 150.0, cemit, nullptr, st);
 #endif
 }
 
 // the implicit-step case (udot given, no sources) has its own instantiation
 // without the runtime tests
 template <int NLIG>
-static int launch_residual(ksfd_ctx *c, VecRef u, const double *udot, const double *src,
+static int launch_residual(ksfd_ctx *c, const HostVec &u, const double *udot, const double *src,
                            double *out, cudaStream_t st)
 {
     if (udot && !src) return launch_residual_f<NLIG, true>(c, u, udot, src, out, st);
     return launch_residual_f<NLIG, false>(c, u, udot, src, out, st);
 }
 
-int KSFD_CAT(ksfd_march_residual_d, KSFD_MARCH_DIM)(ksfd_ctx *c, VecRef u,
+int KSFD_CAT(ksfd_march_residual_d, KSFD_MARCH_DIM)(ksfd_ctx *c, const HostVec &u,
                                                     const double *udot, const double *src,
                                                     double *out, cudaStream_t st)
 {

@@ -22,9 +22,9 @@
 //     partial (it recomputes a few outputs of its neighbour, writing identical
 //     values), so every tile is full and lies inside the domain.
 //
-// Tensor maps (host: tma_host.h): every input vector is described as a rank-3
-// tensor (x, y, plane*nc + field) over its plane-SoA storage; coordinate 2 of a
-// box = kofs + k*nc selects the nc fields of plane k at once.
+// Tensor maps (host: tma_host.h; passed in the kernel parameter block): every input
+// vector is described as a rank-3 tensor (x, y, plane*nc + field) over its plane-SoA
+// storage; coordinate 2 of a box = kofs + k*nc selects the nc fields of plane k at once.
 //
 // Shared memory (doubles): [staged ring 2 x NF x SP][log/exp tables]
 //   [centre ring SC x NPRE x TX*TY][halo ring SH x NPRE x NH][mbarriers SC + SH]
@@ -33,14 +33,22 @@
 
 #include "march_kernels.cuh"
 
+// One input vector: the owned planes live in one buffer (map set 0), the four ghost planes
+// of the last axis either are periodic images of owned planes (wrap, one rank) or live in a
+// second buffer (map set 1): the halo slot the neighbours fill (several ranks; double-
+// buffered on the parity of a device-side exchange counter), or the same buffer (the
+// coefficient field, which is stored ghosted).
 struct TmaVecIn {
-    int kofs[3];    // coordinate 2 of plane 0 of: [0] owned planes, [1] ghost lo (planes -2,-1),
-                    // [2] ghost hi (planes nloc, nloc+1)
-    int wrap;       // 1: ghost planes are periodic images of the owned planes (one rank)
+    int kofs[3];    // coordinate 2 of: [0] plane 0 in set 0, [1] plane -2 in set 1, [2] plane nloc in set 1
+    int wrap;       // 1: ghost planes = periodic images of the owned planes
+    const unsigned long long *par;      // exchange counter (nullptr: none)
+    int parshift;   // added to kofs[1], kofs[2] when the counter is odd
+    int pad_;
 };
-struct TmaIn {
-    const CUtensorMap *maps;    // [input vector][buffer 0..2][box shape: centre, y strip, x strip]
-    TmaVecIn v[3];
+template <int NIN>
+struct TmaInT {
+    CUtensorMap m[NIN][2][3];   // [input vector][map set][box shape: centre, y strip, x strip]
+    TmaVecIn v[NIN];
 };
 
 namespace ktma {
@@ -121,7 +129,8 @@ struct TmaMarcher {
     const MarchArgs &g;
     const DevPhys &P;
     const Op &op;
-    const TmaIn &tin;
+    const TmaInT<Op::NIN> &tin;
+    int pshift[Op::NIN];        // (elected thread) parity shift of the ghost planes
     double q[NF][5];
     double aux[NAUX];
     typename Op::State st;
@@ -139,7 +148,7 @@ struct TmaMarcher {
     }
 
     __device__ __forceinline__ TmaMarcher(const MarchArgs &g_, const DevPhys &P_, const Op &op_,
-                                          const TmaIn &tin_)
+                                          const TmaInT<Op::NIN> &tin_)
         : g(g_), P(P_), op(op_), tin(tin_)
     {
         const int tid = threadIdx.x;
@@ -215,6 +224,9 @@ struct TmaMarcher {
         if (tid == 0) {
             const int np = k1 - k0 + 2 * KSFD_SW;
 #pragma unroll
+            for (int i = 0; i < NIN; ++i)
+                pshift[i] = tin.v[i].par ? (int)(*tin.v[i].par & 1ull) * tin.v[i].parshift : 0;
+#pragma unroll
             for (int s = 0; s < SC; ++s)
                 if (s < np) issue_centre(k0 - KSFD_SW + s, s);
 #pragma unroll
@@ -223,21 +235,21 @@ struct TmaMarcher {
         }
     }
 
-    // coordinate 2 of plane k of input vector i; buf = which of its three buffers
-    __device__ __forceinline__ int plane_coord(int i, int k, int &buf) const
+    // coordinate 2 of plane k of input vector i; set = which of its two map sets
+    __device__ __forceinline__ int plane_coord(int i, int k, int &set) const
     {
         const TmaVecIn &v = tin.v[i];
         const int nc = Op::nc(i);
-        buf = 0;
+        set = 0;
         if (k < 0) {
             if (v.wrap) return v.kofs[0] + (k + g.nloc) * nc;
-            buf = 1;
-            return v.kofs[1] + (k + KSFD_SW) * nc;
+            set = 1;
+            return v.kofs[1] + pshift[i] + (k + KSFD_SW) * nc;
         }
         if (k >= g.nloc) {
             if (v.wrap) return v.kofs[0] + (k - g.nloc) * nc;
-            buf = 2;
-            return v.kofs[2] + (k - g.nloc) * nc;
+            set = 1;
+            return v.kofs[2] + pshift[i] + (k - g.nloc) * nc;
         }
         return v.kofs[0] + k * nc;
     }
@@ -250,10 +262,10 @@ struct TmaMarcher {
         const int i0 = tile_x0(), j0 = tile_y0();
 #pragma unroll
         for (int i = 0; i < NIN; ++i) {
-            int buf;
-            const int kc = plane_coord(i, k, buf);
+            int set;
+            const int kc = plane_coord(i, k, set);
             ktma::load3(ktma::s32(ksfd_smem + CRING + slot * CSLOT + Op::coff(i) * NTH),
-                        tin.maps + (i * 3 + buf) * 3, i0, j0, kc, bar);
+                        &tin.m[i][set][0], i0, j0, kc, bar);
         }
     }
     // (elected thread) fetch the halo boxes of plane k into halo slot `slot`
@@ -267,9 +279,9 @@ struct TmaMarcher {
         const double *base = ksfd_smem + HRING + slot * HSLOT;
 #pragma unroll
         for (int i = 0; i < NIN; ++i) {
-            int buf;
-            const int kc = plane_coord(i, k, buf);
-            const CUtensorMap *m = tin.maps + (i * 3 + buf) * 3;
+            int set;
+            const int kc = plane_coord(i, k, set);
+            const CUtensorMap *m = &tin.m[i][set][0];
             if (DIM == 2) {
                 ktma::load3(ktma::s32(base + hbox(i, 0)), m + 2, xl, 0, kc, bar);
                 ktma::load3(ktma::s32(base + hbox(i, 1)), m + 2, xr, 0, kc, bar);
@@ -388,7 +400,7 @@ struct TmaMarcher {
 template <int DIM, int TX, int TY, class Op, int MINB, bool UNR, int SC, int SH>
 __global__ void __launch_bounds__((DIM == 2 ? TX : TX * TY), MINB)
 k_tma_march(const __grid_constant__ MarchArgs g, const __grid_constant__ DevPhys P,
-            const __grid_constant__ Op op, const __grid_constant__ TmaIn tin,
+            const __grid_constant__ Op op, const __grid_constant__ TmaInT<Op::NIN> tin,
             const int *__restrict__ skip)
 {
     KSFD_PDL_ENTER();

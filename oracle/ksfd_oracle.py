@@ -210,7 +210,16 @@ def dfdt(u, ph, sources=None):
     """
     ua = np.asarray(u, dtype=float).reshape(ph.Vshape, order='F')
     farr = ghost_fill(ua, ph.dim)                     # :919-921
-    farr = groom(farr, ph)                            # :922 clamp ghosted COPY
+    return dfdt_ghosted(farr, ph, sources)
+
+
+def dfdt_ghosted(farr, ph, sources=None):
+    """f(u) on the interior of an already ghosted array (dof,)+(n+2*SW): the body
+    of `dfdt` after the ghost exchange.  With ph.n = the extents of a sub-box and
+    farr cut (with wrap) out of a larger periodic field this is what ONE RANK of
+    the reference computes on its DMDA patch (ksfdsym.py:919-940) — the tests use
+    it to check full-size CUDA results box by box."""
+    farr = groom(np.array(farr, dtype=float), ph)     # :922 clamp ghosted COPY
     G = G_of(farr, ph)                                # :797-803 incl. ghosts
     out = np.empty(ph.Vshape)
     # f_rho = grad(rho).grad(G) + rho*lap(G)          # :531-571, :804
@@ -342,8 +351,12 @@ def jvp(u_lin, v, shift, ph):
     the CUDA J.v kernel uses; checked against `ijacobian` in the tests)."""
     ua = np.asarray(u_lin, dtype=float).reshape(ph.Vshape, order='F')
     va = np.asarray(v, dtype=float).reshape(ph.Vshape, order='F')
-    farr = groom(ghost_fill(ua, ph.dim), ph)
-    vg = ghost_fill(va, ph.dim)
+    return jvp_ghosted(ghost_fill(ua, ph.dim), ghost_fill(va, ph.dim), shift, ph)
+
+
+def jvp_ghosted(farr, vg, shift, ph):
+    """`jvp` on the interior of already ghosted u_lin and v (see dfdt_ghosted)."""
+    farr = groom(np.array(farr, dtype=float), ph)
     G = G_of(farr, ph)
     g_rho, g_U = dG_of(farr, ph)
     dGv = g_rho * vg[0]
@@ -367,6 +380,17 @@ def jvp(u_lin, v, shift, ph):
         JvU = (-lig['gamma'] * center(vg[l + 1], ph)
                + lig['s'] * center(vg[0], ph) + lig['D'] * lapV)
         out[l + 1] = shift * center(vg[l + 1], ph) - JvU
+    return out
+
+
+def cut_box(arr, lo, size, sw=SW):
+    """Ghosted sub-box of a periodic global array (dof,)+N: points lo-sw .. lo+size+sw-1
+    of every axis, wrapped periodically (what DMDA globalToLocal delivers to the rank
+    owning [lo, lo+size))."""
+    out = arr
+    for d, (l, n) in enumerate(zip(lo, size)):
+        idx = np.arange(l - sw, l + n + sw) % arr.shape[d + 1]
+        out = np.take(out, idx, axis=d + 1)
     return out
 
 

@@ -107,7 +107,6 @@ struct Problem {
     int nrot, nout;
     std::vector<double *> u, v, out;
     double *coef, *pc, *ref;
-    CUtensorMap *dmaps;     // device scratch for tensor maps
 };
 
 static int g_ordinal = 0;
@@ -203,7 +202,7 @@ static void run_ref(const char *name, Problem &pb, const DevPhys &P, Op op_proto
 template <int DIM, int TX, int TY, class Op, int MINB, bool UNR, int SC, int SH>
 static void run_tma(const char *name, Problem &pb, const DevPhys &P, Op op_proto,
                     void (*bind)(Op &, const Problem &, int),
-                    void (*bind_tma)(TmaIn &, CUtensorMap *, const Problem &, int, int, int),
+                    void (*bind_tma)(TmaInT<Op::NIN> &, const Problem &, int, int, int),
                     const int *rzs, int nrz)
 {
     using M = TmaMarcher<DIM, TX, TY, Op, UNR, SC, SH>;
@@ -234,9 +233,8 @@ static void run_tma(const char *name, Problem &pb, const DevPhys &P, Op op_proto
     int oy = DIM == 3 ? (pb.n1 + nty - 1) / nty : 1;
     if (DIM == 3) oy += oy & 1;
     // tensor maps per buffer set (host encode + upload once)
-    std::vector<TmaIn> tins(pb.nrot);
-    for (int i = 0; i < pb.nrot; ++i)
-        bind_tma(tins[i], pb.dmaps + (size_t)i * 27, pb, i, TX, TY);
+    std::vector<TmaInT<Op::NIN>> tins(pb.nrot);
+    for (int i = 0; i < pb.nrot; ++i) bind_tma(tins[i], pb, i, TX, TY);
     for (int r = 0; r < nrz; ++r) {
         const int rz = pick_rz(rzs[r], (long long)ntx * nty, occ, pb.nloc);
         const int nch = (pb.nloc + rz - 1) / rz;
@@ -304,45 +302,38 @@ static void bind_jvp(JvpOp<DIM, 2, PC> &op, const Problem &pb, int i)
     op.out = pb.out[i];
 }
 
-static void upload_maps(CUtensorMap *dst, const CUtensorMap *src, int n)
+static void maps_or_die(CUtensorMap out[3], const double *base, const Problem &pb, long long nfp,
+                        int nc, int TX, int TY)
 {
-    CHECK(cudaMemcpy(dst, src, sizeof(CUtensorMap) * n, cudaMemcpyHostToDevice));
-}
-static void tma_res(TmaIn &t, CUtensorMap *d, const Problem &pb, int i, int TX, int TY)
-{
-    CUtensorMap h[27];
-    memset(h, 0, sizeof(h));
-    std::string e = ksfd_make_tmaps(h, pb.u[i], pb.n0, pb.n1, 3LL * pb.nloc, 3, TX, TY);
+    std::string e = ksfd_make_tmaps(out, base, pb.n0, pb.n1, nfp, nc, TX, TY);
     if (!e.empty()) {
         printf("%s\n", e.c_str());
         exit(1);
     }
-    upload_maps(d, h, 27);
-    t.maps = d;
-    t.v[0] = TmaVecIn{{0, 0, 0}, 1};
-    t.v[1] = t.v[2] = t.v[0];
 }
-static void tma_jvp(TmaIn &t, CUtensorMap *d, const Problem &pb, int i, int TX, int TY)
+static void tma_res(TmaInT<1> &t, const Problem &pb, int i, int TX, int TY)
 {
-    CUtensorMap h[27];
-    memset(h, 0, sizeof(h));
-    std::string e = ksfd_make_tmaps(h, pb.coef, pb.n0, pb.n1, 5LL * (pb.nloc + 4), 5, TX, TY);
-    if (e.empty()) e = ksfd_make_tmaps(h + 9, pb.v[i], pb.n0, pb.n1, 3LL * pb.nloc, 3, TX, TY);
-    if (e.empty()) e = ksfd_make_tmaps(h + 18, pb.pc, pb.n0, pb.n1, 1LL * pb.nloc, 1, TX, TY);
-    if (!e.empty()) {
-        printf("%s\n", e.c_str());
-        exit(1);
+    memset(&t, 0, sizeof(t));
+    maps_or_die(t.m[0][0], pb.u[i], pb, 3LL * pb.nloc, 3, TX, TY);
+    memcpy(t.m[0][1], t.m[0][0], sizeof(t.m[0][0]));
+    t.v[0] = TmaVecIn{{0, 0, 0}, 1, nullptr, 0, 0};
+}
+template <int NIN>
+static void tma_jvp(TmaInT<NIN> &t, const Problem &pb, int i, int TX, int TY)
+{
+    memset(&t, 0, sizeof(t));
+    // coef is stored ghosted: plane 0 is plane 2 of the buffer, its ghost planes are in place
+    maps_or_die(t.m[0][0], pb.coef, pb, 5LL * (pb.nloc + 4), 5, TX, TY);
+    memcpy(t.m[0][1], t.m[0][0], sizeof(t.m[0][0]));
+    t.v[0] = TmaVecIn{{2 * 5, 0, (2 + pb.nloc) * 5}, 0, nullptr, 0, 0};
+    maps_or_die(t.m[1][0], pb.v[i], pb, 3LL * pb.nloc, 3, TX, TY);
+    memcpy(t.m[1][1], t.m[1][0], sizeof(t.m[1][0]));
+    t.v[1] = TmaVecIn{{0, 0, 0}, 1, nullptr, 0, 0};
+    if (NIN > 2) {
+        maps_or_die(t.m[NIN - 1][0], pb.pc, pb, 1LL * pb.nloc, 1, TX, TY);
+        memcpy(t.m[NIN - 1][1], t.m[NIN - 1][0], sizeof(t.m[0][0]));
+        t.v[NIN - 1] = TmaVecIn{{0, 0, 0}, 1, nullptr, 0, 0};
     }
-    upload_maps(d, h, 27);
-    t.maps = d;
-    // coef is stored ghosted: plane 0 is plane 2 of the buffer, ghost planes are in place
-    t.v[0] = TmaVecIn{{2 * 5, 0, (2 + pb.nloc) * 5}, 0};
-    // all three buffers of coef use map set 0: point lo/hi at the same maps
-    memcpy(h + 3, h, 3 * sizeof(CUtensorMap));
-    memcpy(h + 6, h, 3 * sizeof(CUtensorMap));
-    upload_maps(d, h, 9);
-    t.v[1] = TmaVecIn{{0, 0, 0}, 1};
-    t.v[2] = TmaVecIn{{0, 0, 0}, 1};
 }
 
 static Problem make_problem(int dim, int n)
@@ -375,7 +366,6 @@ static Problem make_problem(int dim, int n)
     CHECK(cudaMalloc(&pb.pc, pb.npts * 8));
     k_fill<<<(unsigned)((pb.npts + 255) / 256), 256>>>(pb.pc, pb.npts, 4e-4, 1e-5, 78);
     CHECK(cudaMalloc(&pb.ref, N * 8));
-    CHECK(cudaMalloc(&pb.dmaps, sizeof(CUtensorMap) * 27 * pb.nrot));
     CHECK(cudaDeviceSynchronize());
     return pb;
 }
@@ -388,7 +378,6 @@ static void free_problem(Problem &pb)
     cudaFree(pb.coef);
     cudaFree(pb.pc);
     cudaFree(pb.ref);
-    cudaFree(pb.dmaps);
 }
 
 #define REF_RES(DIM, TX, TY, MINB, REC) \
@@ -398,7 +387,7 @@ static void free_problem(Problem &pb)
 #define TMA_RES(DIM, TX, TY, MINB, UNR, SC, SH) \
     run_tma<DIM, TX, TY, ResidualOp<DIM, 2, true>, MINB, UNR, SC, SH>("residual", pb, P, ResidualOp<DIM, 2, true>{}, bind_res<DIM>, tma_res, rzs, nrz)
 #define TMA_JVP(DIM, TX, TY, MINB, UNR, PC, SC, SH) \
-    run_tma<DIM, TX, TY, JvpOp<DIM, 2, PC>, MINB, UNR, SC, SH>(PC ? "jvp_pc" : "jvp", pb, P, JvpOp<DIM, 2, PC>{}, bind_jvp<DIM, PC>, tma_jvp, rzs, nrz)
+    run_tma<DIM, TX, TY, JvpOp<DIM, 2, PC>, MINB, UNR, SC, SH>(PC ? "jvp_pc" : "jvp", pb, P, JvpOp<DIM, 2, PC>{}, bind_jvp<DIM, PC>, tma_jvp<PC ? 3 : 2>, rzs, nrz)
 
 int main(int argc, char **argv)
 {

@@ -33,7 +33,7 @@ def test_python_binding_matches_header(built_lib):
     from ksfd_b200 import _lib
     assert sorted(_lib.EXPORTS) == header_symbols()
     lib = _lib.load()
-    assert lib.ksfd_abi_version() == 1
+    assert lib.ksfd_abi_version() == 2
     assert _lib.launch_count() == 0
 
 

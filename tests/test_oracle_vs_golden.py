@@ -90,3 +90,22 @@ def test_jacobian_is_derivative_3d():
     eps = 1e-3
     fd = (O.dfdt(u + eps * v, ph) - O.dfdt(u - eps * v, ph)).reshape(-1, order='F') / (2 * eps)
     assert relerr(J @ v, fd, ph.dof) < 1e-6
+
+
+def test_ghosted_subbox_equals_global():
+    """dfdt_ghosted / jvp_ghosted on a wrapped sub-box == the same region of the global
+    evaluation, bit for bit (the full-size GPU tests rely on it)."""
+    from helpers import oracle_physics, phys84, random_state
+    from oracle import ksfd_oracle as O
+    for n, lo, size in (((20, 16), (14, 0), (12, 16)), ((10, 12, 9), (7, 10, 0), (6, 5, 9))):
+        p = phys84(len(n), n)
+        ph = oracle_physics(p)
+        u = random_state(p, 3).reshape(ph.Vshape, order='F')
+        v = np.random.default_rng(4).standard_normal(ph.Vshape)
+        f = O.dfdt(u, ph)
+        jv = O.jvp(u, v, 123.0, ph)
+        phb = oracle_physics(phys84(len(n), size))
+        fb = O.dfdt_ghosted(O.cut_box(u, lo, size), phb)
+        jb = O.jvp_ghosted(O.cut_box(u, lo, size), O.cut_box(v, lo, size), 123.0, phb)
+        assert np.array_equal(fb, O.cut_box(f, lo, size, sw=0))
+        assert np.array_equal(jb, O.cut_box(jv, lo, size, sw=0))
