@@ -401,6 +401,66 @@ __global__ void k_p2p_allreduce(P2PRed pr, double *buf, int n, int op)
 }
 
 // ---------------------------------------------------------------------------
+// Halo push fused into the PRODUCER of a vector (several ranks, NVLink peer memory).
+// The kernel that writes a Krylov vector also stores its two bottom planes into the
+// lower neighbour's ghost buffer and its two top planes into the upper neighbour's
+// (plain stores over NVLink; in the plane-SoA layout the planes are the first and the
+// last `cnt` doubles of the vector), and the block that finishes last publishes the
+// exchange number in the neighbours' flag words and advances this rank's counter.
+// Nobody waits here: the consumer (the TMA-fed marcher, tma_march.cuh: halo_arrived)
+// waits in the CTAs that read ghost planes.  No exchange kernel is launched at all.
+// ---------------------------------------------------------------------------
+struct HaloPush {
+    double *up_lo0, *dn_hi0;                // parity-0 destinations (nullptr: no push)
+    long long pstride;                      // doubles between the two parity buffers
+    long long cnt;                          // doubles in the two boundary planes
+    long long top0;                         // first element of the two top planes (n - cnt)
+    volatile unsigned long long *up_flag_lo, *dn_flag_hi;
+    unsigned long long *ctr;                // this rank's exchange counter of the slot
+    unsigned *done;                         // block counter
+    const volatile unsigned long long *dead;
+};
+__device__ __forceinline__ bool halo_push_on(const HaloPush &hp)
+{
+    return hp.up_lo0 != nullptr && !(hp.dead && *hp.dead);
+}
+// parity shift of the exchange this launch makes; every block reads the counter
+// before the last one (which only exists after all blocks have stored) advances it
+__device__ __forceinline__ long long halo_push_shift(const HaloPush &hp, unsigned long long &q)
+{
+    q = *reinterpret_cast<volatile unsigned long long *>(hp.ctr) + 1;
+    return (long long)(q & 1ull) * hp.pstride;
+}
+__device__ __forceinline__ void halo_push1(const HaloPush &hp, long long sh, long long e, double v)
+{
+    if (e < hp.cnt) hp.dn_hi0[sh + e] = v;
+    if (e >= hp.top0) hp.up_lo0[sh + e - hp.top0] = v;
+}
+// elements 2e, 2e+1 (cnt and top0 are even whenever the double2 path runs)
+__device__ __forceinline__ void halo_push2(const HaloPush &hp, long long sh, long long e2, double2 v)
+{
+    const long long e = 2 * e2;
+    if (e < hp.cnt) *reinterpret_cast<double2 *>(hp.dn_hi0 + sh + e) = v;
+    if (e >= hp.top0) *reinterpret_cast<double2 *>(hp.up_lo0 + sh + e - hp.top0) = v;
+}
+// every thread of every block calls this after its stores
+__device__ __forceinline__ void halo_push_publish(const HaloPush &hp, unsigned long long q)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(hp.done, 1u);
+        if (t == gridDim.x - 1) {               // last block: all planes are on their way
+            atomicExch(hp.done, 0u);
+            __threadfence_system();
+            *hp.up_flag_lo = q;
+            *hp.dn_flag_hi = q;
+            *hp.ctr = q;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Pipelined GMRES: the Hessenberg/Givens bookkeeping, the convergence test and
 // the back substitution run on the device; the host only polls a pinned status
 // word (no stream synchronisation inside a solve) and may launch ahead.
@@ -583,13 +643,17 @@ k_gm_norm_begin(long long n, const double *__restrict__ r, double *__restrict__ 
     gm_begin_in_last_block(a);
 }
 
-// y = x * (sign / gm[GM_BETA])    (first Krylov vector)
+// y = x * (sign / gm[GM_BETA])    (first Krylov vector); hp: fused halo push of y
 __global__ void k_gm_first_vector(long long n, const double *x, const double *__restrict__ gm,
-                                  const int *__restrict__ gmi, double sign, double *y)
+                                  const int *__restrict__ gmi, double sign, double *y,
+                                  HaloPush hp)
 {
     KSFD_PDL_ENTER();
     if (KSFD_FLAG(gmi + GMI_FINAL)) return;
     const double f = sign / KSFD_FLAG(gm + GM_BETA);
+    const bool push = halo_push_on(hp);
+    unsigned long long q = 0;
+    const long long sh = push ? halo_push_shift(hp, q) : 0;
     if ((n & 1) == 0 && aligned16(x) && aligned16(y)) {
         const double2 *x2 = reinterpret_cast<const double2 *>(x);
         double2 *y2 = reinterpret_cast<double2 *>(y);
@@ -599,12 +663,17 @@ __global__ void k_gm_first_vector(long long n, const double *x, const double *__
             v.x *= f;
             v.y *= f;
             y2[e] = v;
+            if (push) halo_push2(hp, sh, e, v);
         }
-        return;
+    } else {
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+             e += (long long)gridDim.x * blockDim.x) {
+            const double v = x[e] * f;
+            y[e] = v;
+            if (push) halo_push1(hp, sh, e, v);
+        }
     }
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
-         e += (long long)gridDim.x * blockDim.x)
-        y[e] = x[e] * f;
+    if (push) halo_push_publish(hp, q);
 }
 
 // partial[i][block] = <vs[i], w>, skipping when the cycle is closed
@@ -838,11 +907,12 @@ k_gm_mdot(long long n, VecList vs, const double *__restrict__ w,
 
 
 // w = (w - sum_i h[i]*V_i) * inv   with h, inv from the device state
+// hp: fused halo push of the finished vector (last batch of a long column only)
 template <int NV>
 __global__ void __launch_bounds__(KSFD_RED_THREADS)
 k_gm_orth_scale(long long n, VecList vs, int off, int do_scale,
                 const double *__restrict__ gm, const int *__restrict__ gmi,
-                double *__restrict__ w)
+                double *__restrict__ w, HaloPush hp)
 {
     // the step that closed the cycle does not need its new basis vector
     KSFD_PDL_ENTER();
@@ -851,6 +921,9 @@ k_gm_orth_scale(long long n, VecList vs, int off, int do_scale,
 #pragma unroll
     for (int i = 0; i < NV; ++i) hh[i] = KSFD_FLAG(gm + GM_HCOL + off + i);
     const double sc = do_scale ? KSFD_FLAG(gm + GM_INV) : 1.0;
+    const bool push = halo_push_on(hp);
+    unsigned long long q = 0;
+    const long long sh = push ? halo_push_shift(hp, q) : 0;
     if (all_aligned16<NV>(n, vs, w)) {
         double2 *w2 = reinterpret_cast<double2 *>(w);
         for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (n >> 1);
@@ -865,16 +938,20 @@ k_gm_orth_scale(long long n, VecList vs, int off, int do_scale,
             s.x *= sc;
             s.y *= sc;
             w2[e] = s;
+            if (push) halo_push2(hp, sh, e, s);
         }
-        return;
-    }
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
-         e += (long long)gridDim.x * blockDim.x) {
-        double s = w[e];
+    } else {
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+             e += (long long)gridDim.x * blockDim.x) {
+            double s = w[e];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) s = fma(-hh[i], __ldg(vs.v[i] + e), s);
-        w[e] = s * sc;
+            for (int i = 0; i < NV; ++i) s = fma(-hh[i], __ldg(vs.v[i] + e), s);
+            s *= sc;
+            w[e] = s;
+            if (push) halo_push1(hp, sh, e, s);
+        }
     }
+    if (push) halo_push_publish(hp, q);
 }
 
 // r = sign*rhs - Ax (in place in ax) with the partial sums of <r,r>

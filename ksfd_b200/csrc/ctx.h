@@ -92,7 +92,11 @@ struct ksfd_ctx {
     bool p2p_on = false;
     // device-side exchange counters: [0..3] halo slots, [4] all-reduce
     unsigned long long *p2p_ctr = nullptr;
-    unsigned *p2p_done = nullptr;
+    unsigned *p2p_done = nullptr;           // [0] exchange kernels, [1] fused producer pushes
+    // Krylov vector whose boundary planes were pushed by the kernel that produced it
+    // (consumed by the next jvp_impl on that vector; host-side bookkeeping only)
+    const double *pushed_vec = nullptr;
+    bool gm_no_push = false;
     int *p2p_err = nullptr, *p2p_err_dev = nullptr;    // pinned + mapped: a peer wait timed out
     // Jacobian state
     double *coef = nullptr;      // ghosted (nloc+4 planes) x (dof+2)
@@ -153,6 +157,10 @@ struct TmaSrc {
     int wrap = 1;
     const unsigned long long *par = nullptr;    // device-side exchange counter (parity)
     int parshift = 0;               // fields between the two parity buffers
+    // peer-memory exchange: flag words the neighbours publish, error words
+    const volatile unsigned long long *flag_lo = nullptr, *flag_hi = nullptr;
+    volatile int *err = nullptr;
+    volatile unsigned long long *dead = nullptr;
 };
 struct HostVec {
     VecRef r;

@@ -87,15 +87,6 @@ struct Geom {
 };
 
 // A vector plus its ghost planes along the last axis.
-// Deferred halo wait (experimental, compiled out: -DKSFD_HALO_DEFER=1 and
-// KSFD_HALO_DEFER=1 in the environment): the halo-exchange kernel of the J.v
-// operand only pushes and publishes its flags; the marching kernel waits for the
-// neighbours' flags itself, and only in the CTAs that read ghost planes
-// (plane_of), so that the NVLink round trip hides behind the interior planes.
-#ifndef KSFD_HALO_DEFER
-#define KSFD_HALO_DEFER 0
-#endif
-
 struct VecRef {
     const double *base;         // plane 0 .. nloc-1
     const double *lo;           // planes -2, -1
@@ -104,31 +95,7 @@ struct VecRef {
     // exchange counter: the ghost planes live at lo/hi + (*par & 1) * pstride
     const unsigned long long *par;
     long long pstride;
-#if KSFD_HALO_DEFER
-    // wait until *flag >= *par before reading lo / hi (nullptr: already complete)
-    const volatile unsigned long long *flag_lo, *flag_hi;
-    volatile int *err;
-#endif
 };
-
-#if KSFD_HALO_DEFER
-// bounded spin (as p2p_spin): a dead peer raises the host-visible error word
-__device__ __forceinline__ void halo_wait(const volatile unsigned long long *flag, const VecRef &v)
-{
-    if (!flag) return;
-    const unsigned long long q = *reinterpret_cast<const volatile unsigned long long *>(v.par);
-    const long long t0 = clock64();
-    unsigned spins = 0;
-    while (*flag < q) {
-        __nanosleep(32);
-        if ((++spins & 0xfff) == 0 && clock64() - t0 > 60000000000ll) {
-            if (v.err) *v.err = 1;
-            break;
-        }
-    }
-    __threadfence_system();
-}
-#endif
 
 __device__ __forceinline__ long long ghost_shift(const VecRef &v)
 {

@@ -316,10 +316,6 @@ static VecRef make_ref(const ksfd_ctx *c, const double *base, int stride, int sl
     r.base = base;
     r.par = nullptr;
     r.pstride = 0;
-#if KSFD_HALO_DEFER
-    r.flag_lo = r.flag_hi = nullptr;
-    r.err = nullptr;
-#endif
     const long long ps = c->g.plane_pts * stride;
     if (c->nranks == 1) {
         r.lo = base + (long long)(c->g.nloc - KSFD_SW) * ps;
@@ -358,6 +354,13 @@ static HostVec make_hvec(const ksfd_ctx *c, const double *base, int stride, int 
         t.khi = (int)(KSFD_SW * hp);
         t.par = c->p2p_ctr + slot;
         t.parshift = (int)(2 * KSFD_SW * hp);
+        // the marcher waits for the neighbours' flags itself (already satisfied when the
+        // exchange was made by k_halo_xchg, which waits)
+        typedef const volatile unsigned long long *cflag_t;
+        t.flag_lo = reinterpret_cast<cflag_t>(c->p2p_mine) + slot * 2 + 0;
+        t.flag_hi = reinterpret_cast<cflag_t>(c->p2p_mine) + slot * 2 + 1;
+        t.err = c->p2p_err_dev;
+        t.dead = c->p2p_ctr + KSFD_HALO_SLOTS + 1;
     } else {
         t.wrap = 0;
         t.halo = c->halo[slot];
@@ -446,16 +449,18 @@ __global__ void k_halo_xchg(const double *__restrict__ top, const double *__rest
     }
 }
 
-#if KSFD_HALO_DEFER
-// push-only variant: the consumer (k_march, halo_wait in plane_of) waits for the flags
+// push-only variant: the consumer (the TMA-fed marcher, tma_march.cuh: halo_arrived) waits
+// for the flags in the CTAs that read ghost planes
 __global__ void k_halo_push(const double *__restrict__ top, const double *__restrict__ bot,
                             long long cnt, double *__restrict__ up_lo0,
                             double *__restrict__ dn_hi0, long long pstride,
                             volatile unsigned long long *up_flag_lo,
                             volatile unsigned long long *dn_flag_hi, unsigned long long *ctr,
-                            unsigned *done, const int *__restrict__ skip)
+                            unsigned *done, const int *__restrict__ skip,
+                            const volatile unsigned long long *dead)
 {
     if (skip && *skip) return;
+    if (*dead) return;
     const unsigned long long q = *ctr + 1;
     const long long sh = (long long)(q & 1ull) * pstride;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < cnt;
@@ -476,7 +481,7 @@ __global__ void k_halo_push(const double *__restrict__ top, const double *__rest
         }
     }
 }
-#endif
+
 
 extern "C" int ksfd_p2p_export(ksfd_ctx *c, char handle_out[64])
 {
@@ -486,8 +491,8 @@ extern "C" int ksfd_p2p_export(ksfd_ctx *c, char handle_out[64])
     if (!c->p2p_mine) {
         CK(cudaMalloc(&c->p2p_mine, sizeof(double) * p2p_total_doubles(c)));
         CK(cudaMemset(c->p2p_mine, 0, sizeof(double) * KSFD_P2P_FLAGS));
-        CK(cudaMalloc(&c->p2p_done, sizeof(unsigned)));
-        CK(cudaMemset(c->p2p_done, 0, sizeof(unsigned)));
+        CK(cudaMalloc(&c->p2p_done, 2 * sizeof(unsigned)));
+        CK(cudaMemset(c->p2p_done, 0, 2 * sizeof(unsigned)));
         CK(cudaHostAlloc(&c->p2p_err, sizeof(int), cudaHostAllocMapped));
         *c->p2p_err = 0;
         CK(cudaHostGetDevicePointer(&c->p2p_err_dev, c->p2p_err, 0));
@@ -540,22 +545,44 @@ static int exchange_p2p(ksfd_ctx *c, const double *vec, int stride, int slot, cu
     flag_t my_flag_lo = reinterpret_cast<flag_t>(c->p2p_mine) + slot * 2 + 0;
     flag_t my_flag_hi = reinterpret_cast<flag_t>(c->p2p_mine) + slot * 2 + 1;
     const unsigned blocks = (unsigned)std::min<size_t>((cnt + 255) / 256, 64);
-#if KSFD_HALO_DEFER
     if (defer) {
+        // the consumer is the TMA-fed marcher: push only, it waits where it reads ghosts
         k_halo_push<<<blocks, 256, 0, st>>>(top, vec, (long long)cnt, up_lo0, dn_hi0,
                                             (long long)p2p_buf_doubles(c), up_flag_lo, dn_flag_hi,
-                                            c->p2p_ctr + slot, c->p2p_done, skip);
+                                            c->p2p_ctr + slot, c->p2p_done, skip,
+                                            c->p2p_ctr + KSFD_HALO_SLOTS + 1);
         CKL();
         return 0;
     }
-#endif
-    (void)defer;
     k_halo_xchg<<<blocks, 256, 0, st>>>(top, vec, (long long)cnt, up_lo0, dn_hi0,
                                         (long long)p2p_buf_doubles(c), up_flag_lo, dn_flag_hi,
                                         my_flag_lo, my_flag_hi, c->p2p_ctr + slot, c->p2p_done,
                                         skip, c->p2p_err_dev, c->p2p_ctr + KSFD_HALO_SLOTS + 1);
     CKL();
     return 0;
+}
+
+// Fused producer push (blas1_kernels.cuh: HaloPush) of a dof-strided vector into halo slot
+// `slot`; an all-null descriptor when this context does not push (one rank, NCCL
+// fallback, or a consumer that is not the TMA-fed marcher)
+static bool tma_consumer(const ksfd_ctx *c);
+static HaloPush make_push(const ksfd_ctx *c, int slot)
+{
+    HaloPush hp{};
+    if (c->nranks == 1 || !c->p2p_on || !tma_consumer(c) || c->gm_no_push) return hp;
+    const long long n = nlocal(c);
+    typedef volatile unsigned long long *flag_t;
+    hp.up_lo0 = p2p_buf(c, c->p2p_up, slot, 0);
+    hp.dn_hi0 = p2p_buf(c, c->p2p_dn, slot, 0) + KSFD_SW * c->halo_plane_doubles;
+    hp.pstride = (long long)p2p_buf_doubles(c);
+    hp.cnt = (long long)KSFD_SW * c->g.plane_pts * c->dof;
+    hp.top0 = n - hp.cnt;
+    hp.up_flag_lo = reinterpret_cast<flag_t>(c->p2p_up) + slot * 2 + 0;
+    hp.dn_flag_hi = reinterpret_cast<flag_t>(c->p2p_dn) + slot * 2 + 1;
+    hp.ctr = c->p2p_ctr + slot;
+    hp.done = c->p2p_done + 1;              // own block counter (p2p_done[0]: exchange kernels)
+    hp.dead = c->p2p_ctr + KSFD_HALO_SLOTS + 1;
+    return hp;
 }
 
 static int exchange(ksfd_ctx *c, const double *vec, int stride, int slot,
@@ -648,6 +675,8 @@ void ksfd_invalidate_plans(ksfd_ctx *c)
     if (c->plan_cache) static_cast<PlanMap *>(c->plan_cache)->clear();
 }
 
+static bool use_march(const ksfd_ctx *c);
+static bool tma_consumer(const ksfd_ctx *c) { return use_march(c) && ksfd_use_tma(c); }
 static bool use_march(const ksfd_ctx *c)
 {
     if (c->variant == 1) return false;
@@ -705,7 +734,7 @@ extern "C" int ksfd_from_internal(ksfd_ctx *c, const double *in, double *ref, in
 static int residual_impl(ksfd_ctx *c, const double *u, const double *udot,
                          const double *src, double *f, cudaStream_t st)
 {
-    TRY(exchange(c, u, c->dof, 0, st));
+    TRY(exchange(c, u, c->dof, 0, st, nullptr, c->p2p_on && tma_consumer(c)));
     const HostVec uh = make_hvec(c, u, c->dof, 0);
     if (use_march(c)) {
         return c->dim == 2 ? ksfd_march_residual_d2(c, uh, udot, src, f, st)
@@ -728,7 +757,7 @@ extern "C" int ksfd_residual(ksfd_ctx *c, const double *u, const double *udot,
 static int velocity_impl(ksfd_ctx *c, const double *u, double *vel, double *vmax,
                          cudaStream_t st)
 {
-    TRY(exchange(c, u, c->dof, 0, st));
+    TRY(exchange(c, u, c->dof, 0, st, nullptr, c->p2p_on && tma_consumer(c)));
     const HostVec uh = make_hvec(c, u, c->dof, 0);
     if (vmax) CK(cudaMemsetAsync(vmax, 0, sizeof(double) * c->dim, st));
     if (use_march(c)) {
@@ -762,10 +791,6 @@ static VecRef coef_ref(const ksfd_ctx *c)
     VecRef r;
     r.par = nullptr;
     r.pstride = 0;
-#if KSFD_HALO_DEFER
-    r.flag_lo = r.flag_hi = nullptr;
-    r.err = nullptr;
-#endif
     r.lo = c->coef;
     r.base = c->coef + KSFD_SW * ps;
     r.hi = c->coef + (long long)(KSFD_SW + c->g.nloc) * ps;
@@ -838,27 +863,21 @@ static int jvp_impl(ksfd_ctx *c, const double *v, double *out, bool precond,
 {
     if (!c->have_jac) return fail("ksfd_jvp_setup has not been called");
     if (v == out) return fail("ksfd_jvp: in-place application is not supported");
-#if KSFD_HALO_DEFER
-    // experimental: push only; the marching kernel waits where it reads ghost planes
-    static const bool defer_env = getenv("KSFD_HALO_DEFER") && atoi(getenv("KSFD_HALO_DEFER")) != 0;
-    const bool defer = defer_env && c->p2p_on && c->nranks > 1 && use_march(c);
-#else
-    const bool defer = false;
-#endif
-    TRY(exchange(c, v, c->dof, 1, st, skip, defer));
+    // several ranks over peer memory + TMA-fed marcher: nobody waits for the halo on the
+    // stream.  Either the producer of v already pushed its boundary planes (Krylov
+    // vectors: fused into k_gm_first_vector / k_gm_orth_scale, c->pushed_vec), or a
+    // push-only kernel goes out; the marcher waits in the CTAs that read ghost planes.
+    const bool defer = c->p2p_on && c->nranks > 1 && tma_consumer(c);
+    if (defer && v == c->pushed_vec) {
+        c->pushed_vec = nullptr;            // consumed: pushed by its producer
+    } else {
+        TRY(exchange(c, v, c->dof, 1, st, skip, defer));
+    }
     HostVec vh = make_hvec(c, v, c->dof, 1);
     const HostVec ph = make_hvec(c, c->pc, 1, 2);
     const HostVec ch = coef_hvec(c);
     VecRef &vr = vh.r;
     const VecRef &pr = ph.r, &cr = ch.r;
-#if KSFD_HALO_DEFER
-    if (defer) {
-        typedef const volatile unsigned long long *cflag_t;
-        vr.flag_lo = reinterpret_cast<cflag_t>(c->p2p_mine) + 1 * 2 + 0;     // slot 1
-        vr.flag_hi = reinterpret_cast<cflag_t>(c->p2p_mine) + 1 * 2 + 1;
-        vr.err = c->p2p_err_dev;
-    }
-#endif
     if (use_march(c)) {
         return c->dim == 2 ? ksfd_march_jvp_d2(c, ch, vh, ph, precond, out, skip, st)
                            : ksfd_march_jvp_d3(c, ch, vh, ph, precond, out, skip, st);
@@ -1665,8 +1684,15 @@ template <int NV>
 static int gm_orth_launch(ksfd_ctx *c, const VecList &vl, int off, int do_scale, double *w,
                           cudaStream_t st)
 {
+    // the launch that finishes the new basis vector also pushes its boundary planes to
+    // the neighbours (the vector is the operand of the next J.v)
+    HaloPush hp{};
+    if (do_scale) {
+        hp = make_push(c, 1);
+        if (hp.up_lo0) c->pushed_vec = w;
+    }
     KSFD_KLAUNCH((k_gm_orth_scale<NV>), KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st, nlocal(c), vl, off,
-                 do_scale, c->gm, c->gmi, w);
+                 do_scale, c->gm, c->gmi, w, hp);
     CKL();
     return 0;
 }
@@ -1785,6 +1811,8 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
     InvD id;
     for (int l = 0; l < KSFD_MAX_LIGANDS; ++l) id.v[l] = c->invd[l];
 
+    c->pushed_vec = nullptr;
+    c->gm_no_push = pcm == 2;       // the spectral preconditioner sits between V_j and the stencil pass
     // the previous solve on this context has been waited for (see the end of
     // this function), so the status block is ours
     hs->seq = 0;
@@ -1798,7 +1826,7 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
         double sign = rhs_sign;
         // one rank: the block that finishes the <r,r> reduction last also starts
         // the cycle (no separate one-block launch)
-        const bool fuse_begin = c->nranks == 1;
+        const bool fuse_begin = c->nranks == 1 || c->p2p_on;
         GmBegin gb{KSFD_RED_BLOCKS, c->partial, c->gm, c->gmi, hsd, cycle, go, p2p_red(c),
                    c->gm_done};
         if (cycle == 0) {
@@ -1840,8 +1868,13 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
             k_gm_cycle_begin<<<1, 32, 0, st>>>(g1);
             CKL();
         }
-        KSFD_KLAUNCH(k_gm_first_vector, KSFD_RED_BLOCKS, 256, 0, st, n, r, c->gm, c->gmi, sign, V);
-        CKL();
+        {
+            const HaloPush hp = make_push(c, 1);
+            if (hp.up_lo0) c->pushed_vec = V;
+            KSFD_KLAUNCH(k_gm_first_vector, KSFD_RED_BLOCKS, 256, 0, st, n, r, c->gm, c->gmi, sign, V,
+                         hp);
+            CKL();
+        }
         const int seq = 2 * cycle + 1;
         if (free_running) {
             for (int j = 0; j < m; ++j) {

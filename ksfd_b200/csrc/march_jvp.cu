@@ -29,10 +29,10 @@ static int launch_jvp_p(ksfd_ctx *c, const HostVec &coef, const HostVec &v, cons
 #endif
     }
 #if KSFD_MARCH_DIM == 2
-    return launch_op<DIM, JvpOp<DIM, NLIG, PRECOND>, true, 0, 124, 1, 4, 252, 1, 2>(
+    return launch_op<DIM, JvpOp<DIM, NLIG, PRECOND>, true, 124, 1, 4, 252, 1, 2>(
         c, op, PRECOND ? 2 : 3, cstage, cemit, skip, st);
 #else
-    return launch_op<DIM, JvpOp<DIM, NLIG, PRECOND>, true, 0, 32, 8, 1, 16, 16, 1>(
+    return launch_op<DIM, JvpOp<DIM, NLIG, PRECOND>, true, 32, 8, 1, 16, 16, 1>(
         c, op, PRECOND ? 2 : 3, cstage, cemit, skip, st);
 #endif
 }

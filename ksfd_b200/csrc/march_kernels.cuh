@@ -39,18 +39,6 @@
 #include "device_common.cuh"
 #include "fastmath.cuh"
 
-// Experimental code paths, compiled in only by the stand-alone tuner
-// (scripts/tune_march.cu -DKSFD_MARCH_VARIANT=bits); the library builds with 0.
-//   bit 0: policies with STAGE_FIRST stage from the prefetch registers before refilling
-//          them (see Marcher::step).  Measured (profiles/r01_tuner_variant_stage_first.txt,
-//          bit-identical outputs): residual +3 %, J.v -2 % => residual / velocity only.
-//   bit 1: column clusters (ClusterMarcher at the end of this file)
-//   bit 2: register prefetch TWO planes deep (pre, pre2): twice the bytes in flight per
-//          thread for NPRE more doubles of registers (pair with a lower MINB)
-#ifndef KSFD_MARCH_VARIANT
-#define KSFD_MARCH_VARIANT 0
-#endif
-
 // uniform launch parameters (32-bit: a rank-local vector has < 2^31 elements,
 // checked on the host)
 struct MarchArgs {
@@ -95,10 +83,6 @@ struct SmemTabs {
 __device__ __forceinline__ const double *plane_of(const VecRef &v, int k, int nloc,
                                                   int ps)
 {
-#if KSFD_HALO_DEFER
-    if (k < 0) halo_wait(v.flag_lo, v);
-    if (k >= nloc) halo_wait(v.flag_hi, v);
-#endif
     if (k < 0) return v.lo + ghost_shift(v) + (k + KSFD_SW) * (long long)ps;
     if (k >= nloc) return v.hi + ghost_shift(v) + (k - nloc) * (long long)ps;
     return v.base + k * (long long)ps;
@@ -123,32 +107,11 @@ struct InCursor {
     }
 };
 
-// Where the loads of a plane go.  RegSink: straight into registers (__ldg).
-// AsyncSink: cp.async into this lane's column of a shared-memory pipeline slot
-// (several planes in flight per thread without holding registers; the values
-// are read back by the same thread after cp.async.wait_group).
+// the loads of a plane go straight into registers (read-only path)
 struct RegSink {
     double *r;
     __device__ __forceinline__ void put(int c, const double *p) const { r[c] = __ldg(p); }
 };
-struct AsyncSink {
-    unsigned addr;              // shared-space byte address of field 0 of this lane
-    int stride;                 // bytes between fields
-    __device__ __forceinline__ void put(int c, const double *p) const
-    {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(addr + c * stride), "l"(p)
-                     : "memory");
-    }
-};
-__device__ __forceinline__ void cp_async_commit()
-{
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
-{
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 
 // stencil access of one interior lane at emit time.  PH = phase of the
 // unrolled plane loop: plane kk (newest) sits in q[.][PH], plane kk-4+s in
@@ -285,7 +248,6 @@ struct ResidualOp {
     static constexpr int NAUX = NLIG + 1;      // udot of the output plane
     static constexpr bool HAS_AUX = true;
     static constexpr bool TABS = true;
-    static constexpr bool STAGE_FIRST = (KSFD_MARCH_VARIANT & 1) != 0;
     static constexpr bool JACOBIAN = false;     // runs on the current physics (ctx.P)
     // input vectors of the TMA-fed marcher (tma_march.cuh): u
     static constexpr int NIN = 1;
@@ -317,18 +279,6 @@ struct ResidualOp {
 #pragma unroll
         for (int c = 0; c < NLIG + 1; ++c) sink.put(c, st.in.p + c * g.fs);
         st.in.next(u, k, g.nloc, g.fs * (NLIG + 1), poff);
-    }
-    // (cluster variant) load the plane under the cursor without moving it; move it by d planes
-    template <class Sink>
-    __device__ __forceinline__ void load_here(const MarchArgs &g, const State &st,
-                                              const Sink &sink) const
-    {
-#pragma unroll
-        for (int c = 0; c < NLIG + 1; ++c) sink.put(c, st.in.p + c * g.fs);
-    }
-    __device__ __forceinline__ void move_by(const MarchArgs &g, State &st, int d) const
-    {
-        st.in.p += (long long)d * (g.fs * (NLIG + 1));
     }
     // udot of output plane ko (element index e of this lane), fields [off, off+NAUX)
     template <class Sink>
@@ -407,7 +357,6 @@ struct JvpOp {
     static constexpr int NAUX = 1;
     static constexpr bool HAS_AUX = false;
     static constexpr bool TABS = false;
-    static constexpr bool STAGE_FIRST = false;
     static constexpr bool JACOBIAN = true;      // runs on the physics of the linearisation (ctx.Pjac)
     // input vectors of the TMA-fed marcher (tma_march.cuh): coef, v, pc
     static constexpr int NIN = PRECOND ? 3 : 2;
@@ -447,23 +396,6 @@ struct JvpOp {
         st.ic.next(coef, k, g.nloc, g.fs * (NLIG + 3), poff);
         st.iv.next(v, k, g.nloc, g.fs * (NLIG + 1), poff);
         if (PRECOND) st.ip.next(pc, k, g.nloc, g.fs, poff);
-    }
-    // (cluster variant) load the plane under the cursors without moving them; move them
-    template <class Sink>
-    __device__ __forceinline__ void load_here(const MarchArgs &g, const State &st,
-                                              const Sink &sink) const
-    {
-#pragma unroll
-        for (int c = 0; c < NLIG + 3; ++c) sink.put(c, st.ic.p + c * g.fs);
-#pragma unroll
-        for (int c = 0; c < NLIG + 1; ++c) sink.put(NLIG + 3 + c, st.iv.p + c * g.fs);
-        if (PRECOND) sink.put(2 * NLIG + 4, st.ip.p);
-    }
-    __device__ __forceinline__ void move_by(const MarchArgs &g, State &st, int d) const
-    {
-        st.ic.p += (long long)d * (g.fs * (NLIG + 3));
-        st.iv.p += (long long)d * (g.fs * (NLIG + 1));
-        if (PRECOND) st.ip.p += (long long)d * g.fs;
     }
     template <class Sink>
     __device__ __forceinline__ void load_aux(const MarchArgs &, int, int, const Sink &) const {}
@@ -534,7 +466,6 @@ struct VelocityOp {
     static constexpr int NAUX = 1;
     static constexpr bool HAS_AUX = false;
     static constexpr bool TABS = true;
-    static constexpr bool STAGE_FIRST = (KSFD_MARCH_VARIANT & 1) != 0;
     static constexpr bool JACOBIAN = false;
     static constexpr int NIN = 1;
     __host__ __device__ static constexpr int nc(int) { return NLIG + 1; }
@@ -609,35 +540,25 @@ struct VelocityOp {
 };
 
 // ---------------------------------------------------------------------------
-// The marching skeleton
+// The marching skeleton (register-prefetch version: the fallback of the TMA-fed
+// marcher of tma_march.cuh, e.g. for odd grid extents)
 // ---------------------------------------------------------------------------
 // UNR: unroll the plane loop five times (queue rotates by register renaming);
 // otherwise the queue is shifted with moves (smaller code, fewer registers).
-// DEPTH: 0 = the next plane is prefetched into registers (one plane in flight);
-// 3 = planes are fetched with cp.async into a 4-slot shared-memory pipeline per
-// lane, three planes in flight and no registers held across iterations (a CTA
-// handling few planes is otherwise bound by one DRAM round trip per plane).
-// The auxiliary fields of the OUTPUT plane (udot of plane kk-2) travel in the
-// group of plane kk.
-template <int DIM, int TX, int TY, class Op, bool UNR, int DEPTH>
+// The next plane is prefetched into registers while the current one is staged.
+template <int DIM, int TX, int TY, class Op, bool UNR>
 struct Marcher {
     using T = TileT<DIM, TX, TY>;
     static constexpr int NF = Op::NF, NPRE = Op::NPRE, NAUX = Op::NAUX;
-    static constexpr int RING = 2 * NF * T::SP;     // doubles; tables follow, then the pipeline
-    static constexpr int TABS = Op::TABS ? KSFD_TAB_DOUBLES : 0;
-    static constexpr int NIN = NPRE + (Op::HAS_AUX ? NAUX : 0);
-    static constexpr int NSLOT = DEPTH + 1;
-    static constexpr int PIPE = RING + TABS;        // index of the pipeline in ksfd_smem
+    static constexpr int RING = 2 * NF * T::SP;     // doubles; the tables follow
     const MarchArgs &g;
     const DevPhys &P;
     const Op &op;
     double q[NF][5];
-    double pre[DEPTH == 0 ? NPRE : 1];
-    double pre2[(DEPTH == 0 && (KSFD_MARCH_VARIANT & 4)) ? NPRE : 1];
+    double pre[NPRE];
     double aux[NAUX];
     typename Op::State st;
-    int poff, spos, k0, k1, it, e_aux;
-    unsigned pipe_addr;         // shared byte address of pipeline slot 0, field 0, this lane
+    int poff, spos, k0, k1, e_aux;
     bool active, emits;
 
     __device__ __forceinline__ Marcher(const MarchArgs &g_, const DevPhys &P_, const Op &op_)
@@ -651,7 +572,6 @@ struct Marcher {
                     (long long)(i < 256 ? g_log_tab[i] : g_exp_tab[i - 256]));
             __syncthreads();
         }
-        pipe_addr = (unsigned)__cvta_generic_to_shared(ksfd_smem + PIPE + tid);
         const int i0 = blockIdx.x * g.ox;
         int x, y = 0;               // tile-relative position incl. halo
         bool interior;
@@ -692,78 +612,27 @@ struct Marcher {
         }
         k0 = blockIdx.z * g.rz;
         k1 = min(k0 + g.rz, g.nloc);
-        it = 0;
 #pragma unroll
         for (int f = 0; f < NF; ++f)
 #pragma unroll
             for (int s = 0; s < 5; ++s) q[f][s] = 0.0;
     }
 
-    // fetch plane k (and the aux fields of output plane k-2) into pipeline slot
-    // `slot`; always commits a group so that group counting stays uniform
-    __device__ __forceinline__ void issue(int k, int slot)
-    {
-        if (k < k1 + KSFD_SW) {
-            AsyncSink sink{pipe_addr + (unsigned)(slot * NIN * T::NT * 8), T::NT * 8};
-            if (active) op.load(g, st, k, poff, sink);
-            if (Op::HAS_AUX && emits && k - KSFD_SW >= k0) {
-                op.load_aux(g, e_aux, NPRE, sink);
-                e_aux += Op::out_fields(DIM) * g.fs;
-            }
-        }
-        cp_async_commit();
-    }
-
     template <int PH>
     __device__ __forceinline__ void step(int kk)
     {
         double cur[NPRE];
-        if (DEPTH == 0 && (KSFD_MARCH_VARIANT & 4)) {
-            // stage from pre, pre <- pre2, refill pre2 with plane kk+2
-            if (active) {
-                double f[NF];
-                op.stage(P, SmemTabs<RING>(), pre, f);
 #pragma unroll
-                for (int c = 0; c < NF; ++c) q[c][PH] = f[c];
-#pragma unroll
-                for (int c = 0; c < NPRE; ++c) pre[c] = pre2[c];
-                if (kk + 2 < k1 + KSFD_SW) op.load(g, st, kk + 2, poff, RegSink{pre2});
-            }
-        } else if (DEPTH == 0 && Op::STAGE_FIRST) {
-            // experimental (tuner only): stage straight from the prefetch registers,
-            // then refill them — no register copy of the plane (18 moves per plane in
-            // the 2-D J.v kernel), the prefetch goes out one stage later
-            if (active) {
-                double f[NF];
-                op.stage(P, SmemTabs<RING>(), pre, f);
-#pragma unroll
-                for (int c = 0; c < NF; ++c) q[c][PH] = f[c];
-                if (kk + 1 < k1 + KSFD_SW) op.load(g, st, kk + 1, poff, RegSink{pre});
-            }
-        } else if (DEPTH == 0) {
-#pragma unroll
-            for (int c = 0; c < NPRE; ++c) cur[c] = pre[c];
-            if (active && kk + 1 < k1 + KSFD_SW) op.load(g, st, kk + 1, poff, RegSink{pre});
-        } else {
-            cp_async_wait<DEPTH - 1>();             // the group of plane kk has landed
-            const int base = PIPE + (it & (NSLOT - 1)) * NIN * T::NT + threadIdx.x;
-#pragma unroll
-            for (int c = 0; c < NPRE; ++c) cur[c] = ksfd_smem[base + c * T::NT];
-            if (Op::HAS_AUX) {
-#pragma unroll
-                for (int c = 0; c < NAUX; ++c) aux[c] = ksfd_smem[base + (NPRE + c) * T::NT];
-            }
-            issue(kk + DEPTH, (it + DEPTH) & (NSLOT - 1));
-            ++it;
-        }
-        if (active && !(DEPTH == 0 && (Op::STAGE_FIRST || (KSFD_MARCH_VARIANT & 4)))) {
+        for (int c = 0; c < NPRE; ++c) cur[c] = pre[c];
+        if (active && kk + 1 < k1 + KSFD_SW) op.load(g, st, kk + 1, poff, RegSink{pre});
+        if (active) {
             double f[NF];
             op.stage(P, SmemTabs<RING>(), cur, f);
 #pragma unroll
             for (int c = 0; c < NF; ++c) q[c][PH] = f[c];
         }
         if (kk - KSFD_SW >= k0) {                       // uniform over the CTA
-            if (DEPTH == 0 && Op::HAS_AUX && emits) {
+            if (Op::HAS_AUX && emits) {
                 // after the register-hungry stage; the barrier wait hides some latency
                 op.load_aux(g, e_aux, 0, RegSink{aux});
                 e_aux += Op::out_fields(DIM) * g.fs;
@@ -784,19 +653,11 @@ struct Marcher {
 
     __device__ __forceinline__ void run()
     {
-        static_assert(DEPTH == 0 || (NSLOT & (NSLOT - 1)) == 0, "pipeline slots: power of two");
         int kk = k0 - KSFD_SW;
         const int kend = k1 + KSFD_SW;
         op.init(g, st, kk, k0, poff);
         e_aux = k0 * Op::out_fields(DIM) * g.fs + poff;
-        if (DEPTH == 0) {
-            if (active) op.load(g, st, kk, poff, RegSink{pre});
-            if ((KSFD_MARCH_VARIANT & 4) && active && kk + 1 < kend)
-                op.load(g, st, kk + 1, poff, RegSink{pre2});
-        } else {
-#pragma unroll
-            for (int d = 0; d < DEPTH; ++d) issue(kk + d, d);
-        }
+        if (active) op.load(g, st, kk, poff, RegSink{pre});
         if (!UNR) {
             for (; kk < kend; ++kk) {
                 step<4>(kk);
@@ -820,20 +681,17 @@ struct Marcher {
                 if (++kk >= kend) break;
             }
         }
-        if (DEPTH > 0) cp_async_wait<0>();
         op.finish(st);
     }
 };
 
-template <class Op, int SP, int NT, int DEPTH>
+template <class Op, int SP>
 constexpr size_t march_smem_bytes()
 {
-    return sizeof(double) * (2 * Op::NF * SP + (Op::TABS ? KSFD_TAB_DOUBLES : 0) +
-                             (DEPTH > 0 ? (DEPTH + 1) * (Op::NPRE + (Op::HAS_AUX ? Op::NAUX : 0)) * NT
-                                        : 0));
+    return sizeof(double) * (2 * Op::NF * SP + (Op::TABS ? KSFD_TAB_DOUBLES : 0));
 }
 
-template <int DIM, int TX, int TY, class Op, int MINB, bool UNR, int DEPTH>
+template <int DIM, int TX, int TY, class Op, int MINB, bool UNR>
 __global__ void __launch_bounds__(TileT<DIM, TX, TY>::NT, MINB)
 k_march(const __grid_constant__ MarchArgs g, const __grid_constant__ DevPhys P,
         const __grid_constant__ Op op, const int *__restrict__ skip)
@@ -841,212 +699,6 @@ k_march(const __grid_constant__ MarchArgs g, const __grid_constant__ DevPhys P,
     KSFD_PDL_ENTER();
     // pipelined Krylov solver: launched ahead of the convergence test
     if (skip && KSFD_FLAG(skip)) return;
-    Marcher<DIM, TX, TY, Op, UNR, DEPTH> m(g, P, op);
+    Marcher<DIM, TX, TY, Op, UNR> m(g, P, op);
     m.run();
 }
-
-
-#if KSFD_MARCH_VARIANT & 2
-// ---------------------------------------------------------------------------
-// Experimental (tuner only): column clusters.  The CTAs that own consecutive
-// chunks of the marching axis form a thread-block cluster (1,1,CZ), CZ even.
-// Neighbouring chunks march in OPPOSITE directions (even cluster rank: down,
-// odd: up), so that two neighbours either both START or both END at their
-// common boundary, and the two staged planes each needs from beyond that
-// boundary are read from the neighbour's shared memory (distributed shared
-// memory) instead of being staged a second time: a CTA stages rz planes, not
-// rz+4 (the two CTAs at the ends of a cluster: rz+2).  The stencil code is
-// untouched: the queue is kept in MARCH order, and first derivatives along the
-// marching axis only enter the residual and J.v as products of two of them
-// (grad a . grad b), which are invariant — bit for bit — under the reversal.
-// (VelocityOp needs the sign and is not supported.)
-//   prologue : stage own planes 0,1 (march order), export them, cluster.sync,
-//              import the start partner's planes 0,1 as my planes -1,-2
-//   steps    : own planes 2 .. n-1 as in Marcher::step (prefetch one ahead)
-//   epilogue : export my planes n-1,n-2, cluster.sync, my planes n,n+1 are the
-//              end partner's n'-1,n'-2 (or, at a cluster end, two real halo
-//              planes staged from global memory); final cluster.sync before exit.
-// Shared memory: ring, tables, then two export areas [2][NF][NT].
-// ---------------------------------------------------------------------------
-#include <cooperative_groups.h>
-namespace ksfd_cg = cooperative_groups;
-
-template <int DIM, int TX, int TY, class Op, bool UNR>
-struct ClusterMarcher : Marcher<DIM, TX, TY, Op, UNR, 0> {
-    using B = Marcher<DIM, TX, TY, Op, UNR, 0>;
-    using T = typename B::T;
-    static constexpr int NF = Op::NF, NPRE = Op::NPRE;
-    static constexpr int EXPS = B::RING + B::TABS;              // start export
-    static constexpr int EXPE = EXPS + 2 * NF * T::NT;          // end export
-    int n_own, dir;
-    const double *rem_end;          // the end partner's export area (nullptr at a cluster end)
-
-    __device__ __forceinline__ ClusterMarcher(const MarchArgs &g_, const DevPhys &P_, const Op &op_)
-        : B(g_, P_, op_) {}
-
-    template <int PH>
-    __device__ __forceinline__ void emit_plane(int i)
-    {
-        // the centre plane (march index i-2) goes to a ring slot, then the stencil
-        const int ri = (i & 1) * (NF * T::SP) + this->spos;
-        if (Op::HAS_AUX && this->emits) {
-            this->op.load_aux(this->g, this->e_aux, 0, RegSink{this->aux});
-            this->e_aux += dir * (Op::out_fields(DIM) * this->g.fs);
-        }
-        if (this->active) {
-#pragma unroll
-            for (int c = 0; c < NF; ++c) ksfd_smem[ri + c * T::SP] = this->q[c][(PH + 3) % 5];
-        }
-        __syncthreads();
-        if (this->emits) {
-            LaneAcc<DIM, NF, T::SP, T::SY, PH> a(this->q, ri);
-            this->op.emit(this->P, this->g, a, this->aux, this->st);
-        }
-        this->st.e += dir * (Op::out_fields(DIM) * this->g.fs);
-    }
-
-    // march index i >= 2: plane i enters the queue at phase PH, plane i-2 is emitted
-    template <int PH>
-    __device__ __forceinline__ void step(int i)
-    {
-        auto cluster = ksfd_cg::this_cluster();
-        if (i < n_own) {
-            double cur[NPRE];
-#pragma unroll
-            for (int c = 0; c < NPRE; ++c) cur[c] = this->pre[c];
-            if (this->active && i + 1 < n_own) {
-                this->op.load_here(this->g, this->st, RegSink{this->pre});
-                this->op.move_by(this->g, this->st, dir);
-            }
-            if (this->active) {
-                double f[NF];
-                this->op.stage(this->P, SmemTabs<B::RING>(), cur, f);
-#pragma unroll
-                for (int c = 0; c < NF; ++c) this->q[c][PH] = f[c];
-            }
-        } else {
-            const int j = i - n_own;                    // 0 or 1
-            if (j == 0) {
-                // my two newest planes (n-1 at phase PH-1, n-2 at PH-2) for the end partner
-                if (this->active) {
-#pragma unroll
-                    for (int c = 0; c < NF; ++c) {
-                        ksfd_smem[EXPE + (0 * NF + c) * T::NT + threadIdx.x] = this->q[c][(PH + 4) % 5];
-                        ksfd_smem[EXPE + (1 * NF + c) * T::NT + threadIdx.x] = this->q[c][(PH + 3) % 5];
-                    }
-                }
-                cluster.sync();
-            }
-            if (rem_end) {
-                if (this->active) {
-#pragma unroll
-                    for (int c = 0; c < NF; ++c)
-                        this->q[c][PH] = rem_end[(j * NF + c) * T::NT + threadIdx.x];
-                }
-            } else if (this->active) {
-                // end of the cluster: a real halo plane (periodic wrap / ghost planes)
-                typename Op::State s2;
-                const int kstart = dir > 0 ? this->k0 : this->k1 - 1;
-                this->op.init(this->g, s2, kstart + dir * i, 0, this->poff);
-                double cur[NPRE], f[NF];
-                this->op.load_here(this->g, s2, RegSink{cur});
-                this->op.stage(this->P, SmemTabs<B::RING>(), cur, f);
-#pragma unroll
-                for (int c = 0; c < NF; ++c) this->q[c][PH] = f[c];
-            }
-        }
-        emit_plane<PH>(i);
-    }
-
-    __device__ __forceinline__ void run()
-    {
-        auto cluster = ksfd_cg::this_cluster();
-        const unsigned rank = cluster.block_rank(), csize = cluster.num_blocks();
-        const bool up = (rank & 1u) != 0;
-        dir = up ? 1 : -1;
-        n_own = this->k1 - this->k0;                    // >= 2 (host)
-        const int kstart = up ? this->k0 : this->k1 - 1;
-        const unsigned start_partner = up ? rank - 1 : rank + 1;
-        const int end_partner = up ? (int)rank + 1 : (int)rank - 1;
-        const bool has_end = end_partner >= 0 && end_partner < (int)csize;
-        this->op.init(this->g, this->st, kstart, kstart, this->poff);
-        this->e_aux = kstart * Op::out_fields(DIM) * this->g.fs + this->poff;
-        // own planes 0 and 1 -> queue phases 2, 3 and the start export
-        if (this->active) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                double cur[NPRE], f[NF];
-                this->op.load_here(this->g, this->st, RegSink{cur});
-                this->op.move_by(this->g, this->st, dir);
-                this->op.stage(this->P, SmemTabs<B::RING>(), cur, f);
-#pragma unroll
-                for (int c = 0; c < NF; ++c) {
-                    this->q[c][2 + j] = f[c];
-                    ksfd_smem[EXPS + (j * NF + c) * T::NT + threadIdx.x] = f[c];
-                }
-            }
-            if (n_own > 2) {                            // prefetch own plane 2
-                this->op.load_here(this->g, this->st, RegSink{this->pre});
-                this->op.move_by(this->g, this->st, dir);
-            }
-        }
-        cluster.sync();
-        {
-            const double *rem = cluster.map_shared_rank(&ksfd_smem[EXPS], start_partner);
-            if (this->active) {
-#pragma unroll
-                for (int c = 0; c < NF; ++c) {
-                    this->q[c][1] = rem[(0 * NF + c) * T::NT + threadIdx.x];    // my plane -1
-                    this->q[c][0] = rem[(1 * NF + c) * T::NT + threadIdx.x];    // my plane -2
-                }
-            }
-        }
-        rem_end = has_end ? cluster.map_shared_rank(&ksfd_smem[EXPE], (unsigned)end_partner)
-                          : nullptr;
-        int i = 2;
-        const int iend = n_own + 2;
-        step<4>(i);
-        ++i;
-        if (!UNR) {
-            // (the shifting-queue form keeps every new plane at phase 4)
-            for (; i < iend; ++i) {
-#pragma unroll
-                for (int c = 0; c < NF; ++c) {
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) this->q[c][s] = this->q[c][s + 1];
-                }
-                step<4>(i);
-            }
-        } else {
-            for (; i < iend;) {
-                step<0>(i);
-                if (++i >= iend) break;
-                step<1>(i);
-                if (++i >= iend) break;
-                step<2>(i);
-                if (++i >= iend) break;
-                step<3>(i);
-                if (++i >= iend) break;
-                step<4>(i);
-                if (++i >= iend) break;
-            }
-        }
-        cluster.sync();         // nobody leaves while a neighbour may still read its exports
-    }
-};
-
-template <class Op, int SP, int NT>
-constexpr size_t march_cl_smem_bytes()
-{
-    return sizeof(double) * (2 * Op::NF * SP + (Op::TABS ? KSFD_TAB_DOUBLES : 0) + 4 * Op::NF * NT);
-}
-
-template <int DIM, int TX, int TY, class Op, int MINB, bool UNR>
-__global__ void __launch_bounds__(TileT<DIM, TX, TY>::NT, MINB)
-k_march_cl(const __grid_constant__ MarchArgs g, const __grid_constant__ DevPhys P,
-           const __grid_constant__ Op op)
-{
-    ClusterMarcher<DIM, TX, TY, Op, UNR> m(g, P, op);
-    m.run();
-}
-#endif

@@ -106,7 +106,7 @@ static MarchPlan plan_march(ksfd_ctx *c, long long key, const TileCand *cand, in
     return p;
 }
 
-template <int DIM, int TX, int TY, class Op, int MINB, bool UNR, int DEPTH>
+template <int DIM, int TX, int TY, class Op, int MINB, bool UNR>
 static int tile_occupancy(int device)
 {
     // per device: the dynamic-shared-memory opt-in below is a per-device attribute
@@ -115,8 +115,8 @@ static int tile_occupancy(int device)
     if (it != occ_of.end()) return it->second;
     int occ;
     using T = TileT<DIM, TX, TY>;
-    auto kern = k_march<DIM, TX, TY, Op, MINB, UNR, DEPTH>;
-    const size_t smem = march_smem_bytes<Op, T::SP, T::NT, DEPTH>();
+    auto kern = k_march<DIM, TX, TY, Op, MINB, UNR>;
+    const size_t smem = march_smem_bytes<Op, T::SP>();
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess) {
         cudaGetLastError();
@@ -134,13 +134,13 @@ static int tile_occupancy(int device)
     return occ;
 }
 
-template <int DIM, int TX, int TY, class Op, int MINB, bool UNR, int DEPTH>
+template <int DIM, int TX, int TY, class Op, int MINB, bool UNR>
 static int launch_tile(const ksfd_ctx *c, const Op &op, const MarchPlan &p, const int *skip,
                        cudaStream_t st)
 {
     using T = TileT<DIM, TX, TY>;
-    auto kern = k_march<DIM, TX, TY, Op, MINB, UNR, DEPTH>;
-    const size_t smem = march_smem_bytes<Op, T::SP, T::NT, DEPTH>();
+    auto kern = k_march<DIM, TX, TY, Op, MINB, UNR>;
+    const size_t smem = march_smem_bytes<Op, T::SP>();
     // Jacobian-side operators run on the physics of the linearisation (ctx.h: Pjac)
     const DevPhys &P = Op::JACOBIAN ? c->Pjac : c->P;
     KSFD_KLAUNCH(kern, p.grid, T::NT, smem, st, p.a, P, op, skip);
@@ -149,8 +149,7 @@ static int launch_tile(const ksfd_ctx *c, const Op &op, const MarchPlan &p, cons
 }
 
 // two tile candidates per operator: (AX, AY, AMINB) and (BX, BY, BMINB)
-template <int DIM, class Op, bool UNR, int DEPTH, int AX, int AY, int AMINB, int BX, int BY,
-          int BMINB>
+template <int DIM, class Op, bool UNR, int AX, int AY, int AMINB, int BX, int BY, int BMINB>
 static int launch_op(ksfd_ctx *c, const Op &op, int opkey, double cstage, double cemit,
                      const int *skip, cudaStream_t st)
 {
@@ -159,14 +158,14 @@ static int launch_op(ksfd_ctx *c, const Op &op, int opkey, double cstage, double
         return fail("rank-local slab too large for the 32-bit indexed kernels; "
                     "decompose over more ranks");
     TileCand cand[2] = {
-        {AX, AY, TileT<DIM, AX, AY>::NT, tile_occupancy<DIM, AX, AY, Op, AMINB, UNR, DEPTH>(c->device)},
-        {BX, BY, TileT<DIM, BX, BY>::NT, tile_occupancy<DIM, BX, BY, Op, BMINB, UNR, DEPTH>(c->device)}};
+        {AX, AY, TileT<DIM, AX, AY>::NT, tile_occupancy<DIM, AX, AY, Op, AMINB, UNR>(c->device)},
+        {BX, BY, TileT<DIM, BX, BY>::NT, tile_occupancy<DIM, BX, BY, Op, BMINB, UNR>(c->device)}};
     if (cand[0].occ == 0 && cand[1].occ == 0)
         return fail("marching kernel does not fit on this device");
     MarchPlan p = plan_march(c, opkey * 100 + DIM * 10 + Op::NF, cand, 2, cstage, cemit);
     if (p.tile < 0) return fail("no marching tile fits");
-    if (p.tile == 0) return launch_tile<DIM, AX, AY, Op, AMINB, UNR, DEPTH>(c, op, p, skip, st);
-    return launch_tile<DIM, BX, BY, Op, BMINB, UNR, DEPTH>(c, op, p, skip, st);
+    if (p.tile == 0) return launch_tile<DIM, AX, AY, Op, AMINB, UNR>(c, op, p, skip, st);
+    return launch_tile<DIM, BX, BY, Op, BMINB, UNR>(c, op, p, skip, st);
 }
 
 // ---------------------------------------------------------------------------
@@ -222,6 +221,10 @@ static int tma_bind(ksfd_ctx *c, TmaInT<Op::NIN> &tin, const TmaSrc *src, int TX
         tin.v[i].par = t.par;
         tin.v[i].parshift = t.parshift;
         tin.v[i].pad_ = 0;
+        tin.v[i].flag_lo = t.flag_lo;
+        tin.v[i].flag_hi = t.flag_hi;
+        tin.v[i].err = t.err;
+        tin.v[i].dead = t.dead;
     }
     return 0;
 }

@@ -22,10 +22,10 @@ static int launch_residual_f(ksfd_ctx *c, const HostVec &u, const double *udot, 
 #endif
     }
 #if KSFD_MARCH_DIM == 2
-    return launch_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 0, 124, 1, 6, 252, 1, 3>(
+    return launch_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 124, 1, 6, 252, 1, 3>(
         c, op, FIXED ? 1 : 5, 150.0, cemit, nullptr, st);
 #else
-    return launch_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 0, 16, 16, 2, 32, 16, 1>(
+    return launch_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 16, 16, 2, 32, 16, 1>(
         c, op, FIXED ? 1 : 5, 150.0, cemit, nullptr, st);
 #endif
 }

@@ -22,10 +22,10 @@ static int launch_velocity(ksfd_ctx *c, const HostVec &u, double *vel, double *v
 #endif
     }
 #if KSFD_MARCH_DIM == 2
-    return launch_op<DIM, VelocityOp<DIM, NLIG>, false, 0, 124, 1, 6, 252, 1, 3>(
+    return launch_op<DIM, VelocityOp<DIM, NLIG>, false, 124, 1, 6, 252, 1, 3>(
         c, op, 4, 150.0, cemit, nullptr, st);
 #else
-    return launch_op<DIM, VelocityOp<DIM, NLIG>, false, 0, 16, 16, 2, 32, 16, 1>(
+    return launch_op<DIM, VelocityOp<DIM, NLIG>, false, 16, 16, 2, 32, 16, 1>(
         c, op, 4, 150.0, cemit, nullptr, st);
 #endif
 }

@@ -44,6 +44,16 @@ struct TmaVecIn {
     const unsigned long long *par;      // exchange counter (nullptr: none)
     int parshift;   // added to kofs[1], kofs[2] when the counter is odd
     int pad_;
+    // Several ranks over NVLink peer memory: the neighbours store the ghost planes into
+    // this rank's halo slot and then publish the exchange number in flag_lo / flag_hi.
+    // The producer of the vector only PUSHES (ksfd.cu: k_halo_push, or fused into the
+    // BLAS-1 kernel that writes the vector); the wait happens here, in the elected
+    // thread of the CTAs that fetch ghost planes, right before their first ghost box —
+    // CTAs that own interior chunks never wait, and the NVLink round trip hides behind
+    // the owned planes.  nullptr: nothing to wait for.
+    const volatile unsigned long long *flag_lo, *flag_hi;
+    volatile int *err;                      // host-visible: a wait timed out
+    volatile unsigned long long *dead;      // device-side sticky copy of it
 };
 template <int NIN>
 struct TmaInT {
@@ -131,6 +141,8 @@ struct TmaMarcher {
     const Op &op;
     const TmaInT<Op::NIN> &tin;
     int pshift[Op::NIN];        // (elected thread) parity shift of the ghost planes
+    unsigned long long xq[Op::NIN];     // (elected thread) exchange number to wait for
+    unsigned waited;            // (elected thread) bit 2i / 2i+1: lo / hi flag of vector i seen
     double q[NF][5];
     double aux[NAUX];
     typename Op::State st;
@@ -223,9 +235,14 @@ struct TmaMarcher {
         __syncthreads();                    // barriers initialised, tables staged
         if (tid == 0) {
             const int np = k1 - k0 + 2 * KSFD_SW;
+            waited = 0;
 #pragma unroll
-            for (int i = 0; i < NIN; ++i)
-                pshift[i] = tin.v[i].par ? (int)(*tin.v[i].par & 1ull) * tin.v[i].parshift : 0;
+            for (int i = 0; i < NIN; ++i) {
+                xq[i] = tin.v[i].par ? *reinterpret_cast<const volatile unsigned long long *>(
+                                           tin.v[i].par)
+                                     : 0ull;
+                pshift[i] = (int)(xq[i] & 1ull) * tin.v[i].parshift;
+            }
 #pragma unroll
             for (int s = 0; s < SC; ++s)
                 if (s < np) issue_centre(k0 - KSFD_SW + s, s);
@@ -235,8 +252,34 @@ struct TmaMarcher {
         }
     }
 
+    // (elected thread) the neighbour's ghost planes of vector i have landed: bounded spin
+    // on the flag word it publishes after its stores (blas1_kernels.cuh: p2p_spin), then
+    // order the TMA reads (async proxy) after the observation
+    __device__ __forceinline__ void halo_arrived(int i, int side)
+    {
+        const unsigned bit = 1u << (2 * i + side);
+        if (waited & bit) return;
+        waited |= bit;
+        const TmaVecIn &v = tin.v[i];
+        const volatile unsigned long long *f = side ? v.flag_hi : v.flag_lo;
+        if (!f) return;
+        const long long t0 = clock64();
+        unsigned spins = 0;
+        while (*f < xq[i]) {
+            __nanosleep(20);
+            if ((++spins & 0xfff) == 0 &&
+                (clock64() - t0 > 240000000000ll || (v.dead && *v.dead))) {
+                if (v.dead) *v.dead = 1ull;
+                if (v.err) *v.err = 1;
+                break;
+            }
+        }
+        __threadfence_system();
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+
     // coordinate 2 of plane k of input vector i; set = which of its two map sets
-    __device__ __forceinline__ int plane_coord(int i, int k, int &set) const
+    __device__ __forceinline__ int plane_coord(int i, int k, int &set)
     {
         const TmaVecIn &v = tin.v[i];
         const int nc = Op::nc(i);
@@ -244,18 +287,20 @@ struct TmaMarcher {
         if (k < 0) {
             if (v.wrap) return v.kofs[0] + (k + g.nloc) * nc;
             set = 1;
+            halo_arrived(i, 0);
             return v.kofs[1] + pshift[i] + (k + KSFD_SW) * nc;
         }
         if (k >= g.nloc) {
             if (v.wrap) return v.kofs[0] + (k - g.nloc) * nc;
             set = 1;
+            halo_arrived(i, 1);
             return v.kofs[2] + pshift[i] + (k - g.nloc) * nc;
         }
         return v.kofs[0] + k * nc;
     }
 
     // (elected thread) fetch the centre boxes of plane k into centre slot `slot`
-    __device__ __forceinline__ void issue_centre(int k, int slot) const
+    __device__ __forceinline__ void issue_centre(int k, int slot)
     {
         const unsigned bar = bar0 + 8 * slot;
         ktma::mbar_expect(bar, CSLOT * 8);
@@ -269,7 +314,7 @@ struct TmaMarcher {
         }
     }
     // (elected thread) fetch the halo boxes of plane k into halo slot `slot`
-    __device__ __forceinline__ void issue_halo(int k, int slot) const
+    __device__ __forceinline__ void issue_halo(int k, int slot)
     {
         const unsigned bar = bar0 + 8 * (SC + slot);
         ktma::mbar_expect(bar, HBYTES);

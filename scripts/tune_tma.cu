@@ -167,8 +167,8 @@ static void run_ref(const char *name, Problem &pb, const DevPhys &P, Op op_proto
     using T = TileT<DIM, TX, TY>;
     const int ord = g_ordinal;
     if (!selected() && !record) return;
-    auto kern = k_march<DIM, TX, TY, Op, MINB, UNR, 0>;
-    const size_t smem = march_smem_bytes<Op, T::SP, T::NT, 0>();
+    auto kern = k_march<DIM, TX, TY, Op, MINB, UNR>;
+    const size_t smem = march_smem_bytes<Op, T::SP>();
     CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T::NT, smem));

@@ -171,7 +171,7 @@ def test_start_and_resume_values_on_two_ranks(tmp_path):
              for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in range(world)]
+    res = [q.get(timeout=900) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, True) for r in range(world)]
