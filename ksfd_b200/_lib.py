@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libksfd_b200.so')
+# KSFD_B200_LIB: an experimental build of the same sources (ksfd_b200/build.py --out)
+LIB_PATH = os.environ.get('KSFD_B200_LIB') or os.path.join(HERE, 'libksfd_b200.so')
 
 MAX_LIGANDS = 7
 MAX_GROUPS = 7

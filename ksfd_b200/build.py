@@ -19,7 +19,7 @@ UNITS = [('ksfd.cu', [], 'ksfd.o')] + [
     (src, ['-DKSFD_MARCH_DIM=%d' % d], '%s_d%d.o' % (src[:-3], d))
     for src in ('march_res.cu', 'march_jvp.cu', 'march_vel.cu') for d in (2, 3)]
 HEADERS = ['device_common.cuh', 'naive_kernels.cuh', 'march_kernels.cuh',
-           'march_launch.cuh', 'ctx.h', 'blas1_kernels.cuh', 'fftpc.cuh', 'fastmath.cuh',
+           'march_launch.cuh', 'tma_march.cuh', 'tma_host.h', 'ctx.h', 'blas1_kernels.cuh', 'fftpc.cuh', 'fastmath.cuh',
            'fastmath_tables.h',
            os.path.join('..', '..', 'include', 'ksfd_b200.h')]
 OBJDIR = os.path.join(HERE, 'build')
@@ -59,8 +59,25 @@ def _compile(unit, verbose):
     return unit, r
 
 
-def build(force=False, verbose=False):
-    """Compile libksfd_b200.so if missing or older than its sources."""
+def build(force=False, verbose=False, out=None, extra=()):
+    """Compile libksfd_b200.so if missing or older than its sources.
+    out / extra: an experimental build next to it (other file name, extra nvcc flags,
+    own object directory), selected at run time with KSFD_B200_LIB=<path>."""
+    global OBJDIR, LIB
+    if out:
+        saved = (OBJDIR, LIB, list(NVCC_FLAGS))
+        OBJDIR = os.path.join(HERE, 'build', os.path.splitext(os.path.basename(out))[0])
+        LIB = os.path.join(HERE, out)
+        NVCC_FLAGS.extend(extra)
+        try:
+            return _build(True, verbose)
+        finally:
+            OBJDIR, LIB = saved[0], saved[1]
+            NVCC_FLAGS[:] = saved[2]
+    return _build(force, verbose)
+
+
+def _build(force, verbose):
     if not force and not is_stale():
         return LIB
     from concurrent.futures import ThreadPoolExecutor
@@ -81,4 +98,8 @@ def build(force=False, verbose=False):
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    if '--out' in sys.argv:         # python -m ksfd_b200.build --out libksfd_b200_pdl.so -DKSFD_PDL=1
+        i = sys.argv.index('--out')
+        print(build(out=sys.argv[i + 1], extra=sys.argv[i + 2:], verbose='-v' in sys.argv))
+    else:
+        print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -95,7 +95,33 @@ struct VecRef {
     // exchange counter: the ghost planes live at lo/hi + (*par & 1) * pstride
     const unsigned long long *par;
     long long pstride;
+    // Several ranks over NVLink peer memory: the neighbours store the ghost planes and then
+    // publish the exchange number in flag_lo / flag_hi.  The exchange kernels only PUSH;
+    // the marching kernels wait here, in the CTAs that actually read ghost planes and
+    // right before they do (march_kernels.cuh: plane_of, tma_march.cuh: tma_halo_wait),
+    // so the NVLink round trip hides behind the owned planes.  nullptr: nothing to wait for.
+    const volatile unsigned long long *flag_lo, *flag_hi;
+    volatile int *err;                      // host-visible: a wait timed out
+    volatile unsigned long long *dead;      // device-side sticky copy of it
 };
+
+// bounded spin until the neighbour's flag reaches exchange number q (cf. p2p_spin)
+static __device__ __noinline__ void halo_flag_wait(const volatile unsigned long long *f,
+                                                   unsigned long long q, volatile int *err,
+                                                   volatile unsigned long long *dead)
+{
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while (*f < q) {
+        __nanosleep(20);
+        if ((++spins & 0xfff) == 0 && (clock64() - t0 > 240000000000ll || (dead && *dead))) {
+            if (dead) *dead = 1ull;
+            if (err) *err = 1;
+            break;
+        }
+    }
+    __threadfence_system();
+}
 
 __device__ __forceinline__ long long ghost_shift(const VecRef &v)
 {

@@ -316,6 +316,9 @@ static VecRef make_ref(const ksfd_ctx *c, const double *base, int stride, int sl
     r.base = base;
     r.par = nullptr;
     r.pstride = 0;
+    r.flag_lo = r.flag_hi = nullptr;
+    r.err = nullptr;
+    r.dead = nullptr;
     const long long ps = c->g.plane_pts * stride;
     if (c->nranks == 1) {
         r.lo = base + (long long)(c->g.nloc - KSFD_SW) * ps;
@@ -326,6 +329,13 @@ static VecRef make_ref(const ksfd_ctx *c, const double *base, int stride, int sl
         r.hi = r.lo + KSFD_SW * c->halo_plane_doubles;
         r.par = c->p2p_ctr + slot;
         r.pstride = (long long)p2p_buf_doubles(c);
+        // the marching kernels wait for the neighbours' flags themselves (already
+        // satisfied when the exchange was made by k_halo_xchg, which waits)
+        typedef const volatile unsigned long long *cflag_t;
+        r.flag_lo = reinterpret_cast<cflag_t>(c->p2p_mine) + slot * 2 + 0;
+        r.flag_hi = reinterpret_cast<cflag_t>(c->p2p_mine) + slot * 2 + 1;
+        r.err = c->p2p_err_dev;
+        r.dead = c->p2p_ctr + KSFD_HALO_SLOTS + 1;
     } else {
         r.lo = c->halo[slot];
         r.hi = c->halo[slot] + KSFD_SW * c->halo_plane_doubles;
@@ -356,11 +366,10 @@ static HostVec make_hvec(const ksfd_ctx *c, const double *base, int stride, int 
         t.parshift = (int)(2 * KSFD_SW * hp);
         // the marcher waits for the neighbours' flags itself (already satisfied when the
         // exchange was made by k_halo_xchg, which waits)
-        typedef const volatile unsigned long long *cflag_t;
-        t.flag_lo = reinterpret_cast<cflag_t>(c->p2p_mine) + slot * 2 + 0;
-        t.flag_hi = reinterpret_cast<cflag_t>(c->p2p_mine) + slot * 2 + 1;
-        t.err = c->p2p_err_dev;
-        t.dead = c->p2p_ctr + KSFD_HALO_SLOTS + 1;
+        t.flag_lo = h.r.flag_lo;
+        t.flag_hi = h.r.flag_hi;
+        t.err = h.r.err;
+        t.dead = h.r.dead;
     } else {
         t.wrap = 0;
         t.halo = c->halo[slot];
@@ -676,7 +685,8 @@ void ksfd_invalidate_plans(ksfd_ctx *c)
 }
 
 static bool use_march(const ksfd_ctx *c);
-static bool tma_consumer(const ksfd_ctx *c) { return use_march(c) && ksfd_use_tma(c); }
+// both marching kernels wait for the neighbours' flags themselves (the direct kernels do not)
+static bool tma_consumer(const ksfd_ctx *c) { return use_march(c); }
 static bool use_march(const ksfd_ctx *c)
 {
     if (c->variant == 1) return false;

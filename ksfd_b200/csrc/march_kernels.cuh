@@ -80,12 +80,18 @@ struct SmemTabs {
 };
 
 // pointer to plane k of a vector whose planes hold `ps` doubles
-__device__ __forceinline__ const double *plane_of(const VecRef &v, int k, int nloc,
-                                                  int ps)
+__device__ __forceinline__ const double *plane_of(const VecRef &v, int k, int nloc, int ps)
 {
-    if (k < 0) return v.lo + ghost_shift(v) + (k + KSFD_SW) * (long long)ps;
-    if (k >= nloc) return v.hi + ghost_shift(v) + (k - nloc) * (long long)ps;
-    return v.base + k * (long long)ps;
+    if (k >= 0 && k < nloc) return v.base + k * (long long)ps;
+    // ghost plane: wait (every thread of the CTA, they all load from it) until the
+    // neighbour's planes of the current exchange have landed
+    const unsigned long long q =
+        v.par ? *reinterpret_cast<const volatile unsigned long long *>(v.par) : 0ull;
+    const long long shift = (long long)(q & 1ull) * v.pstride;
+    const volatile unsigned long long *f = k < 0 ? v.flag_lo : v.flag_hi;
+    if (f) halo_flag_wait(f, q, v.err, v.dead);
+    if (k < 0) return v.lo + shift + (k + KSFD_SW) * (long long)ps;
+    return v.hi + shift + (k - nloc) * (long long)ps;
 }
 
 // input cursor: per-thread pointer to this lane's point in the next plane to
@@ -107,10 +113,18 @@ struct InCursor {
     }
 };
 
-// the loads of a plane go straight into registers (read-only path)
+// The loads of a plane go straight into registers.  Plain coherent loads, not the
+// non-coherent read-only path: with several ranks the ghost planes are written by the
+// neighbouring GPU WHILE this kernel runs (it waits for them in plane_of), which ld.global.nc
+// does not allow; ghost lines are first touched after the wait, so the L1 holds no stale copy.
 struct RegSink {
     double *r;
-    __device__ __forceinline__ void put(int c, const double *p) const { r[c] = __ldg(p); }
+    __device__ __forceinline__ void put(int c, const double *p) const
+    {
+        double v;
+        asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+        r[c] = v;
+    }
 };
 
 // stencil access of one interior lane at emit time.  PH = phase of the
@@ -546,11 +560,19 @@ struct VelocityOp {
 // UNR: unroll the plane loop five times (queue rotates by register renaming);
 // otherwise the queue is shifted with moves (smaller code, fewer registers).
 // The next plane is prefetched into registers while the current one is staged.
-template <int DIM, int TX, int TY, class Op, bool UNR>
+// RINGS = 2: the centre plane kk-2 is shared right before its stencil is formed (store,
+//   barrier, neighbour loads: the barrier sits in the middle of the iteration).
+// RINGS = 4: every plane is shared as soon as it is staged, into slot kk & 3, and the
+//   stencil of plane kk-2 reads the slot written two iterations (two barriers) earlier:
+//   the iteration body has no barrier between its stores and its loads, the one barrier
+//   sits at its end, and the neighbour loads of plane kk-2 can be issued before / under
+//   the staging arithmetic of plane kk (software pipelining across the barrier).
+template <int DIM, int TX, int TY, class Op, bool UNR, int RINGS = 2>
 struct Marcher {
     using T = TileT<DIM, TX, TY>;
     static constexpr int NF = Op::NF, NPRE = Op::NPRE, NAUX = Op::NAUX;
-    static constexpr int RING = 2 * NF * T::SP;     // doubles; the tables follow
+    static constexpr int RING = RINGS * NF * T::SP;     // doubles; the tables follow
+    static_assert(RINGS == 2 || RINGS == 4, "2 or 4 ring slots");
     const MarchArgs &g;
     const DevPhys &P;
     const Op &op;
@@ -630,6 +652,26 @@ struct Marcher {
             op.stage(P, SmemTabs<RING>(), cur, f);
 #pragma unroll
             for (int c = 0; c < NF; ++c) q[c][PH] = f[c];
+            if (RINGS == 4) {
+                const int wi = (kk & 3) * (NF * T::SP) + spos;
+#pragma unroll
+                for (int c = 0; c < NF; ++c) ksfd_smem[wi + c * T::SP] = f[c];
+            }
+        }
+        if (RINGS == 4) {
+            if (kk - KSFD_SW >= k0) {                   // uniform over the CTA
+                if (Op::HAS_AUX && emits) {
+                    op.load_aux(g, e_aux, 0, RegSink{aux});
+                    e_aux += Op::out_fields(DIM) * g.fs;
+                }
+                if (emits) {
+                    LaneAcc<DIM, NF, T::SP, T::SY, PH> a(q, ((kk - KSFD_SW) & 3) * (NF * T::SP) + spos);
+                    op.emit(P, g, a, aux, st);
+                }
+                op.advance_out(g, st);
+            }
+            __syncthreads();
+            return;
         }
         if (kk - KSFD_SW >= k0) {                       // uniform over the CTA
             if (Op::HAS_AUX && emits) {
@@ -685,13 +727,13 @@ struct Marcher {
     }
 };
 
-template <class Op, int SP>
+template <class Op, int SP, int RINGS = 2>
 constexpr size_t march_smem_bytes()
 {
-    return sizeof(double) * (2 * Op::NF * SP + (Op::TABS ? KSFD_TAB_DOUBLES : 0));
+    return sizeof(double) * (RINGS * Op::NF * SP + (Op::TABS ? KSFD_TAB_DOUBLES : 0));
 }
 
-template <int DIM, int TX, int TY, class Op, int MINB, bool UNR>
+template <int DIM, int TX, int TY, class Op, int MINB, bool UNR, int RINGS = 2>
 __global__ void __launch_bounds__(TileT<DIM, TX, TY>::NT, MINB)
 k_march(const __grid_constant__ MarchArgs g, const __grid_constant__ DevPhys P,
         const __grid_constant__ Op op, const int *__restrict__ skip)
@@ -699,6 +741,6 @@ k_march(const __grid_constant__ MarchArgs g, const __grid_constant__ DevPhys P,
     KSFD_PDL_ENTER();
     // pipelined Krylov solver: launched ahead of the convergence test
     if (skip && KSFD_FLAG(skip)) return;
-    Marcher<DIM, TX, TY, Op, UNR> m(g, P, op);
+    Marcher<DIM, TX, TY, Op, UNR, RINGS> m(g, P, op);
     m.run();
 }

@@ -221,6 +221,8 @@ static int tma_bind(ksfd_ctx *c, TmaInT<Op::NIN> &tin, const TmaSrc *src, int TX
         tin.v[i].par = t.par;
         tin.v[i].parshift = t.parshift;
         tin.v[i].pad_ = 0;
+        tin.v[i].nc = nc;
+        tin.v[i].coff = Op::coff(i);
         tin.v[i].flag_lo = t.flag_lo;
         tin.v[i].flag_hi = t.flag_hi;
         tin.v[i].err = t.err;

@@ -12,15 +12,9 @@ static int launch_residual_f(ksfd_ctx *c, const HostVec &u, const double *udot, 
 {
     ResidualOp<DIM, NLIG, FIXED> op{u.r, udot, src, out};
     const double cemit = 35.0 * DIM + 30.0;
-    if (ksfd_use_tma(c)) {
-#if KSFD_MARCH_DIM == 2
-        return launch_tma_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 128, 1, 6, 3, 256, 1, 3, 3>(
-            c, op, &u.t, FIXED ? 1 : 5, 150.0, cemit, nullptr, st);
-#else
-        return launch_tma_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 16, 16, 3, 3, 32, 8, 3, 3>(
-            c, op, &u.t, FIXED ? 1 : 5, 150.0, cemit, nullptr, st);
-#endif
-    }
+    // (the TMA-fed marcher is not used here: measured slower for the transcendental-heavy
+    // staging of the residual, whose halo points would be one warp's extra pass —
+    // profiles/r02_tma_tuner_runs.txt)
 #if KSFD_MARCH_DIM == 2
     return launch_op<DIM, ResidualOp<DIM, NLIG, FIXED>, false, 124, 1, 6, 252, 1, 3>(
         c, op, FIXED ? 1 : 5, 150.0, cemit, nullptr, st);

@@ -12,15 +12,6 @@ static int launch_velocity(ksfd_ctx *c, const HostVec &u, double *vel, double *v
 {
     VelocityOp<DIM, NLIG> op{u.r, vel, vmax};
     const double cemit = 8.0 * DIM + 10.0;
-    if (ksfd_use_tma(c)) {
-#if KSFD_MARCH_DIM == 2
-        return launch_tma_op<DIM, VelocityOp<DIM, NLIG>, false, 128, 1, 6, 3, 256, 1, 3, 3>(
-            c, op, &u.t, 4, 150.0, cemit, nullptr, st);
-#else
-        return launch_tma_op<DIM, VelocityOp<DIM, NLIG>, false, 16, 16, 3, 3, 32, 8, 3, 3>(
-            c, op, &u.t, 4, 150.0, cemit, nullptr, st);
-#endif
-    }
 #if KSFD_MARCH_DIM == 2
     return launch_op<DIM, VelocityOp<DIM, NLIG>, false, 124, 1, 6, 252, 1, 3>(
         c, op, 4, 150.0, cemit, nullptr, st);

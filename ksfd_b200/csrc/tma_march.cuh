@@ -44,6 +44,7 @@ struct TmaVecIn {
     const unsigned long long *par;      // exchange counter (nullptr: none)
     int parshift;   // added to kofs[1], kofs[2] when the counter is odd
     int pad_;
+    int nc, coff;   // fields per plane; index of the first one among the operator's raw fields
     // Several ranks over NVLink peer memory: the neighbours store the ghost planes into
     // this rank's halo slot and then publish the exchange number in flag_lo / flag_hi.
     // The producer of the vector only PUSHES (ksfd.cu: k_halo_push, or fused into the
@@ -55,9 +56,22 @@ struct TmaVecIn {
     volatile int *err;                      // host-visible: a wait timed out
     volatile unsigned long long *dead;      // device-side sticky copy of it
 };
+// Where the tensor maps live: inside the kernel parameter block (__grid_constant__, the
+// default: nothing to allocate or copy) or in global memory (-DKSFD_TMAP_PARAM=0, a device
+// pool owned by the caller).  Measured on B200 with otherwise identical kernels
+// (profiles/r02_tma_tuner_runs.txt, runs 4g / 4p): no difference.
+#ifndef KSFD_TMAP_PARAM
+#define KSFD_TMAP_PARAM 1
+#endif
 template <int NIN>
 struct TmaInT {
+#if KSFD_TMAP_PARAM
     CUtensorMap m[NIN][2][3];   // [input vector][map set][box shape: centre, y strip, x strip]
+    __device__ __forceinline__ const CUtensorMap *maps(int i, int set) const { return &m[i][set][0]; }
+#else
+    const CUtensorMap *m[NIN][2];   // device memory: the three box shapes of [vector][map set]
+    __device__ __forceinline__ const CUtensorMap *maps(int i, int set) const { return m[i][set]; }
+#endif
     TmaVecIn v[NIN];
 };
 
@@ -105,12 +119,13 @@ __device__ __forceinline__ void load3(unsigned dst, const CUtensorMap *m, int c0
 }
 }   // namespace ktma
 
-template <int DIM, int TX, int TY, class Op, bool UNR, int SC, int SH>
-struct TmaMarcher {
+// layout constants shared by the marcher and the issuer
+template <int DIM, int TX, int TY, class Op, int SC, int SH>
+struct TmaLayout {
     using T = TileT<DIM, TX, TY>;
     static constexpr int NTH = (DIM == 2) ? TX : TX * TY;           // threads = outputs
     static constexpr int NH = (DIM == 2) ? 4 : 4 * TX + 4 * TY;     // halo points per plane
-    static constexpr int NF = Op::NF, NPRE = Op::NPRE, NAUX = Op::NAUX, NIN = Op::NIN;
+    static constexpr int NF = Op::NF, NPRE = Op::NPRE, NIN = Op::NIN;
     static constexpr int r16(int x) { return (x + 15) / 16 * 16; }
     static constexpr int RING = r16(2 * NF * T::SP);
     static constexpr int TABS = Op::TABS ? KSFD_TAB_DOUBLES : 0;
@@ -122,27 +137,64 @@ struct TmaMarcher {
     static constexpr int HBYTES = (DIM == 2) ? NPRE * 4 * 8 : NPRE * NH * 8;
     static constexpr int BAR = HRING + SH * HSLOT;
     static constexpr int SMEM_DOUBLES = BAR + SC + SH;
-    static_assert(NTH % 32 == 0 && TABS % 16 == 0, "alignment of the TMA destinations");
-    static_assert(DIM == 2 || (TX % 8 == 0 && TY % 8 == 0), "3-D tiles: multiples of 8");
-    static_assert(NH <= NTH, "halo pass: one halo point per thread");
-
-    // halo slot: offset of the box of (vector i, piece p); field stride of piece p
+    // halo slot: offset of the box of (vector i, piece p)
     //   3-D pieces: 0 bottom rows, 1 top rows, 2 left columns, 3 right columns
     //   2-D pieces: 0 left, 1 right
-    __device__ static constexpr int hbox(int i, int p)
+    __host__ __device__ static constexpr int hbox(int i, int p)
     {
         if (DIM == 2) return (2 * i + p) * HVEC2;
         const int po = p == 0 ? 0 : p == 1 ? 2 * TX : p == 2 ? 4 * TX : 4 * TX + 2 * TY;
         return Op::coff(i) * NH + Op::nc(i) * po;
     }
+};
+
+// The neighbour's ghost planes have landed: bounded spin on the flag word it publishes
+// after its stores (blas1_kernels.cuh: p2p_spin), then order the TMA reads (async proxy)
+// after the observation.  Out of line, arguments by value: only reached with several ranks.
+static __device__ __noinline__ void tma_halo_wait(const volatile unsigned long long *f,
+                                                  unsigned long long q, volatile int *err,
+                                                  volatile unsigned long long *dead)
+{
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while (*f < q) {
+        __nanosleep(20);
+        if ((++spins & 0xfff) == 0 && (clock64() - t0 > 240000000000ll || (dead && *dead))) {
+            if (dead) *dead = 1ull;
+            if (err) *err = 1;
+            break;
+        }
+    }
+    __threadfence_system();
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+template <int DIM, int TX, int TY, class Op, bool UNR, int SC, int SH>
+struct TmaMarcher {
+    using T = TileT<DIM, TX, TY>;
+    using L = TmaLayout<DIM, TX, TY, Op, SC, SH>;
+    static constexpr int NTH = L::NTH, NH = L::NH;
+    static constexpr int NF = Op::NF, NPRE = Op::NPRE, NAUX = Op::NAUX, NIN = Op::NIN;
+    static constexpr int RING = L::RING, CRING = L::CRING, CSLOT = L::CSLOT, HRING = L::HRING;
+    static constexpr int HSLOT = L::HSLOT, BAR = L::BAR, SMEM_DOUBLES = L::SMEM_DOUBLES;
+    static_assert(NTH % 32 == 0 && L::TABS % 16 == 0, "alignment of the TMA destinations");
+    static_assert(DIM == 2 || (TX % 8 == 0 && TY % 8 == 0), "3-D tiles: multiples of 8");
+    static_assert(NH <= NTH, "halo pass: one halo point per thread");
+    __device__ static constexpr int hbox(int i, int p) { return L::hbox(i, p); }
 
     const MarchArgs &g;
     const DevPhys &P;
     const Op &op;
     const TmaInT<Op::NIN> &tin;
-    int pshift[Op::NIN];        // (elected thread) parity shift of the ghost planes
-    unsigned long long xq[Op::NIN];     // (elected thread) exchange number to wait for
-    unsigned waited;            // (elected thread) bit 2i / 2i+1: lo / hi flag of vector i seen
+    // Issuers: input vector i is fetched by lane 0 of warp NW-1-i — the LAST warps, which
+    // have slack while the first ones stage the halo points — so the ~100 instructions of
+    // coordinate set-up and TMA issues per vector and plane run in parallel instead of all
+    // on thread 0 (which also runs the halo pass).  Every issuer arrives on the slot's
+    // mbarrier with the byte count of its own boxes (arrival count NIN).
+    int ivec;                   // input vector this thread fetches, -1: none
+    int ipshift;                // parity shift of its ghost planes
+    unsigned long long ixq;     // exchange number its ghost planes must have reached
+    unsigned iwaited;           // bit 0 / 1: lo / hi flag seen
     double q[NF][5];
     double aux[NAUX];
     typename Op::State st;
@@ -167,7 +219,7 @@ struct TmaMarcher {
         bar0 = ktma::s32(ksfd_smem + BAR);
         if (tid == 0) {
 #pragma unroll
-            for (int s = 0; s < SC + SH; ++s) ktma::mbar_init(bar0 + 8 * s, 1);
+            for (int s = 0; s < SC + SH; ++s) ktma::mbar_init(bar0 + 8 * s, NIN);
             ktma::mbar_fence_init();
         }
         if (Op::TABS) {
@@ -233,111 +285,83 @@ struct TmaMarcher {
 #pragma unroll
             for (int s = 0; s < 5; ++s) q[f][s] = 0.0;
         __syncthreads();                    // barriers initialised, tables staged
-        if (tid == 0) {
+        {
+            constexpr int NW = NTH / 32;
+            const int w = tid >> 5;
+            static_assert(NW >= NIN, "one issuing warp per input vector");
+            ivec = ((tid & 31) == 0 && NW - 1 - w < NIN) ? NW - 1 - w : -1;
+            ipshift = 0;
+            ixq = 0ull;
+            iwaited = 0;
+        }
+        if (ivec != -1) {
             const int np = k1 - k0 + 2 * KSFD_SW;
-            waited = 0;
-#pragma unroll
-            for (int i = 0; i < NIN; ++i) {
-                xq[i] = tin.v[i].par ? *reinterpret_cast<const volatile unsigned long long *>(
-                                           tin.v[i].par)
-                                     : 0ull;
-                pshift[i] = (int)(xq[i] & 1ull) * tin.v[i].parshift;
+            if (tin.v[ivec].par) {
+                ixq = *reinterpret_cast<const volatile unsigned long long *>(tin.v[ivec].par);
+                ipshift = (int)(ixq & 1ull) * tin.v[ivec].parshift;
             }
-#pragma unroll
+#if KSFD_TMAP_PARAM
+            for (int sh = 0; sh < 3; ++sh)
+                    asm volatile("prefetch.tensormap [%0];" ::"l"(tin.maps(ivec, 0) + sh) : "memory");
+#endif
             for (int s = 0; s < SC; ++s)
-                if (s < np) issue_centre(k0 - KSFD_SW + s, s);
-#pragma unroll
+                if (s < np) issue(0, k0 - KSFD_SW + s, s);
             for (int s = 0; s < SH; ++s)
-                if (s < k1 - k0) issue_halo(k0 + s, s);
+                if (s < k1 - k0) issue(1, k0 + s, s);
         }
     }
 
-    // (elected thread) the neighbour's ghost planes of vector i have landed: bounded spin
-    // on the flag word it publishes after its stores (blas1_kernels.cuh: p2p_spin), then
-    // order the TMA reads (async proxy) after the observation
-    __device__ __forceinline__ void halo_arrived(int i, int side)
+    // (issuer) fetch plane k of this thread's input vector into ring slot `slot`:
+    // halo == 0 the centre box, halo == 1 the strips
+    __device__ __forceinline__ void issue(int halo, int k, int slot)
     {
-        const unsigned bit = 1u << (2 * i + side);
-        if (waited & bit) return;
-        waited |= bit;
+        issue_vec(ivec, halo, k, slot);
+    }
+    __device__ __forceinline__ void issue_vec(int i, int halo, int k, int slot)
+    {
         const TmaVecIn &v = tin.v[i];
-        const volatile unsigned long long *f = side ? v.flag_hi : v.flag_lo;
-        if (!f) return;
-        const long long t0 = clock64();
-        unsigned spins = 0;
-        while (*f < xq[i]) {
-            __nanosleep(20);
-            if ((++spins & 0xfff) == 0 &&
-                (clock64() - t0 > 240000000000ll || (v.dead && *v.dead))) {
-                if (v.dead) *v.dead = 1ull;
-                if (v.err) *v.err = 1;
-                break;
+        const int nc = v.nc;
+        const unsigned bar = bar0 + 8 * (halo ? SC + slot : slot);
+        ktma::mbar_expect(bar, (halo ? (DIM == 2 ? 4 : NH) : NTH) * 8 * nc);
+        // coordinate 2 of plane k and which of the two map sets holds it
+        int set = 0, kc;
+        if (k < 0 || k >= g.nloc) {
+            const int side = k < 0 ? 0 : 1;
+            const int kk = side ? k - g.nloc : k + KSFD_SW;
+            if (v.wrap) {
+                kc = v.kofs[0] + (side ? kk : k + g.nloc) * nc;
+            } else {
+                set = 1;
+                const volatile unsigned long long *f = side ? v.flag_hi : v.flag_lo;
+                if (f && !(iwaited & (1u << side))) {
+                    iwaited |= 1u << side;
+                    tma_halo_wait(f, ixq, v.err, v.dead);
+                }
+                kc = v.kofs[1 + side] + ipshift + kk * nc;
             }
+        } else {
+            kc = v.kofs[0] + k * nc;
         }
-        __threadfence_system();
-        asm volatile("fence.proxy.async;" ::: "memory");
-    }
-
-    // coordinate 2 of plane k of input vector i; set = which of its two map sets
-    __device__ __forceinline__ int plane_coord(int i, int k, int &set)
-    {
-        const TmaVecIn &v = tin.v[i];
-        const int nc = Op::nc(i);
-        set = 0;
-        if (k < 0) {
-            if (v.wrap) return v.kofs[0] + (k + g.nloc) * nc;
-            set = 1;
-            halo_arrived(i, 0);
-            return v.kofs[1] + pshift[i] + (k + KSFD_SW) * nc;
-        }
-        if (k >= g.nloc) {
-            if (v.wrap) return v.kofs[0] + (k - g.nloc) * nc;
-            set = 1;
-            halo_arrived(i, 1);
-            return v.kofs[2] + pshift[i] + (k - g.nloc) * nc;
-        }
-        return v.kofs[0] + k * nc;
-    }
-
-    // (elected thread) fetch the centre boxes of plane k into centre slot `slot`
-    __device__ __forceinline__ void issue_centre(int k, int slot)
-    {
-        const unsigned bar = bar0 + 8 * slot;
-        ktma::mbar_expect(bar, CSLOT * 8);
+        const CUtensorMap *m = tin.maps(i, set);
         const int i0 = tile_x0(), j0 = tile_y0();
-#pragma unroll
-        for (int i = 0; i < NIN; ++i) {
-            int set;
-            const int kc = plane_coord(i, k, set);
-            ktma::load3(ktma::s32(ksfd_smem + CRING + slot * CSLOT + Op::coff(i) * NTH),
-                        &tin.m[i][set][0], i0, j0, kc, bar);
+        if (!halo) {
+            ktma::load3(ktma::s32(ksfd_smem + CRING + slot * CSLOT + v.coff * NTH), m, i0, j0, kc, bar);
+            return;
         }
-    }
-    // (elected thread) fetch the halo boxes of plane k into halo slot `slot`
-    __device__ __forceinline__ void issue_halo(int k, int slot)
-    {
-        const unsigned bar = bar0 + 8 * (SC + slot);
-        ktma::mbar_expect(bar, HBYTES);
-        const int i0 = tile_x0(), j0 = tile_y0();
         const int xl = i0 >= KSFD_SW ? i0 - KSFD_SW : i0 - KSFD_SW + g.n0;
         const int xr = i0 + g.ox < g.n0 ? i0 + g.ox : i0 + g.ox - g.n0;
-        const double *base = ksfd_smem + HRING + slot * HSLOT;
-#pragma unroll
-        for (int i = 0; i < NIN; ++i) {
-            int set;
-            const int kc = plane_coord(i, k, set);
-            const CUtensorMap *m = &tin.m[i][set][0];
-            if (DIM == 2) {
-                ktma::load3(ktma::s32(base + hbox(i, 0)), m + 2, xl, 0, kc, bar);
-                ktma::load3(ktma::s32(base + hbox(i, 1)), m + 2, xr, 0, kc, bar);
-            } else {
-                const int yl = j0 >= KSFD_SW ? j0 - KSFD_SW : j0 - KSFD_SW + g.n1;
-                const int yr = j0 + g.oy < g.n1 ? j0 + g.oy : j0 + g.oy - g.n1;
-                ktma::load3(ktma::s32(base + hbox(i, 0)), m + 1, i0, yl, kc, bar);
-                ktma::load3(ktma::s32(base + hbox(i, 1)), m + 1, i0, yr, kc, bar);
-                ktma::load3(ktma::s32(base + hbox(i, 2)), m + 2, xl, j0, kc, bar);
-                ktma::load3(ktma::s32(base + hbox(i, 3)), m + 2, xr, j0, kc, bar);
-            }
+        const double *hb = ksfd_smem + HRING + slot * HSLOT;
+        if (DIM == 2) {
+            ktma::load3(ktma::s32(hb + (2 * i) * L::HVEC2), m + 2, xl, 0, kc, bar);
+            ktma::load3(ktma::s32(hb + (2 * i + 1) * L::HVEC2), m + 2, xr, 0, kc, bar);
+        } else {
+            const int yl = j0 >= KSFD_SW ? j0 - KSFD_SW : j0 - KSFD_SW + g.n1;
+            const int yr = j0 + g.oy < g.n1 ? j0 + g.oy : j0 + g.oy - g.n1;
+            const double *hv = hb + v.coff * NH;            // = hbox(i, 0)
+            ktma::load3(ktma::s32(hv), m + 1, i0, yl, kc, bar);
+            ktma::load3(ktma::s32(hv + nc * 2 * TX), m + 1, i0, yr, kc, bar);
+            ktma::load3(ktma::s32(hv + nc * 4 * TX), m + 2, xl, j0, kc, bar);
+            ktma::load3(ktma::s32(hv + nc * (4 * TX + 2 * TY)), m + 2, xr, j0, kc, bar);
         }
     }
 
@@ -395,11 +419,11 @@ struct TmaMarcher {
         }
         __syncthreads();
         // 4. refill the slots that every thread has finished reading
-        if (tid == 0) {
+        if (ivec != -1) {
             const int np = k1 - k0 + 2 * KSFD_SW;
-            if (it + SC < np) issue_centre(k0 - KSFD_SW + it + SC, cs_used);
+            if (it + SC < np) issue(0, k0 - KSFD_SW + it + SC, cs_used);
             if (emitting && it - 2 * KSFD_SW + SH < k1 - k0)
-                issue_halo(k0 + it - 2 * KSFD_SW + SH, hs_used);
+                issue(1, k0 + it - 2 * KSFD_SW + SH, hs_used);
         }
         // 5. the stencil of plane kk - 2
         if (emitting) {
@@ -457,5 +481,5 @@ k_tma_march(const __grid_constant__ MarchArgs g, const __grid_constant__ DevPhys
 template <int DIM, int TX, int TY, class Op, bool UNR, int SC, int SH>
 constexpr size_t tma_march_smem_bytes()
 {
-    return sizeof(double) * TmaMarcher<DIM, TX, TY, Op, UNR, SC, SH>::SMEM_DOUBLES;
+    return sizeof(double) * TmaLayout<DIM, TX, TY, Op, SC, SH>::SMEM_DOUBLES;
 }

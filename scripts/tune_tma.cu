@@ -160,15 +160,15 @@ static double time_launches(F launch, int nrot)
 }
 
 // reference kernels: record out[0] of one launch on buffer set 0 in pb.ref
-template <int DIM, int TX, int TY, class Op, int MINB, bool UNR>
+template <int DIM, int TX, int TY, class Op, int MINB, bool UNR, int RINGS = 2>
 static void run_ref(const char *name, Problem &pb, const DevPhys &P, Op op_proto,
-                    void (*bind)(Op &, const Problem &, int), bool record)
+                    void (*bind)(Op &, const Problem &, int), bool record, int waves = 0)
 {
     using T = TileT<DIM, TX, TY>;
     const int ord = g_ordinal;
     if (!selected() && !record) return;
-    auto kern = k_march<DIM, TX, TY, Op, MINB, UNR>;
-    const size_t smem = march_smem_bytes<Op, T::SP>();
+    auto kern = k_march<DIM, TX, TY, Op, MINB, UNR, RINGS>;
+    const size_t smem = march_smem_bytes<Op, T::SP, RINGS>();
     CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T::NT, smem));
@@ -176,7 +176,11 @@ static void run_ref(const char *name, Problem &pb, const DevPhys &P, Op op_proto
     CHECK(cudaFuncGetAttributes(&fa, kern));
     const int ntx = (pb.n0 + TX - 1) / TX, ox = (pb.n0 + ntx - 1) / ntx;
     const int nty = DIM == 3 ? (pb.n1 + TY - 1) / TY : 1, oy = DIM == 3 ? (pb.n1 + nty - 1) / nty : 1;
-    const int rz = pick_rz(0, (long long)ntx * nty, occ, pb.nloc);
+    if (occ < 1) {
+        printf("#%02d %-12s REF TX%3d TY%2d MINB%d R%d: occupancy 0\n", ord, name, TX, TY, MINB, RINGS);
+        return;
+    }
+    const int rz = pick_rz(-waves, (long long)ntx * nty, occ, pb.nloc);
     const int nch = (pb.nloc + rz - 1) / rz;
     MarchArgs a{pb.n0, pb.n1, pb.nloc, pb.n0 * pb.n1, ox, oy, rz};
     dim3 grid(ntx, nty, nch);
@@ -186,15 +190,29 @@ static void run_ref(const char *name, Problem &pb, const DevPhys &P, Op op_proto
         kern<<<grid, T::NT, smem>>>(a, P, op, nullptr);
     };
     const double us = time_launches(launch, pb.nrot);
+    unsigned long long hcnt = 0;
     if (record) {
         launch(0);
         CHECK(cudaMemcpy(pb.ref, pb.out[0], pb.npts * pb.nout * 8, cudaMemcpyDeviceToDevice));
+    } else {
+        CHECK(cudaMemset(pb.out[0], 0xff, pb.npts * pb.nout * 8));
+        launch(0);
+        unsigned long long *dcnt;
+        double *dmax;
+        CHECK(cudaMalloc(&dcnt, 8));
+        CHECK(cudaMalloc(&dmax, 8));
+        CHECK(cudaMemset(dcnt, 0, 8));
+        CHECK(cudaMemset(dmax, 0, 8));
+        k_diff<<<592, 256>>>(pb.out[0], pb.ref, pb.npts * pb.nout, dcnt, dmax);
+        CHECK(cudaMemcpy(&hcnt, dcnt, 8, cudaMemcpyDeviceToHost));
+        CHECK(cudaFree(dcnt));
+        CHECK(cudaFree(dmax));
     }
     CHECK(cudaDeviceSynchronize());
     const double gpts = pb.npts / us / 1e3;
-    printf("#%02d %-12s REF TX%3d TY%2d MINB%d regs%3d occ%d rz%4d grid %4dx%3dx%4d smem %6zu  %9.2f us  %6.2f Gpts/s  frac %.3f\n",
-           ord, name, TX, TY, MINB, fa.numRegs, occ, rz, ntx, nty, nch, smem, us, gpts,
-           gpts * 72.0 / 6544.7);
+    printf("#%02d %-12s REF TX%3d TY%2d MINB%d UNR%d R%d regs%3d occ%d rz%4d grid %4dx%3dx%4d smem %6zu  %9.2f us  %6.2f Gpts/s  frac %.3f  diff %llu %s\n",
+           ord, name, TX, TY, MINB, (int)UNR, RINGS, fa.numRegs, occ, rz, ntx, nty, nch, smem, us, gpts,
+           gpts * 72.0 / 6544.7, hcnt, record ? "(recorded)" : hcnt ? "MISMATCH" : "ok");
     fflush(stdout);
 }
 
@@ -302,37 +320,69 @@ static void bind_jvp(JvpOp<DIM, 2, PC> &op, const Problem &pb, int i)
     op.out = pb.out[i];
 }
 
-static void maps_or_die(CUtensorMap out[3], const double *base, const Problem &pb, long long nfp,
-                        int nc, int TX, int TY)
+static CUtensorMap *g_dmaps = nullptr;      // device pool of tensor maps (global-memory variant)
+static int g_dmaps_used = 0;
+// encode the three box shapes of one buffer; returns where the kernel finds them
+static void put_maps(void *dst, const double *base, const Problem &pb, long long nfp, int nc,
+                     int TX, int TY)
 {
-    std::string e = ksfd_make_tmaps(out, base, pb.n0, pb.n1, nfp, nc, TX, TY);
+    CUtensorMap h[3];
+    std::string e = ksfd_make_tmaps(h, base, pb.n0, pb.n1, nfp, nc, TX, TY);
     if (!e.empty()) {
         printf("%s\n", e.c_str());
         exit(1);
     }
+#if KSFD_TMAP_PARAM
+    memcpy(dst, h, sizeof(h));
+#else
+    if (!g_dmaps) CHECK(cudaMalloc(&g_dmaps, sizeof(CUtensorMap) * 3 * 4096));
+    if (g_dmaps_used + 3 > 3 * 4096) g_dmaps_used = 0;
+    CUtensorMap *d = g_dmaps + g_dmaps_used;
+    g_dmaps_used += 3;
+    CHECK(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice));
+    *reinterpret_cast<const CUtensorMap **>(dst) = d;
+#endif
 }
+#if KSFD_TMAP_PARAM
+#define MAPSLOT(t, i, set) ((void *)(t).m[i][set])
+#define MAPCOPY(t, i) memcpy((t).m[i][1], (t).m[i][0], sizeof((t).m[i][0]))
+#else
+#define MAPSLOT(t, i, set) ((void *)&(t).m[i][set])
+#define MAPCOPY(t, i) ((t).m[i][1] = (t).m[i][0])
+#endif
 static void tma_res(TmaInT<1> &t, const Problem &pb, int i, int TX, int TY)
 {
     memset(&t, 0, sizeof(t));
-    maps_or_die(t.m[0][0], pb.u[i], pb, 3LL * pb.nloc, 3, TX, TY);
-    memcpy(t.m[0][1], t.m[0][0], sizeof(t.m[0][0]));
-    t.v[0] = TmaVecIn{{0, 0, 0}, 1, nullptr, 0, 0};
+    put_maps(MAPSLOT(t, 0, 0), pb.u[i], pb, 3LL * pb.nloc, 3, TX, TY);
+    MAPCOPY(t, 0);
+    t.v[0].wrap = 1;
+    t.v[0].nc = 3;
+    t.v[0].coff = 0;
 }
 template <int NIN>
 static void tma_jvp(TmaInT<NIN> &t, const Problem &pb, int i, int TX, int TY)
 {
     memset(&t, 0, sizeof(t));
     // coef is stored ghosted: plane 0 is plane 2 of the buffer, its ghost planes are in place
-    maps_or_die(t.m[0][0], pb.coef, pb, 5LL * (pb.nloc + 4), 5, TX, TY);
-    memcpy(t.m[0][1], t.m[0][0], sizeof(t.m[0][0]));
-    t.v[0] = TmaVecIn{{2 * 5, 0, (2 + pb.nloc) * 5}, 0, nullptr, 0, 0};
-    maps_or_die(t.m[1][0], pb.v[i], pb, 3LL * pb.nloc, 3, TX, TY);
-    memcpy(t.m[1][1], t.m[1][0], sizeof(t.m[1][0]));
-    t.v[1] = TmaVecIn{{0, 0, 0}, 1, nullptr, 0, 0};
+    put_maps(MAPSLOT(t, 0, 0), pb.coef, pb, 5LL * (pb.nloc + 4), 5, TX, TY);
+    MAPCOPY(t, 0);
+    t.v[0].kofs[0] = 2 * 5;
+    t.v[0].kofs[1] = 0;
+    t.v[0].kofs[2] = (2 + pb.nloc) * 5;
+    t.v[0].wrap = 0;
+    t.v[0].nc = 5;
+    t.v[0].coff = 0;
+    put_maps(MAPSLOT(t, 1, 0), pb.v[i], pb, 3LL * pb.nloc, 3, TX, TY);
+    MAPCOPY(t, 1);
+    t.v[1].wrap = 1;
+    t.v[1].nc = 3;
+    t.v[1].coff = 5;
     if (NIN > 2) {
-        maps_or_die(t.m[NIN - 1][0], pb.pc, pb, 1LL * pb.nloc, 1, TX, TY);
-        memcpy(t.m[NIN - 1][1], t.m[NIN - 1][0], sizeof(t.m[0][0]));
-        t.v[NIN - 1] = TmaVecIn{{0, 0, 0}, 1, nullptr, 0, 0};
+        put_maps(MAPSLOT(t, NIN - 1, 0), pb.pc, pb, 1LL * pb.nloc, 1, TX, TY);
+        MAPCOPY(t, NIN - 1);
+        t.v[NIN - 1].wrap = 1;
+        t.v[NIN - 1].nc = 1;
+        t.v[NIN - 1].coff = 8;
     }
 }
 
@@ -384,6 +434,11 @@ static void free_problem(Problem &pb)
     run_ref<DIM, TX, TY, ResidualOp<DIM, 2, true>, MINB, false>("residual", pb, P, ResidualOp<DIM, 2, true>{}, bind_res<DIM>, REC)
 #define REF_JVP(DIM, TX, TY, MINB, PC, REC) \
     run_ref<DIM, TX, TY, JvpOp<DIM, 2, PC>, MINB, true>(PC ? "jvp_pc" : "jvp", pb, P, JvpOp<DIM, 2, PC>{}, bind_jvp<DIM, PC>, REC)
+// R4: four ring slots, the stencil lags the shared plane by two barriers
+#define R4_RES(DIM, TX, TY, MINB, UNR, W) \
+    run_ref<DIM, TX, TY, ResidualOp<DIM, 2, true>, MINB, UNR, 4>("residual", pb, P, ResidualOp<DIM, 2, true>{}, bind_res<DIM>, false, W)
+#define R4_JVP(DIM, TX, TY, MINB, UNR, PC, W) \
+    run_ref<DIM, TX, TY, JvpOp<DIM, 2, PC>, MINB, UNR, 4>(PC ? "jvp_pc" : "jvp", pb, P, JvpOp<DIM, 2, PC>{}, bind_jvp<DIM, PC>, false, W)
 #define TMA_RES(DIM, TX, TY, MINB, UNR, SC, SH) \
     run_tma<DIM, TX, TY, ResidualOp<DIM, 2, true>, MINB, UNR, SC, SH>("residual", pb, P, ResidualOp<DIM, 2, true>{}, bind_res<DIM>, tma_res, rzs, nrz)
 #define TMA_JVP(DIM, TX, TY, MINB, UNR, PC, SC, SH) \
@@ -400,43 +455,30 @@ int main(int argc, char **argv)
         DevPhys P = make_phys(dim);
         printf("== %dD n=%d  (%lld points, %d buffer sets)\n", dim, n, pb.npts, pb.nrot);
         if (dim == 2) {
-            REF_RES(2, 252, 1, 3, false);
             REF_RES(2, 124, 1, 6, true);
             TMA_RES(2, 128, 1, 6, false, 3, 3);
-            TMA_RES(2, 128, 1, 5, false, 4, 4);
             TMA_RES(2, 256, 1, 3, false, 3, 3);
-            TMA_RES(2, 256, 1, 2, false, 4, 4);
-            REF_JVP(2, 252, 1, 2, true, false);
             REF_JVP(2, 124, 1, 4, true, true);
             TMA_JVP(2, 128, 1, 4, true, true, 3, 3);
-            TMA_JVP(2, 128, 1, 4, true, true, 4, 4);
-            TMA_JVP(2, 128, 1, 3, true, true, 4, 4);
-            TMA_JVP(2, 128, 1, 4, false, true, 3, 3);
+            TMA_JVP(2, 128, 1, 4, true, true, 2, 2);
             TMA_JVP(2, 256, 1, 2, true, true, 3, 3);
-            TMA_JVP(2, 256, 1, 2, true, true, 4, 4);
             REF_JVP(2, 124, 1, 4, false, true);
             TMA_JVP(2, 128, 1, 4, true, false, 3, 3);
             TMA_JVP(2, 256, 1, 2, true, false, 3, 3);
         } else {
-            REF_RES(3, 32, 16, 1, false);
             REF_RES(3, 16, 16, 2, true);
             TMA_RES(3, 16, 16, 2, false, 3, 3);
-            TMA_RES(3, 16, 16, 3, false, 2, 2);
-            TMA_RES(3, 16, 16, 3, false, 3, 3);
-            TMA_RES(3, 16, 16, 4, false, 3, 3);
-            TMA_RES(3, 32, 8, 3, false, 3, 3);
-            TMA_RES(3, 32, 16, 1, false, 3, 3);
-            REF_JVP(3, 32, 8, 1, true, false);
+            TMA_RES(3, 16, 8, 4, false, 3, 3);
             REF_JVP(3, 16, 16, 1, true, true);
             TMA_JVP(3, 16, 16, 2, true, true, 2, 2);
             TMA_JVP(3, 16, 16, 2, true, true, 3, 2);
-            TMA_JVP(3, 16, 16, 2, false, true, 2, 2);
-            TMA_JVP(3, 16, 16, 1, true, true, 3, 3);
+            TMA_JVP(3, 16, 8, 4, true, true, 2, 2);
+            TMA_JVP(3, 16, 8, 3, true, true, 3, 3);
             TMA_JVP(3, 32, 8, 2, true, true, 2, 2);
-            TMA_JVP(3, 32, 8, 1, true, true, 3, 3);
             REF_JVP(3, 16, 16, 1, false, true);
             TMA_JVP(3, 16, 16, 2, true, false, 2, 2);
             TMA_JVP(3, 16, 16, 2, true, false, 3, 3);
+            TMA_JVP(3, 16, 8, 4, true, false, 2, 2);
         }
         free_problem(pb);
     }

@@ -49,7 +49,9 @@ def variants_for(p):
     dof = 1 + sum(len(g[2]) for g in p['groups'])
     if p['dim'] == 1 or dof - 1 > 4:
         return [1]
-    return [1, 2]
+    # 1 direct kernels, 2 marching (J.v through the TMA-fed marcher where the grid is
+    # eligible), 3 marching with the register-prefetch kernels only
+    return [1, 2, 3]
 
 
 def per_dof_err(a, b, dof):
@@ -431,8 +433,13 @@ def test_full_size_properties(label, p):
     Jv2 = ctx.jvp(v)
     ctx.set_option('variant', 1)
     Jv1 = ctx.jvp(v)
+    ctx.set_option('variant', 3)
+    Jv3 = ctx.jvp(v)
+    Jp3 = ctx.jvp(v, precond=True)
     ctx.set_option('variant', 2)
     assert (Jv2 - Jv1).abs().max().item() / Jv1.abs().max().item() < 1e-12
+    # the TMA-fed and the register-prefetch marcher share the stage / emit arithmetic
+    assert torch.equal(Jv2, Jv3) and torch.equal(ctx.jvp(v, precond=True), Jp3)
     eps = 1e-4
     fd = (ctx.residual(u + eps * v) - ctx.residual(u - eps * v)) / (2 * eps)
     Jv = ctx.from_internal(shift * v - ctx.jvp(v))
