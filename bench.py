@@ -172,6 +172,33 @@ def cpu_baseline(nsteps=1, n=96, procs=1):
                 seconds=wall)
 
 
+def cpu_operator_timing(n=TILE, reps=2):
+    """Same-config CPU operator numbers: the oracle's residual f(u) and
+    matrix-free J.v (numpy, one core) on the FULL 1024x1024 grid of the GPU roofline
+    kernels.  (The reference's own Derivatives.dfdt runs through oracle/refharness only
+    where /root/reference exists, which is not the case on the bench box: kind 'port'.)"""
+    from helpers import oracle_physics, random_state
+    from oracle import ksfd_oracle as O
+    p = phys_dict(2, (n, n))
+    ph = oracle_physics(p)
+    u = random_state(p, 7, rel=0.0)
+    v = np.random.default_rng(8).standard_normal(u.size)
+    shift = 1.0 / (ROSW_GAMMA * DT)
+    out = {}
+    for name, fn in (('residual', lambda: O.dfdt(u, ph)),
+                     ('jvp', lambda: O.jvp(u, v, shift, ph))):
+        fn()
+        best = 1e30
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t0)
+        out[name] = dict(seconds=best, mpts_per_s=n * n / best / 1e6)
+    return dict(grid='%dx%d' % (n, n), cores=1, kind='port',
+                sample='oracle numpy residual f(u) and matrix-free J.v on the full grid, best of %d' % reps,
+                **out)
+
+
 def reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -296,6 +323,141 @@ def step_timing_3d(n=256, nsteps=5, warm=2):
                 gmres_its_per_step=its / nsteps, steps=nsteps)
 
 
+def build_ctx(dim, n, local, rank, world):
+    from helpers import product_physics
+    from ksfd_b200 import core
+    ctx = core.Context(dim, n, 3, device=local, rank=rank, nranks=world)
+    ctx.set_physics(product_physics(phys_dict(dim, n)))
+    if world > 1:
+        from ksfd_b200 import parallel
+        parallel.init_comm(ctx)
+    return ctx
+
+
+def synthetic_state(ctx, rank, world):
+    """rho = 9000 + 90 N(0,1) from the rank's spawned stream, U = rho (internal layout)"""
+    import torch
+    rng = np.random.default_rng(np.random.SeedSequence(SEED).spawn(world)[rank])
+    rho = 9000.0 + 90.0 * rng.standard_normal(ctx.npts)
+    host = torch.from_numpy(np.repeat(rho, 3)).pin_memory()
+    return host, ctx.to_internal(host.cuda())
+
+
+def timed_steps(ctx, u, opts, nsteps, warm, world):
+    """ms per step (max over ranks), GMRES iterations per step"""
+    import torch
+    import torch.distributed as dist
+    t, its = 0.0, 0
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    for k in range(warm + nsteps):
+        if k == warm:
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0.record()
+            its = 0
+        ctx.groom(u)
+        r = ctx.ts_step(u, t, DT, opts)
+        if not r.accepted:
+            raise RuntimeError('time step failed (ksp_fail=%d)' % r.ksp_fail)
+        t = r.t_new
+        its += r.ksp_its
+        ctx.velocity_max(u)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()) / nsteps, its / nsteps
+
+
+def strong_scaling_records(local, rank, world, opts, nsteps=5, warm=2):
+    """BASELINE configs[2] / configs[3] inside the one bench line: the fixed GLOBAL grids
+    1024^2 and 256^3 split into `world` slabs (all ranks), and — on rank 0 alone — the same
+    grids on one GPU, so that the strong-scaling efficiency is measured in this run."""
+    import torch
+    import torch.distributed as dist
+    out = {}
+    for key, dim, n in (('strong_1024x1024', 2, (TILE, TILE)),
+                        ('strong_256x256x256', 3, (256, 256, 256))):
+        ctx = build_ctx(dim, n, local, rank, world)
+        _, u = synthetic_state(ctx, rank, world)
+        ms, its = timed_steps(ctx, u, opts, nsteps, warm, world)
+        rows = ctx.last_count
+        ctx.close()
+        del u
+        torch.cuda.empty_cache()
+        rec = dict(n_gpus=world, ms_per_step=ms, steps_per_sec=1e3 / ms,
+                   gmres_its_per_step=its, planes_per_gpu=rows, steps=nsteps)
+        if world > 1:
+            if rank == 0:
+                c1 = build_ctx(dim, n, local, 0, 1)
+                _, u1 = synthetic_state(c1, 0, 1)
+                ms1, its1 = timed_steps(c1, u1, opts, nsteps, warm, 1)
+                c1.close()
+                del u1
+                torch.cuda.empty_cache()
+                rec.update(ms_per_step_1gpu=ms1, speedup=ms1 / ms,
+                           efficiency=ms1 / ms / world, gmres_its_per_step_1gpu=its1)
+            dist.barrier()
+        out[key] = rec
+    return out
+
+
+def multi_gpu_parity(ctx, u, local, rank, world, n, opts):
+    """Correctness of the distributed run inside the bench line (VERDICT r1 #3b): residual,
+    J.v, fused A*M^-1 v and one ROSW step of the slab-decomposed problem against a
+    single-GPU recomputation of the same global problem on rank 0."""
+    import torch
+    import torch.distributed as dist
+    gen = torch.Generator(device='cuda').manual_seed(SEED + 17 + rank)
+    N = ctx.npts * 3
+    ud = torch.randn(N, generator=gen, device='cuda', dtype=torch.float64)
+    v = torch.randn(N, generator=gen, device='cuda', dtype=torch.float64)
+    shift = 1.0 / (ROSW_GAMMA * DT)
+    F = ctx.residual(u, ud)
+    ctx.jvp_setup(u, shift)
+    Jv = ctx.jvp(v)
+    Jp = ctx.jvp(v, precond=True)
+    u1 = u.clone()
+    ctx.groom(u1)
+    r = ctx.ts_step(u1, 0.0, DT, opts)
+    mine = [u, ud, v, F, Jv, Jp, u1]
+
+    def gather(t):
+        parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, parts, dst=0)
+        return torch.cat(parts) if rank == 0 else None      # slabs of the last axis: planes are outermost
+
+    full = [gather(t) for t in mine]
+    rec = None
+    if rank == 0:
+        c1 = build_ctx(2, n, local, 0, 1)
+        U, UD, V, Fm, Jvm, Jpm, U1m = full
+        F1 = c1.residual(U, UD)
+        c1.jvp_setup(U, shift)
+        Jv1 = c1.jvp(V)
+        Jp1 = c1.jvp(V, precond=True)
+        U1 = U.clone()
+        c1.groom(U1)
+        r1 = c1.ts_step(U1, 0.0, DT, opts)
+        rel = float(((U1m - U1).abs().max() / U1.abs().max()).item())
+        rec = dict(residual_bit_identical=bool(torch.equal(Fm, F1)),
+                   jvp_bit_identical=bool(torch.equal(Jvm, Jv1)),
+                   jvp_precond_bit_identical=bool(torch.equal(Jpm, Jp1)),
+                   rosw_step_max_rel_err=rel, rosw_step_tol=1e-12,
+                   gmres_its=[int(r.ksp_its), int(r1.ksp_its)],
+                   ok=bool(torch.equal(Fm, F1) and torch.equal(Jvm, Jv1)
+                           and torch.equal(Jpm, Jp1) and rel < 1e-12),
+                   reference='rank 0 recomputes the same global %dx%d problem on one GPU' % n)
+        c1.close()
+    dist.barrier()
+    return rec
+
+
 def native_arm(args):
     # stdout carries the ONE JSON line: NCCL's own log lines ("NCCL version ...",
     # NCCL_DEBUG=INFO output) go to stderr instead of their default, stdout
@@ -405,7 +567,24 @@ def native_arm(args):
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
     e2e_val = gpts * esteps / (float(ems.item()) * 1e-3) / 1e6
     nbytes = ctx.npts * 3 * 8
+    ctx_npts_local = ctx.npts
+    # ---- the stencil kernels INSIDE the step loop (CUDA events around every launch; a
+    # separate pass, not the timed one: the events cost a little on the stream)
+    ctx.set_option('profile', 1)
+    for _ in range(3):
+        step()
+    prof = ctx.profile_fetch()
+    ctx.set_option('profile', 0)
+    # ---- several GPUs: correctness of the distributed run in this very line
+    parity = None
+    if world > 1 and args.workload == 'weak-1024':
+        parity = multi_gpu_parity(ctx, u, local, rank, world, n, opts)
     ctx.close()
+    strong = None
+    if not args.quick and args.workload == 'weak-1024' and world > 1:
+        del u
+        torch.cuda.empty_cache()
+        strong = strong_scaling_records(local, rank, world, opts)
 
     extra = {}
     roof = None
@@ -419,18 +598,51 @@ def native_arm(args):
             extra['kernels_256x256x256'] = k3
             if world == 1:
                 extra['step_256x256x256'] = step_timing_3d()
+            if world == 1:
+                # BASELINE configs[4]: per-GPU tiles 512^2 .. 4096^2
+                sweep = {'1024x1024': k2, '256x256x256': k3}
+                for m in (512, 2048, 4096):
+                    sweep['%dx%d' % (m, m)], _, _ = kernel_rooflines(2, (m, m))
+                extra['kernel_sweep'] = sweep
         dom = k2['jvp_precond']
-        traffic = None
+        traffic, tsrc = None, None
         tp = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get('jvp_precond_1024x1024_bytes_per_launch')
-        roof = dict(bound='hbm', kernel='k_march<2,JvpOp<2,2,precond>> (fused A*M^-1 v)',
+            tj = json.load(open(tp))
+            traffic = tj.get('jvp_precond_1024x1024_bytes_per_launch')
+            tsrc = tj.get('source')
+        roof = dict(bound='hbm', kernel='k_tma_march<2,256,1,JvpOp<2,2,precond>> (fused A*M^-1 v, TMA-fed)',
                     achieved=dom['achieved_gbs'], peak=peak, unit='GB/s',
-                    frac=dom['frac'], traffic=traffic, peak_source=psrc,
+                    frac=dom['frac'], traffic=traffic, traffic_source=tsrc, peak_source=psrc,
                     algorithmic_bytes_per_point=ALG_BYTES_PER_PT,
-                    points_per_launch=TILE * TILE, us_per_launch=dom['us'])
+                    points_per_launch=TILE * TILE, us_per_launch=dom['us'],
+                    timing='CUDA events, 20 launches rotating over buffer sets > 2.5x L2 (cold)')
+        if prof['jvp_launches'] > 0:
+            # the same kernel where it actually runs: inside the ROSW/GMRES step loop, its
+            # operands partly L2-resident (coefficient field 42 MB, Krylov vectors 25 MB)
+            us_in = 1e3 * prof['jvp_ms'] / prof['jvp_launches']
+            ach = ctx_npts_local * ALG_BYTES_PER_PT / (us_in * 1e-6) / 1e9
+            roof['in_step'] = dict(us_per_launch=us_in, achieved=ach, frac=ach / peak,
+                                   launches=prof['jvp_launches'],
+                                   launches_incl_skipped=prof['jvp_launches_all'],
+                                   points_per_launch=ctx_npts_local,
+                                   timing='CUDA events around every J.v launch of 3 ROSW steps '
+                                          '(separate pass after the timed region)')
+        if prof['residual_launches'] > 0:
+            us_r = 1e3 * prof['residual_ms'] / prof['residual_launches']
+            ach = ctx_npts_local * ALG_BYTES_PER_PT / (us_r * 1e-6) / 1e9
+            extra['residual_in_step'] = dict(us_per_launch=us_r, achieved_gbs=ach, frac=ach / peak,
+                                             launches=prof['residual_launches'])
+        # where the step goes: mean device time of the active launches of each kind
+        extra['in_step_kernel_us'] = {
+            nm: dict(us=1e3 * prof[nm + '_ms'] / max(prof[nm + '_launches'], 1),
+                     launches_per_step=prof[nm + '_launches'] / 3.0)
+            for nm in ('jvp', 'residual', 'mdot', 'orth', 'first_vector', 'cycle_begin')}
         if world == 1 and not args.no_cpu:
             cpu = cpu_baseline(2, 96, 1)
+            extra['cpu_operator_1024x1024'] = cpu_operator_timing()
+    if strong is not None:
+        extra.update(strong)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -455,7 +667,7 @@ def native_arm(args):
                 e2e=dict(value=e2e_val, unit='Mpts*steps/s',
                          h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes,
                          steps=esteps),
-                roofline=roof, cpu_baseline=cpu, **extra)
+                roofline=roof, cpu_baseline=cpu, parity=parity, **extra)
     print(json.dumps(line), flush=True)
 
 

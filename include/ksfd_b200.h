@@ -81,14 +81,27 @@ int ksfd_ctx_create(ksfd_ctx **out, int dim, const int64_t n_global[3],
 int ksfd_ctx_destroy(ksfd_ctx *ctx);
 int ksfd_set_physics(ksfd_ctx *ctx, const ksfd_physics *phys);
 /* kernel selection / tuning: key in {"variant","tile","rz","gmres_pipeline",
-   "gmres_runahead","gmres_cycle_exp","halo_p2p"};
-   variant 0 = auto, 1 = naive direct kernels, 2 = marching kernels;
+   "gmres_runahead","gmres_cycle_exp","halo_p2p","profile"};
+   variant 0 = auto, 1 = naive direct kernels, 2 = marching kernels (J.v through the
+   TMA-fed marcher where the grid is eligible), 3 = marching, register-prefetch kernels only;
+   profile 1 = bracket every residual / J.v stencil launch with CUDA events
+   (ksfd_profile_fetch), 0 = off (default);
    tile = index of the marching tile shape (-1 = auto), rz = planes per CTA;
    gmres_pipeline 1 = device-decided launch-ahead GMRES (default), 0 = host
    driven; gmres_runahead = Arnoldi steps launched ahead; gmres_cycle_exp = k:
    close a cycle after a 1e-k residual reduction; halo_p2p 0/1 */
 int ksfd_set_option(ksfd_ctx *ctx, const char *key, int64_t value);
 int64_t ksfd_local_size(const ksfd_ctx *ctx);   /* dof * owned points */
+/* In-situ kernel timing (option "profile"): synchronises `stream`, then for each kind
+   k < 8 of bracketed launch (0 J.v stencil, 1 residual stencil, 2 multi-dot incl. rank
+   sum and Givens update, 3 orthogonalise-and-scale incl. halo push, 4 first Krylov
+   vector, 5 start of a GMRES cycle, 6-7 unused):
+   out[3k] = ACTIVE launches since the last fetch, out[3k+1] = their summed device time
+   in ms, out[3k+2] = all bracketed launches; resets the counters.  Launches the
+   pipelined solver made ahead of a convergence test and that returned at once are not
+   real passes: a launch is ACTIVE when it lasted at least a quarter of the longest
+   launch of its kind. */
+int ksfd_profile_fetch(ksfd_ctx *ctx, double out[24], void *stream);
 
 /* ---- layout boundary: reference layout (what PETSc Vec.array / the HDF5
  *      TimeSeries hold, KSFD/ksfdtimeseries.py:485-488) <-> internal ------ */

@@ -17,7 +17,7 @@ MAX_GROUPS = 7
 EXPORTS = [
     'ksfd_abi_version', 'ksfd_last_error', 'ksfd_launch_count',
     'ksfd_ctx_create', 'ksfd_ctx_destroy', 'ksfd_set_physics',
-    'ksfd_set_option', 'ksfd_local_size',
+    'ksfd_set_option', 'ksfd_local_size', 'ksfd_profile_fetch',
     'ksfd_to_internal', 'ksfd_from_internal',
     'ksfd_nccl_unique_id', 'ksfd_comm_init', 'ksfd_p2p_export', 'ksfd_p2p_import',
     'ksfd_halo_exchange',
@@ -103,6 +103,7 @@ def load():
     lib.ksfd_ctx_destroy.argtypes = [vp]
     lib.ksfd_set_physics.argtypes = [vp, C.POINTER(Physics)]
     lib.ksfd_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.ksfd_profile_fetch.argtypes = [vp, C.POINTER(C.c_double), vp]
     lib.ksfd_to_internal.argtypes = [vp, dp, dp, i32, vp]
     lib.ksfd_from_internal.argtypes = [vp, dp, dp, i32, vp]
     lib.ksfd_nccl_unique_id.argtypes = [C.c_char_p, C.c_char_p]

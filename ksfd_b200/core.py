@@ -185,6 +185,19 @@ class Context:
     def set_option(self, key, value):
         _lib.check(self.lib.ksfd_set_option(self.h, key.encode(), int(value)))
 
+    def profile_fetch(self):
+        """in-situ stencil kernel timing (set_option('profile', 1)): dict of launch
+        counts and summed device milliseconds since the last fetch"""
+        out = (C.c_double * 24)()
+        _lib.check(self.lib.ksfd_profile_fetch(self.h, out, _stream()))
+        names = ['jvp', 'residual', 'mdot', 'orth', 'first_vector', 'cycle_begin']
+        d = {}
+        for k, nm in enumerate(names):
+            d[nm + '_launches'] = int(out[3 * k])
+            d[nm + '_ms'] = out[3 * k + 1]
+            d[nm + '_launches_all'] = int(out[3 * k + 2])
+        return d
+
     def comm_init(self, nccl_path, unique_id):
         _lib.check(self.lib.ksfd_comm_init(self.h, (nccl_path or '').encode(),
                                            self.nranks, self.rank, unique_id))

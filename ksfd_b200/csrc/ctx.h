@@ -78,6 +78,9 @@ struct ksfd_ctx {
     bool have_phys = false;
     // options
     int variant = 0, opt_tx = -1, opt_rz = 0;
+    // in-situ kernel timing (option "profile"): event pairs around the stencil launches
+    bool prof_on = false;
+    void *prof = nullptr;        // ProfState* (ksfd.cu)
     bool opt_tile_set = false;
     // comm
     int nranks = 1, rank = 0;

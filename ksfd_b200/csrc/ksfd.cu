@@ -92,6 +92,52 @@ static int nccl_load(const char *path)
 #define SC_AUX 126               // [inv h_{j+1}, cancellation flag], right after the column
 static long long nlocal(const ksfd_ctx *c) { return c->g.npts * c->dof; }
 
+// in-situ kernel timing: CUDA event pairs around launches (kind 0 J.v stencil, 1 residual
+// stencil, 2 multi-dot (+ rank sum, Givens), 3 orthogonalise-and-scale (+ halo push),
+// 4 first Krylov vector, 5 start of a cycle (norm / true residual), 6-7 unused); scopes nest
+struct ProfRec {
+    int kind, start, stop;
+};
+struct ProfState {
+    std::vector<cudaEvent_t> pool;          // reused events
+    std::vector<ProfRec> recs;
+    size_t used = 0;
+};
+static int prof_event(ProfState *ps, cudaStream_t st)
+{
+    if (ps->used == ps->pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ps->pool.push_back(e);
+    }
+    cudaEventRecord(ps->pool[ps->used], st);
+    return (int)ps->used++;
+}
+struct ProfScope {
+    ksfd_ctx *c;
+    cudaStream_t st;
+    int kind, start;
+    ProfScope(ksfd_ctx *c_, int kind_, cudaStream_t st_)
+        : c(c_->prof_on ? c_ : nullptr), st(st_), kind(kind_), start(-1)
+    {
+        if (!c) return;
+        if (!c->prof) c->prof = new ProfState();
+        ProfState *ps = static_cast<ProfState *>(c->prof);
+        if (ps->used > 200000) {        // a forgotten profile switch must not grow without bound
+            c = nullptr;
+            return;
+        }
+        start = prof_event(ps, st);
+    }
+    ~ProfScope()
+    {
+        if (!c) return;
+        ProfState *ps = static_cast<ProfState *>(c->prof);
+        const int stop = prof_event(ps, st);
+        ps->recs.push_back(ProfRec{kind, start, stop});
+    }
+};
+
 static int ensure_work(ksfd_ctx *c, int i)
 {
     if (!c->work[i]) CK(cudaMalloc(&c->work[i], sizeof(double) * nlocal(c)));
@@ -178,12 +224,51 @@ extern "C" int ksfd_ctx_destroy(ksfd_ctx *c)
     if (c->p2p_err) cudaFreeHost(c->p2p_err);
     if (c->gm_status) cudaFreeHost(c->gm_status);
     for (auto &w : c->work) cudaFree(w);
+    if (c->prof) {
+        ProfState *ps = static_cast<ProfState *>(c->prof);
+        for (cudaEvent_t e : ps->pool) cudaEventDestroy(e);
+        delete ps;
+    }
     ksfd_free_plans(c);
     delete c;
     return 0;
 }
 
 extern "C" int64_t ksfd_local_size(const ksfd_ctx *c) { return c ? nlocal(c) : 0; }
+
+#define KSFD_PROF_KINDS 8
+extern "C" int ksfd_profile_fetch(ksfd_ctx *c, double out[3 * KSFD_PROF_KINDS], void *stream)
+{
+    if (!c || !out) return fail("ksfd_profile_fetch: NULL argument");
+    for (int i = 0; i < 3 * KSFD_PROF_KINDS; ++i) out[i] = 0.0;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    ProfState *ps = static_cast<ProfState *>(c->prof);
+    if (!ps) return 0;
+    std::vector<float> ms(ps->recs.size(), 0.f);
+    float mx[KSFD_PROF_KINDS] = {0.f};
+    for (size_t i = 0; i < ps->recs.size(); ++i) {
+        const ProfRec &o = ps->recs[i];
+        if (cudaEventElapsedTime(&ms[i], ps->pool[o.start], ps->pool[o.stop]) != cudaSuccess) {
+            cudaGetLastError();
+            ms[i] = 0.f;
+        }
+        mx[o.kind] = std::max(mx[o.kind], ms[i]);
+    }
+    // launches of the pipelined solver that were made ahead of a convergence test and
+    // returned at once are not real passes: only launches of at least a quarter of the
+    // longest one of their kind count as ACTIVE
+    for (size_t i = 0; i < ps->recs.size(); ++i) {
+        const int k = ps->recs[i].kind;
+        out[3 * k + 2] += 1.0;
+        if (ms[i] >= 0.25f * mx[k] && ms[i] > 0.f) {
+            out[3 * k] += 1.0;
+            out[3 * k + 1] += ms[i];
+        }
+    }
+    ps->recs.clear();
+    ps->used = 0;
+    return 0;
+}
 
 extern "C" int ksfd_set_physics(ksfd_ctx *c, const ksfd_physics *p)
 {
@@ -267,6 +352,7 @@ extern "C" int ksfd_set_option(ksfd_ctx *c, const char *key, int64_t v)
     if (k == "variant") c->variant = (int)v;
     else if (k == "tile") { c->opt_tx = (int)v; c->opt_tile_set = v >= 0; }
     else if (k == "rz") c->opt_rz = (int)v;
+    else if (k == "profile") c->prof_on = v != 0;
     else if (k == "gmres_pipeline") c->gm_pipeline = (int)v;
     else if (k == "halo_p2p") c->p2p_on = v != 0 && c->p2p_up != nullptr;   // same on all ranks
     else if (k == "gmres_cycle_exp") c->gm_cycle_factor = v <= 0 ? 0.0 : std::pow(10.0, -(double)v);
@@ -746,6 +832,7 @@ static int residual_impl(ksfd_ctx *c, const double *u, const double *udot,
 {
     TRY(exchange(c, u, c->dof, 0, st, nullptr, c->p2p_on && tma_consumer(c)));
     const HostVec uh = make_hvec(c, u, c->dof, 0);
+    ProfScope prof(c, 1, st);
     if (use_march(c)) {
         return c->dim == 2 ? ksfd_march_residual_d2(c, uh, udot, src, f, st)
                            : ksfd_march_residual_d3(c, uh, udot, src, f, st);
@@ -888,6 +975,7 @@ static int jvp_impl(ksfd_ctx *c, const double *v, double *out, bool precond,
     const HostVec ch = coef_hvec(c);
     VecRef &vr = vh.r;
     const VecRef &pr = ph.r, &cr = ch.r;
+    ProfScope prof(c, 0, st);
     if (use_march(c)) {
         return c->dim == 2 ? ksfd_march_jvp_d2(c, ch, vh, ph, precond, out, skip, st)
                            : ksfd_march_jvp_d3(c, ch, vh, ph, precond, out, skip, st);
@@ -1679,6 +1767,7 @@ template <int NV>
 static int gm_mdot_launch(ksfd_ctx *c, const VecList &vl, const double *w, const GmFin *fin,
                           cudaStream_t st)
 {
+    ProfScope prof(c, 2, st);
     if (fin) {
         KSFD_KLAUNCH((k_gm_mdot<NV, true>), KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st, nlocal(c), vl, w,
                      c->gmi, c->partial, *fin);
@@ -1696,6 +1785,7 @@ static int gm_orth_launch(ksfd_ctx *c, const VecList &vl, int off, int do_scale,
 {
     // the launch that finishes the new basis vector also pushes its boundary planes to
     // the neighbours (the vector is the operand of the next J.v)
+    ProfScope prof(c, 3, st);
     HaloPush hp{};
     if (do_scale) {
         hp = make_push(c, 1);
@@ -1839,6 +1929,8 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
         const bool fuse_begin = c->nranks == 1 || c->p2p_on;
         GmBegin gb{KSFD_RED_BLOCKS, c->partial, c->gm, c->gmi, hsd, cycle, go, p2p_red(c),
                    c->gm_done};
+        {
+        ProfScope prof_begin(c, 5, st);
         if (cycle == 0) {
             if (fuse_begin) {
                 KSFD_KLAUNCH(k_gm_norm_begin, KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st, n, rhs,
@@ -1878,7 +1970,9 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
             k_gm_cycle_begin<<<1, 32, 0, st>>>(g1);
             CKL();
         }
+        }
         {
+            ProfScope prof(c, 4, st);
             const HaloPush hp = make_push(c, 1);
             if (hp.up_lo0) c->pushed_vec = V;
             KSFD_KLAUNCH(k_gm_first_vector, KSFD_RED_BLOCKS, 256, 0, st, n, r, c->gm, c->gmi, sign, V,
