@@ -636,7 +636,8 @@ def native_arm(args):
         # where the step goes: mean device time of the active launches of each kind
         extra['in_step_kernel_us'] = {
             nm: dict(us=1e3 * prof[nm + '_ms'] / max(prof[nm + '_launches'], 1),
-                     launches_per_step=prof[nm + '_launches'] / 3.0)
+                     launches_per_step=prof[nm + '_launches'] / 3.0,
+                     ms_per_step=prof[nm + '_ms_all'] / 3.0)
             for nm in ('jvp', 'residual', 'mdot', 'orth', 'first_vector', 'cycle_begin')}
         if world == 1 and not args.no_cpu:
             cpu = cpu_baseline(2, 96, 1)

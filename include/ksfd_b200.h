@@ -96,12 +96,12 @@ int64_t ksfd_local_size(const ksfd_ctx *ctx);   /* dof * owned points */
    k < 8 of bracketed launch (0 J.v stencil, 1 residual stencil, 2 multi-dot incl. rank
    sum and Givens update, 3 orthogonalise-and-scale incl. halo push, 4 first Krylov
    vector, 5 start of a GMRES cycle, 6-7 unused):
-   out[3k] = ACTIVE launches since the last fetch, out[3k+1] = their summed device time
-   in ms, out[3k+2] = all bracketed launches; resets the counters.  Launches the
-   pipelined solver made ahead of a convergence test and that returned at once are not
-   real passes: a launch is ACTIVE when it lasted at least a quarter of the longest
-   launch of its kind. */
-int ksfd_profile_fetch(ksfd_ctx *ctx, double out[24], void *stream);
+   out[4k] = ACTIVE launches since the last fetch, out[4k+1] = their summed device time
+   in ms, out[4k+2] = all bracketed launches, out[4k+3] = their summed time; resets the
+   counters.  Launches the pipelined solver made ahead of a convergence test and that
+   returned at once (~2 us) are not real passes: a launch is ACTIVE when it lasted at
+   least 4 us and at least 1/20 of the longest launch of its kind. */
+int ksfd_profile_fetch(ksfd_ctx *ctx, double out[32], void *stream);
 
 /* ---- layout boundary: reference layout (what PETSc Vec.array / the HDF5
  *      TimeSeries hold, KSFD/ksfdtimeseries.py:485-488) <-> internal ------ */
@@ -172,6 +172,11 @@ int ksfd_maxpy(ksfd_ctx *ctx, int nv, const double *coef_host,
 int ksfd_norm2(ksfd_ctx *ctx, const double *x, double *out_host, void *stream);
 int ksfd_sum_dof0(ksfd_ctx *ctx, const double *u, double *out_host, void *stream);
 int ksfd_scale_dof0(ksfd_ctx *ctx, double *u, double factor, void *stream);
+/* u[dof 0] *= exp(sd * z): the lognormal noise injection of KSFDTS.add_variance
+   (KSFD/ksfdts.py:268-284).  z_dev: one standard-normal value per owned point (x fastest),
+   drawn by the caller from the rank's numpy stream — the reference's stream — and copied
+   to the device; the field stays on the device. */
+int ksfd_mul_exp_dof0(ksfd_ctx *ctx, double *u, const double *z_dev, double sd, void *stream);
 
 /* ---- linear solve: replaces KSP preonly + PC LU (MUMPS) with a
  *      device-resident restarted GMRES, right-preconditioned by block

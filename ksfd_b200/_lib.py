@@ -25,7 +25,7 @@ EXPORTS = [
     'ksfd_jvp_setup', 'ksfd_jvp', 'ksfd_jvp_precond', 'ksfd_pc_apply',
     'ksfd_block_diagonal',
     'ksfd_mdot', 'ksfd_maxpy', 'ksfd_norm2', 'ksfd_sum_dof0',
-    'ksfd_scale_dof0', 'ksfd_gmres', 'ksfd_ts_step',
+    'ksfd_scale_dof0', 'ksfd_mul_exp_dof0', 'ksfd_gmres', 'ksfd_ts_step',
     'ksfd_allreduce_max', 'ksfd_allreduce_sum',
 ]
 
@@ -126,6 +126,7 @@ def load():
     lib.ksfd_norm2.argtypes = [vp, dp, C.POINTER(C.c_double), vp]
     lib.ksfd_sum_dof0.argtypes = [vp, dp, C.POINTER(C.c_double), vp]
     lib.ksfd_scale_dof0.argtypes = [vp, dp, C.c_double, vp]
+    lib.ksfd_mul_exp_dof0.argtypes = [vp, dp, dp, C.c_double, vp]
     lib.ksfd_gmres.argtypes = [vp, dp, dp, C.POINTER(KspOpts),
                                C.POINTER(KspResult), vp]
     lib.ksfd_ts_step.argtypes = [vp, dp, C.c_double, C.c_double,

@@ -28,7 +28,7 @@ NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
     '-std=c++17', '-Xcompiler', '-fPIC',
 ]
-# experiments: e.g. KSFD_NVCC_EXTRA="-DKSFD_PDL=1" python -m ksfd_b200.build --force
+# experiments: e.g. KSFD_NVCC_EXTRA="-DKSFD_TMAP_PARAM=0" python -m ksfd_b200.build --force
 NVCC_FLAGS += os.environ.get('KSFD_NVCC_EXTRA', '').split()
 
 
@@ -98,7 +98,7 @@ def _build(force, verbose):
 
 
 if __name__ == '__main__':
-    if '--out' in sys.argv:         # python -m ksfd_b200.build --out libksfd_b200_pdl.so -DKSFD_PDL=1
+    if '--out' in sys.argv:         # python -m ksfd_b200.build --out libksfd_b200_x.so -DSOME_SWITCH=1
         i = sys.argv.index('--out')
         print(build(out=sys.argv[i + 1], extra=sys.argv[i + 2:], verbose='-v' in sys.argv))
     else:

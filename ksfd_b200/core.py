@@ -188,14 +188,15 @@ class Context:
     def profile_fetch(self):
         """in-situ stencil kernel timing (set_option('profile', 1)): dict of launch
         counts and summed device milliseconds since the last fetch"""
-        out = (C.c_double * 24)()
+        out = (C.c_double * 32)()
         _lib.check(self.lib.ksfd_profile_fetch(self.h, out, _stream()))
         names = ['jvp', 'residual', 'mdot', 'orth', 'first_vector', 'cycle_begin']
         d = {}
         for k, nm in enumerate(names):
-            d[nm + '_launches'] = int(out[3 * k])
-            d[nm + '_ms'] = out[3 * k + 1]
-            d[nm + '_launches_all'] = int(out[3 * k + 2])
+            d[nm + '_launches'] = int(out[4 * k])
+            d[nm + '_ms'] = out[4 * k + 1]
+            d[nm + '_launches_all'] = int(out[4 * k + 2])
+            d[nm + '_ms_all'] = out[4 * k + 3]
         return d
 
     def comm_init(self, nccl_path, unique_id):
@@ -290,6 +291,16 @@ class Context:
     def scale_dof0(self, u, f):
         _lib.check(self.lib.ksfd_scale_dof0(self.h, _ptr(self._chk(u)), float(f),
                                             _stream()))
+
+    def mul_exp_dof0(self, u, z_host, sd):
+        """u[dof 0] *= exp(sd*z) on the device; z_host: numpy sample, one value per owned
+        point in Fortran (x fastest) order"""
+        import torch
+        z = torch.from_numpy(np.ascontiguousarray(
+            np.asarray(z_host, dtype=np.float64).reshape(-1, order='F'))).to(self.tdev)
+        self._chk(z, self.npts)
+        _lib.check(self.lib.ksfd_mul_exp_dof0(self.h, _ptr(self._chk(u)), _ptr(z), float(sd),
+                                              _stream()))
 
     # -- solvers -----------------------------------------------------------
     def gmres(self, rhs, x=None, rtol=1e-5, atol=1e-50, dtol=1e5, max_it=10000,

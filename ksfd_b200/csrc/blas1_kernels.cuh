@@ -285,6 +285,20 @@ __global__ void k_scale_dof0(long long npts, long long plane_pts, int dof, doubl
     }
 }
 
+// rho[p] *= exp(sd * z[p]): lognormal multiplicative noise on the cell density
+// (KSFD/ksfdts.py:268-284; z = the standard-normal sample of the rank's numpy stream, one
+// value per owned point in x-fastest order, drawn on the host so that the stream is the
+// reference's; the field itself never leaves the device)
+__global__ void k_mul_exp_dof0(long long npts, long long plane_pts, int dof, double sd,
+                               const double *__restrict__ z, double *__restrict__ u)
+{
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npts;
+         p += (long long)gridDim.x * blockDim.x) {
+        const long long k = p / plane_pts;
+        u[k * dof * plane_pts + (p - k * plane_pts)] *= exp(sd * z[p]);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // All-reduce of a few doubles over NVLink peer memory, INSIDE a single-block
 // kernel (fused with the reduction / Givens kernels of the solver: no NCCL call
@@ -344,6 +358,13 @@ struct P2PRed {
 // skip (identically on all ranks: the skip flag is a function of reduced data)
 // make no exchange and leave no gap, so the host may launch ahead by different
 // amounts on different ranks.
+//
+// Wire format ("LL", as NCCL's low-latency protocol): every double travels as two 8-byte
+// words {32 data bits, 32-bit exchange number}; an aligned 8-byte store is indivisible,
+// so a word whose tag equals the current exchange number carries valid data — no
+// separate flag, no system-scope fence on either side, one NVLink store latency per
+// all-reduce (measured against the fence + flag version: multi-dot tail 9 us -> see
+// profiles/r02_multi_gpu_step_breakdown.txt).  Double-buffered on q&1 as before.
 __device__ __forceinline__ void p2p_allreduce(const P2PRed &pr, double *vals, int n, int op)
 {
     __shared__ unsigned long long q_;
@@ -352,42 +373,59 @@ __device__ __forceinline__ void p2p_allreduce(const P2PRed &pr, double *vals, in
         q_ = *pr.ctr + 1;
         ok_ = !(pr.dead && *pr.dead);
     }
-    __syncthreads();
+    __syncthreads();                         // also: vals complete
     if (!ok_) return;                        // uniform: a peer is gone, the host will report it
     const unsigned long long q = q_;
+    const unsigned tag = (unsigned)q;
     const int par = (int)(q & 1);
-    const long long slot0 = pr.red_off + (long long)par * pr.nranks * KSFD_P2P_RED_MAX;
-    __syncthreads();                         // vals complete
-    for (int t = threadIdx.x; t < n * pr.nranks; t += blockDim.x) {
-        const int r = t / n, i = t - r * n;
-        pr.base[r][slot0 + (long long)pr.rank * KSFD_P2P_RED_MAX + i] = vals[i];
+    // words of rank s's contribution in rank r's area: [par][s][2 * KSFD_P2P_RED_MAX]
+    const long long slot0 = pr.red_off + (long long)par * pr.nranks * (2 * KSFD_P2P_RED_MAX);
+    const int nw = 2 * n;
+    for (int t = threadIdx.x; t < nw * pr.nranks; t += blockDim.x) {
+        const int r = t / nw, wd = t - r * nw;
+        if (r == pr.rank) continue;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[wd >> 1]);
+        const unsigned half = (wd & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
+        volatile unsigned long long *dst = reinterpret_cast<volatile unsigned long long *>(
+            pr.base[r] + slot0 + (long long)pr.rank * (2 * KSFD_P2P_RED_MAX) + wd);
+        *dst = ((unsigned long long)tag << 32) | half;
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < pr.nranks && threadIdx.x != pr.rank) {
-        volatile unsigned long long *f =
-            reinterpret_cast<volatile unsigned long long *>(pr.base[threadIdx.x]) +
-            KSFD_P2P_RFLAG0 + pr.rank;
-        *f = q;
-        volatile unsigned long long *mine =
-            reinterpret_cast<volatile unsigned long long *>(pr.base[pr.rank]) +
-            KSFD_P2P_RFLAG0 + threadIdx.x;
-        if (!p2p_spin(mine, q, pr.err, pr.dead)) ok_ = 0;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (!ok_) return;                        // counter not advanced, contributions not summed
-    const volatile double *area = pr.base[pr.rank] + slot0;
+    __syncthreads();                         // every word is on its way before vals is overwritten
+    // collect: thread i < n assembles element i of every rank and reduces in rank order
+    // (bitwise identical on all ranks)
+    const volatile unsigned long long *area =
+        reinterpret_cast<const volatile unsigned long long *>(pr.base[pr.rank] + slot0);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        double s = area[i];
-        for (int r = 1; r < pr.nranks; ++r) {
-            const double v = area[(long long)r * KSFD_P2P_RED_MAX + i];
-            s = op == 1 ? fmax(s, v) : s + v;
+        double s = 0.0;
+        for (int r = 0; r < pr.nranks; ++r) {
+            double v;
+            if (r == pr.rank) {
+                v = vals[i];
+            } else {
+                const volatile unsigned long long *src = area + (long long)r * (2 * KSFD_P2P_RED_MAX) + 2 * i;
+                unsigned long long lo, hi;
+                const long long t0 = clock64();
+                unsigned spins = 0;
+                for (;;) {
+                    lo = src[0];
+                    hi = src[1];
+                    if ((unsigned)(lo >> 32) == tag && (unsigned)(hi >> 32) == tag) break;
+                    if ((++spins & 0xfff) == 0 &&
+                        (clock64() - t0 > KSFD_P2P_TIMEOUT_CYCLES || (pr.dead && *pr.dead))) {
+                        if (pr.dead) *pr.dead = 1ull;
+                        if (pr.err) *pr.err = 1;
+                        ok_ = 0;
+                        break;
+                    }
+                }
+                v = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+            }
+            s = r == 0 ? v : (op == 1 ? fmax(s, v) : s + v);
         }
         vals[i] = s;
     }
     __syncthreads();
-    if (threadIdx.x == 0) *pr.ctr = q;
+    if (threadIdx.x == 0 && ok_) *pr.ctr = q;
 }
 
 // stand-alone version for the remaining small reductions (norms, error norm,
@@ -431,24 +469,46 @@ __device__ __forceinline__ long long halo_push_shift(const HaloPush &hp, unsigne
     q = *reinterpret_cast<volatile unsigned long long *>(hp.ctr) + 1;
     return (long long)(q & 1ull) * hp.pstride;
 }
-__device__ __forceinline__ void halo_push1(const HaloPush &hp, long long sh, long long e, double v)
+// returns true when this thread stored into peer memory
+__device__ __forceinline__ bool halo_push1(const HaloPush &hp, long long sh, long long e, double v)
 {
-    if (e < hp.cnt) hp.dn_hi0[sh + e] = v;
-    if (e >= hp.top0) hp.up_lo0[sh + e - hp.top0] = v;
+    bool did = false;
+    if (e < hp.cnt) {
+        hp.dn_hi0[sh + e] = v;
+        did = true;
+    }
+    if (e >= hp.top0) {
+        hp.up_lo0[sh + e - hp.top0] = v;
+        did = true;
+    }
+    return did;
 }
 // elements 2e, 2e+1 (cnt and top0 are even whenever the double2 path runs)
-__device__ __forceinline__ void halo_push2(const HaloPush &hp, long long sh, long long e2, double2 v)
+__device__ __forceinline__ bool halo_push2(const HaloPush &hp, long long sh, long long e2, double2 v)
 {
     const long long e = 2 * e2;
-    if (e < hp.cnt) *reinterpret_cast<double2 *>(hp.dn_hi0 + sh + e) = v;
-    if (e >= hp.top0) *reinterpret_cast<double2 *>(hp.up_lo0 + sh + e - hp.top0) = v;
+    bool did = false;
+    if (e < hp.cnt) {
+        *reinterpret_cast<double2 *>(hp.dn_hi0 + sh + e) = v;
+        did = true;
+    }
+    if (e >= hp.top0) {
+        *reinterpret_cast<double2 *>(hp.up_lo0 + sh + e - hp.top0) = v;
+        did = true;
+    }
+    return did;
 }
-// every thread of every block calls this after its stores
-__device__ __forceinline__ void halo_push_publish(const HaloPush &hp, unsigned long long q)
+// Every thread of every block calls this after its stores.  Only the threads that wrote
+// peer memory pay for a system-scope fence (measured: with the fence in all 150k threads
+// the producer kernels took 12-13 us longer, profiles/r02_multi_gpu_step_breakdown.txt);
+// the block counter is a device-scope atomic, and the block that finishes last orders
+// its flag stores after everything it observed with one more system fence.
+__device__ __forceinline__ void halo_push_publish(const HaloPush &hp, unsigned long long q, bool did)
 {
-    __threadfence_system();
+    if (did) __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();
         const unsigned t = atomicAdd(hp.done, 1u);
         if (t == gridDim.x - 1) {               // last block: all planes are on their way
             atomicExch(hp.done, 0u);
@@ -652,6 +712,7 @@ __global__ void k_gm_first_vector(long long n, const double *x, const double *__
     if (KSFD_FLAG(gmi + GMI_FINAL)) return;
     const double f = sign / KSFD_FLAG(gm + GM_BETA);
     const bool push = halo_push_on(hp);
+    bool did = false;
     unsigned long long q = 0;
     const long long sh = push ? halo_push_shift(hp, q) : 0;
     if ((n & 1) == 0 && aligned16(x) && aligned16(y)) {
@@ -663,17 +724,17 @@ __global__ void k_gm_first_vector(long long n, const double *x, const double *__
             v.x *= f;
             v.y *= f;
             y2[e] = v;
-            if (push) halo_push2(hp, sh, e, v);
+            if (push) did |= halo_push2(hp, sh, e, v);
         }
     } else {
         for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
              e += (long long)gridDim.x * blockDim.x) {
             const double v = x[e] * f;
             y[e] = v;
-            if (push) halo_push1(hp, sh, e, v);
+            if (push) did |= halo_push1(hp, sh, e, v);
         }
     }
-    if (push) halo_push_publish(hp, q);
+    if (push) halo_push_publish(hp, q, did);
 }
 
 // partial[i][block] = <vs[i], w>, skipping when the cycle is closed
@@ -922,6 +983,7 @@ k_gm_orth_scale(long long n, VecList vs, int off, int do_scale,
     for (int i = 0; i < NV; ++i) hh[i] = KSFD_FLAG(gm + GM_HCOL + off + i);
     const double sc = do_scale ? KSFD_FLAG(gm + GM_INV) : 1.0;
     const bool push = halo_push_on(hp);
+    bool did = false;
     unsigned long long q = 0;
     const long long sh = push ? halo_push_shift(hp, q) : 0;
     if (all_aligned16<NV>(n, vs, w)) {
@@ -938,7 +1000,7 @@ k_gm_orth_scale(long long n, VecList vs, int off, int do_scale,
             s.x *= sc;
             s.y *= sc;
             w2[e] = s;
-            if (push) halo_push2(hp, sh, e, s);
+            if (push) did |= halo_push2(hp, sh, e, s);
         }
     } else {
         for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
@@ -948,10 +1010,10 @@ k_gm_orth_scale(long long n, VecList vs, int off, int do_scale,
             for (int i = 0; i < NV; ++i) s = fma(-hh[i], __ldg(vs.v[i] + e), s);
             s *= sc;
             w[e] = s;
-            if (push) halo_push1(hp, sh, e, s);
+            if (push) did |= halo_push1(hp, sh, e, s);
         }
     }
-    if (push) halo_push_publish(hp, q);
+    if (push) halo_push_publish(hp, q, did);
 }
 
 // r = sign*rhs - Ax (in place in ax) with the partial sums of <r,r>

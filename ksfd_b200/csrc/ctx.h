@@ -38,30 +38,7 @@ typedef struct ncclComm *ncclComm_t;
 #define KSFD_HALO_SLOTS 4
 #define KSFD_NSCAL 512          // device/host scalar scratch
 
-// Launch of a Krylov-loop kernel: plain <<<>>> unless the library was built with
-// -DKSFD_PDL=1 and KSFD_PDL=1 is set in the environment (device_common.cuh)
-#if KSFD_PDL
-extern bool g_ksfd_pdl;
-template <class... KA, class... A>
-static inline void ksfd_launch_pdl(void (*k)(KA...), dim3 g, dim3 b, size_t sm, cudaStream_t st,
-                                   A... a)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = g;
-    cfg.blockDim = b;
-    cfg.dynamicSmemBytes = sm;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = g_ksfd_pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, k, KA(a)...);
-}
-#define KSFD_KLAUNCH(k, g, b, sm, st, ...) ksfd_launch_pdl(k, dim3(g), dim3(b), sm, st, __VA_ARGS__)
-#else
 #define KSFD_KLAUNCH(k, g, b, sm, st, ...) k<<<g, b, sm, st>>>(__VA_ARGS__)
-#endif
 
 struct ksfd_ctx {
     int dim = 0, dof = 0, device = 0;

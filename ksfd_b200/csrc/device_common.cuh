@@ -19,35 +19,13 @@
 #include "../../include/ksfd_b200.h"
 #include "fastmath.cuh"
 
-// Programmatic dependent launch (experimental, off: -DKSFD_PDL=1 compiles it in,
-// KSFD_PDL=1 in the environment switches it on).  The kernels of the Krylov loop
-// start with griddepcontrol.wait (results of the previous grid are complete and
-// visible) followed by griddepcontrol.launch_dependents (the next grid of the
-// stream, if launched with the attribute, may become resident while this one
-// drains): hides the launch latency between the ~110 dependent launches of a step.
-// Without the launch attribute both instructions do nothing.
-#ifndef KSFD_PDL
-#define KSFD_PDL 0
-#endif
-// Under PDL a CTA of the next grid can land on an SM whose L1 still holds lines
-// that CTAs of the previous grid loaded through the read-only path BEFORE that
-// grid's last block rewrote them (the solver's skip flags): flags are therefore
-// read from L2 (KSFD_FLAG) in a PDL build.  Vectors are written once and only
-// read by later grids, never re-read by the grid that writes them.
-#if KSFD_PDL
-#define KSFD_FLAG(p) __ldcg(p)
-#else
+// Flags of the pipelined solver (skip / cycle state) are plain device words.
+// (Programmatic dependent launch of the Krylov-loop kernels — griddepcontrol.wait +
+// launch_dependents at kernel entry, flags read from L2 — was built and measured in round 2:
+// 2.229 -> 2.192 ms per 1024^2 step on one B200, 2.952 -> 3.022 ms on two
+// (profiles/r02_pdl_ab.txt); not worth a second code path, removed.)
 #define KSFD_FLAG(p) (*(p))
-#endif
-#if KSFD_PDL
-#define KSFD_PDL_ENTER()                                                \
-    do {                                                                \
-        asm volatile("griddepcontrol.wait;" ::: "memory");              \
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
-    } while (0)
-#else
 #define KSFD_PDL_ENTER() do { } while (0)
-#endif
 
 #define KSFD_SW 2                       // stencil width (order 3)
 #define KSFD_RING 4                     // smem ring slots of the marching kernels

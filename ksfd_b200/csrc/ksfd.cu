@@ -22,9 +22,6 @@
 // ---------------------------------------------------------------------------
 static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
-#if KSFD_PDL
-bool g_ksfd_pdl = false;        // KSFD_PDL=1 in the environment (read at context creation)
-#endif
 
 int ksfd_fail(const std::string &m)
 {
@@ -190,9 +187,6 @@ extern "C" int ksfd_ctx_create(ksfd_ctx **out, int dim, const int64_t n_global[3
     CK(cudaMallocHost(&c->hscal, sizeof(double) * KSFD_NSCAL));
     c->halo_plane_doubles = (size_t)g.plane_pts * (dof + 2);
     if (const char *e = getenv("KSFD_GM_RUNAHEAD")) c->gm_runahead = std::max(0, std::min(atoi(e), 8));
-#if KSFD_PDL
-    if (const char *e = getenv("KSFD_PDL")) g_ksfd_pdl = atoi(e) != 0;
-#endif
     *out = c;
     return 0;
 }
@@ -237,10 +231,10 @@ extern "C" int ksfd_ctx_destroy(ksfd_ctx *c)
 extern "C" int64_t ksfd_local_size(const ksfd_ctx *c) { return c ? nlocal(c) : 0; }
 
 #define KSFD_PROF_KINDS 8
-extern "C" int ksfd_profile_fetch(ksfd_ctx *c, double out[3 * KSFD_PROF_KINDS], void *stream)
+extern "C" int ksfd_profile_fetch(ksfd_ctx *c, double out[4 * KSFD_PROF_KINDS], void *stream)
 {
     if (!c || !out) return fail("ksfd_profile_fetch: NULL argument");
-    for (int i = 0; i < 3 * KSFD_PROF_KINDS; ++i) out[i] = 0.0;
+    for (int i = 0; i < 4 * KSFD_PROF_KINDS; ++i) out[i] = 0.0;
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     ProfState *ps = static_cast<ProfState *>(c->prof);
     if (!ps) return 0;
@@ -255,14 +249,15 @@ extern "C" int ksfd_profile_fetch(ksfd_ctx *c, double out[3 * KSFD_PROF_KINDS], 
         mx[o.kind] = std::max(mx[o.kind], ms[i]);
     }
     // launches of the pipelined solver that were made ahead of a convergence test and
-    // returned at once are not real passes: only launches of at least a quarter of the
-    // longest one of their kind count as ACTIVE
+    // returned at once (~2 us) are not real passes: a launch is ACTIVE when it lasted at
+    // least 4 us and at least 1/20 of the longest launch of its kind
     for (size_t i = 0; i < ps->recs.size(); ++i) {
         const int k = ps->recs[i].kind;
-        out[3 * k + 2] += 1.0;
-        if (ms[i] >= 0.25f * mx[k] && ms[i] > 0.f) {
-            out[3 * k] += 1.0;
-            out[3 * k + 1] += ms[i];
+        out[4 * k + 2] += 1.0;
+        out[4 * k + 3] += ms[i];
+        if (ms[i] >= 0.004f && ms[i] >= 0.05f * mx[k]) {
+            out[4 * k] += 1.0;
+            out[4 * k + 1] += ms[i];
         }
     }
     ps->recs.clear();
@@ -485,7 +480,8 @@ static size_t p2p_red_off(const ksfd_ctx *c)
 }
 static size_t p2p_total_doubles(const ksfd_ctx *c)
 {
-    return p2p_red_off(c) + (size_t)2 * KSFD_P2P_MAXR * KSFD_P2P_RED_MAX;
+    // two parities x 16 ranks x 72 doubles, each as two tagged 8-byte words
+    return p2p_red_off(c) + (size_t)2 * KSFD_P2P_MAXR * 2 * KSFD_P2P_RED_MAX;
 }
 static P2PRed p2p_red(const ksfd_ctx *c)
 {
@@ -585,7 +581,8 @@ extern "C" int ksfd_p2p_export(ksfd_ctx *c, char handle_out[64])
     CK(cudaSetDevice(c->device));
     if (!c->p2p_mine) {
         CK(cudaMalloc(&c->p2p_mine, sizeof(double) * p2p_total_doubles(c)));
-        CK(cudaMemset(c->p2p_mine, 0, sizeof(double) * KSFD_P2P_FLAGS));
+        // flags AND the all-reduce area: its words carry their exchange number, 0 = never written
+        CK(cudaMemset(c->p2p_mine, 0, sizeof(double) * p2p_total_doubles(c)));
         CK(cudaMalloc(&c->p2p_done, 2 * sizeof(unsigned)));
         CK(cudaMemset(c->p2p_done, 0, 2 * sizeof(unsigned)));
         CK(cudaHostAlloc(&c->p2p_err, sizeof(int), cudaHostAllocMapped));
@@ -1414,6 +1411,15 @@ extern "C" int ksfd_sum_dof0(ksfd_ctx *c, const double *u, double *out, void *st
     TRY(allreduce_dev(c, c->dscal + SC_USER + 1, 1, ncclSum_, st));
     TRY(fetch(c, SC_USER + 1, 1, st));
     *out = c->hscal[SC_USER + 1];
+    return 0;
+}
+
+extern "C" int ksfd_mul_exp_dof0(ksfd_ctx *c, double *u, const double *z, double sd, void *stream)
+{
+    if (!c || !u || !z) return fail("ksfd_mul_exp_dof0: bad argument");
+    k_mul_exp_dof0<<<KSFD_RED_BLOCKS, 256, 0, (cudaStream_t)stream>>>(c->g.npts, c->g.plane_pts,
+                                                                      c->dof, sd, z, u);
+    CKL();
     return 0;
 }
 

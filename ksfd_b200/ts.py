@@ -271,15 +271,20 @@ class KSFDTS:
         return fnow - flast >= 1.0
 
     def add_variance(self, u, dt):
-        """Lognormal multiplicative noise on rho (reference ksfdts.py:268-284);
-        host RNG stream, as in the reference."""
+        """Lognormal multiplicative noise on rho (reference ksfdts.py:268-284).
+        The standard-normal sample comes from the rank's numpy stream exactly as in
+        the reference (same seed -> same sample); only the sample (8 bytes per point)
+        goes to the device, where rho *= exp(sd*z) is applied in place — the field
+        itself is not copied to the host and back."""
         from .random import Generator
         vrate = self.derivs.ps.values(self.getTime())['variance_rate']
         if not vrate or vrate <= 0.0:
             return u
-        fva = u.array.reshape(self.derivs.grid.Vlshape, order='F')
         sd = np.sqrt(vrate * dt)
-        fva[0] *= np.exp(sd * Generator.get_rng().normal(size=fva[0].shape))
+        z = Generator.get_rng().normal(size=self.derivs.grid.Slshape)
+        ctx = self.derivs.ctx
+        ctx.mul_exp_dof0(u.device(ctx), z, sd)
+        u.mark_device_written()
         return u
 
     def CFL_check(self):

@@ -258,3 +258,57 @@ def test_shipped_option_files_run_through_the_solver_entry(name, over, tmp_path,
     out = capsys.readouterr().out
     assert 'SNES failures =  0' in out, out[-2000:]
     assert out.count('clock:') >= over['maxsteps']
+
+
+def test_noise_injection_on_device_uses_the_reference_stream():
+    """KSFDTS.add_variance (reference ksfdts.py:268-284): rho *= exp(sd * N(0,1)) with the
+    sample drawn from the rank's numpy stream as the reference does.  The field stays on
+    the device (only the sample is uploaded); the result equals the host formula to
+    rounding, the ligand fields are untouched, and conserve_worms restores the total."""
+    from ksfd_b200.random import Generator
+    from ksfd_b200.ts import make_implicitTS
+    args = ['@' + os.path.join(HERE, 'options', 'options113a.args')]
+    cl, ps, grid, sources, u0, derivs = build(args)
+    ts = make_implicitTS(derivs, t0=0.0, dt=1e-3, tmax=1.0, maxsteps=1)
+    before = np.array(u0.array_r).reshape(grid.Vlshape, order='F').copy()
+    N0 = ts.count_worms(u0)
+    assert abs(N0 - before[0].sum()) <= 1e-9 * abs(N0)
+    Generator(seed=1234, comm=grid.comm)
+    z = np.random.default_rng(np.random.SeedSequence(1234).spawn(1)[0]).normal(size=grid.Slshape)
+    vrate = ps.values(0.0)['variance_rate']
+    dt = 7.0
+    ts.getTime = lambda: 0.0
+    u = ts.add_variance(u0, dt)
+    after = np.array(u.array_r).reshape(grid.Vlshape, order='F')
+    want = before[0] * np.exp(np.sqrt(vrate * dt) * z)
+    assert np.abs(after[0] - want).max() <= 4e-16 * np.abs(want).max()
+    assert np.array_equal(after[1:], before[1:])
+    u = ts.conserve_worms(u, N0)
+    assert abs(ts.count_worms(u) - N0) <= 1e-12 * N0
+
+
+def test_in_step_profile_counts_stencil_launches():
+    """option 'profile': CUDA events around the stencil launches (what bench.py reports as
+    the in-step kernel time)."""
+    import torch
+    from helpers import product_physics
+    from ksfd_b200 import core
+    p = phys84(2, (64, 48))
+    ctx = core.Context(2, p['n'], 3)
+    ctx.set_physics(product_physics(p))
+    u = ctx.upload(np.full(64 * 48 * 3, 9000.0))
+    v = torch.randn(ctx.npts * 3, device='cuda', dtype=torch.float64)
+    ctx.jvp_setup(u, 100.0)
+    ctx.set_option('profile', 1)
+    for _ in range(5):
+        ctx.jvp(v, precond=True)
+    for _ in range(3):
+        ctx.residual(u, v)
+    d = ctx.profile_fetch()
+    assert d['jvp_launches_all'] == 5 and d['residual_launches_all'] == 3
+    assert d['jvp_ms_all'] > 0.0 and d['residual_ms_all'] > 0.0
+    assert ctx.profile_fetch()['jvp_launches_all'] == 0          # fetch resets
+    ctx.set_option('profile', 0)
+    ctx.jvp(v)
+    assert ctx.profile_fetch()['jvp_launches_all'] == 0
+    ctx.close()
