@@ -100,7 +100,7 @@ int64_t ksfd_local_size(const ksfd_ctx *ctx);   /* dof * owned points */
    in ms, out[4k+2] = all bracketed launches, out[4k+3] = their summed time; resets the
    counters.  Launches the pipelined solver made ahead of a convergence test and that
    returned at once (~2 us) are not real passes: a launch is ACTIVE when it lasted at
-   least 4 us and at least 1/20 of the longest launch of its kind. */
+   least 4 us. */
 int ksfd_profile_fetch(ksfd_ctx *ctx, double out[32], void *stream);
 
 /* ---- layout boundary: reference layout (what PETSc Vec.array / the HDF5

@@ -703,7 +703,22 @@ k_gm_norm_begin(long long n, const double *__restrict__ r, double *__restrict__ 
     gm_begin_in_last_block(a);
 }
 
-// y = x * (sign / gm[GM_BETA])    (first Krylov vector); hp: fused halo push of y
+// Element order of the producers that push: the two boundary plane pairs FIRST (the
+// first 2*cnt elements of the order), then the interior.  The peer stores go out at the
+// start of the kernel and are acknowledged while the same threads stream the interior,
+// so the system-scope fence before the flag is published (halo_push_publish) finds
+// nothing outstanding instead of adding an NVLink round trip to the kernel's tail.  Maps position p of the order to the element index (units: elements,
+// or element pairs when everything is counted in double2).
+__device__ __forceinline__ long long push_order(long long p, long long cnt, long long n)
+{
+    if (p < cnt) return p;                          // bottom planes
+    if (p < 2 * cnt) return n - 2 * cnt + p;        // top planes
+    return p - cnt;                                 // interior: cnt .. n - cnt
+}
+
+// y = x * (sign / gm[GM_BETA])    (first Krylov vector)
+// PUSH: the halo push of y is fused in (several ranks over peer memory)
+template <bool PUSH>
 __global__ void k_gm_first_vector(long long n, const double *x, const double *__restrict__ gm,
                                   const int *__restrict__ gmi, double sign, double *y,
                                   HaloPush hp)
@@ -711,27 +726,32 @@ __global__ void k_gm_first_vector(long long n, const double *x, const double *__
     KSFD_PDL_ENTER();
     if (KSFD_FLAG(gmi + GMI_FINAL)) return;
     const double f = sign / KSFD_FLAG(gm + GM_BETA);
-    const bool push = halo_push_on(hp);
-    bool did = false;
+    const bool push = PUSH && halo_push_on(hp);
     unsigned long long q = 0;
     const long long sh = push ? halo_push_shift(hp, q) : 0;
+    // (with nloc < 4 the plane pairs overlap: plain order)
+    const bool reorder = push && 2 * hp.cnt <= n;
+    bool did = false;
     if ((n & 1) == 0 && aligned16(x) && aligned16(y)) {
         const double2 *x2 = reinterpret_cast<const double2 *>(x);
         double2 *y2 = reinterpret_cast<double2 *>(y);
-        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (n >> 1);
-             e += (long long)gridDim.x * blockDim.x) {
+        const long long n2 = n >> 1, c2 = hp.cnt >> 1;
+        for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n2;
+             p += (long long)gridDim.x * blockDim.x) {
+            const long long e = reorder ? push_order(p, c2, n2) : p;
             double2 v = x2[e];
             v.x *= f;
             v.y *= f;
             y2[e] = v;
-            if (push) did |= halo_push2(hp, sh, e, v);
+            if (push && halo_push2(hp, sh, e, v)) did = true;
         }
     } else {
-        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
-             e += (long long)gridDim.x * blockDim.x) {
+        for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n;
+             p += (long long)gridDim.x * blockDim.x) {
+            const long long e = reorder ? push_order(p, hp.cnt, n) : p;
             const double v = x[e] * f;
             y[e] = v;
-            if (push) did |= halo_push1(hp, sh, e, v);
+            if (push && halo_push1(hp, sh, e, v)) did = true;
         }
     }
     if (push) halo_push_publish(hp, q, did);
@@ -968,8 +988,8 @@ k_gm_mdot(long long n, VecList vs, const double *__restrict__ w,
 
 
 // w = (w - sum_i h[i]*V_i) * inv   with h, inv from the device state
-// hp: fused halo push of the finished vector (last batch of a long column only)
-template <int NV>
+// PUSH: fused halo push of the finished vector (last batch of a long column only)
+template <int NV, bool PUSH>
 __global__ void __launch_bounds__(KSFD_RED_THREADS)
 k_gm_orth_scale(long long n, VecList vs, int off, int do_scale,
                 const double *__restrict__ gm, const int *__restrict__ gmi,
@@ -982,14 +1002,17 @@ k_gm_orth_scale(long long n, VecList vs, int off, int do_scale,
 #pragma unroll
     for (int i = 0; i < NV; ++i) hh[i] = KSFD_FLAG(gm + GM_HCOL + off + i);
     const double sc = do_scale ? KSFD_FLAG(gm + GM_INV) : 1.0;
-    const bool push = halo_push_on(hp);
-    bool did = false;
+    const bool push = PUSH && halo_push_on(hp);
     unsigned long long q = 0;
     const long long sh = push ? halo_push_shift(hp, q) : 0;
+    const bool reorder = push && 2 * hp.cnt <= n;       // boundary planes first (push_order)
+    bool did = false;
     if (all_aligned16<NV>(n, vs, w)) {
         double2 *w2 = reinterpret_cast<double2 *>(w);
-        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (n >> 1);
-             e += (long long)gridDim.x * blockDim.x) {
+        const long long n2 = n >> 1, c2 = hp.cnt >> 1;
+        for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n2;
+             p += (long long)gridDim.x * blockDim.x) {
+            const long long e = reorder ? push_order(p, c2, n2) : p;
             double2 s = w2[e];
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
@@ -1000,17 +1023,18 @@ k_gm_orth_scale(long long n, VecList vs, int off, int do_scale,
             s.x *= sc;
             s.y *= sc;
             w2[e] = s;
-            if (push) did |= halo_push2(hp, sh, e, s);
+            if (push && halo_push2(hp, sh, e, s)) did = true;
         }
     } else {
-        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
-             e += (long long)gridDim.x * blockDim.x) {
+        for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n;
+             p += (long long)gridDim.x * blockDim.x) {
+            const long long e = reorder ? push_order(p, hp.cnt, n) : p;
             double s = w[e];
 #pragma unroll
             for (int i = 0; i < NV; ++i) s = fma(-hh[i], __ldg(vs.v[i] + e), s);
             s *= sc;
             w[e] = s;
-            if (push) did |= halo_push1(hp, sh, e, s);
+            if (push && halo_push1(hp, sh, e, s)) did = true;
         }
     }
     if (push) halo_push_publish(hp, q, did);

@@ -250,12 +250,12 @@ extern "C" int ksfd_profile_fetch(ksfd_ctx *c, double out[4 * KSFD_PROF_KINDS], 
     }
     // launches of the pipelined solver that were made ahead of a convergence test and
     // returned at once (~2 us) are not real passes: a launch is ACTIVE when it lasted at
-    // least 4 us and at least 1/20 of the longest launch of its kind
+    // least 4 us
     for (size_t i = 0; i < ps->recs.size(); ++i) {
         const int k = ps->recs[i].kind;
         out[4 * k + 2] += 1.0;
         out[4 * k + 3] += ms[i];
-        if (ms[i] >= 0.004f && ms[i] >= 0.05f * mx[k]) {
+        if (ms[i] >= 0.004f) {
             out[4 * k] += 1.0;
             out[4 * k + 1] += ms[i];
         }
@@ -1061,14 +1061,17 @@ static void fftpc_destroy(ksfd_ctx *c)
     }
 }
 
-// one rank; several ranks only on request (KSFD_FFT_MULTI=1: slab-distributed
-// transform over NCCL send/recv, not yet validated on hardware), 2-D / 3-D, with the
-// DMDA ownership ranges (every rank must be able to compute every other rank's)
+// Several ranks: slab-distributed transform (plane transforms of the own planes, one
+// all-to-all per direction over NCCL send/recv, last-axis transform; fftpc.cuh), 2-D / 3-D,
+// with the DMDA ownership ranges (every rank must be able to compute every other rank's).
+// Validated on 2 B200 against the single-GPU preconditioner: same Arnoldi counts, solutions
+// to 1e-16 (scripts/multi_gpu_spectral_check.py, tests/test_gpu_multi.py);
+// KSFD_FFT_MULTI=0 switches it off (block Jacobi is used instead).
 static bool fftpc_dist_wanted(const ksfd_ctx *c)
 {
     if (c->nranks == 1) return false;
     const char *e = getenv("KSFD_FFT_MULTI");
-    if (!e || atoi(e) == 0 || !c->comm || c->dim < 2) return false;
+    if ((e && atoi(e) == 0) || !c->comm || c->dim < 2) return false;
     const long long M = c->last_global, P = c->nranks, r = c->rank;
     const long long cnt = M / P + (M % P > r ? 1 : 0);
     const long long start = r * (M / P) + std::min(r, M % P);
@@ -1797,8 +1800,12 @@ static int gm_orth_launch(ksfd_ctx *c, const VecList &vl, int off, int do_scale,
         hp = make_push(c, 1);
         if (hp.up_lo0) c->pushed_vec = w;
     }
-    KSFD_KLAUNCH((k_gm_orth_scale<NV>), KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st, nlocal(c), vl, off,
-                 do_scale, c->gm, c->gmi, w, hp);
+    if (hp.up_lo0)
+        KSFD_KLAUNCH((k_gm_orth_scale<NV, true>), KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st, nlocal(c), vl,
+                     off, do_scale, c->gm, c->gmi, w, hp);
+    else
+        KSFD_KLAUNCH((k_gm_orth_scale<NV, false>), KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st, nlocal(c), vl,
+                     off, do_scale, c->gm, c->gmi, w, hp);
     CKL();
     return 0;
 }
@@ -1981,8 +1988,12 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
             ProfScope prof(c, 4, st);
             const HaloPush hp = make_push(c, 1);
             if (hp.up_lo0) c->pushed_vec = V;
-            KSFD_KLAUNCH(k_gm_first_vector, KSFD_RED_BLOCKS, 256, 0, st, n, r, c->gm, c->gmi, sign, V,
-                         hp);
+            if (hp.up_lo0)
+                KSFD_KLAUNCH(k_gm_first_vector<true>, KSFD_RED_BLOCKS, 256, 0, st, n, r, c->gm, c->gmi,
+                             sign, V, hp);
+            else
+                KSFD_KLAUNCH(k_gm_first_vector<false>, KSFD_RED_BLOCKS, 256, 0, st, n, r, c->gm, c->gmi,
+                             sign, V, hp);
             CKL();
         }
         const int seq = 2 * cycle + 1;
