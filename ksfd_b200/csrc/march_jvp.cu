@@ -21,10 +21,10 @@ static int launch_jvp_p(ksfd_ctx *c, const HostVec &coef, const HostVec &v, cons
     if (ksfd_use_tma(c)) {
         const TmaSrc src[3] = {coef.t, v.t, pc.t};
 #if KSFD_MARCH_DIM == 2
-        return launch_tma_op<DIM, JvpOp<DIM, NLIG, PRECOND>, true, 256, 1, 2, 3, 128, 1, 4, 3>(
+        return launch_tma_op<DIM, JvpOp<DIM, NLIG, PRECOND>, true, 256, 1, 2, 4, 128, 1, 4, 3>(
             c, op, src, PRECOND ? 2 : 3, cstage, cemit, skip, st);
 #else
-        return launch_tma_op<DIM, JvpOp<DIM, NLIG, PRECOND>, true, 16, 16, 2, 2, 32, 8, 2, 2>(
+        return launch_tma_op<DIM, JvpOp<DIM, NLIG, PRECOND>, true, 16, 16, 2, 2, 32, 16, 1, 2>(
             c, op, src, PRECOND ? 2 : 3, cstage, cemit, skip, st);
 #endif
     }

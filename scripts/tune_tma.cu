@@ -454,7 +454,8 @@ int main(int argc, char **argv)
         Problem pb = make_problem(dim, n);
         DevPhys P = make_phys(dim);
         printf("== %dD n=%d  (%lld points, %d buffer sets)\n", dim, n, pb.npts, pb.nrot);
-        if (dim == 2) {
+        const bool more = getenv("TUNE_MORE") != nullptr;       // only the extra variants
+        if (dim == 2 && !more) {
             REF_RES(2, 124, 1, 6, true);
             TMA_RES(2, 128, 1, 6, false, 3, 3);
             TMA_RES(2, 256, 1, 3, false, 3, 3);
@@ -465,7 +466,16 @@ int main(int argc, char **argv)
             REF_JVP(2, 124, 1, 4, false, true);
             TMA_JVP(2, 128, 1, 4, true, false, 3, 3);
             TMA_JVP(2, 256, 1, 2, true, false, 3, 3);
-        } else {
+        } else if (dim == 2) {
+            {
+                REF_JVP(2, 124, 1, 4, true, true);
+                TMA_JVP(2, 256, 1, 2, true, true, 3, 3);
+                TMA_JVP(2, 256, 1, 2, false, true, 3, 3);
+                TMA_JVP(2, 256, 1, 2, true, true, 2, 2);
+                TMA_JVP(2, 256, 1, 2, true, true, 4, 4);
+                TMA_JVP(2, 128, 1, 4, false, true, 3, 3);
+            }
+        } else if (!more) {
             REF_RES(3, 16, 16, 2, true);
             TMA_RES(3, 16, 16, 2, false, 3, 3);
             TMA_RES(3, 16, 8, 4, false, 3, 3);
@@ -479,6 +489,16 @@ int main(int argc, char **argv)
             TMA_JVP(3, 16, 16, 2, true, false, 2, 2);
             TMA_JVP(3, 16, 16, 2, true, false, 3, 3);
             TMA_JVP(3, 16, 8, 4, true, false, 2, 2);
+        } else {
+            {
+                REF_JVP(3, 16, 16, 1, true, true);
+                TMA_JVP(3, 16, 16, 2, true, true, 2, 2);
+                TMA_JVP(3, 16, 16, 2, false, true, 2, 2);
+                TMA_JVP(3, 16, 16, 2, true, true, 2, 3);
+                TMA_JVP(3, 32, 16, 1, true, true, 2, 2);
+                TMA_JVP(3, 16, 32, 1, true, true, 2, 2);
+                TMA_JVP(3, 8, 32, 2, true, true, 2, 2);
+            }
         }
         free_problem(pb);
     }
