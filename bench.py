@@ -228,6 +228,9 @@ def reference_arm(args):
                                   kind='port', sample=cb['sample']),
                 e2e=dict(value=cb['value'], unit='Mpts*steps/s',
                          h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                same_config=False,
+                # the SAME-config CPU numbers: the port's residual and J.v on the full 1024^2 grid
+                cpu_operator_1024x1024=cpu_operator_timing(),
                 wall_s=wall)
     print(json.dumps(line), flush=True)
 

@@ -498,19 +498,27 @@ __device__ __forceinline__ bool halo_push2(const HaloPush &hp, long long sh, lon
     }
     return did;
 }
-// Every thread of every block calls this after its stores.  Only the threads that wrote
-// peer memory pay for a system-scope fence (measured: with the fence in all 150k threads
-// the producer kernels took 12-13 us longer, profiles/r02_multi_gpu_step_breakdown.txt);
-// the block counter is a device-scope atomic, and the block that finishes last orders
-// its flag stores after everything it observed with one more system fence.
-__device__ __forceinline__ void halo_push_publish(const HaloPush &hp, unsigned long long q, bool did)
+// Called by every thread of the blocks that stored boundary planes, right after those
+// stores and BEFORE the interior stream (`expected` = number of such blocks).
+// Hierarchical release: the storing threads do not fence themselves (a system-scope fence
+// in a thread of an SM that is streaming stores waits for all of them: measured +2 us per
+// producer kernel on top of the rest, profiles/r02_multi_gpu_step_breakdown.txt).  The CTA
+// barrier orders every thread's peer stores before thread 0's device-scope fence and its
+// (device-scope) arrival on the block counter; the block that arrives last has therefore
+// observed all of them and orders its flag stores after them with ONE system-scope fence
+// (fences are cumulative in the PTX memory model), so a neighbour that sees the flag sees the
+// planes.  Publishing EARLY matters: a kernel whose last action is a store to peer memory
+// ends one NVLink round trip later (grid completion waits for the acknowledgement) — measured
+// +6-9 us per producer kernel when the flags went out at the end; now the round trip of the
+// planes and of the flags hides behind the interior stream of the same kernel.
+__device__ __forceinline__ void halo_push_publish(const HaloPush &hp, unsigned long long q,
+                                                  unsigned expected)
 {
-    if (did) __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned t = atomicAdd(hp.done, 1u);
-        if (t == gridDim.x - 1) {               // last block: all planes are on their way
+        if (t == expected - 1) {                // last boundary block: all planes are on their way
             atomicExch(hp.done, 0u);
             __threadfence_system();
             *hp.up_flag_lo = q;
@@ -518,6 +526,36 @@ __device__ __forceinline__ void halo_push_publish(const HaloPush &hp, unsigned l
             *hp.ctr = q;
         }
     }
+}
+// Work split of a pushing producer.  When the boundary positions [0, nb) of the push order
+// need only a few blocks (2-D: 24 of 592), those blocks do NOTHING else: they store the
+// planes, publish (the publishing thread sits in a system-scope fence for about two NVLink
+// round trips) and exit, while the other blocks share the interior — the wait is off the
+// kernel's critical path (measured: with statically shared interior work the late block
+// extended the kernel by 5-8 us).  Returns false when the boundary needs most of the grid
+// (3-D slabs): then every block does boundary and interior work as usual.
+struct PushSplit {
+    bool split;
+    unsigned nbA;           // blocks that own boundary positions
+    long long p0, stride;   // first interior position / stride of this thread when split
+};
+__device__ __forceinline__ unsigned push_blocks(long long nb);
+__device__ __forceinline__ PushSplit push_split(bool push, long long nb)
+{
+    PushSplit ps;
+    ps.nbA = push ? push_blocks(nb) : 0;
+    ps.split = push && ps.nbA * 4u <= gridDim.x;
+    const long long rest = (long long)(gridDim.x - ps.nbA) * blockDim.x;
+    ps.stride = ps.split ? rest : (long long)gridDim.x * blockDim.x;
+    ps.p0 = nb + ((long long)blockIdx.x - ps.nbA) * blockDim.x + threadIdx.x;
+    return ps;
+}
+// number of blocks that own boundary positions [0, nb) of the push order, and whether this
+// block is one of them
+__device__ __forceinline__ unsigned push_blocks(long long nb)
+{
+    const long long need = (nb + blockDim.x - 1) / blockDim.x;
+    return (unsigned)(need < (long long)gridDim.x ? need : (long long)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------
@@ -729,32 +767,56 @@ __global__ void k_gm_first_vector(long long n, const double *x, const double *__
     const bool push = PUSH && halo_push_on(hp);
     unsigned long long q = 0;
     const long long sh = push ? halo_push_shift(hp, q) : 0;
-    // (with nloc < 4 the plane pairs overlap: plain order)
-    const bool reorder = push && 2 * hp.cnt <= n;
-    bool did = false;
+    // (with nloc < 4 the plane pairs overlap: every position is a boundary position)
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if ((n & 1) == 0 && aligned16(x) && aligned16(y)) {
         const double2 *x2 = reinterpret_cast<const double2 *>(x);
         double2 *y2 = reinterpret_cast<double2 *>(y);
         const long long n2 = n >> 1, c2 = hp.cnt >> 1;
-        for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n2;
-             p += (long long)gridDim.x * blockDim.x) {
+        const bool reorder = push && 2 * c2 <= n2;
+        const long long nb = push ? (reorder ? 2 * c2 : n2) : 0;     // boundary positions
+        for (; p < nb; p += stride) {
             const long long e = reorder ? push_order(p, c2, n2) : p;
             double2 v = x2[e];
             v.x *= f;
             v.y *= f;
             y2[e] = v;
-            if (push && halo_push2(hp, sh, e, v)) did = true;
+            halo_push2(hp, sh, e, v);
+        }
+        const PushSplit ps = push_split(push, nb);
+        if (push && blockIdx.x < ps.nbA) halo_push_publish(hp, q, ps.nbA);
+        if (ps.split) {
+            if (blockIdx.x < ps.nbA) return;
+            p = ps.p0;
+        }
+        for (; p < n2; p += ps.stride) {
+            const long long e = reorder ? push_order(p, c2, n2) : p;
+            double2 v = x2[e];
+            v.x *= f;
+            v.y *= f;
+            y2[e] = v;
         }
     } else {
-        for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n;
-             p += (long long)gridDim.x * blockDim.x) {
+        const bool reorder = push && 2 * hp.cnt <= n;
+        const long long nb = push ? (reorder ? 2 * hp.cnt : n) : 0;
+        for (; p < nb; p += stride) {
             const long long e = reorder ? push_order(p, hp.cnt, n) : p;
             const double v = x[e] * f;
             y[e] = v;
-            if (push && halo_push1(hp, sh, e, v)) did = true;
+            halo_push1(hp, sh, e, v);
+        }
+        const PushSplit ps = push_split(push, nb);
+        if (push && blockIdx.x < ps.nbA) halo_push_publish(hp, q, ps.nbA);
+        if (ps.split) {
+            if (blockIdx.x < ps.nbA) return;
+            p = ps.p0;
+        }
+        for (; p < n; p += ps.stride) {
+            const long long e = reorder ? push_order(p, hp.cnt, n) : p;
+            y[e] = x[e] * f;
         }
     }
-    if (push) halo_push_publish(hp, q, did);
 }
 
 // partial[i][block] = <vs[i], w>, skipping when the cycle is closed
@@ -1005,14 +1067,14 @@ k_gm_orth_scale(long long n, VecList vs, int off, int do_scale,
     const bool push = PUSH && halo_push_on(hp);
     unsigned long long q = 0;
     const long long sh = push ? halo_push_shift(hp, q) : 0;
-    const bool reorder = push && 2 * hp.cnt <= n;       // boundary planes first (push_order)
-    bool did = false;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (all_aligned16<NV>(n, vs, w)) {
         double2 *w2 = reinterpret_cast<double2 *>(w);
         const long long n2 = n >> 1, c2 = hp.cnt >> 1;
-        for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n2;
-             p += (long long)gridDim.x * blockDim.x) {
-            const long long e = reorder ? push_order(p, c2, n2) : p;
+        const bool reorder = push && 2 * c2 <= n2;      // boundary planes first (push_order)
+        const long long nb = push ? (reorder ? 2 * c2 : n2) : 0;
+        auto body = [&](long long e) {
             double2 s = w2[e];
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
@@ -1023,21 +1085,42 @@ k_gm_orth_scale(long long n, VecList vs, int off, int do_scale,
             s.x *= sc;
             s.y *= sc;
             w2[e] = s;
-            if (push && halo_push2(hp, sh, e, s)) did = true;
+            return s;
+        };
+        for (; p < nb; p += stride) {
+            const long long e = reorder ? push_order(p, c2, n2) : p;
+            halo_push2(hp, sh, e, body(e));
         }
+        const PushSplit ps = push_split(push, nb);
+        if (push && blockIdx.x < ps.nbA) halo_push_publish(hp, q, ps.nbA);
+        if (ps.split) {
+            if (blockIdx.x < ps.nbA) return;
+            p = ps.p0;
+        }
+        for (; p < n2; p += ps.stride) body(reorder ? push_order(p, c2, n2) : p);
     } else {
-        for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n;
-             p += (long long)gridDim.x * blockDim.x) {
-            const long long e = reorder ? push_order(p, hp.cnt, n) : p;
+        const bool reorder = push && 2 * hp.cnt <= n;
+        const long long nb = push ? (reorder ? 2 * hp.cnt : n) : 0;
+        auto body = [&](long long e) {
             double s = w[e];
 #pragma unroll
             for (int i = 0; i < NV; ++i) s = fma(-hh[i], __ldg(vs.v[i] + e), s);
             s *= sc;
             w[e] = s;
-            if (push && halo_push1(hp, sh, e, s)) did = true;
+            return s;
+        };
+        for (; p < nb; p += stride) {
+            const long long e = reorder ? push_order(p, hp.cnt, n) : p;
+            halo_push1(hp, sh, e, body(e));
         }
+        const PushSplit ps = push_split(push, nb);
+        if (push && blockIdx.x < ps.nbA) halo_push_publish(hp, q, ps.nbA);
+        if (ps.split) {
+            if (blockIdx.x < ps.nbA) return;
+            p = ps.p0;
+        }
+        for (; p < n; p += ps.stride) body(reorder ? push_order(p, hp.cnt, n) : p);
     }
-    if (push) halo_push_publish(hp, q, did);
 }
 
 // r = sign*rhs - Ax (in place in ax) with the partial sums of <r,r>
