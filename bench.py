@@ -38,6 +38,13 @@ KSP_RTOL = 1e-8
 SEED = 793817931
 ROSW_GAMMA = 0.435866521508459
 ALG_BYTES_PER_PT = 72.0          # read u/v + read udot/coef-equivalent + write
+ALG_BYTES_SWEEP = 120.0          # Richardson sweep: read u_lin, r, x; write x, r_new (5 x 24 B)
+# stage-system solver: KSFD_BENCH_KSP=gmres|richardson|auto (default auto: the library's choice)
+KSP_TYPE = os.environ.get('KSFD_BENCH_KSP', 'auto')
+SOLVER_DESC = {'gmres': 'GMRES(30)',
+               'richardson': 'stationary block-Jacobi sweeps fused into the stencil kernel',
+               'auto': 'stationary block-Jacobi sweeps fused into the stencil kernel, '
+                       'GMRES(30) fallback (not taken at this dt)'}
 
 
 def phys_dict(dim, n):
@@ -275,13 +282,18 @@ def kernel_rooflines(dim, n, reps=20):
     outs = [torch.empty(N, device='cuda', dtype=torch.float64) for _ in range(nrot)]
     ctx.jvp_setup(us[0], 1.0 / (ROSW_GAMMA * DT))
     out = {}
-    for name, fn in (('residual', lambda i: ctx.residual(us[i], vs[i], None, outs[i])),
-                     ('jvp', lambda i: ctx.jvp(vs[i], outs[i])),
-                     ('jvp_precond', lambda i: ctx.jvp(vs[i], outs[i], precond=True))):
+    # the sweep updates x in place: the u buffers (not read by the J.v-side kernels once the
+    # linearisation is set up) serve as its rotating x operands
+    for name, fn, bpp in (('residual', lambda i: ctx.residual(us[i], vs[i], None, outs[i]), ALG_BYTES_PER_PT),
+                          ('jvp', lambda i: ctx.jvp(vs[i], outs[i]), ALG_BYTES_PER_PT),
+                          ('jvp_precond', lambda i: ctx.jvp(vs[i], outs[i], precond=True), ALG_BYTES_PER_PT),
+                          ('sweep', lambda i: ctx.sweep(vs[i], us[i], outs[i], norms=False), ALG_BYTES_SWEEP)):
+        if name == 'sweep':
+            ctx.residual(us[0], vs[0], None, outs[0])       # (the residual above needed us intact)
         us_ = time_kernel(fn, nrot, reps)
-        ach = npts * ALG_BYTES_PER_PT / (us_ * 1e-6) / 1e9
+        ach = npts * bpp / (us_ * 1e-6) / 1e9
         out[name] = dict(us=us_, gpts_per_s=npts / us_ / 1e3, achieved_gbs=ach,
-                         frac=ach / peak)
+                         frac=ach / peak, algorithmic_bytes_per_point=bpp)
     ctx.close()
     del us, vs, outs
     torch.cuda.empty_cache()
@@ -301,7 +313,7 @@ def step_timing_3d(n=256, nsteps=5, warm=2):
     rho = 9000.0 + 90.0 * rng.standard_normal(ctx.npts)
     u = ctx.to_internal(torch.from_numpy(np.repeat(rho, 3)).cuda())
     opts = core.ts_options(ts_type='rosw', adapt='none', atol=0.01, rtol=1e-6,
-                           ksp_rtol=KSP_RTOL, ksp_max_it=2000, restart=30)
+                           ksp_rtol=KSP_RTOL, ksp_max_it=2000, restart=30, ksp_type=KSP_TYPE)
     t, its = 0.0, 0
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -503,7 +515,7 @@ def native_arm(args):
     u_ref = u_host.cuda()
     u = ctx.to_internal(u_ref)                                  # internal layout
     opts = core.ts_options(ts_type='rosw', adapt='none', atol=0.01, rtol=1e-6,
-                           ksp_rtol=KSP_RTOL, ksp_max_it=2000, restart=30)
+                           ksp_rtol=KSP_RTOL, ksp_max_it=2000, restart=30, ksp_type=KSP_TYPE)
     state = dict(t=0.0, its=0)
 
     def step():
@@ -607,30 +619,40 @@ def native_arm(args):
                 for m in (512, 2048, 4096):
                     sweep['%dx%d' % (m, m)], _, _ = kernel_rooflines(2, (m, m))
                 extra['kernel_sweep'] = sweep
-        dom = k2['jvp_precond']
+        # the dominant kernel of the step: the Richardson sweep (fused A*M^-1 stencil +
+        # x / r update + norms) when the stage solves ran on sweeps, else the fused J.v
+        swept = prof['sweep_launches'] > prof['jvp_launches']
+        domkey, dombytes = ('sweep', ALG_BYTES_SWEEP) if swept else ('jvp_precond', ALG_BYTES_PER_PT)
+        dom = k2[domkey]
         traffic, tsrc = None, None
         tp = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tp):
             tj = json.load(open(tp))
-            traffic = tj.get('jvp_precond_1024x1024_bytes_per_launch')
-            tsrc = tj.get('source')
-        roof = dict(bound='hbm', kernel='k_tma_march<2,256,1,JvpOp<2,2,precond>> (fused A*M^-1 v, TMA-fed)',
+            traffic = tj.get(domkey + '_1024x1024_bytes_per_launch')
+            tsrc = tj.get(domkey + '_source', tj.get('source'))
+        roof = dict(bound='hbm',
+                    kernel='k_tma_march<2,256,1,SweepOp<2,2>> (Richardson sweep: fused A*M^-1 stencil, '
+                           'x and r update, norms; TMA-fed)' if swept else
+                           'k_tma_march<2,256,1,JvpOp<2,2,precond>> (fused A*M^-1 v, TMA-fed)',
                     achieved=dom['achieved_gbs'], peak=peak, unit='GB/s',
                     frac=dom['frac'], traffic=traffic, traffic_source=tsrc, peak_source=psrc,
-                    algorithmic_bytes_per_point=ALG_BYTES_PER_PT,
+                    algorithmic_bytes_per_point=dombytes,
+                    algorithmic_bytes='sweep: read u_lin, r, x; write x, r_new = 5 x 24 B/point'
+                                      if swept else 'J.v: read u_lin, v; write out = 3 x 24 B/point',
                     points_per_launch=TILE * TILE, us_per_launch=dom['us'],
                     timing='CUDA events, 20 launches rotating over buffer sets > 2.5x L2 (cold)')
-        if prof['jvp_launches'] > 0:
-            # the same kernel where it actually runs: inside the ROSW/GMRES step loop, its
-            # operands partly L2-resident (coefficient field 42 MB, Krylov vectors 25 MB)
-            us_in = 1e3 * prof['jvp_ms'] / prof['jvp_launches']
-            ach = ctx_npts_local * ALG_BYTES_PER_PT / (us_in * 1e-6) / 1e9
+        pk = 'sweep' if swept else 'jvp'
+        if prof[pk + '_launches'] > 0:
+            # the same kernel where it actually runs: inside the ROSW step loop, its
+            # operands partly L2-resident (coefficient field 42 MB, vectors 25 MB)
+            us_in = 1e3 * prof[pk + '_ms'] / prof[pk + '_launches']
+            ach = ctx_npts_local * dombytes / (us_in * 1e-6) / 1e9
             roof['in_step'] = dict(us_per_launch=us_in, achieved=ach, frac=ach / peak,
-                                   launches=prof['jvp_launches'],
-                                   launches_incl_skipped=prof['jvp_launches_all'],
+                                   launches=prof[pk + '_launches'],
+                                   launches_incl_skipped=prof[pk + '_launches_all'],
                                    points_per_launch=ctx_npts_local,
-                                   timing='CUDA events around every J.v launch of 3 ROSW steps '
-                                          '(separate pass after the timed region)')
+                                   timing='CUDA events around every launch of the kernel in 3 ROSW '
+                                          'steps (separate pass after the timed region)')
         if prof['residual_launches'] > 0:
             us_r = 1e3 * prof['residual_ms'] / prof['residual_launches']
             ach = ctx_npts_local * ALG_BYTES_PER_PT / (us_r * 1e-6) / 1e9
@@ -641,7 +663,7 @@ def native_arm(args):
             nm: dict(us=1e3 * prof[nm + '_ms'] / max(prof[nm + '_launches'], 1),
                      launches_per_step=prof[nm + '_launches'] / 3.0,
                      ms_per_step=prof[nm + '_ms_all'] / 3.0)
-            for nm in ('jvp', 'residual', 'mdot', 'orth', 'first_vector', 'cycle_begin')}
+            for nm in ('sweep', 'jvp', 'residual', 'mdot', 'orth', 'first_vector', 'cycle_begin')}
         if world == 1 and not args.no_cpu:
             cpu = cpu_baseline(2, 96, 1)
             extra['cpu_operator_1024x1024'] = cpu_operator_timing()
@@ -660,12 +682,14 @@ def native_arm(args):
                 steps_per_sec=args.steps / (ms * 1e-3),
                 config=dict(workload='%s, dof 3, '
                                      'options84 physics, h=1/384, dt=1e-3, ROSW ra34pw2, '
-                                     'GMRES(30)+point-block-Jacobi rtol %.0e' % (wl, KSP_RTOL),
+                                     'stage solves: %s, point-block Jacobi, rtol %.0e'
+                                     % (wl, SOLVER_DESC[KSP_TYPE], KSP_RTOL),
+                            ksp_type=KSP_TYPE,
                             parallelism='slab%d' % world,
-                            l2='step working set ~1 GB (31 Krylov + 10 stage vectors of '
-                               '25 MB) exceeds the 126 MB L2; kernel-only timings rotate '
+                            l2='step working set (coefficient field 42 MB, 2 residual + 10 stage '
+                               'vectors of 25 MB; GMRES: + 31 Krylov vectors) exceeds the 126 MB L2; kernel-only timings rotate '
                                'over >2.5x L2 of distinct buffers'),
-                gmres_its_per_step=its_per_step,
+                gmres_its_per_step=its_per_step, ksp_its_per_step=its_per_step,
                 gpu_launches=int(launches),
                 clocks=cs.summary(),
                 e2e=dict(value=e2e_val, unit='Mpts*steps/s',

@@ -36,7 +36,8 @@ extern "C" {
 
 #define KSFD_MAX_LIGANDS 7      /* dof <= 8 */
 #define KSFD_MAX_GROUPS 7
-#define KSFD_ABI_VERSION 2      /* 2: stream argument on norm2 / sum_dof0 / allreduce_* */
+#define KSFD_ABI_VERSION 3      /* 2: stream argument on norm2 / sum_dof0 / allreduce_*;
+                                   3: ksfd_ksp_opts.ksp_type, ksfd_ksp_solve */
 
 typedef struct ksfd_ctx ksfd_ctx;
 
@@ -189,13 +190,30 @@ typedef struct ksfd_ksp_opts {
                                   (FFT inverse of the frozen-coefficient operator;
                                   one rank, needs cuFFT, else 1), 3 = automatic:
                                   1 until a solve needs >= 16 steps, then 2 */
+    int32_t ksp_type;          /* -ksp_type: 0 = gmres, 1 = richardson (stationary sweeps
+                                  x += M^-1 r fused into the stencil kernel, block Jacobi
+                                  only), 2 = automatic: sweeps while they contract the
+                                  residual by >= 65 % per sweep, else GMRES from the iterate
+                                  reached; ignored (gmres) where sweeps are not available */
+    int32_t reserved;
 } ksfd_ksp_opts;
 typedef struct ksfd_ksp_result {
     int32_t its, reason;       /* reason > 0 converged, < 0 diverged      */
     double rnorm0, rnorm;
 } ksfd_ksp_result;
+/* GMRES whatever opts->ksp_type says */
 int ksfd_gmres(ksfd_ctx *ctx, const double *rhs, double *x,
                const ksfd_ksp_opts *opts, ksfd_ksp_result *res, void *stream);
+/* the solver opts->ksp_type selects (what ksfd_ts_step calls for its stage systems) */
+int ksfd_ksp_solve(ksfd_ctx *ctx, const double *rhs, double *x,
+                   const ksfd_ksp_opts *opts, ksfd_ksp_result *res, void *stream);
+
+/* one stationary sweep of the block-Jacobi preconditioned iteration, fused into the
+   stencil kernel (what ksp_type 1/2 iterate):  r_out = r_in - A M^-1 r_in,
+   x = (first ? 0 : x) + M^-1 r_in;  norms (host, may be NULL) = ||r_in||, ||r_out|| over
+   all ranks.  The three vectors must be distinct. */
+int ksfd_sweep(ksfd_ctx *ctx, const double *r_in, double *x, double *r_out, int first,
+               double norms[2], void *stream);
 
 /* ---- time step: replaces PETSc TS.step() for -ts_type rosw (ra34pw2) and
  *      beuler with -snes_type ksponly (call site KSFD/ksfdts.py:211) ------ */

@@ -25,7 +25,7 @@ EXPORTS = [
     'ksfd_jvp_setup', 'ksfd_jvp', 'ksfd_jvp_precond', 'ksfd_pc_apply',
     'ksfd_block_diagonal',
     'ksfd_mdot', 'ksfd_maxpy', 'ksfd_norm2', 'ksfd_sum_dof0',
-    'ksfd_scale_dof0', 'ksfd_mul_exp_dof0', 'ksfd_gmres', 'ksfd_ts_step',
+    'ksfd_scale_dof0', 'ksfd_mul_exp_dof0', 'ksfd_gmres', 'ksfd_ksp_solve', 'ksfd_sweep', 'ksfd_ts_step',
     'ksfd_allreduce_max', 'ksfd_allreduce_sum',
 ]
 
@@ -48,7 +48,8 @@ class Physics(C.Structure):
 class KspOpts(C.Structure):
     _fields_ = [('rtol', C.c_double), ('atol', C.c_double), ('dtol', C.c_double),
                 ('max_it', C.c_int32), ('restart', C.c_int32),
-                ('reorth', C.c_int32), ('precond', C.c_int32)]
+                ('reorth', C.c_int32), ('precond', C.c_int32),
+                ('ksp_type', C.c_int32), ('reserved', C.c_int32)]
 
 
 class KspResult(C.Structure):
@@ -129,6 +130,9 @@ def load():
     lib.ksfd_mul_exp_dof0.argtypes = [vp, dp, dp, C.c_double, vp]
     lib.ksfd_gmres.argtypes = [vp, dp, dp, C.POINTER(KspOpts),
                                C.POINTER(KspResult), vp]
+    lib.ksfd_ksp_solve.argtypes = [vp, dp, dp, C.POINTER(KspOpts),
+                                   C.POINTER(KspResult), vp]
+    lib.ksfd_sweep.argtypes = [vp, dp, dp, dp, i32, C.POINTER(C.c_double), vp]
     lib.ksfd_ts_step.argtypes = [vp, dp, C.c_double, C.c_double,
                                  C.POINTER(TsOpts), dp, TIME_CB, vp,
                                  C.POINTER(TsResult), vp]

@@ -190,7 +190,7 @@ class Context:
         counts and summed device milliseconds since the last fetch"""
         out = (C.c_double * 32)()
         _lib.check(self.lib.ksfd_profile_fetch(self.h, out, _stream()))
-        names = ['jvp', 'residual', 'mdot', 'orth', 'first_vector', 'cycle_begin']
+        names = ['jvp', 'residual', 'mdot', 'orth', 'first_vector', 'cycle_begin', 'sweep']
         d = {}
         for k, nm in enumerate(names):
             d[nm + '_launches'] = int(out[4 * k])
@@ -306,11 +306,33 @@ class Context:
     def gmres(self, rhs, x=None, rtol=1e-5, atol=1e-50, dtol=1e5, max_it=10000,
               restart=30, reorth=0, precond=1):
         x = self.empty() if x is None else self._chk(x)
-        o = KspOpts(rtol, atol, dtol, max_it, restart, reorth, precond)
+        o = KspOpts(rtol, atol, dtol, max_it, restart, reorth, precond, 0, 0)
         r = KspResult()
         _lib.check(self.lib.ksfd_gmres(self.h, _ptr(self._chk(rhs)), _ptr(x),
                                        C.byref(o), C.byref(r), _stream()))
         return x, r
+
+    def ksp_solve(self, rhs, x=None, ksp_type='auto', rtol=1e-5, atol=1e-50, dtol=1e5,
+                  max_it=10000, restart=30, reorth=0, precond=1):
+        """The linear solve of a stage system with the solver -ksp_type names: 'gmres',
+        'richardson' (stationary sweeps fused into the stencil kernel) or 'auto' (sweeps
+        while they contract fast enough, else GMRES from the iterate reached)."""
+        x = self.empty() if x is None else self._chk(x)
+        o = KspOpts(rtol, atol, dtol, max_it, restart, reorth, precond, KSP_TYPES[ksp_type], 0)
+        r = KspResult()
+        _lib.check(self.lib.ksfd_ksp_solve(self.h, _ptr(self._chk(rhs)), _ptr(x),
+                                           C.byref(o), C.byref(r), _stream()))
+        return x, r
+
+    def sweep(self, r_in, x, r_out=None, first=False, norms=True):
+        """One stationary sweep (csrc/sweep_op.cuh): r_out = r_in - A M^-1 r_in,
+        x = (0 if first else x) + M^-1 r_in.  Returns (r_out, (||r_in||, ||r_out||))."""
+        r_out = self.empty() if r_out is None else self._chk(r_out)
+        nr = (C.c_double * 2)()
+        _lib.check(self.lib.ksfd_sweep(self.h, _ptr(self._chk(r_in)), _ptr(self._chk(x)),
+                                       _ptr(r_out), 1 if first else 0,
+                                       nr if norms else None, _stream()))
+        return r_out, (nr[0], nr[1])
 
     def ts_step(self, u, t, h, opts, src=None, time_cb=None):
         """One accepted step (or a failure report); u is advanced in place."""
@@ -340,10 +362,14 @@ class Context:
         return res
 
 
+KSP_TYPES = {'gmres': 0, 'richardson': 1, 'auto': 2}
+
+
 def ts_options(ts_type='rosw', adapt='none', atol=1e-5, rtol=1e-5,
                clip=(0.1, 10.0), dt_min=1e-20, dt_max=1e50, safety=0.9,
                reject_safety=0.5, max_reject=10, ksp_rtol=1e-5, ksp_atol=1e-50,
-               ksp_dtol=1e5, ksp_max_it=10000, restart=30, reorth=0, precond=1):
+               ksp_dtol=1e5, ksp_max_it=10000, restart=30, reorth=0, precond=1,
+               ksp_type='auto'):
     o = TsOpts()
     o.ts_type = {'rosw': 0, 'beuler': 1}[ts_type]
     o.adapt = {'none': 0, 'basic': 1}[adapt]
@@ -353,5 +379,6 @@ def ts_options(ts_type='rosw', adapt='none', atol=1e-5, rtol=1e-5,
     o.safety, o.reject_safety = float(safety), float(reject_safety)
     o.max_reject = int(max_reject)
     o.ksp = KspOpts(float(ksp_rtol), float(ksp_atol), float(ksp_dtol),
-                    int(ksp_max_it), int(restart), int(reorth), int(precond))
+                    int(ksp_max_it), int(restart), int(reorth), int(precond),
+                    KSP_TYPES[ksp_type], 0)
     return o

@@ -97,6 +97,12 @@ struct ksfd_ctx {
     unsigned *gm_done = nullptr;                            // block counter of the fused multi-dot
     int gm_pipeline = 1, gm_runahead = 2;
     int gm_pred[2] = {0, 0};     // columns of the last first / later cycle (launch-ahead hint)
+    // Richardson sweeps (sweep_op.cuh): per-CTA partial sums, launch-ahead hint, and the
+    // automatic choice: after a solve that had to fall back to GMRES the next
+    // `sw_backoff` solves start with GMRES directly
+    double *sw_partial = nullptr;
+    int sw_hist[4] = {0, 0, 0, 0}, sw_hist_pos = 0, sw_backoff = 0;     // sweeps of the last solves
+    double sw_slow = 0.35;
     // Single-pass classical Gram-Schmidt loses orthogonality like eps*kappa^2,
     // kappa ~ the residual reduction inside the cycle, so a cycle is closed
     // after this reduction and restarted from the TRUE residual (measured on
@@ -147,6 +153,15 @@ struct HostVec {
     TmaSrc t;
 };
 
+// arguments of one Richardson sweep (sweep_op.cuh; ksfd.cu: sweep_solve_impl)
+struct SweepHost {
+    double *x, *rout;           // solution (updated in place), next residual
+    double rsign;               // sign applied to the input residual (first sweep: sign of the rhs)
+    int first;                  // x_0 = 0: x is written, not read
+    int partial_cap;            // CTAs the partial-sum buffer has room for
+    const void *fin;            // SweepFin (device-state pointers, options)
+};
+
 // marching-kernel launchers (march_res.cu, march_jvp.cu, march_vel.cu); each is
 // compiled once per dimension (-DKSFD_MARCH_DIM=2|3)
 #define KSFD_DECL_MARCH(D)                                                            \
@@ -156,7 +171,10 @@ struct HostVec {
                             const HostVec &pc, bool precond, double *out,             \
                             const int *skip, cudaStream_t st);                        \
     int ksfd_march_velocity_d##D(ksfd_ctx *c, const HostVec &u, double *vel,          \
-                                 double *vmax, cudaStream_t st);
+                                 double *vmax, cudaStream_t st);                      \
+    int ksfd_march_sweep_d##D(ksfd_ctx *c, const HostVec &coef, const HostVec &r,     \
+                              const HostVec &pc, const SweepHost &a, const int *skip, \
+                              cudaStream_t st);
 KSFD_DECL_MARCH(2)
 KSFD_DECL_MARCH(3)
 void ksfd_free_plans(ksfd_ctx *c);

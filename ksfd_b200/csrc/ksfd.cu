@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "blas1_kernels.cuh"
+#include "sweep_op.cuh"
 #include "ctx.h"
 #include "march_launch.cuh"
 #include "naive_kernels.cuh"
@@ -91,7 +92,8 @@ static long long nlocal(const ksfd_ctx *c) { return c->g.npts * c->dof; }
 
 // in-situ kernel timing: CUDA event pairs around launches (kind 0 J.v stencil, 1 residual
 // stencil, 2 multi-dot (+ rank sum, Givens), 3 orthogonalise-and-scale (+ halo push),
-// 4 first Krylov vector, 5 start of a cycle (norm / true residual), 6-7 unused); scopes nest
+// 4 first Krylov vector, 5 start of a cycle (norm / true residual), 6 Richardson sweep,
+// 7 unused); scopes nest
 struct ProfRec {
     int kind, start, stop;
 };
@@ -208,6 +210,7 @@ extern "C" int ksfd_ctx_destroy(ksfd_ctx *c)
     cudaFree(c->fft_spec2);
     cudaFree(c->fft_means);
     cudaFree(c->gm);
+    cudaFree(c->sw_partial);
     cudaFree(c->gmi);
     cudaFree(c->gm_done);
     for (int r = 0; r < 16; ++r)
@@ -1878,8 +1881,12 @@ static int gm_step(ksfd_ctx *c, int j, double *V, int pcm, const GmOpts &go, cud
     return 0;
 }
 
+// cycle0 = 1: continue a solve the Richardson sweeps started (sweep_solve_impl): x holds their
+// iterate, the device state their tolerance, ||b|| and iteration count; the first cycle
+// starts from the true residual of that x
 static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x,
-                           const ksfd_ksp_opts &o, ksfd_ksp_result *res, cudaStream_t st)
+                           const ksfd_ksp_opts &o, ksfd_ksp_result *res, cudaStream_t st,
+                           int cycle0 = 0)
 {
     const long long n = nlocal(c);
     if (o.restart > KSFD_MAX_RESTART)
@@ -1932,9 +1939,10 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
     hs->iters_done = 0;
     hs->cycle_done = hs->final_ = hs->reason = hs->its_total = 0;
     hs->k_cols = 0;
-    CK(cudaMemsetAsync(c->gmi, 0, sizeof(int) * GMI_INTS, st));
+    // (continuing: only the skip flags GMI_CYCLE_DONE, GMI_FINAL, GMI_NOUPD are cleared)
+    CK(cudaMemsetAsync(c->gmi, 0, sizeof(int) * (cycle0 ? 3 : GMI_INTS), st));
     // x = 0 is not stored: the first cycle's update WRITES x (x_zero below)
-    for (int cycle = 0;; ++cycle) {
+    for (int cycle = cycle0;; ++cycle) {
         const double *r = rhs;
         double sign = rhs_sign;
         // one rank: the block that finishes the <r,r> reduction last also starts
@@ -2091,9 +2099,155 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Preconditioned Richardson sweeps (sweep_op.cuh): one fused stencil pass per iteration,
+// convergence decided on the device, the host launches ahead and polls the pinned
+// status block exactly as for the pipelined GMRES.  Needs the marching kernels, the fused
+// block-Jacobi preconditioner and (several ranks) the peer-memory exchange.
+// ---------------------------------------------------------------------------
+#define KSFD_SWEEP_CTAS 65536
+static bool sweep_eligible(const ksfd_ctx *c, const ksfd_ksp_opts &o)
+{
+    if (o.ksp_type == 0 || o.reorth || !c->gm_pipeline) return false;
+    if (!use_march(c) || o.precond == 0 || o.precond == 2) return false;
+    if (o.precond == 3 && c->pc_auto_fft) return false;    // large steps: spectral + GMRES
+    if (c->nranks > 1 && !c->p2p_on) return false;
+    return true;
+}
+
+static int sweep_solve_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x,
+                            const ksfd_ksp_opts &o, ksfd_ksp_result *res, cudaStream_t st)
+{
+    const long long n = nlocal(c);
+    const int m = std::max(1, o.restart > 0 ? o.restart : 30);
+    if (c->krylov_cap < m + 1) {            // sized as the GMRES fallback wants it
+        cudaFree(c->krylov);
+        c->krylov = nullptr;
+        CK(cudaMalloc(&c->krylov, sizeof(double) * n * (m + 1)));
+        c->krylov_cap = m + 1;
+    }
+    TRY(gm_alloc(c));
+    if (!c->sw_partial) CK(cudaMalloc(&c->sw_partial, sizeof(double) * 2 * KSFD_SWEEP_CTAS));
+    double *buf[2] = {c->krylov, c->krylov + n};
+    GmStatus *hs = static_cast<GmStatus *>(c->gm_status);
+    GmStatus *hsd = static_cast<GmStatus *>(c->gm_status_dev);
+    const bool pure = o.ksp_type == 1;      // no fallback: stop on max_it / dtol only
+    GmOpts go{o.rtol, o.atol, o.dtol, o.max_it > 0 ? o.max_it : 10000, m, 0, 0.0};
+    hs->seq = 0;
+    hs->iters_done = 0;
+    hs->cycle_done = hs->final_ = hs->reason = hs->its_total = 0;
+    hs->k_cols = 0;
+    CK(cudaMemsetAsync(c->gmi, 0, sizeof(int) * GMI_INTS, st));
+    c->pushed_vec = nullptr;
+    const int R = c->gm_runahead;
+    const int *skip = c->gmi + GMI_CYCLE_DONE;
+    const bool defer = c->p2p_on && c->nranks > 1 && tma_consumer(c);
+    const HostVec ph = make_hvec(c, c->pc, 1, 2);
+    const HostVec ch = coef_hvec(c);
+    auto launch = [&](int it) -> int {
+        const double *rin = it == 0 ? rhs : buf[(it - 1) & 1];
+        TRY(exchange(c, rin, c->dof, 1, st, skip, defer));
+        const HostVec rh = make_hvec(c, rin, c->dof, 1);
+        SweepFin fin{c->sw_partial, c->gm, c->gmi, hsd, it, 0, go,
+                     pure ? 1e300 : c->sw_slow, p2p_red(c), c->gm_done};
+        SweepHost a{x, buf[it & 1], it == 0 ? rhs_sign : 1.0, it == 0 ? 1 : 0, KSFD_SWEEP_CTAS, &fin};
+        ProfScope prof(c, 6, st);
+        return c->dim == 2 ? ksfd_march_sweep_d2(c, ch, rh, ph, a, skip, st)
+                           : ksfd_march_sweep_d3(c, ch, rh, ph, a, skip, st);
+    };
+    // Consecutive solves take (almost) the same number of sweeps.  The predicted number —
+    // the longest of the last four solves: a sweep launched in vain returns at once (~2 us),
+    // a sweep launched late costs a host round trip (~10 us) — goes out without waiting;
+    // beyond it the host launches one sweep at a time, each once the previous one is known
+    // not to have ended the solve.  Without a prediction: R sweeps ahead of the device.
+    int pred = 0;
+    for (int i = 0; i < 4; ++i) pred = std::max(pred, c->sw_hist[i]);
+    int launched = 0;
+    for (; launched < std::min(pred, go.max_it); ++launched) TRY(launch(launched));
+    for (;;) {
+        const int lag = pred > 0 ? 0 : R;
+        TRY(gm_wait(st, [&] { return hs->cycle_done != 0 || hs->iters_done >= launched - lag; },
+                    "a Richardson sweep", c));
+        if (hs->cycle_done || launched >= go.max_it) break;
+        TRY(launch(launched));
+        ++launched;
+    }
+    TRY(gm_wait(st, [&] { return hs->cycle_done != 0; }, "the end of the sweeps", c));
+    if (getenv("KSFD_DEBUG_GMRES"))
+        fprintf(stderr, "sweeps: its %d reason %d rnorm0 %.3e rnorm %.3e\n", hs->its_total,
+                hs->reason, hs->rnorm0, hs->rnorm);
+    if (hs->reason == KSFD_SWEEP_FALLBACK) {
+        // contraction too slow for a stationary iteration: GMRES takes over, from the
+        // iterate reached so far unless it is worse than x = 0
+        c->sw_backoff = 8;
+        for (int i = 0; i < 4; ++i) c->sw_hist[i] = 0;
+        const bool keep = hs->rnorm < hs->rnorm0;
+        return gmres_pipe_impl(c, rhs, rhs_sign, x, o, res, st, keep ? 1 : 0);
+    }
+    c->sw_hist[c->sw_hist_pos++ & 3] = hs->its_total;
+    if (res) {
+        res->its = hs->its_total;
+        res->reason = hs->reason;
+        res->rnorm0 = hs->rnorm0;
+        res->rnorm = hs->rnorm;
+    }
+    return 0;
+}
+
+// one sweep as a stand-alone operation (tests, kernel timing): r_out = r_in - A M^-1 r_in,
+// x = (first ? 0 : x) + M^-1 r_in, norms[0] = ||r_in||, norms[1] = ||r_out|| (all ranks)
+extern "C" int ksfd_sweep(ksfd_ctx *c, const double *rin, double *x, double *rout, int first,
+                          double norms[2], void *stream)
+{
+    TRY(check_ready(c));
+    if (!c->have_jac) return fail("ksfd_jvp_setup has not been called");
+    if (!rin || !x || !rout) return fail("ksfd_sweep: NULL vector");
+    if (rin == rout || rin == x || x == rout) return fail("ksfd_sweep: the three vectors must be distinct");
+    ksfd_ksp_opts o{};
+    o.precond = 1;
+    o.ksp_type = 1;
+    if (!sweep_eligible(c, o))
+        return fail("ksfd_sweep: needs the marching kernels (2-D/3-D, <= 4 ligands) and, on "
+                    "several ranks, the peer-memory exchange");
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(gm_alloc(c));
+    if (!c->sw_partial) CK(cudaMalloc(&c->sw_partial, sizeof(double) * 2 * KSFD_SWEEP_CTAS));
+    GmStatus *hs = static_cast<GmStatus *>(c->gm_status);
+    GmStatus *hsd = static_cast<GmStatus *>(c->gm_status_dev);
+    hs->iters_done = hs->cycle_done = hs->final_ = 0;
+    CK(cudaMemsetAsync(c->gmi, 0, sizeof(int) * GMI_INTS, st));
+    c->pushed_vec = nullptr;
+    const bool defer = c->p2p_on && c->nranks > 1 && tma_consumer(c);
+    TRY(exchange(c, rin, c->dof, 1, st, nullptr, defer));
+    const HostVec rh = make_hvec(c, rin, c->dof, 1);
+    const HostVec ph = make_hvec(c, c->pc, 1, 2);
+    const HostVec ch = coef_hvec(c);
+    GmOpts go{0.0, 0.0, 0.0, 1 << 30, 1, 0, 0.0};
+    SweepFin fin{c->sw_partial, c->gm, c->gmi, hsd, 0, 0, go, 1e300, p2p_red(c), c->gm_done};
+    SweepHost a{x, rout, 1.0, first ? 1 : 0, KSFD_SWEEP_CTAS, &fin};
+    {
+        ProfScope prof(c, 6, st);
+        TRY(c->dim == 2 ? ksfd_march_sweep_d2(c, ch, rh, ph, a, nullptr, st)
+                        : ksfd_march_sweep_d3(c, ch, rh, ph, a, nullptr, st));
+    }
+    if (norms) {
+        CK(cudaStreamSynchronize(st));
+        norms[0] = hs->rnorm0;
+        norms[1] = hs->rnorm;
+    }
+    return 0;
+}
+
 static int gmres_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x,
                       const ksfd_ksp_opts &o, ksfd_ksp_result *res, cudaStream_t st)
 {
+    if (sweep_eligible(c, o)) {
+        // automatic choice (ksp_type 2): after a fallback the next solves start with GMRES
+        if (o.ksp_type == 2 && c->sw_backoff > 0)
+            --c->sw_backoff;
+        else
+            return sweep_solve_impl(c, rhs, rhs_sign, x, o, res, st);
+    }
     if (c->gm_pipeline && !o.reorth) return gmres_pipe_impl(c, rhs, rhs_sign, x, o, res, st);
     ksfd_ksp_opts o1 = o;                   // the host-driven variant knows block Jacobi only
     if (o1.precond > 1) o1.precond = 1;
@@ -2106,6 +2260,21 @@ extern "C" int ksfd_gmres(ksfd_ctx *c, const double *rhs, double *x,
     TRY(check_ready(c));
     if (!c->have_jac) return fail("ksfd_jvp_setup has not been called");
     if (!rhs || !x || !o) return fail("ksfd_gmres: NULL argument");
+    ksfd_ksp_opts o1 = *o;
+    o1.ksp_type = 0;
+    return gmres_impl(c, rhs, 1.0, x, o1, res, (cudaStream_t)stream);
+}
+
+extern "C" int ksfd_ksp_solve(ksfd_ctx *c, const double *rhs, double *x,
+                              const ksfd_ksp_opts *o, ksfd_ksp_result *res, void *stream)
+{
+    TRY(check_ready(c));
+    if (!c->have_jac) return fail("ksfd_jvp_setup has not been called");
+    if (!rhs || !x || !o) return fail("ksfd_ksp_solve: NULL argument");
+    if (o->ksp_type < 0 || o->ksp_type > 2) return fail("ksfd_ksp_solve: ksp_type must be 0, 1 or 2");
+    if (o->ksp_type == 1 && !sweep_eligible(c, *o))
+        return fail("ksfd_ksp_solve: richardson needs the marching kernels with the block-Jacobi "
+                    "preconditioner (and peer-memory exchange on several ranks)");
     return gmres_impl(c, rhs, 1.0, x, *o, res, (cudaStream_t)stream);
 }
 

@@ -263,6 +263,7 @@ struct ResidualOp {
     static constexpr bool HAS_AUX = true;
     static constexpr bool TABS = true;
     static constexpr bool JACOBIAN = false;     // runs on the current physics (ctx.P)
+    static constexpr bool NEEDS_OWNER = false;
     // input vectors of the TMA-fed marcher (tma_march.cuh): u
     static constexpr int NIN = 1;
     __host__ __device__ static constexpr int nc(int) { return NLIG + 1; }
@@ -372,6 +373,7 @@ struct JvpOp {
     static constexpr bool HAS_AUX = false;
     static constexpr bool TABS = false;
     static constexpr bool JACOBIAN = true;      // runs on the physics of the linearisation (ctx.Pjac)
+    static constexpr bool NEEDS_OWNER = false;   // (sweep_op.cuh) outputs updated in place: one owner per point
     // input vectors of the TMA-fed marcher (tma_march.cuh): coef, v, pc
     static constexpr int NIN = PRECOND ? 3 : 2;
     __host__ __device__ static constexpr int nc(int i) { return i == 0 ? NLIG + 3 : i == 1 ? NLIG + 1 : 1; }
@@ -434,9 +436,9 @@ struct JvpOp {
         f[NLIG + 2] = pre[0];
         f[NLIG + 3] = pre[1];
     }
+    // t = (shift*I - J) z at one output point (all NLIG+1 components)
     template <class Acc>
-    __device__ __forceinline__ void emit(const DevPhys &P, const MarchArgs &g, const Acc &a,
-                                         const double *, State &st) const
+    __device__ __forceinline__ void apply(const DevPhys &P, const Acc &a, double *t) const
     {
         // (J z)_rho = grad(z0).grad(G) + grad(rho).grad(dG) + z0*lap(G) + rho*lap(dG)
         constexpr int FR = NLIG + 2, FG = NLIG + 3;
@@ -446,15 +448,15 @@ struct JvpOp {
             double d1G, d2G, d1dG, d2dG;
             a.D12(FG, ax, d1G, d2G);
             a.D12(1, ax, d1dG, d2dG);
-            double t = a.D1(0, ax) * d1G;
-            t = fma(a.D1(FR, ax), d1dG, t);
-            acc = fma(P.c1sq[ax], t, acc);
+            double t_ = a.D1(0, ax) * d1G;
+            t_ = fma(a.D1(FR, ax), d1dG, t_);
+            acc = fma(P.c1sq[ax], t_, acc);
             lapG = fma(P.c2[ax], d2G, lapG);
             lapdG = fma(P.c2[ax], d2dG, lapdG);
         }
         const double z0 = a.c(0);
         const double Jv0 = fma(a.c(FR), lapdG, fma(z0, lapG, acc));
-        out[st.e] = fma(shift, z0, -Jv0);
+        t[0] = fma(shift, z0, -Jv0);
 #pragma unroll
         for (int l = 0; l < NLIG; ++l) {
             double lapV = 0.0;
@@ -462,8 +464,17 @@ struct JvpOp {
             for (int ax = 0; ax < DIM; ++ax) lapV = fma(P.c2[ax], a.D2(2 + l, ax), lapV);
             const double zl = a.c(2 + l);
             const double JvU = fma(P.D[l], lapV, fma(P.s[l], z0, -P.gamma[l] * zl));
-            out[st.e + (1 + l) * g.fs] = fma(shift, zl, -JvU);
+            t[1 + l] = fma(shift, zl, -JvU);
         }
+    }
+    template <class Acc>
+    __device__ __forceinline__ void emit(const DevPhys &P, const MarchArgs &g, const Acc &a,
+                                         const double *, State &st) const
+    {
+        double t[NLIG + 1];
+        apply(P, a, t);
+#pragma unroll
+        for (int c = 0; c < NLIG + 1; ++c) out[st.e + c * g.fs] = t[c];
     }
     __device__ __forceinline__ void advance_out(const MarchArgs &g, State &st) const
     {
@@ -481,6 +492,7 @@ struct VelocityOp {
     static constexpr bool HAS_AUX = false;
     static constexpr bool TABS = true;
     static constexpr bool JACOBIAN = false;
+    static constexpr bool NEEDS_OWNER = false;
     static constexpr int NIN = 1;
     __host__ __device__ static constexpr int nc(int) { return NLIG + 1; }
     __host__ __device__ static constexpr int coff(int) { return 0; }

@@ -151,7 +151,7 @@ static int launch_tile(const ksfd_ctx *c, const Op &op, const MarchPlan &p, cons
 // two tile candidates per operator: (AX, AY, AMINB) and (BX, BY, BMINB)
 template <int DIM, class Op, bool UNR, int AX, int AY, int AMINB, int BX, int BY, int BMINB>
 static int launch_op(ksfd_ctx *c, const Op &op, int opkey, double cstage, double cemit,
-                     const int *skip, cudaStream_t st)
+                     const int *skip, cudaStream_t st, int max_ctas = 0)
 {
     const long long maxel = (long long)(c->g.nloc + 2 * KSFD_SW) * c->g.plane_pts * (c->dof + 2);
     if (maxel >= (1LL << 31))
@@ -164,6 +164,8 @@ static int launch_op(ksfd_ctx *c, const Op &op, int opkey, double cstage, double
         return fail("marching kernel does not fit on this device");
     MarchPlan p = plan_march(c, opkey * 100 + DIM * 10 + Op::NF, cand, 2, cstage, cemit);
     if (p.tile < 0) return fail("no marching tile fits");
+    if (max_ctas && (long long)p.grid.x * p.grid.y * p.grid.z > max_ctas)
+        return fail("marching grid exceeds the per-CTA reduction buffer");
     if (p.tile == 0) return launch_tile<DIM, AX, AY, Op, AMINB, UNR>(c, op, p, skip, st);
     return launch_tile<DIM, BX, BY, Op, BMINB, UNR>(c, op, p, skip, st);
 }
@@ -270,7 +272,7 @@ static int launch_tma_tile(ksfd_ctx *c, const Op &op, const TmaSrc *src, const M
 template <int DIM, class Op, bool UNR, int AX, int AY, int AMINB, int ASC, int BX, int BY,
           int BMINB, int BSC>
 static int launch_tma_op(ksfd_ctx *c, const Op &op, const TmaSrc *src, int opkey, double cstage,
-                         double cemit, const int *skip, cudaStream_t st)
+                         double cemit, const int *skip, cudaStream_t st, int max_ctas = 0)
 {
     const long long maxel = (long long)(c->g.nloc + 2 * KSFD_SW) * c->g.plane_pts * (c->dof + 2);
     if (maxel >= (1LL << 31))
@@ -284,6 +286,8 @@ static int launch_tma_op(ksfd_ctx *c, const Op &op, const TmaSrc *src, int opkey
         return fail("TMA marching kernel does not fit on this device");
     MarchPlan p = plan_march(c, 1000 + opkey * 100 + DIM * 10 + Op::NF, cand, 2, cstage, cemit, true);
     if (p.tile < 0) return fail("no marching tile fits");
+    if (max_ctas && (long long)p.grid.x * p.grid.y * p.grid.z > max_ctas)
+        return fail("marching grid exceeds the per-CTA reduction buffer");
     if (p.tile == 0)
         return launch_tma_tile<DIM, AX, AY, Op, AMINB, UNR, ASC, ASC>(c, op, src, p, skip, st);
     return launch_tma_tile<DIM, BX, BY, Op, BMINB, UNR, BSC, BSC>(c, op, src, p, skip, st);

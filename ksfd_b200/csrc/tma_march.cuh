@@ -278,6 +278,13 @@ struct TmaMarcher {
         k0 = blockIdx.z * g.rz;
         k1 = min(k0 + g.rz, g.nloc);
         op.init_out(g, st, k0, poff);
+        if constexpr (Op::NEEDS_OWNER) {
+            // the clamped last tile of an axis overlaps its neighbour: the outputs in front
+            // of its unclamped origin belong to the neighbour
+            bool own = active && (DIM == 2 ? tid : tid % TX) >= (int)blockIdx.x * g.ox - i0;
+            if (DIM == 3) own = own && tid / TX >= (int)blockIdx.y * g.oy - j0;
+            st.own = own;
+        }
         cs = hs = 0;
         cph = hph = 0;
 #pragma unroll

@@ -14,6 +14,8 @@ PETSc options understood (from the '--petsc' block of the option files):
   -ts_adapt_safety / -ts_adapt_reject_safety / -ts_adapt_scale_solve_failed
   -ksp_rtol / -ksp_atol / -ksp_divtol / -ksp_max_it / -ksp_gmres_restart
   -ksp_gmres_cgs_refinement_type refine_never|refine_always
+  -ksp_type gmres|richardson (default: the library chooses — stationary block-Jacobi
+   sweeps fused into the stencil kernel while they contract fast, GMRES otherwise)
   -pc_type none|pbjacobi|fft (lu, as shipped in the option files, is mapped to the
    iterative solve with a tight default tolerance and the automatic choice between
    block Jacobi and the spectral preconditioner: there is no LU on the device)
@@ -146,6 +148,11 @@ class KSFDTS:
         pc = po.get('pc_type', 'pbjacobi')
         direct = pc in ('lu', 'cholesky')
         refine = po.get('ksp_gmres_cgs_refinement_type', 'refine_never')
+        # -ksp_type gmres | richardson; anything else (preonly with a direct solver in
+        # the shipped option files, or nothing) leaves the choice to the library
+        ksp_type = po.get('ksp_type', 'auto')
+        if ksp_type not in ('gmres', 'richardson'):
+            ksp_type = 'auto'
         self._ts_kind = tstype
         self._opts = core.ts_options(
             ts_type=tstype, adapt=adapt, atol=self.atol, rtol=self.rtol,
@@ -162,6 +169,7 @@ class KSFDTS:
             ksp_max_it=max(po.getInt('ksp_max_it', 10000), 1),
             restart=po.getInt('ksp_gmres_restart', 30),
             reorth=0 if refine == 'refine_never' else 1,
+            ksp_type=ksp_type,
             # lu/cholesky (the shipped option files): automatic choice between the
             # fused block-Jacobi and the spectral preconditioner; 'fft' forces the latter
             precond={'none': 0, 'pbjacobi': 1, 'bjacobi': 1, 'jacobi': 1, 'fft': 2}.get(pc, 3))

@@ -37,6 +37,14 @@ def main():
         nrm = ctx.norm2(v); wsum = ctx.sum_dof0(u)
         x, res = ctx.gmres(ud, rtol=1e-10, max_it=500)
         xs = ctx.download(x)
+        # stationary sweeps fused into the stencil kernel (peer-memory exchange only)
+        sweeps = dim >= 2 and os.environ.get('KSFD_HALO_P2P', '1') != '0'
+        if sweeps:
+            xw = ctx.zeros()
+            rw, nw = ctx.sweep(v, xw, first=True)
+            rws, xws = ctx.download(rw), ctx.download(xw)
+            xr, rr = ctx.ksp_solve(ud, ksp_type='richardson', rtol=1e-10, max_it=100)
+            xrs = ctx.download(xr)
         opts = core.ts_options(adapt='basic', atol=0.01, rtol=1e-6, clip=(0.1, 5.0), ksp_rtol=1e-12, ksp_max_it=500)
         uu = u.clone(); t, h = 0.0, 1e-6
         for k in range(3):
@@ -52,6 +60,12 @@ def main():
             Jv1 = c1.download(c1.jvp(V)); Jvp1 = c1.download(c1.jvp(V, precond=True))
             vm1 = c1.velocity_max(U); nrm1 = c1.norm2(V); wsum1 = c1.sum_dof0(U)
             x1, res1 = c1.gmres(UD, rtol=1e-10, max_it=500); xs1 = c1.download(x1)
+            if sweeps:
+                xw1 = c1.zeros()
+                rw1, nw1 = c1.sweep(V, xw1, first=True)
+                rws1, xws1 = c1.download(rw1), c1.download(xw1)
+                xr1, rr1 = c1.ksp_solve(UD, ksp_type='richardson', rtol=1e-10, max_it=100)
+                xrs1 = c1.download(xr1)
             uu1 = U.clone(); t1, h1 = 0.0, 1e-6
             for k in range(3):
                 c1.groom(uu1); r1 = c1.ts_step(uu1, t1, h1, opts); t1, h1 = r1.t_new, r1.h_next
@@ -62,7 +76,13 @@ def main():
             errs = dict(F=rel(F, F1[sl]), Jv=rel(Jv, Jv1[sl]), Jvp=rel(Jvp, Jvp1[sl]),
                         vmax=rel(vm, vm1), norm=abs(nrm - nrm1) / nrm1, sum=abs(wsum - wsum1) / wsum1,
                         gmres=rel(xs, xs1[sl]), ts=rel(us, us1[sl]), t=abs(t - t1), h=abs(h - h1) / h1)
+            if sweeps:
+                errs.update(sweep_r=rel(rws, rws1[sl]), sweep_x=rel(xws, xws1[sl]),
+                            sweep_norms=max(abs(nw[0] - nw1[0]) / nw1[0], abs(nw[1] - nw1[1]) / nw1[1]),
+                            richardson=rel(xrs, xrs1[sl]), richardson_its=float(abs(rr.its - rr1.its)))
             ok = all(e < 1e-9 for e in errs.values()) and errs['F'] == 0.0 and errs['Jv'] == 0.0
+            if sweeps:
+                ok = ok and errs['sweep_r'] == 0.0 and errs['sweep_x'] == 0.0
             ok_all = ok_all and ok
             print('dim', dim, n, 'ranks', world, 'OK' if ok else 'FAIL', errs, 'its', res.its, res1.its, flush=True)
         dist.barrier()

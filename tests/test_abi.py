@@ -33,7 +33,7 @@ def test_python_binding_matches_header(built_lib):
     from ksfd_b200 import _lib
     assert sorted(_lib.EXPORTS) == header_symbols()
     lib = _lib.load()
-    assert lib.ksfd_abi_version() == 2
+    assert lib.ksfd_abi_version() == 3
     assert _lib.launch_count() == 0
 
 
@@ -42,7 +42,7 @@ def test_struct_sizes_match_c(built_lib):
     computed from the header layout rules)."""
     from ksfd_b200 import _lib
     assert ctypes.sizeof(_lib.Physics) == 16 + 6 * 8 + 2 * 7 * 8 + 8 * 4 + 4 * 7 * 8 + 2 * 15 * 8
-    assert ctypes.sizeof(_lib.KspOpts) == 3 * 8 + 4 * 4
+    assert ctypes.sizeof(_lib.KspOpts) == 3 * 8 + 6 * 4
     assert ctypes.sizeof(_lib.TsOpts) == 8 + 8 * 8 + 8 + ctypes.sizeof(_lib.KspOpts)
 
 

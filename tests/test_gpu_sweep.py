@@ -1,0 +1,131 @@
+"""
+The stationary (Richardson) block-Jacobi sweeps fused into the marching stencil kernel
+(csrc/sweep_op.cuh; -ksp_type richardson / the automatic choice) against the direct solve of
+the oracle's assembled operator, on grids that exercise every tiling case: exact tiles,
+clamped (overlapping) last tiles of the TMA-fed marcher, odd extents (register-prefetch
+marcher), 3-D.  Tolerance: the solves are made to rtol 1e-12 and must agree with SuperLU
+to 1e-8 relative (the conditioning of the stage matrix), the TRUE residual recomputed
+through ksfd_jvp must meet the tolerance the solver reported.
+"""
+import numpy as np
+import pytest
+
+from helpers import oracle_physics, phys84, random_state, relerr
+from test_gpu_parity import make_ctx
+
+pytestmark = pytest.mark.gpu
+
+GRIDS = [('2d_exact', phys84(2, (96, 64))),
+         ('2d_clamped_tile', phys84(2, (302, 40))),
+         ('2d_odd', phys84(2, (51, 36))),
+         ('3d_exact', phys84(3, (32, 16, 12))),
+         ('3d_clamped_tile', phys84(3, (22, 26, 12))),
+         ('3d_odd', phys84(3, (15, 12, 10)))]
+
+
+@pytest.mark.parametrize('label,p', GRIDS)
+def test_one_sweep_equals_its_parts(label, p):
+    """The fused kernel against the separate kernels it fuses: r_out must equal
+    r - (A M^-1 r) with A M^-1 r from ksfd_jvp_precond BIT FOR BIT (same arithmetic, one
+    more subtraction), x must equal x + M^-1 r from ksfd_pc_apply, and the two norms the
+    device epilogue reports must be those of r and r_out."""
+    import torch
+    ctx = make_ctx(p)
+    u = ctx.upload(random_state(p, 7))
+    ctx.jvp_setup(u, 1.0 / (0.435866521508459 * 1e-3))
+    gen = torch.Generator(device='cuda').manual_seed(3)
+    r = torch.randn(u.numel(), generator=gen, device='cuda', dtype=torch.float64)
+    x0 = torch.randn(u.numel(), generator=gen, device='cuda', dtype=torch.float64)
+    t = ctx.jvp(r, precond=True)
+    z = ctx.pc_apply(r)
+    for first in (True, False):
+        x = x0.clone()
+        rout, (n0, n1) = ctx.sweep(r, x, first=first)
+        assert torch.equal(rout, r - t), (label, first, float((rout - (r - t)).abs().max()))
+        xe = z if first else x0 + z
+        assert float((x - xe).abs().max()) <= 4e-16 * float(xe.abs().max()), (label, first)
+        assert abs(n0 - float(r.norm())) <= 1e-13 * n0, (label, n0)
+        assert abs(n1 - float(rout.norm())) <= 1e-13 * n1, (label, n1)
+    ctx.close()
+
+
+@pytest.mark.parametrize('label,p', GRIDS)
+def test_sweeps_against_direct_solve(label, p):
+    import scipy.sparse.linalg as spla
+    from oracle import ksfd_oracle as O
+    ph = oracle_physics(p)
+    u = random_state(p, 21)
+    rng = np.random.default_rng(22)
+    b = rng.standard_normal(u.size)
+    shift = 1.0 / (O.ROSW_GAMMA * 1e-3)
+    x_ref = spla.splu(O.ijacobian(u, shift, ph).tocsc()).solve(b)
+    ctx = make_ctx(p)
+    ctx.jvp_setup(ctx.upload(u), shift)
+    bd = ctx.upload(b)
+    its = []
+    for rep in range(3):            # launch-ahead: the later solves use the predicted length
+        x, res = ctx.ksp_solve(bd, ksp_type='richardson', rtol=1e-12, max_it=200)
+        assert res.reason > 0, (label, res.reason, res.its)
+        its.append(res.its)
+        assert relerr(ctx.download(x), x_ref) < 1e-8, (label, rep, res.its)
+        true = ctx.norm2(bd - ctx.jvp(x)) / res.rnorm0
+        assert true <= 1.5e-12, (label, rep, true)
+        assert abs(res.rnorm / res.rnorm0 - true) <= 0.05 * true + 1e-15, (label, res.rnorm, true)
+    assert len(set(its)) == 1 and its[0] <= 20, (label, its)
+    # the solution does not depend on the solver: GMRES to the same tolerance
+    xg, rg = ctx.gmres(bd, rtol=1e-12, max_it=2000)
+    assert relerr(ctx.download(xg), ctx.download(x)) < 1e-9, label
+    print('%s: %d sweeps, GMRES %d steps' % (label, its[0], rg.its))
+    ctx.close()
+
+
+@pytest.mark.parametrize('label,p', [('2d', phys84(2, (96, 64))), ('3d', phys84(3, (20, 24, 16)))])
+def test_automatic_choice_falls_back_to_gmres(label, p):
+    """Large time steps: the stationary iteration contracts slowly (or diverges); the
+    automatic choice must notice on the device, hand over to GMRES from the iterate
+    reached, and still return the direct solve's answer; the next solves start with
+    GMRES (back-off), and small steps return to the sweeps."""
+    import scipy.sparse.linalg as spla
+    from oracle import ksfd_oracle as O
+    ph = oracle_physics(p)
+    u = random_state(p, 21)
+    rng = np.random.default_rng(23)
+    b = rng.standard_normal(u.size)
+    ctx = make_ctx(p)
+    bd = ctx.upload(b)
+    for dt in (0.2, 0.02, 1e-3, 1e-5):
+        shift = 1.0 / (O.ROSW_GAMMA * dt)
+        x_ref = spla.splu(O.ijacobian(u, shift, ph).tocsc()).solve(b)
+        ctx.jvp_setup(ctx.upload(u), shift)
+        for rep in range(2):
+            x, res = ctx.ksp_solve(bd, ksp_type='auto', rtol=1e-12, max_it=2000)
+            assert res.reason > 0, (label, dt, res.reason, res.its)
+            assert relerr(ctx.download(x), x_ref) < 1e-8, (label, dt, rep, res.its)
+            true = ctx.norm2(bd - ctx.jvp(x)) / res.rnorm0
+            assert true <= 1.5e-12, (label, dt, rep, true)
+    # pure richardson on a step it cannot handle reports a failure instead of hanging
+    ctx.jvp_setup(ctx.upload(u), 1.0 / (O.ROSW_GAMMA * 0.2))
+    x, res = ctx.ksp_solve(bd, ksp_type='richardson', rtol=1e-12, max_it=40)
+    assert res.reason < 0 or res.its <= 40
+    ctx.close()
+
+
+def test_sweep_sign_and_zero_rhs():
+    """ksfd_ts_step solves A y = -F (sign applied inside the first sweep); b = 0 ends
+    after one sweep with x = 0."""
+    from ksfd_b200 import core
+    p = phys84(2, (64, 48))
+    ctx = make_ctx(p)
+    u = ctx.upload(random_state(p, 5))
+    opts_s = core.ts_options(adapt='none', ksp_rtol=1e-12, ksp_type='richardson')
+    opts_g = core.ts_options(adapt='none', ksp_rtol=1e-12, ksp_type='gmres')
+    us, ug = u.clone(), u.clone()
+    rs = ctx.ts_step(us, 0.0, 1e-3, opts_s)
+    rg = ctx.ts_step(ug, 0.0, 1e-3, opts_g)
+    assert rs.accepted and rg.accepted and not rs.ksp_fail
+    d = (us - ug).abs().max().item() / ug.abs().max().item()
+    assert d < 1e-11, d
+    ctx.jvp_setup(u, 1000.0)
+    x, res = ctx.ksp_solve(ctx.zeros(), ksp_type='richardson', rtol=1e-8)
+    assert res.reason > 0 and res.its == 1 and float(x.abs().max()) == 0.0
+    ctx.close()
