@@ -220,10 +220,16 @@ class Context:
 
     def velocity_max(self, u):
         import torch
-        vm = torch.zeros(3, dtype=torch.float64, device=self.tdev)
+        # persistent device result + pinned host copy: no fill kernel, no pageable staging
+        # (the kernel zeroes the result itself)
+        if getattr(self, '_vm', None) is None:
+            self._vm = torch.empty(3, dtype=torch.float64, device=self.tdev)
+            self._vm_host = torch.empty(3, dtype=torch.float64).pin_memory()
         _lib.check(self.lib.ksfd_velocity_max(self.h, _ptr(self._chk(u)),
-                                              _ptr(vm), _stream()))
-        v = vm.cpu().numpy()[:self.dim].copy()
+                                              _ptr(self._vm), _stream()))
+        self._vm_host.copy_(self._vm, non_blocking=True)
+        torch.cuda.current_stream(self.tdev).synchronize()
+        v = self._vm_host.numpy()[:self.dim].copy()
         if self.nranks > 1:
             arr = (C.c_double * self.dim)(*v)
             _lib.check(self.lib.ksfd_allreduce_max(self.h, arr, self.dim, _stream()))

@@ -6,6 +6,7 @@
 #pragma once
 #include "device_common.cuh"
 #include "solver_state.cuh"
+#include "halo_push.cuh"
 
 #define KSFD_RED_BLOCKS 592          // 4 CTAs per SM on 148 SMs
 #define KSFD_RED_THREADS 256
@@ -214,24 +215,12 @@ __global__ void k_scale_by_inv(long long n, const double *x,
 
 // ROSW stage set-up (PETSc TSStep_RosW):
 //   Z = u + sum_j a[j] Y_j ;  Zdot = sum_j g[j] Y_j
-template <int NV>
+// PUSH: several ranks — the boundary planes of Z (the input of the stage residual) also go
+// to the neighbours' ghost buffers, first and from blocks of their own (cf. k_gm_orth_scale)
+template <int NV, bool PUSH>
 __global__ void k_stage_combine(long long n, const double *__restrict__ u,
                                 VecList Y, CoefList a, CoefList gm,
-                                double *__restrict__ Z, double *__restrict__ Zdot)
-{
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
-         e += (long long)gridDim.x * blockDim.x) {
-        double z = u[e], zd = 0.0;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const double y = __ldg(Y.v[i] + e);
-            z = fma(a.c[i], y, z);
-            zd = fma(gm.c[i], y, zd);
-        }
-        Z[e] = z;
-        Zdot[e] = zd;
-    }
-}
+                                double *__restrict__ Z, double *__restrict__ Zdot, HaloPush hp);
 
 // ROSW completion + embedded error estimate (TSEvaluateStep_RosW +
 // TSErrorWeightedNorm NORM_2):
@@ -310,95 +299,6 @@ __global__ void k_p2p_allreduce(P2PRed pr, double *buf, int n, int op)
     for (int i = threadIdx.x; i < n; i += blockDim.x) buf[i] = v[i];
 }
 
-// ---------------------------------------------------------------------------
-// Halo push fused into the PRODUCER of a vector (several ranks, NVLink peer memory).
-// The kernel that writes a Krylov vector also stores its two bottom planes into the
-// lower neighbour's ghost buffer and its two top planes into the upper neighbour's
-// (plain stores over NVLink; in the plane-SoA layout the planes are the first and the
-// last `cnt` doubles of the vector), and the block that finishes last publishes the
-// exchange number in the neighbours' flag words and advances this rank's counter.
-// Nobody waits here: the consumer (the TMA-fed marcher, tma_march.cuh: halo_arrived)
-// waits in the CTAs that read ghost planes.  No exchange kernel is launched at all.
-// ---------------------------------------------------------------------------
-struct HaloPush {
-    double *up_lo0, *dn_hi0;                // parity-0 destinations (nullptr: no push)
-    long long pstride;                      // doubles between the two parity buffers
-    long long cnt;                          // doubles in the two boundary planes
-    long long top0;                         // first element of the two top planes (n - cnt)
-    volatile unsigned long long *up_flag_lo, *dn_flag_hi;
-    unsigned long long *ctr;                // this rank's exchange counter of the slot
-    unsigned *done;                         // block counter
-    const volatile unsigned long long *dead;
-};
-__device__ __forceinline__ bool halo_push_on(const HaloPush &hp)
-{
-    return hp.up_lo0 != nullptr && !(hp.dead && *hp.dead);
-}
-// parity shift of the exchange this launch makes; every block reads the counter
-// before the last one (which only exists after all blocks have stored) advances it
-__device__ __forceinline__ long long halo_push_shift(const HaloPush &hp, unsigned long long &q)
-{
-    q = *reinterpret_cast<volatile unsigned long long *>(hp.ctr) + 1;
-    return (long long)(q & 1ull) * hp.pstride;
-}
-// returns true when this thread stored into peer memory
-__device__ __forceinline__ bool halo_push1(const HaloPush &hp, long long sh, long long e, double v)
-{
-    bool did = false;
-    if (e < hp.cnt) {
-        hp.dn_hi0[sh + e] = v;
-        did = true;
-    }
-    if (e >= hp.top0) {
-        hp.up_lo0[sh + e - hp.top0] = v;
-        did = true;
-    }
-    return did;
-}
-// elements 2e, 2e+1 (cnt and top0 are even whenever the double2 path runs)
-__device__ __forceinline__ bool halo_push2(const HaloPush &hp, long long sh, long long e2, double2 v)
-{
-    const long long e = 2 * e2;
-    bool did = false;
-    if (e < hp.cnt) {
-        *reinterpret_cast<double2 *>(hp.dn_hi0 + sh + e) = v;
-        did = true;
-    }
-    if (e >= hp.top0) {
-        *reinterpret_cast<double2 *>(hp.up_lo0 + sh + e - hp.top0) = v;
-        did = true;
-    }
-    return did;
-}
-// Called by every thread of the blocks that stored boundary planes, right after those
-// stores and BEFORE the interior stream (`expected` = number of such blocks).
-// Hierarchical release: the storing threads do not fence themselves (a system-scope fence
-// in a thread of an SM that is streaming stores waits for all of them: measured +2 us per
-// producer kernel on top of the rest, profiles/r02_multi_gpu_step_breakdown.txt).  The CTA
-// barrier orders every thread's peer stores before thread 0's device-scope fence and its
-// (device-scope) arrival on the block counter; the block that arrives last has therefore
-// observed all of them and orders its flag stores after them with ONE system-scope fence
-// (fences are cumulative in the PTX memory model), so a neighbour that sees the flag sees the
-// planes.  Publishing EARLY matters: a kernel whose last action is a store to peer memory
-// ends one NVLink round trip later (grid completion waits for the acknowledgement) — measured
-// +6-9 us per producer kernel when the flags went out at the end; now the round trip of the
-// planes and of the flags hides behind the interior stream of the same kernel.
-__device__ __forceinline__ void halo_push_publish(const HaloPush &hp, unsigned long long q,
-                                                  unsigned expected)
-{
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned t = atomicAdd(hp.done, 1u);
-        if (t == expected - 1) {                // last boundary block: all planes are on their way
-            atomicExch(hp.done, 0u);
-            __threadfence_system();
-            *hp.up_flag_lo = q;
-            *hp.dn_flag_hi = q;
-            *hp.ctr = q;
-        }
-    }
-}
 // Work split of a pushing producer.  When the boundary positions [0, nb) of the push order
 // need only a few blocks (2-D: 24 of 592), those blocks do NOTHING else: they store the
 // planes, publish (the publishing thread sits in a system-scope fence for about two NVLink
@@ -954,4 +854,41 @@ k_gm_true_residual(long long n, const double *__restrict__ rhs, double sign,
     }
     block_reduce_store<1>(acc, partial, KSFD_RED_BLOCKS);
     if (FUSE) gm_begin_in_last_block(a);
+}
+
+template <int NV, bool PUSH>
+__global__ void k_stage_combine(long long n, const double *__restrict__ u,
+                                VecList Y, CoefList a, CoefList gm,
+                                double *__restrict__ Z, double *__restrict__ Zdot, HaloPush hp)
+{
+    const bool push = PUSH && halo_push_on(hp);
+    unsigned long long q = 0;
+    const long long sh = push ? halo_push_shift(hp, q) : 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool reorder = push && 2 * hp.cnt <= n;
+    const long long nb = push ? (reorder ? 2 * hp.cnt : n) : 0;     // boundary positions
+    auto body = [&](long long e) {
+        double z = u[e], zd = 0.0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const double y = __ldg(Y.v[i] + e);
+            z = fma(a.c[i], y, z);
+            zd = fma(gm.c[i], y, zd);
+        }
+        Z[e] = z;
+        Zdot[e] = zd;
+        return z;
+    };
+    for (; p < nb; p += stride) {
+        const long long e = reorder ? push_order(p, hp.cnt, n) : p;
+        halo_push1(hp, sh, e, body(e));
+    }
+    const PushSplit ps = push_split(push, nb);
+    if (push && blockIdx.x < ps.nbA) halo_push_publish(hp, q, ps.nbA);
+    if (ps.split) {
+        if (blockIdx.x < ps.nbA) return;
+        p = ps.p0;
+    }
+    for (; p < n; p += ps.stride) body(reorder ? push_order(p, hp.cnt, n) : p);
 }

@@ -76,6 +76,7 @@ struct ksfd_ctx {
     // Krylov vector whose boundary planes were pushed by the kernel that produced it
     // (consumed by the next jvp_impl on that vector; host-side bookkeeping only)
     const double *pushed_vec = nullptr;
+    const double *pushed_vec0 = nullptr;    // same for halo slot 0 (stage vector Z -> residual)
     bool gm_no_push = false;
     int *p2p_err = nullptr, *p2p_err_dev = nullptr;    // pinned + mapped: a peer wait timed out
     // Jacobian state
@@ -101,8 +102,17 @@ struct ksfd_ctx {
     // automatic choice: after a solve that had to fall back to GMRES the next
     // `sw_backoff` solves start with GMRES directly
     double *sw_partial = nullptr;
-    int sw_hist[4] = {0, 0, 0, 0}, sw_hist_pos = 0, sw_backoff = 0;     // sweeps of the last solves
+    // sweeps of the last solve in each SLOT: the time integrator numbers its solves within a
+    // step (ROSW: stage 0..3) and stage i of one step predicts stage i of the next
+    int sw_hist[4] = {0, 0, 0, 0}, sw_slot = 0, sw_backoff = 0;
+    int sw_stable[4] = {0, 0, 0, 0};   // consecutive solves of the slot with the predicted count
     double sw_slow = 0.35;
+    // Every sweep from `lead` sweeps before the predicted end on is tested for convergence:
+    // normally only the predicted last one (a test costs a serial epilogue of 7-12 us),
+    // every 8th solve of a slot one more, so that the prediction can also go DOWN
+    int sw_test_lead = 1;
+    int fuse_push_mask = 7;      // producers that push their output's boundary planes: 2 stage combination, 4 stage residual
+    bool sw_fuse_push = true;    // several ranks: boundary planes pushed by the sweep kernel itself
     // Single-pass classical Gram-Schmidt loses orthogonality like eps*kappa^2,
     // kappa ~ the residual reduction inside the cycle, so a cycle is closed
     // after this reduction and restarted from the TRUE residual (measured on
@@ -160,13 +170,18 @@ struct SweepHost {
     int first;                  // x_0 = 0: x is written, not read
     int partial_cap;            // CTAs the partial-sum buffer has room for
     const void *fin;            // SweepFin (device-state pointers, options)
+    // HaloPush or nullptr: the kernel also stores the boundary planes of rout into the
+    // neighbours' ghost buffers and publishes the exchange (TMA-fed marcher only; the
+    // caller then marks rout as pushed, else it launches the push kernel itself)
+    const void *push;
 };
 
 // marching-kernel launchers (march_res.cu, march_jvp.cu, march_vel.cu); each is
 // compiled once per dimension (-DKSFD_MARCH_DIM=2|3)
 #define KSFD_DECL_MARCH(D)                                                            \
     int ksfd_march_residual_d##D(ksfd_ctx *c, const HostVec &u, const double *udot,   \
-                                 const double *src, double *out, cudaStream_t st);    \
+                                 const double *src, double *out, const void *push,    \
+                                 cudaStream_t st);                                    \
     int ksfd_march_jvp_d##D(ksfd_ctx *c, const HostVec &coef, const HostVec &v,       \
                             const HostVec &pc, bool precond, double *out,             \
                             const int *skip, cudaStream_t st);                        \

@@ -83,6 +83,40 @@ struct VecRef {
     volatile unsigned long long *dead;      // device-side sticky copy of it
 };
 
+// Flag words of the peer-memory exchanges.  The consumer ACQUIRES the flag (ld.acquire.sys:
+// what it reads afterwards is ordered behind the observation, no full fence — a
+// system-scope MEMBAR in an SM that is streaming stores waits for all of them, measured
+// 10-20 us inside the bandwidth-bound kernels), the producer RELEASES it (st.release.sys).
+#ifndef KSFD_FLAG_ACQREL
+#define KSFD_FLAG_ACQREL 1
+#endif
+__device__ __forceinline__ unsigned long long flag_acquire(const volatile unsigned long long *f)
+{
+#if KSFD_FLAG_ACQREL
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+    return v;
+#else
+    return *f;
+#endif
+}
+// after a successful wait
+__device__ __forceinline__ void flag_acquired()
+{
+#if !KSFD_FLAG_ACQREL
+    __threadfence_system();
+#endif
+}
+__device__ __forceinline__ void flag_release(volatile unsigned long long *f, unsigned long long v)
+{
+#if KSFD_FLAG_ACQREL
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(v) : "memory");
+#else
+    __threadfence_system();
+    *f = v;
+#endif
+}
+
 // bounded spin until the neighbour's flag reaches exchange number q (cf. p2p_spin)
 static __device__ __noinline__ void halo_flag_wait(const volatile unsigned long long *f,
                                                    unsigned long long q, volatile int *err,
@@ -90,7 +124,7 @@ static __device__ __noinline__ void halo_flag_wait(const volatile unsigned long 
 {
     const long long t0 = clock64();
     unsigned spins = 0;
-    while (*f < q) {
+    while (flag_acquire(f) < q) {
         __nanosleep(20);
         if ((++spins & 0xfff) == 0 && (clock64() - t0 > 240000000000ll || (dead && *dead))) {
             if (dead) *dead = 1ull;
@@ -98,7 +132,7 @@ static __device__ __noinline__ void halo_flag_wait(const volatile unsigned long 
             break;
         }
     }
-    __threadfence_system();
+    flag_acquired();
 }
 
 __device__ __forceinline__ long long ghost_shift(const VecRef &v)

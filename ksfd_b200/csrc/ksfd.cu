@@ -354,6 +354,9 @@ extern "C" int ksfd_set_option(ksfd_ctx *c, const char *key, int64_t v)
     else if (k == "gmres_pipeline") c->gm_pipeline = (int)v;
     else if (k == "halo_p2p") c->p2p_on = v != 0 && c->p2p_up != nullptr;   // same on all ranks
     else if (k == "gmres_cycle_exp") c->gm_cycle_factor = v <= 0 ? 0.0 : std::pow(10.0, -(double)v);
+    else if (k == "sweep_test_lead") c->sw_test_lead = (int)std::max<int64_t>(1, v);
+    else if (k == "sweep_fuse_push") c->sw_fuse_push = v != 0;
+    else if (k == "fuse_push_mask") c->fuse_push_mask = (int)v;
     else if (k == "gmres_runahead") c->gm_runahead = (int)std::max<int64_t>(0, std::min<int64_t>(v, 8));
     else return fail("unknown option " + k);
     ksfd_invalidate_plans(c);
@@ -562,15 +565,16 @@ __global__ void k_halo_push(const double *__restrict__ top, const double *__rest
         up_lo0[sh + e] = top[e];
         dn_hi0[sh + e] = bot[e];
     }
-    __threadfence_system();
+    // hierarchical release (halo_push.cuh: halo_push_publish): CTA barrier, one device-scope
+    // fence + arrival per block, ONE system-scope fence in the block that arrives last
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();
         const unsigned t = atomicAdd(done, 1u);
         if (t == gridDim.x - 1) {
             atomicExch(done, 0u);
-            __threadfence_system();
-            *up_flag_lo = q;
-            *dn_flag_hi = q;
+            flag_release(up_flag_lo, q);
+            flag_release(dn_flag_hi, q);
             *ctr = q;
         }
     }
@@ -827,15 +831,25 @@ extern "C" int ksfd_from_internal(ksfd_ctx *c, const double *in, double *ref, in
     return 0;
 }
 
+static HaloPush make_push(const ksfd_ctx *c, int slot);
+// push_out: several ranks — the kernel also pushes the boundary planes of f into halo slot 1
+// (f is the right-hand side of a solve by Richardson sweeps, whose first sweep reads them)
 static int residual_impl(ksfd_ctx *c, const double *u, const double *udot,
-                         const double *src, double *f, cudaStream_t st)
+                         const double *src, double *f, cudaStream_t st, bool push_out = false)
 {
-    TRY(exchange(c, u, c->dof, 0, st, nullptr, c->p2p_on && tma_consumer(c)));
+    // ghost planes of u: pushed by the kernel that produced it (k_stage_combine) or here
+    if (c->pushed_vec0 == u && u != nullptr)
+        c->pushed_vec0 = nullptr;
+    else
+        TRY(exchange(c, u, c->dof, 0, st, nullptr, c->p2p_on && tma_consumer(c)));
     const HostVec uh = make_hvec(c, u, c->dof, 0);
     ProfScope prof(c, 1, st);
     if (use_march(c)) {
-        return c->dim == 2 ? ksfd_march_residual_d2(c, uh, udot, src, f, st)
-                           : ksfd_march_residual_d3(c, uh, udot, src, f, st);
+        HaloPush hp{};
+        if (push_out && (c->fuse_push_mask & 4)) hp = make_push(c, 1);
+        if (hp.up_lo0) c->pushed_vec = f;
+        return c->dim == 2 ? ksfd_march_residual_d2(c, uh, udot, src, f, hp.up_lo0 ? &hp : nullptr, st)
+                           : ksfd_march_residual_d3(c, uh, udot, src, f, hp.up_lo0 ? &hp : nullptr, st);
     }
     k_residual_naive<<<nblk(c->g.npts, 128), 128, 0, st>>>(c->g, c->P, uh.r, udot,
                                                            src, f);
@@ -910,8 +924,10 @@ static HostVec coef_hvec(const ksfd_ctx *c)
     return h;
 }
 
+// ghosts_current: the ghost planes of u in halo slot 0 are those of the exchange the stage
+// residual just consumed (same vector, nothing in between): no second exchange
 static int jvp_setup_impl(ksfd_ctx *c, const double *u, double shift,
-                          double *blocks, cudaStream_t st)
+                          double *blocks, cudaStream_t st, bool ghosts_current = false)
 {
     const Geom &g = c->g;
     const long long gpts = (long long)(g.nloc + 2 * KSFD_SW) * g.plane_pts;
@@ -922,7 +938,7 @@ static int jvp_setup_impl(ksfd_ctx *c, const double *u, double shift,
     for (int l = 0; l < c->P.nlig; ++l)
         c->invd[l] = 1.0 / (shift + c->P.gamma[l] - c->P.D[l] * c->P.w2c);
     if (u) {
-        TRY(exchange(c, u, c->dof, 0, st));
+        if (!(ghosts_current && c->p2p_on)) TRY(exchange(c, u, c->dof, 0, st));
         VecRef ur = make_ref(c, u, c->dof, 0);
         k_coef_setup<<<nblk(gpts, 128), 128, 0, st>>>(g, c->P, ur, c->coef);
         CKL();
@@ -2127,7 +2143,7 @@ static int sweep_solve_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, dou
         c->krylov_cap = m + 1;
     }
     TRY(gm_alloc(c));
-    if (!c->sw_partial) CK(cudaMalloc(&c->sw_partial, sizeof(double) * 2 * KSFD_SWEEP_CTAS));
+    if (!c->sw_partial) CK(cudaMalloc(&c->sw_partial, sizeof(double) * 3 * KSFD_SWEEP_CTAS));
     double *buf[2] = {c->krylov, c->krylov + n};
     GmStatus *hs = static_cast<GmStatus *>(c->gm_status);
     GmStatus *hsd = static_cast<GmStatus *>(c->gm_status_dev);
@@ -2138,30 +2154,44 @@ static int sweep_solve_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, dou
     hs->cycle_done = hs->final_ = hs->reason = hs->its_total = 0;
     hs->k_cols = 0;
     CK(cudaMemsetAsync(c->gmi, 0, sizeof(int) * GMI_INTS, st));
-    c->pushed_vec = nullptr;
     const int R = c->gm_runahead;
     const int *skip = c->gmi + GMI_CYCLE_DONE;
     const bool defer = c->p2p_on && c->nranks > 1 && tma_consumer(c);
     const HostVec ph = make_hvec(c, c->pc, 1, 2);
     const HostVec ch = coef_hvec(c);
+    // several ranks: every sweep also pushes the boundary planes of its output into the
+    // neighbours' ghost buffers (no exchange kernel between sweeps); only the right-hand
+    // side, which nobody pushed, goes out through the push kernel
+    const HaloPush hp = make_push(c, 1);
+    const bool fuse_push = defer && hp.up_lo0 != nullptr && ksfd_use_tma(c) && c->sw_fuse_push;
+    const int slot = c->sw_slot & 3;
+    const int pred = c->sw_hist[slot];
+    // one more tested sweep while the count of this slot is not settled, and every 8th solve
+    const bool probe = c->sw_stable[slot] < 2 || c->sw_stable[slot] % 8 == 7;
+    const int lead = c->sw_test_lead + (probe ? 1 : 0);
     auto launch = [&](int it) -> int {
         const double *rin = it == 0 ? rhs : buf[(it - 1) & 1];
-        TRY(exchange(c, rin, c->dof, 1, st, skip, defer));
+        if (it == 0 && fuse_push && c->pushed_vec == rhs)
+            c->pushed_vec = nullptr;            // pushed by the residual kernel that produced it
+        else if (it == 0 || !fuse_push)
+            TRY(exchange(c, rin, c->dof, 1, st, skip, defer));
         const HostVec rh = make_hvec(c, rin, c->dof, 1);
-        SweepFin fin{c->sw_partial, c->gm, c->gmi, hsd, it, 0, go,
+        // sweeps the solve is known to need are not tested (no reduction, no rank sum)
+        const int test = (pred == 0 || it >= pred - lead) ? 1 : 0;
+        SweepFin fin{c->sw_partial, KSFD_SWEEP_CTAS, it, test, 0, c->gm, c->gmi, hsd, go,
                      pure ? 1e300 : c->sw_slow, p2p_red(c), c->gm_done};
-        SweepHost a{x, buf[it & 1], it == 0 ? rhs_sign : 1.0, it == 0 ? 1 : 0, KSFD_SWEEP_CTAS, &fin};
+        SweepHost a{x, buf[it & 1], it == 0 ? rhs_sign : 1.0, it == 0 ? 1 : 0, KSFD_SWEEP_CTAS,
+                    &fin, fuse_push ? &hp : nullptr};
         ProfScope prof(c, 6, st);
         return c->dim == 2 ? ksfd_march_sweep_d2(c, ch, rh, ph, a, skip, st)
                            : ksfd_march_sweep_d3(c, ch, rh, ph, a, skip, st);
     };
-    // Consecutive solves take (almost) the same number of sweeps.  The predicted number —
-    // the longest of the last four solves: a sweep launched in vain returns at once (~2 us),
-    // a sweep launched late costs a host round trip (~10 us) — goes out without waiting;
-    // beyond it the host launches one sweep at a time, each once the previous one is known
-    // not to have ended the solve.  Without a prediction: R sweeps ahead of the device.
-    int pred = 0;
-    for (int i = 0; i < 4; ++i) pred = std::max(pred, c->sw_hist[i]);
+    // Solves of the same slot (ROSW stage) of consecutive steps take the same number of
+    // sweeps.  The predicted number goes out without waiting and only its last sweep (every
+    // 8th solve: its last two) is tested; beyond it the host launches one tested sweep at a
+    // time, each once the previous one is known not to have ended the solve (a host round
+    // trip, ~10 us: the price of a prediction that was too short).  Without a prediction
+    // every sweep is tested and the host stays R sweeps ahead of the device.
     int launched = 0;
     for (; launched < std::min(pred, go.max_it); ++launched) TRY(launch(launched));
     for (;;) {
@@ -2180,11 +2210,12 @@ static int sweep_solve_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, dou
         // contraction too slow for a stationary iteration: GMRES takes over, from the
         // iterate reached so far unless it is worse than x = 0
         c->sw_backoff = 8;
-        for (int i = 0; i < 4; ++i) c->sw_hist[i] = 0;
+        for (int i = 0; i < 4; ++i) c->sw_hist[i] = c->sw_stable[i] = 0;
         const bool keep = hs->rnorm < hs->rnorm0;
         return gmres_pipe_impl(c, rhs, rhs_sign, x, o, res, st, keep ? 1 : 0);
     }
-    c->sw_hist[c->sw_hist_pos++ & 3] = hs->its_total;
+    c->sw_stable[slot] = (pred > 0 && hs->its_total == pred) ? c->sw_stable[slot] + 1 : 0;
+    c->sw_hist[slot] = hs->its_total;
     if (res) {
         res->its = hs->its_total;
         res->reason = hs->reason;
@@ -2211,7 +2242,7 @@ extern "C" int ksfd_sweep(ksfd_ctx *c, const double *rin, double *x, double *rou
                     "several ranks, the peer-memory exchange");
     cudaStream_t st = (cudaStream_t)stream;
     TRY(gm_alloc(c));
-    if (!c->sw_partial) CK(cudaMalloc(&c->sw_partial, sizeof(double) * 2 * KSFD_SWEEP_CTAS));
+    if (!c->sw_partial) CK(cudaMalloc(&c->sw_partial, sizeof(double) * 3 * KSFD_SWEEP_CTAS));
     GmStatus *hs = static_cast<GmStatus *>(c->gm_status);
     GmStatus *hsd = static_cast<GmStatus *>(c->gm_status_dev);
     hs->iters_done = hs->cycle_done = hs->final_ = 0;
@@ -2223,8 +2254,9 @@ extern "C" int ksfd_sweep(ksfd_ctx *c, const double *rin, double *x, double *rou
     const HostVec ph = make_hvec(c, c->pc, 1, 2);
     const HostVec ch = coef_hvec(c);
     GmOpts go{0.0, 0.0, 0.0, 1 << 30, 1, 0, 0.0};
-    SweepFin fin{c->sw_partial, c->gm, c->gmi, hsd, 0, 0, go, 1e300, p2p_red(c), c->gm_done};
-    SweepHost a{x, rout, 1.0, first ? 1 : 0, KSFD_SWEEP_CTAS, &fin};
+    SweepFin fin{c->sw_partial, KSFD_SWEEP_CTAS, 0, 1, 0, c->gm, c->gmi, hsd, go, 1e300, p2p_red(c),
+                 c->gm_done};
+    SweepHost a{x, rout, 1.0, first ? 1 : 0, KSFD_SWEEP_CTAS, &fin, nullptr};
     {
         ProfScope prof(c, 6, st);
         TRY(c->dim == 2 ? ksfd_march_sweep_d2(c, ch, rh, ph, a, nullptr, st)
@@ -2343,7 +2375,14 @@ template <int NV>
 static int combine_launch(ksfd_ctx *c, const double *u, const VecList &Y, const CoefList &a,
                           const CoefList &gm, double *Z, double *Zd, cudaStream_t st)
 {
-    k_stage_combine<NV><<<KSFD_RED_BLOCKS, 256, 0, st>>>(nlocal(c), u, Y, a, gm, Z, Zd);
+    HaloPush hp{};
+    if (c->fuse_push_mask & 2) hp = make_push(c, 0);
+    if (hp.up_lo0) {
+        c->pushed_vec0 = Z;
+        k_stage_combine<NV, true><<<KSFD_RED_BLOCKS, 256, 0, st>>>(nlocal(c), u, Y, a, gm, Z, Zd, hp);
+    } else {
+        k_stage_combine<NV, false><<<KSFD_RED_BLOCKS, 256, 0, st>>>(nlocal(c), u, Y, a, gm, Z, Zd, hp);
+    }
     CKL();
     return 0;
 }
@@ -2379,9 +2418,11 @@ static int rosw_attempt(ksfd_ctx *c, const double *u, double t, double h,
             CK(cudaStreamSynchronize(st));
             cb(ti, user);
         }
-        TRY(residual_impl(c, Zp, Zd, src, F, st));          // F = Zdot - f(Z)
-        if (i == 0) TRY(jvp_setup_impl(c, Zp, 1.0 / (h * T.gamma), nullptr, st));
+        const bool swp = sweep_eligible(c, o.ksp) && !(o.ksp.ksp_type == 2 && c->sw_backoff > 0);
+        TRY(residual_impl(c, Zp, Zd, src, F, st, swp));     // F = Zdot - f(Z)
+        if (i == 0) TRY(jvp_setup_impl(c, Zp, 1.0 / (h * T.gamma), nullptr, st, true));
         ksfd_ksp_result kr{};
+        c->sw_slot = i;
         TRY(gmres_impl(c, F, -1.0, Y[i], o.ksp, &kr, st));  // A Y_i = -F
         *ksp_its += kr.its;
         if (kr.reason < 0) {

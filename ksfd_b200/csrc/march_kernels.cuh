@@ -38,6 +38,7 @@
 #pragma once
 #include "device_common.cuh"
 #include "fastmath.cuh"
+#include "halo_push.cuh"
 
 // uniform launch parameters (32-bit: a rank-local vector has < 2^31 elements,
 // checked on the host)
@@ -46,7 +47,68 @@ struct MarchArgs {
     int fs;                 // field stride = points per plane
     int ox, oy;             // outputs per tile in x, y (balanced pitch <= TX, TY)
     int rz;                 // output planes per CTA
+    // rb > 0 (Richardson sweeps on several ranks, sweep_op.cuh): the two chunks that own
+    // the boundary planes come FIRST in the grid and are rb planes long — chunk 0 =
+    // [0, rb), chunk 1 = [nloc-rb, nloc), chunks 2.. = rz planes each of [rb, nloc-rb) —
+    // so the planes the neighbours wait for are pushed early in the kernel
+    int rb;
 };
+
+// planes [k0, k1) of chunk z
+__device__ __forceinline__ void march_chunk(const MarchArgs &g, int z, int &k0, int &k1)
+{
+    if (g.rb > 0) {
+        if (z == 0) {
+            k0 = 0;
+            k1 = g.rb;
+        } else if (z == 1) {
+            k0 = g.nloc - g.rb;
+            k1 = g.nloc;
+        } else {
+            k0 = g.rb + (z - 2) * g.rz;
+            k1 = min(k0 + g.rz, g.nloc - g.rb);
+        }
+    } else {
+        k0 = z * g.rz;
+        k1 = min(k0 + g.rz, g.nloc);
+    }
+}
+
+// End of a CTA of a marching kernel that also PUSHES the boundary planes of its output
+// (several ranks, NVLink peer memory): the CTAs whose chunk [k0, k1) holds boundary planes
+// copy them from the output they just wrote (every thread re-reads its own stores) into the
+// neighbours' ghost buffers and arrive on the block counter; the last of them publishes
+// the exchange (halo_push_publish).  The exchange counter is read HERE: it cannot advance
+// before this CTA has arrived.  Out of line, every thread of the CTA calls it.
+// nfs = doubles per plane of the output, poff = this thread's column, mine = it has one.
+template <int NC>
+static __device__ __noinline__ void march_push_epilogue(const HaloPush &hp, const MarchArgs &g,
+                                                        const double *out, int k0, int k1,
+                                                        int poff, bool mine)
+{
+    if (!halo_push_on(hp)) return;
+    if (!(k0 < KSFD_SW || k1 > g.nloc - KSFD_SW)) return;       // uniform over the CTA
+    unsigned long long q;
+    const long long sh = halo_push_shift(hp, q);
+    if (mine) {
+        const int nfs = NC * g.fs;
+        for (int k = k0; k < k1; ++k) {
+            if (k >= KSFD_SW && k < g.nloc - KSFD_SW) continue;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const long long e = (long long)k * nfs + c * g.fs + poff;
+                halo_push1(hp, sh, e, out[e]);
+            }
+        }
+    }
+    unsigned nbz = 0;           // chunks that hold boundary planes
+    for (int z = 0; z < (int)gridDim.z; ++z) {
+        int a, b;
+        march_chunk(g, z, a, b);
+        nbz += (a < KSFD_SW || b > g.nloc - KSFD_SW) ? 1u : 0u;
+    }
+    halo_push_publish(hp, q, nbz * gridDim.x * gridDim.y);
+}
 
 template <int DIM, int TX, int TY>
 struct TileT {
@@ -271,6 +333,9 @@ struct ResidualOp {
     VecRef u;
     const double *udot, *src;
     double *out;
+    // several ranks: the boundary planes of the result also go to the neighbours' ghost
+    // buffers (all-null: no push) — the right-hand side of the first Richardson sweep
+    HaloPush hp;
     struct State {
         InCursor in;
         int e;                                 // element index of the next output
@@ -359,7 +424,13 @@ struct ResidualOp {
     {
         st.e += (NLIG + 1) * g.fs;
     }
-    __device__ __forceinline__ void finish(State &) const {}
+    // every thread of the CTA; [k0, k1) = its planes, mine = this thread emitted
+    __device__ __forceinline__ void finish(const MarchArgs &g, State &st, int k0, int k1,
+                                           bool mine) const
+    {
+        if (hp.up_lo0)
+            march_push_epilogue<NLIG + 1>(hp, g, out, k0, k1, st.e - k1 * (NLIG + 1) * g.fs, mine);
+    }
 };
 
 // J.v: out = (shift*I - J(u_lin)) * z,  z = v or M^{-1} v
@@ -480,7 +551,7 @@ struct JvpOp {
     {
         st.e += (NLIG + 1) * g.fs;
     }
-    __device__ __forceinline__ void finish(State &) const {}
+    __device__ __forceinline__ void finish(const MarchArgs &, State &, int, int, bool) const {}
 };
 
 // grad G and max |grad G| per axis (KSFD/ksfdsym.py:1188-1209, ksfdts.py:302-313)
@@ -554,7 +625,7 @@ struct VelocityOp {
         st.e += DIM * g.fs;
     }
     // every thread of the CTA calls this (non-emitting lanes carry zeros)
-    __device__ __forceinline__ void finish(State &st) const
+    __device__ __forceinline__ void finish(const MarchArgs &, State &st, int, int, bool) const
     {
         if (!vmax) return;
 #pragma unroll
@@ -644,8 +715,7 @@ struct Marcher {
             poff = wrapi(j0 - KSFD_SW + y, g.n1) * g.n0 + wrapi(i0 - KSFD_SW + x, g.n0);
             emits = interior && (i0 + x - KSFD_SW) < g.n0 && (j0 + y - KSFD_SW) < g.n1;
         }
-        k0 = blockIdx.z * g.rz;
-        k1 = min(k0 + g.rz, g.nloc);
+        march_chunk(g, blockIdx.z, k0, k1);
 #pragma unroll
         for (int f = 0; f < NF; ++f)
 #pragma unroll
@@ -735,7 +805,7 @@ struct Marcher {
                 if (++kk >= kend) break;
             }
         }
-        op.finish(st);
+        op.finish(g, st, k0, k1, emits);
     }
 };
 

@@ -272,7 +272,8 @@ static int launch_tma_tile(ksfd_ctx *c, const Op &op, const TmaSrc *src, const M
 template <int DIM, class Op, bool UNR, int AX, int AY, int AMINB, int ASC, int BX, int BY,
           int BMINB, int BSC>
 static int launch_tma_op(ksfd_ctx *c, const Op &op, const TmaSrc *src, int opkey, double cstage,
-                         double cemit, const int *skip, cudaStream_t st, int max_ctas = 0)
+                         double cemit, const int *skip, cudaStream_t st, int max_ctas = 0,
+                         bool bnd_first = false)
 {
     const long long maxel = (long long)(c->g.nloc + 2 * KSFD_SW) * c->g.plane_pts * (c->dof + 2);
     if (maxel >= (1LL << 31))
@@ -288,6 +289,15 @@ static int launch_tma_op(ksfd_ctx *c, const Op &op, const TmaSrc *src, int opkey
     if (p.tile < 0) return fail("no marching tile fits");
     if (max_ctas && (long long)p.grid.x * p.grid.y * p.grid.z > max_ctas)
         return fail("marching grid exceeds the per-CTA reduction buffer");
+    if (bnd_first && p.grid.z >= 3) {
+        // the chunks that own the boundary planes first and short (MarchArgs::rb): same
+        // number of CTAs, the middle chunks keep rz planes
+        const int nch = (int)p.grid.z, rz = p.a.rz, nloc = p.a.nloc;
+        int rb = (nloc - (nch - 2) * rz + 1) / 2;
+        rb = std::max(KSFD_SW, std::min(rb, rz));
+        const int mid = nloc - 2 * rb;
+        if (mid <= (nch - 2) * rz && mid > (nch - 3) * rz) p.a.rb = rb;
+    }
     if (p.tile == 0)
         return launch_tma_tile<DIM, AX, AY, Op, AMINB, UNR, ASC, ASC>(c, op, src, p, skip, st);
     return launch_tma_tile<DIM, BX, BY, Op, BMINB, UNR, BSC, BSC>(c, op, src, p, skip, st);

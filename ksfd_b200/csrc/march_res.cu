@@ -8,9 +8,10 @@
 
 template <int NLIG, bool FIXED>
 static int launch_residual_f(ksfd_ctx *c, const HostVec &u, const double *udot, const double *src,
-                             double *out, cudaStream_t st)
+                             double *out, const void *push, cudaStream_t st)
 {
     ResidualOp<DIM, NLIG, FIXED> op{u.r, udot, src, out};
+    if (push) op.hp = *static_cast<const HaloPush *>(push);     // (else all-null: no push)
     const double cemit = 35.0 * DIM + 30.0;
     // (the TMA-fed marcher is not used here: measured slower for the transcendental-heavy
     // staging of the residual, whose halo points would be one warp's extra pass —
@@ -28,15 +29,15 @@ static int launch_residual_f(ksfd_ctx *c, const HostVec &u, const double *udot, 
 // without the runtime tests
 template <int NLIG>
 static int launch_residual(ksfd_ctx *c, const HostVec &u, const double *udot, const double *src,
-                           double *out, cudaStream_t st)
+                           double *out, const void *push, cudaStream_t st)
 {
-    if (udot && !src) return launch_residual_f<NLIG, true>(c, u, udot, src, out, st);
-    return launch_residual_f<NLIG, false>(c, u, udot, src, out, st);
+    if (udot && !src) return launch_residual_f<NLIG, true>(c, u, udot, src, out, push, st);
+    return launch_residual_f<NLIG, false>(c, u, udot, src, out, push, st);
 }
 
 int KSFD_CAT(ksfd_march_residual_d, KSFD_MARCH_DIM)(ksfd_ctx *c, const HostVec &u,
                                                     const double *udot, const double *src,
-                                                    double *out, cudaStream_t st)
+                                                    double *out, const void *push, cudaStream_t st)
 {
-    KSFD_DISPATCH_NLIG(launch_residual, c, u, udot, src, out, st);
+    KSFD_DISPATCH_NLIG(launch_residual, c, u, udot, src, out, push, st);
 }

@@ -26,12 +26,17 @@
 #define KSFD_SWEEP_FALLBACK 100         // reason: contraction too slow, continue with GMRES
 
 struct SweepFin {
-    double *partial;            // [2][number of CTAs]: <r_k,r_k>, <r_{k+1},r_{k+1}>
+    // [3][cap] per-CTA partial sums: <b,b> (written by sweep 0), <r_k,r_k>, <r_{k+1},r_{k+1}>
+    double *partial;
+    int cap;
+    int it;                     // sweep index, 0-based
+    // test = 0: a sweep the solve is known to need (the host predicts the length of a solve
+    // from the previous ones): no reduction, no rank sum, no decision, no epilogue at all
+    int test;
+    int pad_;
     double *gm;
     int *gmi;
     GmStatus *hs;
-    int it;                     // sweep index, 0-based
-    int pad_;
     GmOpts o;
     double slow;                // give up when ||r_{k+1}|| > slow * ||r_k||
     P2PRed pr;
@@ -41,29 +46,44 @@ struct SweepFin {
 // all threads of the CTA that finished last
 __device__ __forceinline__ void sweep_finalize(const SweepFin &a, int ncta)
 {
-    double so = block_sum_partials(a.partial, ncta);
-    double sn = block_sum_partials(a.partial + ncta, ncta);
-    if (a.pr.nranks > 1) {
-        __shared__ double sv[2];
-        if (threadIdx.x == 0) {
-            sv[0] = so;
-            sv[1] = sn;
+    // the three sums in one pass (this runs after everything else of the kernel: every
+    // dependent step of it is exposed latency)
+    __shared__ double sm3[3][32];
+    __shared__ double sv[3];
+    {
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        for (int b = threadIdx.x; b < ncta; b += blockDim.x) {
+            t0 += a.partial[b];
+            t1 += a.partial[a.cap + b];
+            t2 += a.partial[2 * a.cap + b];
         }
-        p2p_allreduce(a.pr, sv, 2, 0);
-        so = sv[0];
-        sn = sv[1];
+        t0 = warp_sum(t0);
+        t1 = warp_sum(t1);
+        t2 = warp_sum(t2);
+        if ((threadIdx.x & 31) == 0) {
+            sm3[0][threadIdx.x >> 5] = t0;
+            sm3[1][threadIdx.x >> 5] = t1;
+            sm3[2][threadIdx.x >> 5] = t2;
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            double t = 0.0;
+            for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) t += sm3[threadIdx.x][i];
+            sv[threadIdx.x] = t;
+        }
+        __syncthreads();
     }
+    if (a.pr.nranks > 1) p2p_allreduce(a.pr, sv, 3, 0);
     if (threadIdx.x != 0) return;
+    const double s0 = sv[0], so = sv[1], sn = sv[2];
     double *gm = a.gm;
     int *gmi = a.gmi;
     GmStatus *hs = a.hs;
     const GmOpts &o = a.o;
-    const double rold = sqrt(so), rn = sqrt(sn);
-    if (a.it == 0) {
-        gm[GM_RNORM0] = rold;
-        gm[GM_TOL] = fmax(o.rtol * rold, o.atol);
-    }
-    const double tol = gm[GM_TOL], r0 = gm[GM_RNORM0];
+    const double rold = sqrt(so), rn = sqrt(sn), r0 = sqrt(s0);
+    const double tol = fmax(o.rtol * r0, o.atol);
+    gm[GM_RNORM0] = r0;
+    gm[GM_TOL] = tol;
     const int its = a.it + 1;
     int fin = 0, reason = 0;
     if (!(rn == rn) || !(rold == rold)) { fin = 1; reason = -9; }
@@ -80,13 +100,49 @@ __device__ __forceinline__ void sweep_finalize(const SweepFin &a, int ncta)
     hs->rnorm0 = r0;
     hs->its_total = its;
     if (fin) {
+        // one fence: a host that sees cycle_done sees the fields above
         hs->reason = reason;
         hs->final_ = 1;
         __threadfence_system();
         hs->cycle_done = 1;
-        __threadfence_system();
     }
     hs->iters_done = its;
+}
+
+// End of a sweep CTA, out of line (the unrolled plane loop has five exits): per-CTA partial
+// sums, and in the CTA that finishes last the decision.
+static __device__ __noinline__ void sweep_epilogue(const SweepFin &fin, double so_, double sn_)
+{
+    if (!fin.test && fin.it != 0) return;
+    __shared__ double sm_[2][32];
+    __shared__ int last_;
+    const double a = warp_sum(so_), b = warp_sum(sn_);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    if (l == 0) {
+        sm_[0][w] = a;
+        sm_[1][w] = b;
+    }
+    __syncthreads();
+    const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const int ncta = gridDim.x * gridDim.y * gridDim.z;
+    if (threadIdx.x < 2) {
+        double s = 0.0;
+        for (int i = 0; i < nw; ++i) s += sm_[threadIdx.x][i];
+        fin.partial[(1 + threadIdx.x) * fin.cap + cta] = s;
+        if (fin.it == 0 && threadIdx.x == 0) fin.partial[cta] = s;      // <b,b>
+    }
+    if (!fin.test) return;
+    if (threadIdx.x < 2) __threadfence();   // this CTA's partial sums are visible
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(fin.done, 1u);
+        last_ = (t == (unsigned)ncta - 1u);
+        if (last_) atomicExch(fin.done, 0u);
+    }
+    __syncthreads();
+    if (!last_) return;
+    __threadfence();                        // see every CTA's partial sums
+    sweep_finalize(fin, ncta);
 }
 
 // One sweep: inputs coef, r_k (ghosted, TMA-fed like the v of J.v), pc; per output point
@@ -104,6 +160,11 @@ struct SweepOp : JvpOp<DIM, NLIG, true> {
     double rsign;
     int first, pad_;
     SweepFin fin;
+    // several ranks: the boundary planes of r_{k+1} also go to the neighbours' ghost buffers
+    // (all-null descriptor: no push).  The CTAs that own boundary planes are the short
+    // chunks the launcher puts first (MarchArgs::rb), so their stores and the flag are on
+    // their way long before the kernel ends (cf. halo_push_publish).
+    HaloPush hp;
     struct State : Base::State {
         double so, sn;
         bool own;
@@ -162,34 +223,11 @@ struct SweepOp : JvpOp<DIM, NLIG, true> {
         }
     }
     // every thread of the CTA (threads without outputs carry zeros)
-    __device__ __forceinline__ void finish(State &st) const
+    __device__ __forceinline__ void finish(const MarchArgs &g, State &st, int k0, int k1,
+                                           bool mine) const
     {
-        __shared__ double sm_[2][32];
-        __shared__ int last_;
-        const double a = warp_sum(st.so), b = warp_sum(st.sn);
-        const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
-        if (l == 0) {
-            sm_[0][w] = a;
-            sm_[1][w] = b;
-        }
-        __syncthreads();
-        const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-        const int ncta = gridDim.x * gridDim.y * gridDim.z;
-        if (threadIdx.x < 2) {
-            double s = 0.0;
-            for (int q = 0; q < nw; ++q) s += sm_[threadIdx.x][q];
-            fin.partial[threadIdx.x * ncta + cta] = s;
-        }
-        __threadfence();                        // this CTA's partial sums are visible
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned t = atomicAdd(fin.done, 1u);
-            last_ = (t == (unsigned)ncta - 1u);
-            if (last_) atomicExch(fin.done, 0u);
-        }
-        __syncthreads();
-        if (!last_) return;
-        __threadfence();                        // see every CTA's partial sums
-        sweep_finalize(fin, ncta);
+        if (hp.up_lo0)
+            march_push_epilogue<NLIG + 1>(hp, g, rout, k0, k1, st.e - k1 * (NLIG + 1) * g.fs, mine);
+        sweep_epilogue(fin, st.so, st.sn);
     }
 };

@@ -157,7 +157,7 @@ static __device__ __noinline__ void tma_halo_wait(const volatile unsigned long l
 {
     const long long t0 = clock64();
     unsigned spins = 0;
-    while (*f < q) {
+    while (flag_acquire(f) < q) {
         __nanosleep(20);
         if ((++spins & 0xfff) == 0 && (clock64() - t0 > 240000000000ll || (dead && *dead))) {
             if (dead) *dead = 1ull;
@@ -165,7 +165,7 @@ static __device__ __noinline__ void tma_halo_wait(const volatile unsigned long l
             break;
         }
     }
-    __threadfence_system();
+    flag_acquired();
     asm volatile("fence.proxy.async;" ::: "memory");
 }
 
@@ -275,8 +275,7 @@ struct TmaMarcher {
                               idx;
             }
         }
-        k0 = blockIdx.z * g.rz;
-        k1 = min(k0 + g.rz, g.nloc);
+        march_chunk(g, blockIdx.z, k0, k1);
         op.init_out(g, st, k0, poff);
         if constexpr (Op::NEEDS_OWNER) {
             // the clamped last tile of an axis overlaps its neighbour: the outputs in front
@@ -469,7 +468,9 @@ struct TmaMarcher {
                 if (++it >= np) break;
             }
         }
-        op.finish(st);
+        bool mine = active;
+        if constexpr (Op::NEEDS_OWNER) mine = st.own;
+        op.finish(g, st, k0, k1, mine);
     }
 };
 

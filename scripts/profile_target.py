@@ -18,10 +18,12 @@ def main():
     v = torch.randn(N, generator=gen, device='cuda', dtype=torch.float64)
     out = torch.empty_like(v)
     ctx.jvp_setup(u, 1.0 / (0.435866521508459 * 1e-3))
+    x = torch.zeros_like(v)
     for _ in range(3):
         ctx.residual(u, v, None, out)
         ctx.jvp(v, out, precond=True)
         ctx.jvp(v, out)
+        ctx.sweep(v, x, out, norms=False)
     torch.cuda.synchronize()
     print('done', ctx.norm2(out))
     ctx.close()
