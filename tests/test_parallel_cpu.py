@@ -21,11 +21,45 @@ def _free_port():
     return p
 
 
+def _run_ranks(target, world, extra, wait=240):
+    """spawn `world` ranks of `target(rank, world, port, *extra, q)`; a rendezvous that does not
+    come up (port taken in between, slow start) is retried once on another port; ranks that
+    are still alive at the end are terminated, never left behind"""
+    import queue
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    for attempt in range(2):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=target, args=(r, world, port) + tuple(extra) + (q,))
+                 for r in range(world)]
+        for p in procs:
+            p.start()
+        res = []
+        try:
+            for _ in range(world):
+                res.append(q.get(timeout=wait))
+        except queue.Empty:
+            res = None
+        finally:
+            for p in procs:
+                p.join(timeout=30 if res is not None else 1)
+                if p.is_alive():
+                    p.terminate()
+                    p.join(timeout=10)
+        if res is not None:
+            return res
+    raise AssertionError('ranks did not report (twice)')
+
+
 def _worker(rank, world, port, n, dof, q):
     import torch.distributed as dist
+    import datetime
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
-    dist.init_process_group('gloo', rank=rank, world_size=world)
+    os.environ.setdefault('GLOO_SOCKET_IFNAME', 'lo')       # the container hostname may not resolve
+    dist.init_process_group('gloo', rank=rank, world_size=world,
+                            timeout=datetime.timedelta(seconds=90))
     try:
         from ksfd_b200.core import dmda_ownership
         from ksfd_b200.grid import Comm, Grid
@@ -65,16 +99,7 @@ def _worker(rank, world, port, n, dof, q):
 
 @pytest.mark.parametrize('world,n,dof', [(2, (6, 10), 3), (3, (5, 4, 11), 2), (2, (9,), 3)])
 def test_slab_halo_exchange_gloo(world, n, dof):
-    import torch.multiprocessing as mp
-    ctx = mp.get_context('spawn')
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, dof, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=120) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=60)
+    res = _run_ranks(_worker, world, (n, dof))
     assert sorted(res) == [(r, True) for r in range(world)]
 
 
@@ -94,9 +119,12 @@ def _ic_worker(rank, world, port, tmp, q):
     """start_values / resume_values on `world` ranks against the single-rank run
     (the advertised torchrun command could not start a fresh run)."""
     import torch.distributed as dist
+    import datetime
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
-    dist.init_process_group('gloo', rank=rank, world_size=world)
+    os.environ.setdefault('GLOO_SOCKET_IFNAME', 'lo')       # the container hostname may not resolve
+    dist.init_process_group('gloo', rank=rank, world_size=world,
+                            timeout=datetime.timedelta(seconds=90))
     try:
         from ksfd_b200 import solver
         from ksfd_b200.grid import Comm, Grid
@@ -162,16 +190,6 @@ def _ic_worker(rank, world, port, tmp, q):
 
 
 def test_start_and_resume_values_on_two_ranks(tmp_path):
-    import torch.multiprocessing as mp
     world = 2
-    ctx = mp.get_context('spawn')
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_ic_worker, args=(r, world, port, str(tmp_path), q))
-             for r in range(world)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=900) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=60)
+    res = _run_ranks(_ic_worker, world, (str(tmp_path),))
     assert sorted(res) == [(r, True) for r in range(world)]
