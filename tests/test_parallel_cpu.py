@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _run_ranks(target, world, extra, wait=240):
+def _run_ranks(target, world, extra, wait=150):
     """spawn `world` ranks of `target(rank, world, port, *extra, q)`; a rendezvous that does not
     come up (port taken in between, slow start) is retried once on another port; ranks that
     are still alive at the end are terminated, never left behind"""
@@ -59,7 +59,7 @@ def _worker(rank, world, port, n, dof, q):
     os.environ['MASTER_PORT'] = str(port)
     os.environ.setdefault('GLOO_SOCKET_IFNAME', 'lo')       # the container hostname may not resolve
     dist.init_process_group('gloo', rank=rank, world_size=world,
-                            timeout=datetime.timedelta(seconds=90))
+                            timeout=datetime.timedelta(seconds=60))
     try:
         from ksfd_b200.core import dmda_ownership
         from ksfd_b200.grid import Comm, Grid
@@ -124,7 +124,7 @@ def _ic_worker(rank, world, port, tmp, q):
     os.environ['MASTER_PORT'] = str(port)
     os.environ.setdefault('GLOO_SOCKET_IFNAME', 'lo')       # the container hostname may not resolve
     dist.init_process_group('gloo', rank=rank, world_size=world,
-                            timeout=datetime.timedelta(seconds=90))
+                            timeout=datetime.timedelta(seconds=60))
     try:
         from ksfd_b200 import solver
         from ksfd_b200.grid import Comm, Grid
