@@ -313,7 +313,8 @@ def step_timing_3d(n=256, nsteps=5, warm=2):
     rho = 9000.0 + 90.0 * rng.standard_normal(ctx.npts)
     u = ctx.to_internal(torch.from_numpy(np.repeat(rho, 3)).cuda())
     opts = core.ts_options(ts_type='rosw', adapt='none', atol=0.01, rtol=1e-6,
-                           ksp_rtol=KSP_RTOL, ksp_max_it=2000, restart=30, ksp_type=KSP_TYPE)
+                           ksp_rtol=KSP_RTOL, ksp_max_it=2000, restart=30, ksp_type=KSP_TYPE,
+                           groom=True, velocity_max=True)
     t, its = 0.0, 0
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -322,13 +323,11 @@ def step_timing_3d(n=256, nsteps=5, warm=2):
             torch.cuda.synchronize()
             e0.record()
             its = 0
-        ctx.groom(u)
-        r = ctx.ts_step(u, t, DT, opts)
-        if not r.accepted:
+        r = ctx.ts_step(u, t, DT, opts)         # clamp + step + CFL maxima (flags in opts)
+        if not r.accepted or not r.have_vmax:
             raise RuntimeError('3-D time step failed')
         t = r.t_new
         its += r.ksp_its
-        ctx.velocity_max(u)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / nsteps
@@ -372,13 +371,11 @@ def timed_steps(ctx, u, opts, nsteps, warm, world):
             torch.cuda.synchronize()
             e0.record()
             its = 0
-        ctx.groom(u)
-        r = ctx.ts_step(u, t, DT, opts)
-        if not r.accepted:
+        r = ctx.ts_step(u, t, DT, opts)         # clamp + step + CFL maxima (flags in opts)
+        if not r.accepted or not r.have_vmax:
             raise RuntimeError('time step failed (ksp_fail=%d)' % r.ksp_fail)
         t = r.t_new
         its += r.ksp_its
-        ctx.velocity_max(u)
     e1.record()
     if world > 1:
         dist.barrier()
@@ -515,17 +512,19 @@ def native_arm(args):
     u_ref = u_host.cuda()
     u = ctx.to_internal(u_ref)                                  # internal layout
     opts = core.ts_options(ts_type='rosw', adapt='none', atol=0.01, rtol=1e-6,
-                           ksp_rtol=KSP_RTOL, ksp_max_it=2000, restart=30, ksp_type=KSP_TYPE)
+                           ksp_rtol=KSP_RTOL, ksp_max_it=2000, restart=30, ksp_type=KSP_TYPE,
+                           groom=True, velocity_max=True)
     state = dict(t=0.0, its=0)
 
     def step():
-        ctx.groom(u)
+        # clamp, ROSW step and CFL maxima — the body of the reference's step loop
+        # (KSFD/ksfdts.py:205-227) — in ONE library call, as ksfd_b200.ts.KSFDTS.solve makes it
         r = ctx.ts_step(u, state['t'], DT, opts)
-        if not r.accepted:
+        if not r.accepted or not r.have_vmax:
             raise RuntimeError('time step failed (ksp_fail=%d)' % r.ksp_fail)
         state['t'] = r.t_new
         state['its'] += r.ksp_its
-        return ctx.velocity_max(u)
+        return [r.vmax[i] for i in range(dim)]
 
     def barrier():
         if world > 1:

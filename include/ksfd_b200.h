@@ -224,12 +224,19 @@ typedef struct ksfd_ts_opts {
     double atol, rtol;         /* TSSetTolerances               */
     double clip_lo, clip_hi, dt_min, dt_max, safety, reject_safety;
     int32_t max_reject;
-    int32_t reserved;
+    int32_t flags;             /* KSFD_TS_*: work of the reference's step loop done inside the call */
     ksfd_ksp_opts ksp;
 } ksfd_ts_opts;
+/* clamp u first (the loop's groom(u), KSFD/ksfdts.py:205,231-237) */
+#define KSFD_TS_GROOM 1
+/* also return max |grad G| per axis of the accepted state (the loop's CFL_check,
+   KSFD/ksfdts.py:287-319): computed on the device and read with the error norm */
+#define KSFD_TS_VELOCITY_MAX 2
 typedef struct ksfd_ts_result {
     double t_new, h_used, h_next, enorm;
     int32_t accepted, rejections, ksp_its, ksp_fail;
+    double vmax[3];            /* valid when have_vmax (KSFD_TS_VELOCITY_MAX, accepted step) */
+    int32_t have_vmax, reserved;
 } ksfd_ts_result;
 /* advance u (in place) from t by one accepted step of size <= h.
    src: device array of source terms or NULL; if cb != NULL it is called with

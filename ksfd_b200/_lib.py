@@ -63,7 +63,7 @@ class TsOpts(C.Structure):
                 ('clip_lo', C.c_double), ('clip_hi', C.c_double),
                 ('dt_min', C.c_double), ('dt_max', C.c_double),
                 ('safety', C.c_double), ('reject_safety', C.c_double),
-                ('max_reject', C.c_int32), ('reserved', C.c_int32),
+                ('max_reject', C.c_int32), ('flags', C.c_int32),
                 ('ksp', KspOpts)]
 
 
@@ -71,7 +71,8 @@ class TsResult(C.Structure):
     _fields_ = [('t_new', C.c_double), ('h_used', C.c_double),
                 ('h_next', C.c_double), ('enorm', C.c_double),
                 ('accepted', C.c_int32), ('rejections', C.c_int32),
-                ('ksp_its', C.c_int32), ('ksp_fail', C.c_int32)]
+                ('ksp_its', C.c_int32), ('ksp_fail', C.c_int32),
+                ('vmax', C.c_double * 3), ('have_vmax', C.c_int32), ('reserved', C.c_int32)]
 
 
 TIME_CB = C.CFUNCTYPE(None, C.c_double, C.c_void_p)

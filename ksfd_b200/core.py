@@ -375,7 +375,9 @@ def ts_options(ts_type='rosw', adapt='none', atol=1e-5, rtol=1e-5,
                clip=(0.1, 10.0), dt_min=1e-20, dt_max=1e50, safety=0.9,
                reject_safety=0.5, max_reject=10, ksp_rtol=1e-5, ksp_atol=1e-50,
                ksp_dtol=1e5, ksp_max_it=10000, restart=30, reorth=0, precond=1,
-               ksp_type='auto'):
+               ksp_type='auto', groom=False, velocity_max=False):
+    """groom / velocity_max: do the step loop's clamp before and CFL maxima after the step
+    inside the one C call (result.vmax), saving two host round trips per step."""
     o = TsOpts()
     o.ts_type = {'rosw': 0, 'beuler': 1}[ts_type]
     o.adapt = {'none': 0, 'basic': 1}[adapt]
@@ -384,6 +386,7 @@ def ts_options(ts_type='rosw', adapt='none', atol=1e-5, rtol=1e-5,
     o.dt_min, o.dt_max = float(dt_min), float(dt_max)
     o.safety, o.reject_safety = float(safety), float(reject_safety)
     o.max_reject = int(max_reject)
+    o.flags = (1 if groom else 0) | (2 if velocity_max else 0)
     o.ksp = KspOpts(float(ksp_rtol), float(ksp_atol), float(ksp_dtol),
                     int(ksp_max_it), int(restart), int(reorth), int(precond),
                     KSP_TYPES[ksp_type], 0)

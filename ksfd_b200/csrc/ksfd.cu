@@ -2390,7 +2390,7 @@ static int combine_launch(ksfd_ctx *c, const double *u, const VecList &Y, const 
 static int rosw_attempt(ksfd_ctx *c, const double *u, double t, double h,
                         const ksfd_ts_opts &o, const double *src, ksfd_time_cb cb,
                         void *user, double *unew, double *enorm, int *ksp_its,
-                        int *ksp_fail, cudaStream_t st)
+                        int *ksp_fail, cudaStream_t st, bool velmax, double *accept_into)
 {
     const RoswTab &T = ra34pw2();
     const long long n = nlocal(c);
@@ -2443,7 +2443,19 @@ static int rosw_attempt(ksfd_ctx *c, const double *u, double t, double h,
     k_reduce_partials<<<1, 128, 0, st>>>(1, KSFD_RED_BLOCKS, c->partial, c->dscal + SC_ENORM, 0);
     CKL();
     TRY(allreduce_dev(c, c->dscal + SC_ENORM, 1, ncclSum_, st));
-    TRY(fetch(c, SC_ENORM, 1, st));
+    // velmax (KSFD_TS_VELOCITY_MAX): the CFL maxima of the step's result are computed right
+    // away (on the candidate: wasted only when the step is rejected) and travel to the host
+    // with the error norm — one synchronisation per step instead of two
+    int nfetch = 1;
+    if (velmax) {
+        TRY(velocity_impl(c, unew, nullptr, c->dscal + SC_ENORM + 1, st));
+        TRY(allreduce_dev(c, c->dscal + SC_ENORM + 1, c->dim, ncclMax_, st));
+        nfetch += c->dim;
+    }
+    // no step-size control: the candidate IS the new state — copied before the host waits
+    if (accept_into)
+        CK(cudaMemcpyAsync(accept_into, unew, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    TRY(fetch(c, SC_ENORM, nfetch, st));
     const double ntot = (double)c->g.plane_pts * (double)c->last_global * c->dof;
     *enorm = std::sqrt(c->hscal[SC_ENORM] / ntot);
     return 0;
@@ -2487,6 +2499,11 @@ extern "C" int ksfd_ts_step(ksfd_ctx *c, double *u, double t, double h,
     TRY(ensure_work(c, 9));
     double *unew = c->work[9];
     memset(res, 0, sizeof(*res));
+    const bool velmax = (o->flags & KSFD_TS_VELOCITY_MAX) != 0;
+    if (o->flags & KSFD_TS_GROOM) {
+        k_groom<<<nblk(n, 256), 256, 0, st>>>(c->g, c->P.rhomin, c->P.Umin, u);
+        CKL();
+    }
     const double safety0 = o->safety > 0 ? o->safety : 0.9;
     const double rsafety = o->reject_safety > 0 ? o->reject_safety : 0.5;
     const double clip_lo = o->clip_lo > 0 ? o->clip_lo : 0.1;
@@ -2502,7 +2519,7 @@ extern "C" int ksfd_ts_step(ksfd_ctx *c, double *u, double t, double h,
             TRY(beuler_attempt(c, u, t, h, *o, src, cb, user, unew, &res->ksp_its, &fail_, st));
         else
             TRY(rosw_attempt(c, u, t, h, *o, src, cb, user, unew, &enorm,
-                             &res->ksp_its, &fail_, st));
+                             &res->ksp_its, &fail_, st, velmax, o->adapt == 1 ? nullptr : u));
         if (fail_) {
             res->ksp_fail = 1;
             res->accepted = 0;
@@ -2526,7 +2543,17 @@ extern "C" int ksfd_ts_step(ksfd_ctx *c, double *u, double t, double h,
             hnext = std::min(std::max(h * hfac, dt_min), dt_max);
         }
         if (accept) {
-            CK(cudaMemcpyAsync(u, unew, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+            if (o->adapt == 1 || o->ts_type == 1)
+                CK(cudaMemcpyAsync(u, unew, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+            if (velmax) {
+                if (o->ts_type == 1) {      // backward Euler has no error-norm read to ride on
+                    TRY(velocity_impl(c, unew, nullptr, c->dscal + SC_ENORM + 1, st));
+                    TRY(allreduce_dev(c, c->dscal + SC_ENORM + 1, c->dim, ncclMax_, st));
+                    TRY(fetch(c, SC_ENORM + 1, c->dim, st));
+                }
+                for (int d = 0; d < c->dim; ++d) res->vmax[d] = c->hscal[SC_ENORM + 1 + d];
+                res->have_vmax = 1;
+            }
             res->accepted = 1;
             res->t_new = t + h;
             res->h_used = h;

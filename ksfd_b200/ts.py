@@ -176,12 +176,17 @@ class KSFDTS:
         return self._opts
 
     # -- the step -------------------------------------------------------------
-    def step(self):
-        """One accepted step of the device integrator (PETSc TS.step())."""
+    def step(self, groom=False, velocity_max=False):
+        """One accepted step of the device integrator (PETSc TS.step()).
+        groom / velocity_max: the clamp before and the CFL maxima after the step (the
+        neighbours of TS.step() in the reference's loop, ksfdts.py:205-227) inside the same
+        C call; the maxima are kept for the next CFL_check of the unchanged state."""
         d = self.derivs
         ctx = d.ctx
         if self._opts is None:
             self.setFromOptions()
+        self._opts.flags = (1 if groom else 0) | (2 if velocity_max else 0)
+        self._vmax_fresh = None
         u = self.u.device(ctx)
         td = d._phys_td or d._src_td
         src = d.source_device(self._t)
@@ -203,6 +208,8 @@ class KSFDTS:
         self._k += 1
         self._t = res.t_new
         self._h = res.h_next
+        if res.have_vmax:
+            self._vmax_fresh = np.array([res.vmax[i] for i in range(d.grid.dim)])
         return res
 
     def _stage_time_cb(self, tt):
@@ -237,8 +244,10 @@ class KSFDTS:
         conserve = False if cw == 'False' else bool(cw)
         self.monitor(k, t, u)
         while (not self.diverged) and k < kmax and t <= tmax and h >= self.hmin:
-            u = self.groom(u)
-            self.step()
+            # groom(u), TS.step() and the velocity maxima of CFL_check in ONE library call
+            # (time-dependent parameters: CFL_check evaluates them at the new time itself)
+            self.step(groom=True,
+                      velocity_max=not (self.derivs._phys_td or self.derivs._src_td))
             if k % 20 == 0:
                 gc.collect()
             k, h, t = self.getStepNumber(), self.getTimeStep(), self.getTime()
@@ -251,6 +260,7 @@ class KSFDTS:
                 if conserve:
                     u = self.conserve_worms(u, Nworms)
                 self.lastvart = t
+                self._vmax_fresh = None         # the state changed after the step
             self.CFL_check()
             self.monitor(k, t, u)
 
@@ -307,7 +317,10 @@ class KSFDTS:
     def CFL_step(self, u, t=None):
         """min_d spacing_d*sw/max|v_d| (reference ksfdts.py:302-319); the max
         is reduced on the device and across ranks."""
-        vmax = self.derivs.velocity_max(u, t)
+        vmax = getattr(self, '_vmax_fresh', None)
+        self._vmax_fresh = None
+        if vmax is None:
+            vmax = self.derivs.velocity_max(u, t)
         sw = self.derivs.grid.stencil_width
         hm = [float('inf') if v == 0.0 else s * sw / v
               for v, s in zip(vmax, self.derivs.grid.spacing)]

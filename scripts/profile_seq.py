@@ -25,14 +25,14 @@ for k in ('sweep_test_lead', 'sweep_fuse_push', 'fuse_push_mask'):
 rng = np.random.default_rng(np.random.SeedSequence(793817931).spawn(world)[rank])
 rho = 9000.0 + 90.0 * rng.standard_normal(ctx.npts)
 u = ctx.upload(np.repeat(rho, 3))
-opts = core.ts_options(ts_type='rosw', adapt='none', atol=0.01, rtol=1e-6, ksp_rtol=1e-8, ksp_max_it=2000, restart=30)
+opts = core.ts_options(ts_type='rosw', adapt='none', atol=0.01, rtol=1e-6, ksp_rtol=1e-8, ksp_max_it=2000, restart=30,
+                       groom=True, velocity_max=True)
 t = 0.0
 def step():
     global t
-    ctx.groom(u)
-    r = ctx.ts_step(u, t, 1e-3, opts)
+    r = ctx.ts_step(u, t, 1e-3, opts)       # clamp + step + CFL maxima in one call
     t = r.t_new
-    return ctx.velocity_max(u)
+    return r.vmax[0]
 for _ in range(5):
     step()
 torch.cuda.synchronize()

@@ -6,7 +6,9 @@ import sys
 from collections import Counter
 
 LIB = sys.argv[1] if len(sys.argv) > 1 else 'ksfd_b200/libksfd_b200.so'
-WANT = [r'k_tma_marchILi2ELi256ELi1E5JvpOpILi2ELi2ELb1E', r'k_tma_marchILi3ELi16ELi16E5JvpOpILi3ELi2ELb1E',
+WANT = [r'k_tma_marchILi2ELi256ELi1E7SweepOpILi2ELi2E', r'k_tma_marchILi3ELi16ELi16E7SweepOpILi3ELi2E',
+        r'k_tma_marchILi3ELi32ELi16E7SweepOpILi3ELi2E',
+        r'k_tma_marchILi2ELi256ELi1E5JvpOpILi2ELi2ELb1E', r'k_tma_marchILi3ELi16ELi16E5JvpOpILi3ELi2ELb1E',
         r'k_tma_marchILi3ELi32ELi16E5JvpOpILi3ELi2ELb1E',
         r'k_marchILi2ELi124ELi1E10ResidualOpILi2ELi2ELb1E', r'k_marchILi2ELi252ELi1E10ResidualOpILi2ELi2ELb1E',
         r'k_marchILi3ELi16ELi16E10ResidualOpILi3ELi2ELb1E']

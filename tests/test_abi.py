@@ -44,6 +44,7 @@ def test_struct_sizes_match_c(built_lib):
     assert ctypes.sizeof(_lib.Physics) == 16 + 6 * 8 + 2 * 7 * 8 + 8 * 4 + 4 * 7 * 8 + 2 * 15 * 8
     assert ctypes.sizeof(_lib.KspOpts) == 3 * 8 + 6 * 4
     assert ctypes.sizeof(_lib.TsOpts) == 8 + 8 * 8 + 8 + ctypes.sizeof(_lib.KspOpts)
+    assert ctypes.sizeof(_lib.TsResult) == 4 * 8 + 4 * 4 + 3 * 8 + 2 * 4
 
 
 def test_no_gpu_means_loud_failure(built_lib):

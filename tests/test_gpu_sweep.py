@@ -130,3 +130,46 @@ def test_sweep_sign_and_zero_rhs():
     x, res = ctx.ksp_solve(ctx.zeros(), ksp_type='richardson', rtol=1e-8)
     assert res.reason > 0 and res.its >= 1 and float(x.abs().max()) == 0.0
     ctx.close()
+
+
+def test_step_flags_do_the_loop_body_in_one_call():
+    """KSFD_TS_GROOM | KSFD_TS_VELOCITY_MAX: the clamp before and the CFL maxima after the
+    step inside ksfd_ts_step (the body of the reference's loop, ksfdts.py:205-227) give exactly
+    what the three separate calls give."""
+    import torch
+    from ksfd_b200 import core
+    for p in (phys84(2, (64, 48)), phys84(3, (16, 16, 8))):
+        # two contexts: the solver's launch-ahead prediction is per context, so both see the
+        # same history and must produce the same bits
+        ca, cb = make_ctx(p), make_ctx(p)
+        u0 = random_state(p, 9)
+        ua, ub = ca.upload(u0), cb.upload(u0)
+        # (1) a tiny step from a state the clamp changes (negative and NaN entries)
+        bad = torch.arange(0, ua.numel(), 97, device=ua.device)
+        ua[bad] = -1.0
+        ub[bad] = -1.0
+        ua[5] = float('nan')
+        ub[5] = float('nan')
+        oa = core.ts_options(adapt='none', ksp_rtol=1e-10)
+        ob = core.ts_options(adapt='none', ksp_rtol=1e-10, groom=True, velocity_max=True)
+        ca.groom(ua)
+        ra = ca.ts_step(ua, 0.0, 1e-9, oa)
+        rb = cb.ts_step(ub, 0.0, 1e-9, ob)
+        assert ra.accepted == rb.accepted == 1 and rb.have_vmax
+        assert torch.equal(ua, ub), float((ua - ub).abs().max())
+        # (2) ordinary steps, with and without step-size control
+        ua, ub = ca.upload(u0), cb.upload(u0)
+        for adapt in ('none', 'basic'):
+            oa = core.ts_options(adapt=adapt, atol=0.01, rtol=1e-6, ksp_rtol=1e-10)
+            ob = core.ts_options(adapt=adapt, atol=0.01, rtol=1e-6, ksp_rtol=1e-10, groom=True,
+                                 velocity_max=True)
+            ca.groom(ua)
+            ra = ca.ts_step(ua, 0.0, 1e-4, oa)
+            va = ca.velocity_max(ua)
+            rb = cb.ts_step(ub, 0.0, 1e-4, ob)
+            assert ra.accepted and rb.accepted and rb.have_vmax and not ra.have_vmax
+            assert torch.equal(ua, ub), float((ua - ub).abs().max())
+            assert rb.h_next == ra.h_next and rb.enorm == ra.enorm
+            assert np.array_equal(np.array([rb.vmax[i] for i in range(p['dim'])]), va)
+        ca.close()
+        cb.close()
