@@ -72,7 +72,7 @@ struct ksfd_ctx {
     bool p2p_on = false;
     // device-side exchange counters: [0..3] halo slots, [4] all-reduce
     unsigned long long *p2p_ctr = nullptr;
-    unsigned *p2p_done = nullptr;           // [0] exchange kernels, [1] fused producer pushes
+    unsigned *p2p_done = nullptr;           // [0] exchange kernels, [1..2] fused producer pushes (combined / bottom)
     // Krylov vector whose boundary planes were pushed by the kernel that produced it
     // (consumed by the next jvp_impl on that vector; host-side bookkeeping only)
     const double *pushed_vec = nullptr;

@@ -20,7 +20,7 @@ struct HaloPush {
     long long top0;                         // first element of the two top planes (n - cnt)
     volatile unsigned long long *up_flag_lo, *dn_flag_hi;
     unsigned long long *ctr;                // this rank's exchange counter of the slot
-    unsigned *done;                         // block counter
+    unsigned *done;                         // block counters: [0] combined, [1] bottom planes (publish_dir)
     const volatile unsigned long long *dead;
 };
 __device__ __forceinline__ bool halo_push_on(const HaloPush &hp)
@@ -88,6 +88,29 @@ __device__ __forceinline__ void halo_push_publish(const HaloPush &hp, unsigned l
             flag_release(hp.up_flag_lo, q);
             flag_release(hp.dn_flag_hi, q);
             *hp.ctr = q;
+        }
+    }
+}
+
+// One direction at a time (marching kernels whose boundary CTAs finish the top planes long
+// before the bottom planes, MarchArgs::rb): dir 0 = the top planes are stored -> the upper
+// neighbour's lo flag; dir 1 = the bottom planes -> the lower neighbour's hi flag, and the
+// exchange is complete: the counter advances.  Same hierarchical release as above.
+__device__ __forceinline__ void halo_push_publish_dir(const HaloPush &hp, unsigned long long q,
+                                                      unsigned expected, int dir)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(hp.done + dir, 1u);
+        if (t == expected - 1) {
+            atomicExch(hp.done + dir, 0u);
+            if (dir == 0) {
+                flag_release(hp.up_flag_lo, q);
+            } else {
+                flag_release(hp.dn_flag_hi, q);
+                *hp.ctr = q;
+            }
         }
     }
 }

@@ -590,8 +590,8 @@ extern "C" int ksfd_p2p_export(ksfd_ctx *c, char handle_out[64])
         CK(cudaMalloc(&c->p2p_mine, sizeof(double) * p2p_total_doubles(c)));
         // flags AND the all-reduce area: its words carry their exchange number, 0 = never written
         CK(cudaMemset(c->p2p_mine, 0, sizeof(double) * p2p_total_doubles(c)));
-        CK(cudaMalloc(&c->p2p_done, 2 * sizeof(unsigned)));
-        CK(cudaMemset(c->p2p_done, 0, 2 * sizeof(unsigned)));
+        CK(cudaMalloc(&c->p2p_done, 4 * sizeof(unsigned)));
+        CK(cudaMemset(c->p2p_done, 0, 4 * sizeof(unsigned)));
         CK(cudaHostAlloc(&c->p2p_err, sizeof(int), cudaHostAllocMapped));
         *c->p2p_err = 0;
         CK(cudaHostGetDevicePointer(&c->p2p_err_dev, c->p2p_err, 0));

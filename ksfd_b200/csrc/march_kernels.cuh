@@ -47,25 +47,24 @@ struct MarchArgs {
     int fs;                 // field stride = points per plane
     int ox, oy;             // outputs per tile in x, y (balanced pitch <= TX, TY)
     int rz;                 // output planes per CTA
-    // rb > 0 (Richardson sweeps on several ranks, sweep_op.cuh): the two chunks that own
-    // the boundary planes come FIRST in the grid and are rb planes long — chunk 0 =
-    // [0, rb), chunk 1 = [nloc-rb, nloc), chunks 2.. = rz planes each of [rb, nloc-rb) —
-    // so the planes the neighbours wait for are pushed early in the kernel
+    // rb > 0 (Richardson sweeps on several ranks, sweep_op.cuh; TMA-fed marcher only): the
+    // boundary planes are owned by the FIRST CTA of every column, which marches two short
+    // chunks one after the other — pass 0 = the top planes [nloc-rb, nloc), pass 1 = the
+    // bottom planes [0, rb) — and pushes each to the neighbour as soon as it is done: the
+    // top planes (which the upper neighbour's next sweep reads FIRST) are on their way a
+    // third into the kernel.  Chunks 1.. = rz planes each of [rb, nloc-rb).
     int rb;
 };
 
-// planes [k0, k1) of chunk z
-__device__ __forceinline__ void march_chunk(const MarchArgs &g, int z, int &k0, int &k1)
+// planes [k0, k1) of chunk z (rb mode: pass 0 / 1 of chunk 0)
+__device__ __forceinline__ void march_chunk(const MarchArgs &g, int z, int &k0, int &k1, int pass = 0)
 {
     if (g.rb > 0) {
         if (z == 0) {
-            k0 = 0;
-            k1 = g.rb;
-        } else if (z == 1) {
-            k0 = g.nloc - g.rb;
-            k1 = g.nloc;
+            k0 = pass == 0 ? g.nloc - g.rb : 0;
+            k1 = k0 + g.rb;
         } else {
-            k0 = g.rb + (z - 2) * g.rz;
+            k0 = g.rb + (z - 1) * g.rz;
             k1 = min(k0 + g.rz, g.nloc - g.rb);
         }
     } else {
@@ -100,6 +99,12 @@ static __device__ __noinline__ void march_push_epilogue(const HaloPush &hp, cons
                 halo_push1(hp, sh, e, out[e]);
             }
         }
+    }
+    if (g.rb > 0) {
+        // one boundary CTA per column, two passes: the top planes' flag goes out after pass 0,
+        // the bottom planes' flag and the exchange counter after pass 1
+        halo_push_publish_dir(hp, q, gridDim.x * gridDim.y, k0 == 0 ? 1 : 0);
+        return;
     }
     unsigned nbz = 0;           // chunks that hold boundary planes
     for (int z = 0; z < (int)gridDim.z; ++z) {

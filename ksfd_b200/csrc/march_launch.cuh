@@ -290,13 +290,13 @@ static int launch_tma_op(ksfd_ctx *c, const Op &op, const TmaSrc *src, int opkey
     if (max_ctas && (long long)p.grid.x * p.grid.y * p.grid.z > max_ctas)
         return fail("marching grid exceeds the per-CTA reduction buffer");
     if (bnd_first && p.grid.z >= 3) {
-        // the chunks that own the boundary planes first and short (MarchArgs::rb): same
-        // number of CTAs, the middle chunks keep rz planes
+        // the boundary planes in the first CTA of every column, as two short chunks
+        // (MarchArgs::rb): same number of CTAs, the other chunks keep rz planes
         const int nch = (int)p.grid.z, rz = p.a.rz, nloc = p.a.nloc;
-        int rb = (nloc - (nch - 2) * rz + 1) / 2;
-        rb = std::max(KSFD_SW, std::min(rb, rz));
+        int rb = (nloc - (nch - 1) * rz + 1) / 2;
+        rb = std::max(KSFD_SW, std::min(rb, rz / 2));
         const int mid = nloc - 2 * rb;
-        if (mid <= (nch - 2) * rz && mid > (nch - 3) * rz) p.a.rb = rb;
+        if (mid <= (nch - 1) * rz && mid > (nch - 2) * rz && rb >= KSFD_SW) p.a.rb = rb;
     }
     if (p.tile == 0)
         return launch_tma_tile<DIM, AX, AY, Op, AMINB, UNR, ASC, ASC>(c, op, src, p, skip, st);

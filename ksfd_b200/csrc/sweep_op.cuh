@@ -182,6 +182,18 @@ struct SweepOp : JvpOp<DIM, NLIG, true> {
         st.so = st.sn = 0.0;
         st.own = true;
     }
+    // (TMA-fed marcher) the CTA goes on with another chunk: outputs restart, sums go on
+    __device__ __forceinline__ void next_chunk(const MarchArgs &g, State &st, int k0, int poff) const
+    {
+        Base::init_out(g, st, k0, poff);
+    }
+    // (TMA-fed marcher) the chunk [k0, k1) is written: push its boundary planes
+    __device__ __forceinline__ void chunk_done(const MarchArgs &g, State &st, int k0, int k1,
+                                               bool mine) const
+    {
+        if (hp.up_lo0)
+            march_push_epilogue<NLIG + 1>(hp, g, rout, k0, k1, st.e - k1 * (NLIG + 1) * g.fs, mine);
+    }
     template <class Sink>
     __device__ __forceinline__ void load_aux(const MarchArgs &g, int e, int off,
                                              const Sink &sink) const
@@ -226,8 +238,6 @@ struct SweepOp : JvpOp<DIM, NLIG, true> {
     __device__ __forceinline__ void finish(const MarchArgs &g, State &st, int k0, int k1,
                                            bool mine) const
     {
-        if (hp.up_lo0)
-            march_push_epilogue<NLIG + 1>(hp, g, rout, k0, k1, st.e - k1 * (NLIG + 1) * g.fs, mine);
         sweep_epilogue(fin, st.so, st.sn);
     }
 };

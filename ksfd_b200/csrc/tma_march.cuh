@@ -198,7 +198,7 @@ struct TmaMarcher {
     double q[NF][5];
     double aux[NAUX];
     typename Op::State st;
-    int spos, k0, k1;
+    int spos, k0, k1, poff_;
     int hspos, hfs, hoff[NIN];
     int cs, hs;                 // ring slots of the next centre / halo plane to consume
     unsigned cph, hph;          // their mbarrier phase parities
@@ -275,6 +275,7 @@ struct TmaMarcher {
                               idx;
             }
         }
+        poff_ = poff;
         march_chunk(g, blockIdx.z, k0, k1);
         op.init_out(g, st, k0, poff);
         if constexpr (Op::NEEDS_OWNER) {
@@ -301,7 +302,6 @@ struct TmaMarcher {
             iwaited = 0;
         }
         if (ivec != -1) {
-            const int np = k1 - k0 + 2 * KSFD_SW;
             if (tin.v[ivec].par) {
                 ixq = *reinterpret_cast<const volatile unsigned long long *>(tin.v[ivec].par);
                 ipshift = (int)(ixq & 1ull) * tin.v[ivec].parshift;
@@ -310,11 +310,20 @@ struct TmaMarcher {
             for (int sh = 0; sh < 3; ++sh)
                     asm volatile("prefetch.tensormap [%0];" ::"l"(tin.maps(ivec, 0) + sh) : "memory");
 #endif
-            for (int s = 0; s < SC; ++s)
-                if (s < np) issue(0, k0 - KSFD_SW + s, s);
-            for (int s = 0; s < SH; ++s)
-                if (s < k1 - k0) issue(1, k0 + s, s);
         }
+        prime();
+    }
+
+    // (issuer) first loads of the chunk [k0, k1): the ring slots continue where the previous
+    // chunk of this CTA (if any) stopped — every load it issued has been consumed
+    __device__ __forceinline__ void prime()
+    {
+        if (ivec == -1) return;
+        const int np = k1 - k0 + 2 * KSFD_SW;
+        for (int s = 0; s < SC; ++s)
+            if (s < np) issue(0, k0 - KSFD_SW + s, (cs + s) % SC);
+        for (int s = 0; s < SH; ++s)
+            if (s < k1 - k0) issue(1, k0 + s, (hs + s) % SH);
     }
 
     // (issuer) fetch plane k of this thread's input vector into ring slot `slot`:
@@ -443,6 +452,26 @@ struct TmaMarcher {
 
     __device__ __forceinline__ void run()
     {
+        // MarchArgs::rb: the first CTA of a column marches two boundary chunks
+        const int npass = (Op::NEEDS_OWNER && g.rb > 0 && blockIdx.z == 0) ? 2 : 1;
+        for (int pass = 0; pass < npass; ++pass) {
+            if (pass > 0) {
+                if constexpr (Op::NEEDS_OWNER) {
+                    march_chunk(g, blockIdx.z, k0, k1, pass);
+                    op.next_chunk(g, st, k0, poff_);
+                    prime();
+                }
+            }
+            run_chunk();
+            if constexpr (Op::NEEDS_OWNER) op.chunk_done(g, st, k0, k1, st.own);
+        }
+        bool mine = active;
+        if constexpr (Op::NEEDS_OWNER) mine = st.own;
+        op.finish(g, st, k0, k1, mine);
+    }
+
+    __device__ __forceinline__ void run_chunk()
+    {
         const int np = k1 - k0 + 2 * KSFD_SW;
         int it = 0;
         if (!UNR) {
@@ -468,9 +497,6 @@ struct TmaMarcher {
                 if (++it >= np) break;
             }
         }
-        bool mine = active;
-        if constexpr (Op::NEEDS_OWNER) mine = st.own;
-        op.finish(g, st, k0, k1, mine);
     }
 };
 
