@@ -948,8 +948,9 @@ static int jvp_setup_impl(ksfd_ctx *c, const double *u, double shift,
     k_pc_setup<<<nblk(g.npts, 128), 128, 0, st>>>(g, c->P, coef_ref(c), shift, id, c->pc,
                                                   blocks);
     CKL();
-    // ghost planes of the preconditioner field for the fused A*M^{-1} kernel
-    TRY(exchange(c, c->pc, 1, 2, st));
+    // ghost planes of the preconditioner field for the fused A*M^{-1} kernel: push only where
+    // the consumers are the marching kernels (they wait for the neighbours' flags themselves)
+    TRY(exchange(c, c->pc, 1, 2, st, nullptr, c->p2p_on && tma_consumer(c)));
     c->have_jac = true;
     c->fft_means_valid = false;
     return 0;

@@ -17,7 +17,10 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     ok_all = True
-    for dim, n in ((2, (96, 64)), (3, (20, 24, 32)), (1, (64,)), (2, (256, 1024))):   # >= 4 planes per rank at 8 ranks: same kernel family as one rank
+    # >= 4 planes per rank at 8 ranks: same kernel family as one rank; the last case forces chunks of 3
+    # planes so that the two-pass boundary CTAs of the sweep kernel (MarchArgs::rb) also run in 3-D
+    for dim, n, rz in ((2, (96, 64), 0), (3, (20, 24, 32), 0), (1, (64,), 0), (2, (256, 1024), 0),
+                       (3, (32, 32, 48), 3)):
         p = phys84(dim, n)
         dof = 3
         u_g = random_state(p, 5)
@@ -26,6 +29,8 @@ def main():
         ctx = core.Context(dim, n, dof, device=local, rank=rank, nranks=world)
         ctx.set_physics(product_physics(p))
         parallel.init_comm(ctx)
+        if rz:
+            ctx.set_option('rz', rz)
         plane = dof * int(np.prod(n[:-1]))
         sl = slice(ctx.last_start * plane, (ctx.last_start + ctx.last_count) * plane)
         u, ud, v = ctx.upload(u_g[sl]), ctx.upload(ud_g[sl]), ctx.upload(v_g[sl])
@@ -55,6 +60,8 @@ def main():
         if rank == 0:
             c1 = core.Context(dim, n, dof, device=local)
             c1.set_physics(product_physics(p))
+            if rz:
+                c1.set_option('rz', rz)
             U, UD, V = c1.upload(u_g), c1.upload(ud_g), c1.upload(v_g)
             F1 = c1.download(c1.residual(U, UD)); c1.jvp_setup(U, shift)
             Jv1 = c1.download(c1.jvp(V)); Jvp1 = c1.download(c1.jvp(V, precond=True))
