@@ -629,12 +629,20 @@ def native_arm(args):
             tj = json.load(open(tp))
             traffic = tj.get(domkey + '_1024x1024_bytes_per_launch')
             tsrc = tj.get(domkey + '_source', tj.get('source'))
+        tmatch = None
+        if os.path.exists(tp) and tj.get('kernel_sources'):
+            import hashlib
+            hh = hashlib.sha256()
+            for f in tj['kernel_sources']:
+                hh.update(open(os.path.join(ROOT, 'ksfd_b200', 'csrc', f), 'rb').read())
+            tmatch = hh.hexdigest() == tj.get('kernel_sources_sha256_at_capture')
         roof = dict(bound='hbm',
                     kernel='k_tma_march<2,256,1,SweepOp<2,2>> (Richardson sweep: fused A*M^-1 stencil, '
                            'x and r update, norms; TMA-fed)' if swept else
                            'k_tma_march<2,256,1,JvpOp<2,2,precond>> (fused A*M^-1 v, TMA-fed)',
                     achieved=dom['achieved_gbs'], peak=peak, unit='GB/s',
-                    frac=dom['frac'], traffic=traffic, traffic_source=tsrc, peak_source=psrc,
+                    frac=dom['frac'], traffic=traffic, traffic_source=tsrc, traffic_matches_build=tmatch,
+                    peak_source=psrc,
                     algorithmic_bytes_per_point=dombytes,
                     algorithmic_bytes='sweep: read u_lin, r, x; write x, r_new = 5 x 24 B/point'
                                       if swept else 'J.v: read u_lin, v; write out = 3 x 24 B/point',
