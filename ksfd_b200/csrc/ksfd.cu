@@ -2122,7 +2122,7 @@ static int gmres_pipe_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, doub
 // status block exactly as for the pipelined GMRES.  Needs the marching kernels, the fused
 // block-Jacobi preconditioner and (several ranks) the peer-memory exchange.
 // ---------------------------------------------------------------------------
-#define KSFD_SWEEP_CTAS 65536
+#define KSFD_SWEEP_CTAS 262144         // CTAs of a sweep grid the partial-sum buffer (3 x 2 MB) has room for
 static bool sweep_eligible(const ksfd_ctx *c, const ksfd_ksp_opts &o)
 {
     if (o.ksp_type == 0 || o.reorth || !c->gm_pipeline) return false;

@@ -11,7 +11,8 @@ sys.path.insert(0, R)
 from ksfd_b200.solver import main
 
 nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-pc_type = sys.argv[2] if len(sys.argv) > 2 else None     # pbjacobi | fft | (default: lu -> automatic)
+pc_type = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] != '-' else None   # pbjacobi | fft | (default: lu -> automatic)
+ksp_type = sys.argv[3] if len(sys.argv) > 3 else None    # gmres | richardson | (default: preonly -> the library's choice)
 lines = []
 for line in open(os.path.join(R, 'tests', 'options', 'options84.args')):
     key = line.split('=', 1)[0].strip()
@@ -21,11 +22,13 @@ for line in open(os.path.join(R, 'tests', 'options', 'options84.args')):
         line = 'maxsteps=%d\n' % nsteps
     if pc_type and line.startswith('-pc_type'):
         line = '-pc_type %s\n' % pc_type
+    if ksp_type and line.startswith('-ksp_type'):
+        line = '-ksp_type %s\n' % ksp_type
     lines.append(line)
 with tempfile.NamedTemporaryFile('w', suffix='.args', delete=False) as f:
     f.write(''.join(lines))
 t0 = time.perf_counter()
 rc = main('ksfdsolver2.py', '@' + f.name)
 wall = time.perf_counter() - t0
-print('options84 full size (pc %s): rc %d, %d steps in %.2f s wall (%.1f ms/step incl. set-up and '
-      'monitors)' % (pc_type or 'auto', rc, nsteps, wall, 1e3 * wall / nsteps))
+print('options84 full size (pc %s, ksp %s): rc %d, %d steps in %.2f s wall (%.1f ms/step incl. set-up and '
+      'monitors)' % (pc_type or 'auto', ksp_type or 'auto', rc, nsteps, wall, 1e3 * wall / nsteps))
