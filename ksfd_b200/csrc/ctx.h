@@ -111,6 +111,9 @@ struct ksfd_ctx {
     // normally only the predicted last one (a test costs a serial epilogue of 7-12 us),
     // every 8th solve of a slot one more, so that the prediction can also go DOWN
     int sw_test_lead = 1;
+    // one rank: the next stage's combination and residual (after the last stage: the completion
+    // kernels) are enqueued behind the predicted sweeps of a solve, before the host waits for it
+    bool spec_on = true;
     int fuse_push_mask = 7;      // producers that push their output's boundary planes: 2 stage combination, 4 stage residual
     bool sw_fuse_push = true;    // several ranks: boundary planes pushed by the sweep kernel itself
     // Single-pass classical Gram-Schmidt loses orthogonality like eps*kappa^2,
@@ -136,7 +139,7 @@ struct ksfd_ctx {
     // solver workspace
     double *krylov = nullptr;    // (restart+1) vectors
     int krylov_cap = 0;
-    double *work[12] = {nullptr};
+    double *work[16] = {nullptr};
     int sm_count = 148;
     int max_smem = 232448;
 };

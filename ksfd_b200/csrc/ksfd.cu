@@ -357,6 +357,7 @@ extern "C" int ksfd_set_option(ksfd_ctx *c, const char *key, int64_t v)
     else if (k == "sweep_test_lead") c->sw_test_lead = (int)std::max<int64_t>(1, v);
     else if (k == "sweep_fuse_push") c->sw_fuse_push = v != 0;
     else if (k == "fuse_push_mask") c->fuse_push_mask = (int)v;
+    else if (k == "speculate") c->spec_on = v != 0;
     else if (k == "gmres_runahead") c->gm_runahead = (int)std::max<int64_t>(0, std::min<int64_t>(v, 8));
     else return fail("unknown option " + k);
     ksfd_invalidate_plans(c);
@@ -2132,8 +2133,49 @@ static bool sweep_eligible(const ksfd_ctx *c, const ksfd_ksp_opts &o)
     return true;
 }
 
-static int sweep_solve_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x,
-                            const ksfd_ksp_opts &o, ksfd_ksp_result *res, cudaStream_t st)
+// State of one solve by sweeps between its two halves: sweep_begin launches the predicted
+// sweeps and returns; the caller may enqueue the work that FOLLOWS the solve (the next
+// stage's combination and residual) before sweep_end waits for the decision, so the device
+// does not idle during the host round trip at the end of a solve.  `clean` tells the caller
+// whether that work saw the final solution (the prediction held) or must be redone.
+struct SweepRun {
+    const double *rhs;
+    double rhs_sign;
+    double *x;
+    ksfd_ksp_opts o;
+    cudaStream_t st;
+    double *buf[2];
+    GmStatus *hs, *hsd;
+    GmOpts go;
+    HaloPush hp;
+    HostVec ph, ch;
+    bool pure, defer, fuse_push;
+    int slot, pred, lead, launched;
+    const int *skip;
+};
+
+static int sweep_launch(ksfd_ctx *c, SweepRun &r, int it)
+{
+    cudaStream_t st = r.st;
+    const double *rin = it == 0 ? r.rhs : r.buf[(it - 1) & 1];
+    if (it == 0 && r.fuse_push && c->pushed_vec == r.rhs)
+        c->pushed_vec = nullptr;            // pushed by the residual kernel that produced it
+    else if (it == 0 || !r.fuse_push)
+        TRY(exchange(c, rin, c->dof, 1, st, r.skip, r.defer));
+    const HostVec rh = make_hvec(c, rin, c->dof, 1);
+    // sweeps the solve is known to need are not tested (no reduction, no rank sum)
+    const int test = (r.pred == 0 || it >= r.pred - r.lead) ? 1 : 0;
+    SweepFin fin{c->sw_partial, KSFD_SWEEP_CTAS, it, test, 0, c->gm, c->gmi, r.hsd, r.go,
+                 r.pure ? 1e300 : c->sw_slow, p2p_red(c), c->gm_done};
+    SweepHost a{r.x, r.buf[it & 1], it == 0 ? r.rhs_sign : 1.0, it == 0 ? 1 : 0, KSFD_SWEEP_CTAS,
+                &fin, r.fuse_push ? &r.hp : nullptr};
+    ProfScope prof(c, 6, st);
+    return c->dim == 2 ? ksfd_march_sweep_d2(c, r.ch, rh, r.ph, a, r.skip, st)
+                       : ksfd_march_sweep_d3(c, r.ch, rh, r.ph, a, r.skip, st);
+}
+
+static int sweep_begin(ksfd_ctx *c, SweepRun &r, const double *rhs, double rhs_sign, double *x,
+                       const ksfd_ksp_opts &o, cudaStream_t st)
 {
     const long long n = nlocal(c);
     const int m = std::max(1, o.restart > 0 ? o.restart : 30);
@@ -2145,78 +2187,84 @@ static int sweep_solve_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, dou
     }
     TRY(gm_alloc(c));
     if (!c->sw_partial) CK(cudaMalloc(&c->sw_partial, sizeof(double) * 3 * KSFD_SWEEP_CTAS));
-    double *buf[2] = {c->krylov, c->krylov + n};
-    GmStatus *hs = static_cast<GmStatus *>(c->gm_status);
-    GmStatus *hsd = static_cast<GmStatus *>(c->gm_status_dev);
-    const bool pure = o.ksp_type == 1;      // no fallback: stop on max_it / dtol only
-    GmOpts go{o.rtol, o.atol, o.dtol, o.max_it > 0 ? o.max_it : 10000, m, 0, 0.0};
+    r.rhs = rhs;
+    r.rhs_sign = rhs_sign;
+    r.x = x;
+    r.o = o;
+    r.st = st;
+    r.buf[0] = c->krylov;
+    r.buf[1] = c->krylov + n;
+    r.hs = static_cast<GmStatus *>(c->gm_status);
+    r.hsd = static_cast<GmStatus *>(c->gm_status_dev);
+    r.pure = o.ksp_type == 1;               // no fallback: stop on max_it / dtol only
+    r.go = GmOpts{o.rtol, o.atol, o.dtol, o.max_it > 0 ? o.max_it : 10000, m, 0, 0.0};
+    GmStatus *hs = r.hs;
     hs->seq = 0;
     hs->iters_done = 0;
     hs->cycle_done = hs->final_ = hs->reason = hs->its_total = 0;
     hs->k_cols = 0;
     CK(cudaMemsetAsync(c->gmi, 0, sizeof(int) * GMI_INTS, st));
-    const int R = c->gm_runahead;
-    const int *skip = c->gmi + GMI_CYCLE_DONE;
-    const bool defer = c->p2p_on && c->nranks > 1 && tma_consumer(c);
-    const HostVec ph = make_hvec(c, c->pc, 1, 2);
-    const HostVec ch = coef_hvec(c);
+    r.skip = c->gmi + GMI_CYCLE_DONE;
+    r.defer = c->p2p_on && c->nranks > 1 && tma_consumer(c);
+    r.ph = make_hvec(c, c->pc, 1, 2);
+    r.ch = coef_hvec(c);
     // several ranks: every sweep also pushes the boundary planes of its output into the
-    // neighbours' ghost buffers (no exchange kernel between sweeps); only the right-hand
-    // side, which nobody pushed, goes out through the push kernel
-    const HaloPush hp = make_push(c, 1);
-    const bool fuse_push = defer && hp.up_lo0 != nullptr && ksfd_use_tma(c) && c->sw_fuse_push;
-    const int slot = c->sw_slot & 3;
-    const int pred = c->sw_hist[slot];
+    // neighbours' ghost buffers (no exchange kernel between sweeps); only a right-hand
+    // side nobody pushed goes out through the push kernel
+    r.hp = make_push(c, 1);
+    r.fuse_push = r.defer && r.hp.up_lo0 != nullptr && ksfd_use_tma(c) && c->sw_fuse_push;
+    r.slot = c->sw_slot & 3;
+    r.pred = c->sw_hist[r.slot];
     // one more tested sweep while the count of this slot is not settled, and every 8th solve
-    const bool probe = c->sw_stable[slot] < 2 || c->sw_stable[slot] % 8 == 7;
-    const int lead = c->sw_test_lead + (probe ? 1 : 0);
-    auto launch = [&](int it) -> int {
-        const double *rin = it == 0 ? rhs : buf[(it - 1) & 1];
-        if (it == 0 && fuse_push && c->pushed_vec == rhs)
-            c->pushed_vec = nullptr;            // pushed by the residual kernel that produced it
-        else if (it == 0 || !fuse_push)
-            TRY(exchange(c, rin, c->dof, 1, st, skip, defer));
-        const HostVec rh = make_hvec(c, rin, c->dof, 1);
-        // sweeps the solve is known to need are not tested (no reduction, no rank sum)
-        const int test = (pred == 0 || it >= pred - lead) ? 1 : 0;
-        SweepFin fin{c->sw_partial, KSFD_SWEEP_CTAS, it, test, 0, c->gm, c->gmi, hsd, go,
-                     pure ? 1e300 : c->sw_slow, p2p_red(c), c->gm_done};
-        SweepHost a{x, buf[it & 1], it == 0 ? rhs_sign : 1.0, it == 0 ? 1 : 0, KSFD_SWEEP_CTAS,
-                    &fin, fuse_push ? &hp : nullptr};
-        ProfScope prof(c, 6, st);
-        return c->dim == 2 ? ksfd_march_sweep_d2(c, ch, rh, ph, a, skip, st)
-                           : ksfd_march_sweep_d3(c, ch, rh, ph, a, skip, st);
-    };
+    const bool probe = c->sw_stable[r.slot] < 2 || c->sw_stable[r.slot] % 8 == 7;
+    r.lead = c->sw_test_lead + (probe ? 1 : 0);
     // Solves of the same slot (ROSW stage) of consecutive steps take the same number of
-    // sweeps.  The predicted number goes out without waiting and only its last sweep (every
-    // 8th solve: its last two) is tested; beyond it the host launches one tested sweep at a
-    // time, each once the previous one is known not to have ended the solve (a host round
-    // trip, ~10 us: the price of a prediction that was too short).  Without a prediction
-    // every sweep is tested and the host stays R sweeps ahead of the device.
-    int launched = 0;
-    for (; launched < std::min(pred, go.max_it); ++launched) TRY(launch(launched));
+    // sweeps.  The predicted number goes out without waiting and only its last sweep (while
+    // the count is not settled, and every 8th solve: its last two) is tested; beyond it the
+    // host launches one tested sweep at a time, each once the previous one is known not to
+    // have ended the solve (a host round trip, ~10 us: the price of a prediction that was too
+    // short).  Without a prediction every sweep is tested and the host stays R sweeps ahead.
+    r.launched = 0;
+    for (; r.launched < std::min(r.pred, r.go.max_it); ++r.launched) TRY(sweep_launch(c, r, r.launched));
+    return 0;
+}
+
+// the prediction of this solve is settled: work enqueued behind the predicted sweeps will
+// most probably see the converged solution
+static bool sweep_settled(const ksfd_ctx *c, const SweepRun &r)
+{
+    return r.pred > 0 && r.launched == r.pred && c->sw_stable[r.slot] >= 2;
+}
+
+static int sweep_end(ksfd_ctx *c, SweepRun &r, ksfd_ksp_result *res, bool *clean)
+{
+    cudaStream_t st = r.st;
+    GmStatus *hs = r.hs;
+    const int R = c->gm_runahead;
+    const int launched0 = r.launched;
     for (;;) {
-        const int lag = pred > 0 ? 0 : R;
-        TRY(gm_wait(st, [&] { return hs->cycle_done != 0 || hs->iters_done >= launched - lag; },
+        const int lag = r.pred > 0 ? 0 : R;
+        TRY(gm_wait(st, [&] { return hs->cycle_done != 0 || hs->iters_done >= r.launched - lag; },
                     "a Richardson sweep", c));
-        if (hs->cycle_done || launched >= go.max_it) break;
-        TRY(launch(launched));
-        ++launched;
+        if (hs->cycle_done || r.launched >= r.go.max_it) break;
+        TRY(sweep_launch(c, r, r.launched));
+        ++r.launched;
     }
     TRY(gm_wait(st, [&] { return hs->cycle_done != 0; }, "the end of the sweeps", c));
     if (getenv("KSFD_DEBUG_GMRES"))
         fprintf(stderr, "sweeps: its %d reason %d rnorm0 %.3e rnorm %.3e\n", hs->its_total,
                 hs->reason, hs->rnorm0, hs->rnorm);
+    if (clean) *clean = r.launched == launched0 && hs->reason > 0 && hs->reason != KSFD_SWEEP_FALLBACK;
     if (hs->reason == KSFD_SWEEP_FALLBACK) {
         // contraction too slow for a stationary iteration: GMRES takes over, from the
         // iterate reached so far unless it is worse than x = 0
         c->sw_backoff = 8;
         for (int i = 0; i < 4; ++i) c->sw_hist[i] = c->sw_stable[i] = 0;
         const bool keep = hs->rnorm < hs->rnorm0;
-        return gmres_pipe_impl(c, rhs, rhs_sign, x, o, res, st, keep ? 1 : 0);
+        return gmres_pipe_impl(c, r.rhs, r.rhs_sign, r.x, r.o, res, st, keep ? 1 : 0);
     }
-    c->sw_stable[slot] = (pred > 0 && hs->its_total == pred) ? c->sw_stable[slot] + 1 : 0;
-    c->sw_hist[slot] = hs->its_total;
+    c->sw_stable[r.slot] = (r.pred > 0 && hs->its_total == r.pred) ? c->sw_stable[r.slot] + 1 : 0;
+    c->sw_hist[r.slot] = hs->its_total;
     if (res) {
         res->its = hs->its_total;
         res->reason = hs->reason;
@@ -2224,6 +2272,14 @@ static int sweep_solve_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, dou
         res->rnorm = hs->rnorm;
     }
     return 0;
+}
+
+static int sweep_solve_impl(ksfd_ctx *c, const double *rhs, double rhs_sign, double *x,
+                            const ksfd_ksp_opts &o, ksfd_ksp_result *res, cudaStream_t st)
+{
+    SweepRun r;
+    TRY(sweep_begin(c, r, rhs, rhs_sign, x, o, st));
+    return sweep_end(c, r, res, nullptr);
 }
 
 // one sweep as a stand-alone operation (tests, kernel timing): r_out = r_in - A M^-1 r_in,
@@ -2397,9 +2453,21 @@ static int rosw_attempt(ksfd_ctx *c, const double *u, double t, double h,
     const long long n = nlocal(c);
     for (int i = 2; i <= 9; ++i) TRY(ensure_work(c, i));
     double *Y[4] = {c->work[2], c->work[3], c->work[4], c->work[5]};
-    double *Z = c->work[6], *Zd = c->work[7], *F = c->work[8];
+    double *Z = c->work[6], *Zd = c->work[7];
     *ksp_fail = 0;
-    for (int i = 0; i < T.s; ++i) {
+    // One rank, no stage callback: the work that FOLLOWS a stage solve — the next stage's
+    // combination and residual, after the last stage the completion kernels — is enqueued
+    // behind the predicted sweeps of the solve, before the host waits for its decision, so
+    // the device does not idle during that round trip.  It is valid when the prediction held
+    // (`clean`); otherwise it is simply done again.  The right-hand sides alternate between
+    // two buffers: a solve that goes on (more sweeps, GMRES) still needs its own.
+    const bool may_spec = c->nranks == 1 && !cb && c->spec_on;
+    double *Fb[2] = {c->work[8], c->work[8]};
+    if (may_spec) {
+        TRY(ensure_work(c, 12));
+        Fb[1] = c->work[12];
+    }
+    auto stage_pre = [&](int i, double *F, bool swp) -> int {
         const double ti = t + h * T.asum[i];
         VecList yl{};
         CoefList a{}, gm{};
@@ -2419,40 +2487,67 @@ static int rosw_attempt(ksfd_ctx *c, const double *u, double t, double h,
             CK(cudaStreamSynchronize(st));
             cb(ti, user);
         }
+        return residual_impl(c, Zp, Zd, src, F, st, swp);   // F = Zdot - f(Z)
+    };
+    // completion, error norm and (velmax, KSFD_TS_VELOCITY_MAX) the CFL maxima of the step's
+    // result, computed right away on the candidate (wasted only when the step is rejected):
+    // they travel to the host with the error norm — one synchronisation per step
+    auto step_tail = [&]() -> int {
+        VecList yl{};
+        CoefList b{}, be{};
+        for (int j = 0; j < 4; ++j) {
+            yl.v[j] = Y[j];
+            b.c[j] = T.bt[j];
+            be.c[j] = T.bet[j];
+        }
+        k_complete_step<4><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(
+            n, u, yl, b, be, o.atol, o.rtol, unew, c->partial);
+        CKL();
+        k_reduce_partials<<<1, 128, 0, st>>>(1, KSFD_RED_BLOCKS, c->partial, c->dscal + SC_ENORM, 0);
+        CKL();
+        TRY(allreduce_dev(c, c->dscal + SC_ENORM, 1, ncclSum_, st));
+        if (velmax) {
+            TRY(velocity_impl(c, unew, nullptr, c->dscal + SC_ENORM + 1, st));
+            TRY(allreduce_dev(c, c->dscal + SC_ENORM + 1, c->dim, ncclMax_, st));
+        }
+        return 0;
+    };
+    bool pre_done = false, tail_done = false;
+    for (int i = 0; i < T.s; ++i) {
+        double *F = Fb[i & 1];
         const bool swp = sweep_eligible(c, o.ksp) && !(o.ksp.ksp_type == 2 && c->sw_backoff > 0);
-        TRY(residual_impl(c, Zp, Zd, src, F, st, swp));     // F = Zdot - f(Z)
-        if (i == 0) TRY(jvp_setup_impl(c, Zp, 1.0 / (h * T.gamma), nullptr, st, true));
+        if (!pre_done) TRY(stage_pre(i, F, swp));
+        pre_done = false;
+        if (i == 0) TRY(jvp_setup_impl(c, u, 1.0 / (h * T.gamma), nullptr, st, true));
         ksfd_ksp_result kr{};
         c->sw_slot = i;
-        TRY(gmres_impl(c, F, -1.0, Y[i], o.ksp, &kr, st));  // A Y_i = -F
+        if (may_spec && swp) {
+            SweepRun r;
+            TRY(sweep_begin(c, r, F, -1.0, Y[i], o.ksp, st));       // A Y_i = -F
+            const bool spec = sweep_settled(c, r);
+            if (spec) {
+                if (i + 1 < T.s)
+                    TRY(stage_pre(i + 1, Fb[(i + 1) & 1], swp));
+                else
+                    TRY(step_tail());
+            }
+            bool clean = false;
+            TRY(sweep_end(c, r, &kr, &clean));
+            if (spec && clean) {
+                pre_done = i + 1 < T.s;
+                tail_done = i + 1 == T.s;
+            }
+        } else {
+            TRY(gmres_impl(c, F, -1.0, Y[i], o.ksp, &kr, st));      // A Y_i = -F
+        }
         *ksp_its += kr.its;
         if (kr.reason < 0) {
             *ksp_fail = 1;
             return 0;
         }
     }
-    VecList yl{};
-    CoefList b{}, be{};
-    for (int j = 0; j < 4; ++j) {
-        yl.v[j] = Y[j];
-        b.c[j] = T.bt[j];
-        be.c[j] = T.bet[j];
-    }
-    k_complete_step<4><<<KSFD_RED_BLOCKS, KSFD_RED_THREADS, 0, st>>>(
-        n, u, yl, b, be, o.atol, o.rtol, unew, c->partial);
-    CKL();
-    k_reduce_partials<<<1, 128, 0, st>>>(1, KSFD_RED_BLOCKS, c->partial, c->dscal + SC_ENORM, 0);
-    CKL();
-    TRY(allreduce_dev(c, c->dscal + SC_ENORM, 1, ncclSum_, st));
-    // velmax (KSFD_TS_VELOCITY_MAX): the CFL maxima of the step's result are computed right
-    // away (on the candidate: wasted only when the step is rejected) and travel to the host
-    // with the error norm — one synchronisation per step instead of two
-    int nfetch = 1;
-    if (velmax) {
-        TRY(velocity_impl(c, unew, nullptr, c->dscal + SC_ENORM + 1, st));
-        TRY(allreduce_dev(c, c->dscal + SC_ENORM + 1, c->dim, ncclMax_, st));
-        nfetch += c->dim;
-    }
+    if (!tail_done) TRY(step_tail());
+    const int nfetch = 1 + (velmax ? c->dim : 0);
     // no step-size control: the candidate IS the new state — copied before the host waits
     if (accept_into)
         CK(cudaMemcpyAsync(accept_into, unew, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
