@@ -504,6 +504,8 @@ def native_arm(args):
     if world > 1:
         from ksfd_b200 import parallel
         parallel.init_comm(ctx)
+    if os.environ.get('KSFD_BENCH_UNDERPREDICT'):       # test knob: exercise the late-sweep path
+        ctx.set_option('sweep_underpredict', int(os.environ['KSFD_BENCH_UNDERPREDICT']))
     # synthetic IC, per-rank stream as the reference spawns it
     # (KSFD/ksfdrandom.py:46-49)
     rng = np.random.default_rng(np.random.SeedSequence(SEED).spawn(world)[rank])

@@ -114,6 +114,7 @@ struct ksfd_ctx {
     // one rank: the next stage's combination and residual (after the last stage: the completion
     // kernels) are enqueued behind the predicted sweeps of a solve, before the host waits for it
     bool spec_on = true;
+    int sw_underpredict = 0;     // test knob: sweeps launched fewer than predicted
     int fuse_push_mask = 7;      // producers that push their output's boundary planes: 2 stage combination, 4 stage residual
     bool sw_fuse_push = true;    // several ranks: boundary planes pushed by the sweep kernel itself
     // Single-pass classical Gram-Schmidt loses orthogonality like eps*kappa^2,

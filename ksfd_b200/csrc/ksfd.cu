@@ -358,6 +358,7 @@ extern "C" int ksfd_set_option(ksfd_ctx *c, const char *key, int64_t v)
     else if (k == "sweep_fuse_push") c->sw_fuse_push = v != 0;
     else if (k == "fuse_push_mask") c->fuse_push_mask = (int)v;
     else if (k == "speculate") c->spec_on = v != 0;
+    else if (k == "sweep_underpredict") c->sw_underpredict = (int)std::max<int64_t>(0, std::min<int64_t>(v, 4));
     else if (k == "gmres_runahead") c->gm_runahead = (int)std::max<int64_t>(0, std::min<int64_t>(v, 8));
     else return fail("unknown option " + k);
     ksfd_invalidate_plans(c);
@@ -2150,7 +2151,11 @@ struct SweepRun {
     HaloPush hp;
     HostVec ph, ch;
     bool pure, defer, fuse_push;
-    int slot, pred, lead, launched;
+    // several ranks: work enqueued behind the predicted sweeps has made exchanges on the halo
+    // slot of the sweeps (the next right-hand side was pushed): a sweep launched after it
+    // must push its input again
+    bool dirty;
+    int slot, pred, lead, launched, first;
     const int *skip;
 };
 
@@ -2164,7 +2169,8 @@ static int sweep_launch(ksfd_ctx *c, SweepRun &r, int it)
         TRY(exchange(c, rin, c->dof, 1, st, r.skip, r.defer));
     const HostVec rh = make_hvec(c, rin, c->dof, 1);
     // sweeps the solve is known to need are not tested (no reduction, no rank sum)
-    const int test = (r.pred == 0 || it >= r.pred - r.lead) ? 1 : 0;
+    // (the last sweep that goes out without waiting is always tested: the host waits for it)
+    const int test = (r.pred == 0 || it >= r.pred - r.lead || it >= r.first - 1) ? 1 : 0;
     SweepFin fin{c->sw_partial, KSFD_SWEEP_CTAS, it, test, 0, c->gm, c->gmi, r.hsd, r.go,
                  r.pure ? 1e300 : c->sw_slow, p2p_red(c), c->gm_done};
     SweepHost a{r.x, r.buf[it & 1], it == 0 ? r.rhs_sign : 1.0, it == 0 ? 1 : 0, KSFD_SWEEP_CTAS,
@@ -2225,7 +2231,10 @@ static int sweep_begin(ksfd_ctx *c, SweepRun &r, const double *rhs, double rhs_s
     // have ended the solve (a host round trip, ~10 us: the price of a prediction that was too
     // short).  Without a prediction every sweep is tested and the host stays R sweeps ahead.
     r.launched = 0;
-    for (; r.launched < std::min(r.pred, r.go.max_it); ++r.launched) TRY(sweep_launch(c, r, r.launched));
+    r.dirty = false;
+    // (test knob sweep_underpredict: launch fewer than predicted, to exercise the late path)
+    r.first = std::max(0, std::min(r.pred, r.go.max_it) - (r.pred > 1 ? c->sw_underpredict : 0));
+    for (; r.launched < r.first; ++r.launched) TRY(sweep_launch(c, r, r.launched));
     return 0;
 }
 
@@ -2233,7 +2242,8 @@ static int sweep_begin(ksfd_ctx *c, SweepRun &r, const double *rhs, double rhs_s
 // most probably see the converged solution
 static bool sweep_settled(const ksfd_ctx *c, const SweepRun &r)
 {
-    return r.pred > 0 && r.launched == r.pred && c->sw_stable[r.slot] >= 2;
+    return r.pred > 0 && r.launched >= r.pred - c->sw_underpredict && r.launched > 0 &&
+           c->sw_stable[r.slot] >= 2;
 }
 
 static int sweep_end(ksfd_ctx *c, SweepRun &r, ksfd_ksp_result *res, bool *clean)
@@ -2247,6 +2257,10 @@ static int sweep_end(ksfd_ctx *c, SweepRun &r, ksfd_ksp_result *res, bool *clean
         TRY(gm_wait(st, [&] { return hs->cycle_done != 0 || hs->iters_done >= r.launched - lag; },
                     "a Richardson sweep", c));
         if (hs->cycle_done || r.launched >= r.go.max_it) break;
+        if (r.dirty && r.launched > 0) {
+            TRY(exchange(c, r.buf[(r.launched - 1) & 1], c->dof, 1, st, r.skip, r.defer));
+            r.dirty = false;
+        }
         TRY(sweep_launch(c, r, r.launched));
         ++r.launched;
     }
@@ -2461,7 +2475,7 @@ static int rosw_attempt(ksfd_ctx *c, const double *u, double t, double h,
     // the device does not idle during that round trip.  It is valid when the prediction held
     // (`clean`); otherwise it is simply done again.  The right-hand sides alternate between
     // two buffers: a solve that goes on (more sweeps, GMRES) still needs its own.
-    const bool may_spec = c->nranks == 1 && !cb && c->spec_on;
+    const bool may_spec = (c->nranks == 1 || c->p2p_on) && !cb && c->spec_on;
     double *Fb[2] = {c->work[8], c->work[8]};
     if (may_spec) {
         TRY(ensure_work(c, 12));
@@ -2530,6 +2544,7 @@ static int rosw_attempt(ksfd_ctx *c, const double *u, double t, double h,
                     TRY(stage_pre(i + 1, Fb[(i + 1) & 1], swp));
                 else
                     TRY(step_tail());
+                r.dirty = c->nranks > 1;
             }
             bool clean = false;
             TRY(sweep_end(c, r, &kr, &clean));
