@@ -19,7 +19,7 @@ UNITS = [('ksfd.cu', [], 'ksfd.o')] + [
     (src, ['-DKSFD_MARCH_DIM=%d' % d], '%s_d%d.o' % (src[:-3], d))
     for src in ('march_res.cu', 'march_jvp.cu', 'march_vel.cu', 'march_sweep.cu') for d in (2, 3)]
 HEADERS = ['device_common.cuh', 'naive_kernels.cuh', 'march_kernels.cuh',
-           'march_launch.cuh', 'tma_march.cuh', 'tma_host.h', 'ctx.h', 'blas1_kernels.cuh', 'solver_state.cuh', 'sweep_op.cuh', 'fftpc.cuh', 'fastmath.cuh',
+           'march_launch.cuh', 'tma_march.cuh', 'tma_host.h', 'ctx.h', 'blas1_kernels.cuh', 'solver_state.cuh', 'sweep_op.cuh', 'halo_push.cuh', 'fftpc.cuh', 'fastmath.cuh',
            'fastmath_tables.h',
            os.path.join('..', '..', 'include', 'ksfd_b200.h')]
 OBJDIR = os.path.join(HERE, 'build')
