@@ -2256,7 +2256,11 @@ static int sweep_end(ksfd_ctx *c, SweepRun &r, ksfd_ksp_result *res, bool *clean
         const int lag = r.pred > 0 ? 0 : R;
         TRY(gm_wait(st, [&] { return hs->cycle_done != 0 || hs->iters_done >= r.launched - lag; },
                     "a Richardson sweep", c));
-        if (hs->cycle_done || r.launched >= r.go.max_it) break;
+        // The sweep that ends a solve writes final_, a system fence, cycle_done and then
+        // iters_done (sweep_finalize); the last two are not ordered against each other, so
+        // iters_done may be seen first.  final_ is older than the fence: whoever sees that
+        // iters_done also sees it, and must not launch one more sweep.
+        if (hs->cycle_done || hs->final_ || r.launched >= r.go.max_it) break;
         if (r.dirty && r.launched > 0) {
             TRY(exchange(c, r.buf[(r.launched - 1) & 1], c->dof, 1, st, r.skip, r.defer));
             r.dirty = false;
@@ -2264,7 +2268,11 @@ static int sweep_end(ksfd_ctx *c, SweepRun &r, ksfd_ksp_result *res, bool *clean
         TRY(sweep_launch(c, r, r.launched));
         ++r.launched;
     }
-    TRY(gm_wait(st, [&] { return hs->cycle_done != 0; }, "the end of the sweeps", c));
+    // iters_done is the LAST word a solve writes into the status block: the block is reset for
+    // the next solve (sweep_begin) only once it has landed, or the late store would be taken
+    // for a finished sweep of that solve (sweeps launched beyond the end skip and write nothing)
+    TRY(gm_wait(st, [&] { return hs->cycle_done != 0 && hs->iters_done == hs->its_total; },
+                "the end of the sweeps", c));
     if (getenv("KSFD_DEBUG_GMRES"))
         fprintf(stderr, "sweeps: its %d reason %d rnorm0 %.3e rnorm %.3e\n", hs->its_total,
                 hs->reason, hs->rnorm0, hs->rnorm);

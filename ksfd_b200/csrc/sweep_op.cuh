@@ -100,17 +100,13 @@ __device__ __forceinline__ void sweep_finalize(const SweepFin &a, int ncta)
     hs->rnorm0 = r0;
     hs->its_total = its;
     if (fin) {
-        // one fence: a host that sees cycle_done sees the fields above.  cycle_done is the
-        // LAST word this solve writes (the host resets the block for the next solve only
-        // after it has seen it) and the only one the host acts on here: iters_done is not
-        // advanced, or the host could see it first and launch one more sweep
+        // one fence: a host that sees cycle_done sees the fields above
         hs->reason = reason;
         hs->final_ = 1;
         __threadfence_system();
         hs->cycle_done = 1;
-    } else {
-        hs->iters_done = its;
     }
+    hs->iters_done = its;
 }
 
 // End of a sweep CTA, out of line (the unrolled plane loop has five exits): per-CTA partial
