@@ -13,9 +13,13 @@ one "step" = one implicit time step as the reference's loop does it
 scaling): global grid 1024 x (1024 N), slab-decomposed along y with an NCCL
 halo ring; value = grid-point-steps per second of the whole job.
 
-Prints ONE JSON line (rank 0).  Extra keys: roofline (dominant kernel = fused
-J.v), residual/jvp kernel numbers at 1024^2 and 256^3, cpu_baseline, e2e,
-clocks, gpu_launches.
+Prints ONE JSON line (rank 0).  Extra keys: roofline (dominant kernel = the
+Richardson sweep, or the fused J.v with GMRES), residual/jvp/sweep kernel numbers at
+1024^2 and 256^3, cpu_baseline, e2e, clocks, gpu_launches.
+
+CPU legs (cpu_baseline at N = 1, and --impl reference): the oracle's C restatement
+(oracle/ksfd_oracle_c.c, OpenMP, every host thread, own process) on the SAME full
+1024^2 configuration; falls back to the numpy port on 96^2 tiles if it cannot be built.
 """
 import argparse
 import json
@@ -179,6 +183,81 @@ def cpu_baseline(nsteps=1, n=96, procs=1):
                 seconds=wall)
 
 
+def _host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def c_leg(nsteps, warm, n=TILE):
+    """Runs in its own process (`bench.py --cpu-leg K,W`): the oracle's C restatement
+    (oracle/ksfd_oracle_c.c, OpenMP on all host threads) on the SAME configuration as the
+    GPU arm — the full n x n grid, options84 physics, h = 1/384, dt = 1e-3, one step = clamp,
+    ROSW ra34pw2 step (4 residuals, Jacobian set-up, 4 stage solves to rtol 1e-8), CFL
+    maxima.  Stage solves: point-block-Jacobi Richardson sweeps (the same iteration the GPU
+    arm runs) instead of the reference's MUMPS LU, which at 3.1 M unknowns takes minutes per
+    step — the substitution favours the CPU."""
+    from helpers import oracle_physics, random_state
+    from oracle import ksfd_oracle_c as OC
+    p = phys_dict(2, (n, n))
+    ph = oracle_physics(p)
+    c = OC.COracle(ph)
+    u = np.ascontiguousarray(random_state(p, 100, rel=0.0))
+    its = 0
+    for _ in range(warm):
+        c.ts_step(u, DT, rtol=KSP_RTOL)
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        _, k = c.ts_step(u, DT, rtol=KSP_RTOL)
+        its += k
+    wall = time.perf_counter() - t0
+    # operator numbers on the same grid (best of 3)
+    v = np.random.default_rng(8).standard_normal(u.size)
+    c.jvp_setup(u, 1.0 / (ROSW_GAMMA * DT))
+    ops = {}
+    for name, fn in (('residual', lambda: c.dfdt(u)), ('jvp', lambda: c.jvp(v))):
+        best = 1e30
+        for _ in range(4):
+            t1 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t1)
+        ops[name] = dict(seconds=best, mpts_per_s=n * n / best / 1e6)
+    finite = bool(np.isfinite(u).all())
+    c.close()
+    return dict(seconds=wall, steps=nsteps, warmup=warm, n=n, cores=OC.threads(),
+                its_per_step=its / max(nsteps, 1), finite=finite, operators=ops)
+
+
+def cpu_baseline_c(nsteps, warm=1, n=TILE, timeout=1500):
+    """cpu_baseline from the C oracle in a fresh process with every host thread (torchrun
+    sets OMP_NUM_THREADS=1 for its ranks; the leg gets its own environment)."""
+    env = dict(os.environ)
+    nth = int(os.environ.get('KSFD_CPU_THREADS', '0')) or _host_threads()
+    env['OMP_NUM_THREADS'] = str(nth)
+    env.setdefault('OMP_PROC_BIND', 'false')
+    for k in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE'):
+        env.pop(k, None)
+    o = subprocess.run([sys.executable, os.path.abspath(__file__), '--cpu-leg',
+                        '%d,%d,%d' % (nsteps, warm, n)],
+                       capture_output=True, text=True, timeout=timeout, env=env)
+    if o.returncode != 0:
+        raise RuntimeError('cpu leg failed: ' + o.stderr[-500:])
+    r = json.loads(o.stdout.strip().splitlines()[-1])
+    if not r['finite']:
+        raise RuntimeError('cpu leg produced non-finite values')
+    val = n * n * r['steps'] / r['seconds'] / 1e6
+    return dict(value=val, unit='Mpts*steps/s', cores=r['cores'], kind='port',
+                sample='%d ROSW step(s) of the FULL %dx%d grid (same configuration as the GPU arm: '
+                       'physics, h, dt, rtol) after %d warm-up step(s); oracle C restatement '
+                       '(oracle/ksfd_oracle_c.c, OpenMP, %d threads); stage solves by point-block-Jacobi '
+                       'Richardson sweeps (%.1f per step) instead of MUMPS LU'
+                       % (r['steps'], n, n, r['warmup'], r['cores'], r['its_per_step']),
+                seconds=r['seconds'], ms_per_step=1e3 * r['seconds'] / max(r['steps'], 1),
+                ksp_its_per_step=r['its_per_step'], same_config=True,
+                operators=r['operators'])
+
+
 def cpu_operator_timing(n=TILE, reps=2):
     """Same-config CPU operator numbers: the oracle's residual f(u) and
     matrix-free J.v (numpy, one core) on the FULL 1024x1024 grid of the GPU roofline
@@ -207,37 +286,59 @@ def cpu_operator_timing(n=TILE, reps=2):
 
 
 def reference_arm(args):
+    """CPU arm on the GPU arm's configuration: the oracle's C restatement on every host
+    thread, K steps of the full 1024^2 grid (at N > 1 the sample stays ONE per-GPU tile of the
+    weak-scaling grid: CPU throughput in points*steps/s does not depend on the number of
+    tiles, and K steps must end within minutes).  The reference itself (PETSc + MUMPS over
+    MPI) cannot be installed in this image: kind 'port'."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    procs = min(os.cpu_count() or 1, 32)
-    # bounded sample: one n x n tile per core and step, sized so that K steps
-    # end within a few minutes (SuperLU factorisation dominates: ~2.2 s per
-    # step at 96^2, ~0.8 s at 64^2)
-    n = 96 if args.steps <= 20 else 64
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_baseline(1, n, procs)
     t0 = time.perf_counter()
-    cb = cpu_baseline(args.steps, n, procs)
+    direct = None
+    try:
+        cb = cpu_baseline_c(args.steps, max(args.warmup, 0))
+        same = max(args.gpus, 1) == 1
+        par = '%d host threads (OpenMP), one process' % cb['cores']
+        how = ('CPU arm: oracle C restatement, stage solves by point-block-Jacobi Richardson sweeps '
+               '(%.1f per step) instead of MUMPS LU' % cb['ksp_its_per_step'])
+        try:        # what a direct solver costs: one step of a 96^2 tile, numpy port + SuperLU
+            d = cpu_baseline(1, 96, 1)
+            direct = dict(value=d['value'], unit=d['unit'], cores=1, sample=d['sample'],
+                          seconds=d['seconds'])
+        except Exception as e:          # noqa: BLE001
+            direct = dict(error=str(e)[:200])
+    except Exception as e:              # noqa: BLE001 — the numpy port is always there
+        sys.stderr.write('bench.py: C oracle leg unavailable (%s); numpy port on 96^2 tiles\n' % e)
+        procs = min(os.cpu_count() or 1, 32)
+        n = 96 if args.steps <= 20 else 64
+        cb = cpu_baseline(args.steps, n, procs)
+        cb['ms_per_step'] = 1e3 * cb['seconds'] / max(args.steps, 1)
+        same = False
+        par = '%d host cores, independent tiles' % procs
+        how = ('CPU arm: numpy port, direct LU (SuperLU), each step a bounded sample = one '
+               '%dx%d tile per core' % (n, n))
     wall = time.perf_counter() - t0
     line = dict(impl='reference', metric='implicit TS throughput (ROSW steps x grid points)',
                 value=cb['value'], unit='Mpts*steps/s', n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 * cb['seconds'] / max(args.steps, 1),
+                ms_per_step=cb['ms_per_step'],
                 higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f64', data='synthetic',
                 config=dict(workload='2-D %dx%d tile per GPU (global %dx%d), dof 3, options84 physics, '
-                                     'h=1/384, dt=1e-3, ROSW ra34pw2; CPU arm: direct LU (SuperLU) instead '
-                                     'of GMRES, each step a bounded sample = one %dx%d tile per core'
-                                     % (TILE, TILE, TILE, TILE * max(args.gpus, 1), n, n),
-                            parallelism='%d host cores, independent tiles' % procs),
-                cpu_baseline=dict(value=cb['value'], unit=cb['unit'], cores=procs,
+                                     'h=1/384, dt=1e-3, ROSW ra34pw2, rtol %.0e; %s'
+                                     % (TILE, TILE, TILE, TILE * max(args.gpus, 1), KSP_RTOL, how),
+                            parallelism=par),
+                cpu_baseline=dict(value=cb['value'], unit=cb['unit'], cores=cb['cores'],
                                   kind='port', sample=cb['sample']),
                 e2e=dict(value=cb['value'], unit='Mpts*steps/s',
                          h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                same_config=False,
-                # the SAME-config CPU numbers: the port's residual and J.v on the full 1024^2 grid
-                cpu_operator_1024x1024=cpu_operator_timing(),
+                same_config=same,
+                # operator numbers on the same full grid: C restatement on all threads, and the
+                # numpy port on one core
+                cpu_operator_1024x1024=dict(cpu_operator_timing(),
+                                            c_all_threads=cb.get('operators')),
+                cpu_direct_solver_sample=direct,
                 wall_s=wall)
     print(json.dumps(line), flush=True)
 
@@ -674,8 +775,13 @@ def native_arm(args):
                      ms_per_step=prof[nm + '_ms_all'] / 3.0)
             for nm in ('sweep', 'jvp', 'residual', 'mdot', 'orth', 'first_vector', 'cycle_begin')}
         if world == 1 and not args.no_cpu:
-            cpu = cpu_baseline(2, 96, 1)
-            extra['cpu_operator_1024x1024'] = cpu_operator_timing()
+            try:        # same configuration, every host thread (C restatement of the oracle)
+                cpu = cpu_baseline_c(20, 1)
+                ops = cpu.pop('operators')
+            except Exception as e:      # noqa: BLE001 — the numpy port is always there
+                sys.stderr.write('bench.py: C oracle leg unavailable (%s); numpy port\n' % e)
+                cpu, ops = cpu_baseline(2, 96, 1), None
+            extra['cpu_operator_1024x1024'] = dict(cpu_operator_timing(), c_all_threads=ops)
     if strong is not None:
         extra.update(strong)
     if world > 1:
@@ -725,10 +831,15 @@ def main():
                          'global 1024^2 / 256^3 grid split over the GPUs')
     ap.add_argument('--quick', action='store_true', help='skip the 256^3 kernel timings')
     ap.add_argument('--no-cpu', action='store_true', help='skip the CPU baseline')
+    ap.add_argument('--cpu-leg', default=None, help=argparse.SUPPRESS)     # internal: K,W,n
     ap.add_argument('--sweep', action='store_true',
                     help='kernel rooflines over per-GPU tiles 512^2..4096^2 and 256^3 '
                          '(BASELINE configs[4]); prints one JSON object, not the bench line')
     args = ap.parse_args()
+    if args.cpu_leg:
+        k, w, n = (int(x) for x in args.cpu_leg.split(','))
+        print(json.dumps(c_leg(k, w, n)), flush=True)
+        return
     if args.sweep:
         sys.path.insert(0, os.path.join(ROOT, 'tests'))
         out = {}
