@@ -383,6 +383,55 @@ def test_rosw_adaptive_matches_oracle():
 
 
 # ---------------------------------------------------------------------------
+# (2b) BASELINE-size ROSW steps against the oracle's C restatement
+# ---------------------------------------------------------------------------
+def _c_oracle(ph):
+    """the oracle in C + OpenMP (oracle/ksfd_oracle_c.c): what makes a full-size step a
+    matter of seconds on the CPU; skipped if the box cannot build / load it"""
+    try:
+        from oracle import ksfd_oracle_c as OC
+        OC.lib()
+    except Exception as e:      # noqa: BLE001
+        pytest.skip('oracle C library unavailable: %s' % e)
+    return OC.COracle(ph)
+
+
+@pytest.mark.parametrize('label,p,nsteps', [('1024^2', phys84(2, (1024, 1024)), 3),
+                                            ('3d_144x80x112', phys84(3, (144, 80, 112)), 2)])
+def test_full_size_rosw_steps_vs_c_oracle(label, p, nsteps):
+    """The benchmark's own step (options84 physics, dt = 1e-3, clamp + ROSW ra34pw2 with the
+    default solver choice, i.e. the fused Richardson sweeps) at the BASELINE 2-D size and on a
+    3-D grid with several tiles, chunks and a clamped last tile, against the C oracle
+    (pinned to the numpy oracle / SuperLU steps in tests/test_oracle_c.py).  Measured per dof
+    relative to the largest INCREMENT of the step (the state itself is 9000 + noise: errors
+    relative to it would hide a wrong step).  Tolerance 1e-8; both sides solve to rtol 1e-13."""
+    from ksfd_b200 import core
+    ph = oracle_physics(p)
+    c = _c_oracle(ph)
+    u0 = random_state(p, 31)
+    ctx = make_ctx(p)
+    opts = core.ts_options(adapt='none', ksp_rtol=1e-13, ksp_max_it=2000)
+    u = ctx.upload(u0)
+    uc = np.ascontiguousarray(u0.copy())
+    t = 0.0
+    for k in range(nsteps):
+        before = uc.copy()
+        ctx.groom(u)
+        res = ctx.ts_step(u, t, 1e-3, opts)
+        assert res.accepted == 1 and res.ksp_fail == 0
+        t = res.t_new
+        c.ts_step(uc, 1e-3, rtol=1e-13)
+        got = ctx.download(u)
+        worst = 0.0
+        for d in range(ph.dof):
+            inc = np.abs(uc[d::ph.dof] - before[d::ph.dof]).max()
+            worst = max(worst, np.abs(got[d::ph.dof] - uc[d::ph.dof]).max() / inc)
+        print('%s step %d: max error / max increment = %.2e (sweeps %d)' % (label, k, worst, res.ksp_its))
+        assert worst < 1e-8, (label, k, worst)
+    ctx.close()
+    c.close()
+
+
 # (3) BASELINE sizes: size-independent properties
 # ---------------------------------------------------------------------------
 @pytest.mark.parametrize('label,p', [('1024^2', phys84(2, (1024, 1024))),
