@@ -237,3 +237,32 @@ class COracle:
         if rc:
             raise RuntimeError('oc_ts_step failed (%d)' % rc)
         return vm[:self.ph.dim], int(info[0])
+
+
+def integrate(c, u0, t0, h, nsteps, groom_each_step=True, adapt=None, rtol=1e-12, ksp_type='auto'):
+    """The reference's step loop (KSFDTS.solve, KSFD/ksfdts.py:202-228) without noise and monitors on
+    the C restatement: clamp, ROSW step; adapt=None -> fixed step (-ts_adapt_type none),
+    adapt=dict(atol, rtol[, clip, dt_min, dt_max]) -> TSAdapt basic exactly as
+    ksfd_oracle.integrate (same `wnorm2` / `adapt_basic`).  `rtol` is the tolerance of the
+    iterative stage solves.  Returns [(t, u)] after each accepted step and the number of
+    rejected attempts."""
+    u = np.ascontiguousarray(np.asarray(u0, dtype=np.float64).reshape(-1, order='F')).copy()
+    t, k, rejected, out = float(t0), 0, 0, []
+    while k < nsteps:
+        if groom_each_step:
+            u = c.groom(u)
+        unew, uemb, _ = c.rosw_step(u, h, rtol=rtol, ksp_type=ksp_type)
+        if adapt is None:
+            u, t, k = unew, t + h, k + 1
+            out.append((t, u.copy()))
+            continue
+        en = O.wnorm2(unew, uemb, adapt['atol'], adapt['rtol'])
+        kw = {a: adapt[a] for a in ('clip', 'dt_min', 'dt_max') if a in adapt}
+        ok, hn = O.adapt_basic(h, en, **kw)
+        if ok:
+            u, t, k = unew, t + h, k + 1
+            out.append((t, u.copy()))
+        else:
+            rejected += 1
+        h = hn
+    return out, rejected

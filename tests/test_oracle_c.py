@@ -187,3 +187,21 @@ def test_bench_cpu_leg_runs_in_its_own_process():
     assert r['finite'] and r['steps'] == 2 and r['n'] == 48 and r['cores'] == 2
     assert 20 <= r['its_per_step'] <= 40            # 4 solves of 7-8 sweeps at dt = 1e-3
     assert r['operators']['residual']['mpts_per_s'] > 0
+
+
+def test_adaptive_trajectory_matches_numpy_oracle():
+    """TSAdapt basic from a tiny first step (as the adaptive option files start): same accepted
+    times, same states, while dt grows by more than three decades."""
+    p = phys84(2, (16, 12))
+    ph = oracle_physics(p)
+    c = OC.COracle(ph)
+    u0 = random_state(p, 12)
+    adapt = dict(atol=1e-2, rtol=1e-6, clip=(0.1, 5.0))
+    ref = O.integrate(u0, 0.0, 1e-6, 12, ph, adapt=adapt)
+    got, rejected = OC.integrate(c, u0, 0.0, 1e-6, 12, adapt=adapt, rtol=1e-13)
+    assert len(got) == len(ref) == 12
+    for (tr, ur), (tg, ug) in zip(ref, got):
+        assert abs(tr - tg) <= 1e-9 * tr
+        assert relerr(ug, ur.reshape(-1, order='F')) < 1e-9
+    assert ref[-1][0] > 1e-3            # dt really grew (from 1e-6)
+    c.close()
