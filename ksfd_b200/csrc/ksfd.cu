@@ -2259,7 +2259,11 @@ static int sweep_end(ksfd_ctx *c, SweepRun &r, ksfd_ksp_result *res, bool *clean
         // The sweep that ends a solve writes final_, a system fence, cycle_done and then
         // iters_done (sweep_finalize); the last two are not ordered against each other, so
         // iters_done may be seen first.  final_ is older than the fence: whoever sees that
-        // iters_done also sees it, and must not launch one more sweep.
+        // iters_done also sees it, and must not launch one more sweep.  (On several ranks an
+        // extra sweep on one rank alone would also make that rank redo the speculated work and
+        // its halo pushes: exchange numbers would run apart.)  The fence keeps the loads below
+        // behind the ones of the wait on hosts that reorder loads.
+        std::atomic_thread_fence(std::memory_order_acquire);
         if (hs->cycle_done || hs->final_ || r.launched >= r.go.max_it) break;
         if (r.dirty && r.launched > 0) {
             TRY(exchange(c, r.buf[(r.launched - 1) & 1], c->dof, 1, st, r.skip, r.defer));
