@@ -193,3 +193,27 @@ def test_ksfd_import_name_resolves_to_this_package():
     assert pl['b'] == 4.5 and pl.defaults['b'] == 2.5 and pl.helps['a'] == 'first'
     with pytest.raises(KSFDException):
         pl.decode(['a=1', 'a=2'])
+
+
+def test_ksfd_alias_covers_the_reference_all_or_says_why():
+    """Every name of the reference's KSFD.__all__ either resolves through the alias package or
+    raises an AttributeError that names what replaces it (code generation, assembled matrix)."""
+    import KSFD
+    ref_all = ['getMat', 'Parser', 'KSFDException', 'Generator', 'random_function', 'TimeSeries',
+               'dillnp', 'dillunp', 'remap_from_files', 'makeKSFDSolver', 'Parameter',
+               'ParameterList', 'Ligand', 'LigandGroup', 'LigandGroups', 'find_duplicates',
+               'SolutionParameters', 'Solution', 'default_parameters', 'UFUNC_MAXARGS',
+               'UfuncifyCodeWrapperMultiple', 'ufuncify', 'Grid', 'safe_sympify',
+               'cartesian_product', 'spatial_expression', 'SpatialExpression', 'StencilUfunc',
+               'Derivatives', 'ksfdTS', 'implicitTS']       # /root/reference/KSFD/__init__.py
+    replaced = []
+    for name in ref_all:
+        try:
+            getattr(KSFD, name)
+        except AttributeError as e:
+            assert 'not provided by ksfd_b200' in str(e), (name, str(e))
+            replaced.append(name)
+    assert sorted(replaced) == sorted(KSFD._REPLACED), replaced
+    for name in ('Grid', 'Derivatives', 'implicitTS', 'ksfdTS', 'TimeSeries', 'SpatialExpression',
+                 'Generator', 'random_function'):
+        assert name not in replaced
