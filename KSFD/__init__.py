@@ -11,7 +11,7 @@ from ksfd_b200 import (KSFDError, KSFDException, Ligand, LigandGroup, LigandGrou
                        default_parameters, find_duplicates, parse_commandline, petsc_init,
                        safe_sympify)
 
-__all__ = ['Parser', 'KSFDException', 'Generator', 'random_function', 'TimeSeries', 'dillnp',
+__all__ = ['Parser', 'KSFDException', 'Generator', 'random_function', 'TimeSeries', 'Gatherer', 'dillnp',
            'dillunp', 'Parameter', 'ParameterList', 'Ligand', 'LigandGroup', 'LigandGroups',
            'find_duplicates', 'SolutionParameters', 'default_parameters', 'Grid',
            'safe_sympify', 'SpatialExpression', 'Derivatives', 'ksfdTS', 'implicitTS']

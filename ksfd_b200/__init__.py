@@ -22,6 +22,7 @@ def __getattr__(name):
         'implicitTS': ('.ts', 'make_implicitTS'), 'ksfdTS': ('.ts', 'ksfdTS'),
         'KSFDTS': ('.ts', 'KSFDTS'),
         'TimeSeries': ('.timeseries', 'TimeSeries'),
+        'Gatherer': ('.timeseries', 'Gatherer'), 'tsmerge': ('.timeseries', 'tsmerge'),
         'dillnp': ('.timeseries', 'dillnp'), 'dillunp': ('.timeseries', 'dillunp'),
         'Generator': ('.random', 'Generator'),
         'random_function': ('.random', 'random_function'),
