@@ -90,9 +90,17 @@ class TimeSeries:
         suffix = '.h5' if HAVE_H5 else '.npz'
         name = '%ss%dr%d%s' % (basename, self.size, self.rank, suffix)
         seq = '%ss1r0%s' % (basename, suffix)
-        if mode in ('r', 'a') and not os.path.isfile(name) and os.path.isfile(seq):
-            name = seq
+        mpi = '%sMPI%s' % (basename, suffix)        # one file for all ranks (parallel HDF5 builds)
+        self.rank_owns_file = True
+        if mode in ('r', 'a') and not os.path.isfile(name):
+            if os.path.isfile(seq):
+                name = seq
+                self.rank_owns_file = self.size == 1
+            elif os.path.isfile(mpi):               # written elsewhere with parallel HDF5: readable
+                name = mpi
+                self.rank_owns_file = self.size == 1
         self.filename = name
+        self.retries, self.retry_interval = int(retries), retry_interval
         self.creating = mode[0] in 'wx' or (mode != 'r' and not os.path.isfile(name))
         self._f = None
         self.ts = np.array([], dtype=float)
@@ -119,15 +127,65 @@ class TimeSeries:
         if mode[0] in 'wxa' or mode == 'r+':
             d = os.path.dirname(os.path.abspath(self.filename))
             os.makedirs(d, exist_ok=True)
-        if HAVE_H5:
-            self._f = h5py.File(self.filename, mode)
-        else:
-            self._f = _NpzStore(self.filename, mode)
+        # a file another process is still writing may fail to open: try again `retries`
+        # times, `retry_interval` seconds apart (reference open_with_retry)
+        import time
+        left = getattr(self, 'retries', 0)
+        while True:
+            try:
+                if HAVE_H5:
+                    self._f = h5py.File(self.filename, mode)
+                else:
+                    if mode == 'r' and not os.path.isfile(self.filename):
+                        raise OSError('no such series file: ' + self.filename)
+                    self._f = _NpzStore(self.filename, mode)
+                return
+            except (OSError, ValueError, EOFError):
+                if left <= 0:
+                    raise
+                left -= 1
+                time.sleep(self.retry_interval)
 
     def is_open(self):
         return self._f is not None
 
-    tsFile = property(lambda s: s._f)
+    tsFile = tsf = property(lambda s: s._f)
+    dim = property(lambda s: s.grid.dim)
+    dof = property(lambda s: s.grid.dof)
+
+    @property
+    def ranges(self):
+        """index ranges of the data in this file (the global ones for a shared / sequential file)"""
+        if self.rank_owns_file or self.grid is None:
+            return tuple(self.grid.ranges) if self.grid is not None else None
+        return tuple((0, int(m)) for m in self.grid.nps)
+
+    @property
+    def myslice(self):
+        """slice of the file's arrays that belongs to this rank (reference set_grid)"""
+        if self.rank_owns_file:
+            return (slice(0, None),) * (self.grid.dim + 1)
+        return (slice(0, None),) + tuple(slice(*r) for r in self.grid.ranges)
+
+    def set_grid(self, grid):
+        self.grid = grid
+        if self.mode != 'r':
+            self._set('ranges', np.array(self.ranges))
+
+    @staticmethod
+    def parse_filename(filename):
+        """'bases2r1.h5' -> ('base', 2, 1, False); 'baseMPI.h5' -> ('base', 1, 0, True)"""
+        import re
+        res = re.fullmatch(r'(.*)MPI\.(?:h5|npz)', filename)
+        if res:
+            return (res[1], 1, 0, True)
+        res = re.fullmatch(r'(.*)s(\d+)r(\d+)\.(?:h5|npz)', filename)
+        if res:
+            return (res[1], int(res[2]), int(res[3]), False)
+        raise ValueError("Couldn't parse filename %s" % filename)
+
+    def get_filename(self, *a, **k):
+        return self.filename
 
     def _set(self, key, val):
         if self.mode == 'r':

@@ -110,3 +110,27 @@ def test_store_slice_completes_a_time_point(tmp_path):
     assert np.array_equal(ts.retrieve_by_number(0), f)
     assert np.array_equal(ts.retrieve_by_number(1), 2 * f)
     ts.close()
+
+
+def test_timeseries_reference_surface(tmp_path):
+    """the small members of the reference's KSFDTimeSeries the tools use (ksfdtimeseries.py:139-243)"""
+    from ksfd_b200.timeseries import TimeSeries
+    assert TimeSeries.parse_filename('bases2r1.h5') == ('base', 2, 1, False)
+    assert TimeSeries.parse_filename('tests/test1MPI.h5') == ('tests/test1', 1, 0, True)
+    with pytest.raises(ValueError):
+        TimeSeries.parse_filename('nonsense.txt')
+    prefix = str(tmp_path / 'seq')
+    fields, gg = _write(prefix, 1, [0.0, 1.0])
+    grids, _ = _grids(2)
+    for g in grids:                                  # two ranks read the sequential file
+        ts = TimeSeries(prefix, grid=g, comm=g.comm, mode='r')
+        assert not ts.rank_owns_file and ts.tsf is ts.tsFile and ts.dim == 2 and ts.dof == 3
+        assert ts.ranges == ((0, 6), (0, 11))        # the FILE holds the global ranges
+        whole = np.array(ts.tsf['data1'])
+        assert np.array_equal(whole[ts.myslice], ts.retrieve_by_number(1))
+        assert np.array_equal(whole[ts.myslice], fields[1][..., g.ranges[-1][0]:g.ranges[-1][1]])
+    own = TimeSeries(prefix, grid=gg, comm=gg.comm, mode='r')
+    assert own.rank_owns_file and own.myslice == (slice(0, None),) * 3
+    with pytest.raises(OSError):                     # nothing to read: an error, after the retries
+        TimeSeries(str(tmp_path / 'missing'), grid=gg, comm=gg.comm, mode='r', retries=1,
+                   retry_interval=0.01)
