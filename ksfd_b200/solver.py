@@ -81,7 +81,9 @@ def start_values(clargs, grid, ps):
 def resume_values(clargs, grid, ps):
     """Last time point of a saved series (reference ksfdsolver2.py:525-578)."""
     name = clargs.resume or clargs.restart
-    cpf = TimeSeries(name, grid=grid, mode='r')
+    cpf = TimeSeries(name, grid=grid, mode='r',
+                     retries=getattr(clargs, 'series_retries', 0) or 0,
+                     retry_interval=getattr(clargs, 'series_retry_interval', 60) or 60)
     times = cpf.sorted_times()
     tlast = times[-1]
     given = {p.split('=', 1)[0] for p in clargs.params}
@@ -168,13 +170,20 @@ def main(*args):
     if clargs.check:
         ts.setMonitor(ts.checkpointMonitor, (),
                       {'prefix': clargs.check, 'mpiok': clargs.mpiok})
+    failed = None
     try:
         ts.solve()
     except KeyboardInterrupt as e:
         print('KeyboardInterrupt:', str(e))
+    except Exception as e:          # noqa: BLE001 — as the reference (ksfdsolver2.py:747-756): report,
+        print('Exception:', str(e))  # then close the series so that what was saved stays readable
+        failed = e
     if clargs.save:
         close_save()
         tseries.close()
+    if failed is not None:
+        # (the reference goes on and returns 0; a job script is better served by the error)
+        raise failed
     ts.cleanup()
     if comm.rank == 0:
         print('SNES failures = ', ts.getSNESFailures())
