@@ -158,9 +158,28 @@ class Parser(argparse.ArgumentParser):
         return ns
 
 
+LIG_HELP = """
+Use --showparams to see ligand and user-defined parameters
+"""
+
+
+def parameter_help(param_list=None, add_help=LIG_HELP):
+    """`--help` epilogue: every name=value parameter with its default and meaning
+    (reference ksfdsolver2.py:366-376)."""
+    text = 'Parameters:\n'
+    for t, d, h in (default_parameters if param_list is None else param_list):
+        text += t + '=' + str(d) + ' -- ' + h + '\n'
+    text += """
+You may define additional user parameters for use in rho0 or sources.
+These should be of type float (e.g. 'k0=10.0' rather than 'k0=10')\n
+"""
+    return text + add_help
+
+
 def parse_commandline(args=None):
     """The ksfdsolver2.py command line (reference ksfdsolver2.py:380-422)."""
-    p = Parser(description='Solve Keller-Segel PDEs (B200-native hot path)')
+    p = Parser(description='Solve Keller-Segel PDEs (B200-native hot path)',
+               epilog=parameter_help(), formatter_class=argparse.RawDescriptionHelpFormatter)
     p.add_argument('--cappotential', choices=['tophat', 'witch'], default='tophat')
     p.add_argument('--save', help='filename prefix in which to save results')
     p.add_argument('--check', help='filename prefix for checkpoints')
