@@ -205,3 +205,40 @@ def test_adaptive_trajectory_matches_numpy_oracle():
         assert relerr(ug, ur.reshape(-1, order='F')) < 1e-9
     assert ref[-1][0] > 1e-3            # dt really grew (from 1e-6)
     c.close()
+
+
+def test_c_oracle_vs_numpy_oracle_random_physics():
+    """random ligand groups (1-3 groups, up to 5 ligands), both cap potentials, odd extents down
+    to the stencil width, all dimensions: residual, J.v and block inverses of the two oracles"""
+    rng = np.random.default_rng(2024)
+    for case in range(24):
+        dim = int(rng.integers(1, 4))
+        n = tuple(int(x) for x in rng.integers(3, 12, size=dim))
+        ngroups = int(rng.integers(1, 4))
+        groups, nlig = [], 0
+        for g in range(ngroups):
+            k = int(rng.integers(1, 3)) if nlig < 4 else 1
+            nlig += k
+            groups.append([float(rng.uniform(500, 2500)), float(rng.choice([-1, 1]) * rng.uniform(1e-4, 9e-4)),
+                           [[float(rng.uniform(0.3, 1.5)), float(rng.uniform(1e-3, 2e-2)),
+                             float(rng.uniform(1e-3, 2e-2)), float(rng.uniform(1e-6, 2e-5))]
+                            for _ in range(k)]])
+        p = dict(dim=dim, n=list(n), h=[float(rng.uniform(0.5, 2.0)) / 384 for _ in range(dim)],
+                 groups=groups, s2=float(rng.uniform(1e-4, 5e-4)), rhomax=float(rng.uniform(9000, 30000)),
+                 cushion=float(rng.uniform(500, 3000)), maxscale=float(rng.uniform(1, 3)),
+                 cap=['tophat', 'witch'][case % 2], rhomin=1e-7, Umin=1e-7)
+        ph = oracle_physics(p)
+        c = OC.COracle(ph)
+        u = random_state(p, 100 + case, rel=0.05)
+        v = rng.standard_normal(u.size)
+        f = c.dfdt(u)
+        fr = O.dfdt(u, ph).reshape(-1, order='F')
+        assert check_field(f, fr, ph.dof, 1e-13, cond_scale(ph, u), ncond=8.0) < 1.0, (case, p)
+        shift = float(rng.uniform(1.0, 3000.0))
+        c.jvp_setup(u, shift)
+        assert relerr(c.jvp(v), O.jvp(u, v, shift, ph).reshape(-1, order='F'), ph.dof) < 1e-13, (case, p)
+        B = O.block_diagonal(u, shift, ph)
+        Mi = c.minv()
+        eye = np.eye(ph.dof)
+        assert max(np.abs(Mi[i] @ B[i] - eye).max() for i in range(ph.npts)) < 1e-10, (case, p)
+        c.close()
