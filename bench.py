@@ -302,6 +302,9 @@ def reference_arm(args):
         par = '%d host threads (OpenMP), one process' % cb['cores']
         how = ('CPU arm: oracle C restatement, stage solves by point-block-Jacobi Richardson sweeps '
                '(%.1f per step) instead of MUMPS LU' % cb['ksp_its_per_step'])
+        if not same:
+            how += ('; each step a bounded sample of the %d-tile grid = ONE %dx%d tile (CPU throughput in '
+                    'points*steps/s does not depend on the number of tiles)' % (args.gpus, TILE, TILE))
         try:        # what a direct solver costs: one step of a 96^2 tile, numpy port + SuperLU
             d = cpu_baseline(1, 96, 1)
             direct = dict(value=d['value'], unit=d['unit'], cores=1, sample=d['sample'],
