@@ -242,3 +242,21 @@ def test_c_oracle_vs_numpy_oracle_random_physics():
         eye = np.eye(ph.dof)
         assert max(np.abs(Mi[i] @ B[i] - eye).max() for i in range(ph.npts)) < 1e-10, (case, p)
         c.close()
+
+
+def test_c_oracle_at_the_benchmark_size():
+    """the grid bench.py's CPU legs run (2-D 1024^2): residual and J.v of the two oracles
+    (at 256^3 the same comparison gives 0.13 of the allowed residual error and 4.9e-16 for J.v;
+    run once by hand: ten seconds of numpy and some GB)"""
+    p = phys84(2, (1024, 1024))
+    ph = oracle_physics(p)
+    c = OC.COracle(ph)
+    u = random_state(p, 5)
+    v = np.random.default_rng(6).standard_normal(u.size)
+    f = c.dfdt(u)
+    fr = O.dfdt(u, ph).reshape(-1, order='F')
+    assert check_field(f, fr, ph.dof, 1e-13, cond_scale(ph, u), ncond=8.0) < 1.0
+    shift = 1.0 / (O.ROSW_GAMMA * 1e-3)
+    c.jvp_setup(u, shift)
+    assert relerr(c.jvp(v), O.jvp(u, v, shift, ph).reshape(-1, order='F'), ph.dof) < 1e-14
+    c.close()
