@@ -26,6 +26,9 @@
  *                   instead of the reference's MUMPS LU: at the benchmark size (3.1 M unknowns)
  *                   a sparse LU per step takes minutes; tests compare with SuperLU solves.
  *
+ * Reproducible to the last bit: reductions are summed over fixed chunks in chunk order, every other
+ * loop is elementwise — the result does not depend on the number of threads or on the run.
+ *
  * Layout: flat fp64, dof fastest then x, y, z (KSFD/ksfdgrid.py:10-28); one process owns the
  * whole periodic grid; ghost points are the periodic images (DMDA globalToLocal on one rank).
  */
@@ -39,6 +42,9 @@
 #define OC_MAXLIG 8
 #define OC_MAXDOF (OC_MAXLIG + 1)
 #define OC_ABI 1
+/* reductions are summed over fixed chunks in chunk order: results do not depend on the number of
+   threads or on the run (a checker should be reproducible to the last bit) */
+#define OC_CHUNK 4096
 
 typedef struct {
     int dim, n[3], nlig, ngroups, witch, pad_;
@@ -68,6 +74,7 @@ typedef struct {
     double *r, *z, *w, *F, *Z, *Zd, *Y[4], *un;
     double *V;                  /* GMRES basis (allocated when first needed) */
     int vcap;
+    double *part;               /* per-chunk partial sums of the reductions */
 } oc_ctx;
 
 int oc_abi(void) { return OC_ABI; }
@@ -99,6 +106,7 @@ void oc_destroy(oc_ctx *c)
     for (int i = 0; i < 4; ++i) free(c->Y[i]);
     free(c->un);
     free(c->V);
+    free(c->part);
     free(c);
 }
 
@@ -127,6 +135,7 @@ oc_ctx *oc_create(const oc_phys *P)
     c->Z = dalloc(nv); c->Zd = dalloc(nv);
     for (int i = 0; i < 4; ++i) c->Y[i] = dalloc(nv);
     c->un = dalloc(nv);
+    c->part = dalloc(nv / OC_CHUNK + 2);
     return c;
 }
 
@@ -457,11 +466,37 @@ void oc_jvp(oc_ctx *c, const double *v, double *out)
             }
 }
 
-static double dot(long n, const double *a, const double *b)
+static double dot(oc_ctx *c, long n, const double *a, const double *b)
 {
+    const long nch = (n + OC_CHUNK - 1) / OC_CHUNK;
+#pragma omp parallel for schedule(static)
+    for (long k = 0; k < nch; ++k) {
+        const long e = (k + 1) * OC_CHUNK < n ? (k + 1) * OC_CHUNK : n;
+        double s = 0.0;
+        for (long i = k * OC_CHUNK; i < e; ++i) s += a[i] * b[i];
+        c->part[k] = s;
+    }
     double s = 0.0;
-#pragma omp parallel for schedule(static) reduction(+ : s)
-    for (long i = 0; i < n; ++i) s += a[i] * b[i];
+    for (long k = 0; k < nch; ++k) s += c->part[k];
+    return s;
+}
+
+/* r -= w, returns ||r||^2 (chunked like dot) */
+static double sub_norm2(oc_ctx *c, long n, double *r, const double *w)
+{
+    const long nch = (n + OC_CHUNK - 1) / OC_CHUNK;
+#pragma omp parallel for schedule(static)
+    for (long k = 0; k < nch; ++k) {
+        const long e = (k + 1) * OC_CHUNK < n ? (k + 1) * OC_CHUNK : n;
+        double s = 0.0;
+        for (long i = k * OC_CHUNK; i < e; ++i) {
+            r[i] -= w[i];
+            s += r[i] * r[i];
+        }
+        c->part[k] = s;
+    }
+    double s = 0.0;
+    for (long k = 0; k < nch; ++k) s += c->part[k];
     return s;
 }
 
@@ -490,7 +525,7 @@ static int gmres(oc_ctx *c, const double *b, double *x, double tol, int m, int m
         double *V0 = c->V;
 #pragma omp parallel for schedule(static)
         for (long i = 0; i < n; ++i) V0[i] = b[i] - c->w[i];
-        double beta = sqrt(dot(n, V0, V0));
+        double beta = sqrt(dot(c, n, V0, V0));
         *rnorm = beta;
         if (beta <= tol || its >= max_it) return its;
         {
@@ -506,11 +541,11 @@ static int gmres(oc_ctx *c, const double *b, double *x, double tol, int m, int m
             oc_pc_apply(c, vk, c->z);
             oc_jvp(c, c->z, wv);
             for (int i = 0; i <= k; ++i) {          /* modified Gram-Schmidt */
-                const double h = dot(n, wv, c->V + (long)i * n);
+                const double h = dot(c, n, wv, c->V + (long)i * n);
                 H[i * 64 + k] = h;
                 axpy(n, -h, c->V + (long)i * n, wv);
             }
-            const double hn = sqrt(dot(n, wv, wv));
+            const double hn = sqrt(dot(c, n, wv, wv));
             H[(k + 1) * 64 + k] = hn;
             if (hn > 0.0) {
                 const double ih = 1.0 / hn;
@@ -547,13 +582,9 @@ static int gmres(oc_ctx *c, const double *b, double *x, double tol, int m, int m
         /* converged by the recurrence: confirmed on the true residual at the top of the loop */
         if (its >= max_it && *rnorm > tol) {
             oc_jvp(c, x, c->w);
-            double s = 0.0;
-#pragma omp parallel for schedule(static) reduction(+ : s)
-            for (long i = 0; i < n; ++i) {
-                const double d = b[i] - c->w[i];
-                s += d * d;
-            }
-            *rnorm = sqrt(s);
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < n; ++i) c->z[i] = b[i] - c->w[i];
+            *rnorm = sqrt(dot(c, n, c->z, c->z));
             return *rnorm <= tol ? its : -its;
         }
     }
@@ -574,7 +605,7 @@ int oc_solve(oc_ctx *c, const double *b, double *x, double rtol, double atol, in
     double *r = c->r, *z = c->z;
     memset(x, 0, sizeof(double) * (size_t)n);
     memcpy(r, b, sizeof(double) * (size_t)n);
-    const double bn = sqrt(dot(n, b, b));
+    const double bn = sqrt(dot(c, n, b, b));
     const double tol = fmax(rtol * bn, atol);
     double rn = bn;
     int its = 0, used_gmres = 0;
@@ -593,13 +624,7 @@ int oc_solve(oc_ctx *c, const double *b, double *x, double rtol, double atol, in
                 }
             }
             oc_jvp(c, z, c->w);
-            double s2 = 0.0;
-#pragma omp parallel for schedule(static) reduction(+ : s2)
-            for (long i = 0; i < n; ++i) {
-                r[i] -= c->w[i];
-                s2 += r[i] * r[i];
-            }
-            const double rnew = sqrt(s2);
+            const double rnew = sqrt(sub_norm2(c, n, r, c->w));
             ++its;
             const int slow = !(rnew <= 0.65 * rn);
             rn = rnew;

@@ -260,3 +260,34 @@ def test_c_oracle_at_the_benchmark_size():
     c.jvp_setup(u, shift)
     assert relerr(c.jvp(v), O.jvp(u, v, shift, ph).reshape(-1, order='F'), ph.dof) < 1e-14
     c.close()
+
+
+def test_c_oracle_is_reproducible_across_thread_counts():
+    """a checker must not depend on the machine: three steps (ill-conditioned state with a clamped
+    point, GMRES fallback on the way) give the same bits with 1, 3 and all threads"""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prog = (
+        "import sys, hashlib; sys.path[:0] = [%r, %r]\n"
+        "import numpy as np\n"
+        "from helpers import phys84, oracle_physics, random_state\n"
+        "from oracle import ksfd_oracle_c as OC\n"
+        "p = phys84(2, (40, 28)); c = OC.COracle(oracle_physics(p))\n"
+        "u = random_state(p, 9); u[0] = -1.0\n"
+        "its = [c.ts_step(u, 1e-3, rtol=1e-13)[1] for _ in range(3)]\n"
+        "print(OC.threads(), its, hashlib.sha256(u.tobytes()).hexdigest())\n"
+    ) % (os.path.join(root, 'tests'), root)
+    seen = {}
+    for nt in ('1', '3', ''):
+        env = dict(os.environ)
+        env.pop('OMP_NUM_THREADS', None)
+        if nt:
+            env['OMP_NUM_THREADS'] = nt
+        o = subprocess.run([sys.executable, '-c', prog], capture_output=True, text=True, timeout=300, env=env)
+        assert o.returncode == 0, o.stderr[-400:]
+        th, rest = o.stdout.strip().split(' ', 1)
+        seen[th] = rest
+    assert len(set(seen.values())) == 1, seen
