@@ -19,6 +19,7 @@
  *   oc_jvp_setup /  implicitIJ, rhoJacobian_arrays, UJacobian_arrays (applied matrix-free:
  *   oc_jvp          the exact derivative of the discrete f) KSFD/ksfdts.py:598-640,
  *                                                 ksfdsym.py:630-761
+ *   oc_beuler_step  PETSc TSBEULER with -snes_type ksponly (one Newton step); not in the tree either
  *   oc_rosw_step    PETSc TSROSW ra34pw2 behind TS.step() (KSFD/ksfdts.py:211), -snes_type
  *                   ksponly; NOT in the reference tree (parity unpinned at that boundary, see
  *                   oracle/ksfd_oracle.py).  The stage systems are solved iteratively
@@ -693,6 +694,22 @@ int oc_rosw_step(oc_ctx *c, const double *u, double h, const oc_tableau *T, doub
             if (uemb) uemb[q] = uemb[q] + be * Y[q];
         }
     }
+    return 0;
+}
+
+/* Backward Euler with -snes_type ksponly: one Newton step from u_n (ksfd_oracle.py beuler_step):
+   (I/h - df/du(u)) y = f(u), unew = u + y.  Returns 0, 1 = solve failed. */
+int oc_beuler_step(oc_ctx *c, const double *u, double h, double rtol, double atol, int max_it,
+                   int restart, int ksp_type, double *unew, int info[2])
+{
+    const long n = c->npts * c->dof;
+    oc_dfdt(c, u, NULL, c->F);
+    if (oc_jvp_setup(c, u, 1.0 / h)) return 1;
+    double nn[2];
+    if (oc_solve(c, c->F, c->Y[0], rtol, atol, max_it, restart, ksp_type, info, nn)) return 1;
+    const double *Y = c->Y[0];
+#pragma omp parallel for schedule(static)
+    for (long q = 0; q < n; ++q) unew[q] = u[q] + Y[q];
     return 0;
 }
 

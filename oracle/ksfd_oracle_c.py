@@ -67,6 +67,9 @@ def lib():
                                    C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp,
                                    C.POINTER(C.c_int)]
         L.oc_rosw_step.restype = C.c_int
+        L.oc_beuler_step.argtypes = [C.c_void_p, _dp, C.c_double, C.c_double, C.c_double, C.c_int,
+                                     C.c_int, C.c_int, _dp, C.POINTER(C.c_int)]
+        L.oc_beuler_step.restype = C.c_int
         L.oc_get_stage.argtypes = [C.c_void_p, C.c_int, _dp]
         L.oc_ts_step.argtypes = [C.c_void_p, _dp, C.c_double, C.POINTER(_Tableau), C.c_double,
                                  C.c_int, _dp, C.POINTER(C.c_int)]
@@ -221,6 +224,16 @@ class COracle:
         if rc:
             raise RuntimeError('oc_rosw_step: stage %d did not converge' % (rc - 1))
         return un, ue, dict(its=int(info[0]), gmres_solves=int(info[1]))
+
+    def beuler_step(self, u, h, rtol=1e-8, atol=0.0, max_it=10000, restart=30, ksp_type='auto'):
+        """backward Euler, one Newton step (-snes_type ksponly) -> u_new"""
+        u = _vec(u, self.nv)
+        un = np.empty(self.nv)
+        info = (C.c_int * 2)()
+        if lib().oc_beuler_step(self.h, _p(u), float(h), rtol, atol, max_it, restart,
+                                self.KSP[ksp_type], _p(un), info):
+            raise RuntimeError('oc_beuler_step: the solve did not converge')
+        return un
 
     def stage(self, j):
         out = np.empty(self.nv)

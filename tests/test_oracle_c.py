@@ -26,7 +26,7 @@ def test_library_abi():
     assert OC.threads() >= 1
     for sym in ('oc_create', 'oc_destroy', 'oc_groom', 'oc_dfdt', 'oc_ifunction', 'oc_velocity',
                 'oc_velocity_max', 'oc_jvp_setup', 'oc_jvp', 'oc_pc_apply', 'oc_get_minv',
-                'oc_solve', 'oc_rosw_step', 'oc_get_stage', 'oc_ts_step'):
+                'oc_solve', 'oc_rosw_step', 'oc_beuler_step', 'oc_get_stage', 'oc_ts_step'):
         assert hasattr(L, sym), sym
 
 
@@ -291,3 +291,17 @@ def test_c_oracle_is_reproducible_across_thread_counts():
         th, rest = o.stdout.strip().split(' ', 1)
         seen[th] = rest
     assert len(set(seen.values())) == 1, seen
+
+
+@pytest.mark.parametrize('dim,n', [(1, (40,)), (2, (16, 12)), (3, (6, 5, 7))])
+def test_beuler_step_vs_numpy_oracle(dim, n):
+    p = phys84(dim, n)
+    ph = oracle_physics(p)
+    c = OC.COracle(ph)
+    u = random_state(p, 2)
+    un = c.beuler_step(u, 1e-3, rtol=1e-13)
+    ur = O.beuler_step(u, 0.0, 1e-3, ph).reshape(-1, order='F')
+    assert relerr(un, ur) < 1e-11
+    inc = np.abs(ur - u).max()
+    assert np.abs(un - ur).max() / inc < 1e-8
+    c.close()
